@@ -1,0 +1,152 @@
+/* mgn_b200.h — C ABI of libmgn_b200.so: the B200 (sm_100a) MeshGraphNet message-passing path.
+ *
+ * Drop-in boundary for NVIDIA PhysicsNeMo's MeshGraphNet hot path.  Every entry point takes
+ * plain device pointers, sizes, a dtype enum and a CUDA stream; no torch types.  The library
+ * never allocates user-visible memory (outputs and workspaces are caller-provided), keeps no
+ * mutable global state, never synchronises the host and is CUDA-graph capturable.
+ *
+ * Return value of every function: 0 = ok, <0 = argument error (MGN_E*), >0 = cudaError_t.
+ *
+ * Conventions
+ *   - feature tables are row-major [rows, D]; dtype is MGN_F32 or MGN_BF16 (fp32 accumulate)
+ *   - weights / biases / LayerNorm affine parameters are ALWAYS fp32 and are read in place
+ *     (nn.Linear layout [out, in]) -- the optimizer's tensors, no shadow copies
+ *   - graph indices are int32; a graph is a CSC (offsets[n_dst+1], indices[E] = source id of
+ *     each in-edge), edge e of the CSC is row e of every edge-feature table
+ *   - "reference" citations are paths inside NVIDIA/modulus (physicsnemo 1.1.0a0)
+ */
+#ifndef MGN_B200_H_
+#define MGN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mgn_stream_t; /* cudaStream_t */
+
+enum { MGN_F32 = 0, MGN_BF16 = 1 };
+
+enum {
+  MGN_OK = 0,
+  MGN_EINVAL = -1,       /* bad argument (null pointer, negative size, unknown enum) */
+  MGN_EUNSUPPORTED = -2, /* shape/dtype combination this kernel family does not cover */
+  MGN_EALIGN = -3,       /* pointer or leading dimension not 16-byte aligned */
+  MGN_EWORKSPACE = -4    /* workspace too small */
+};
+
+/* activation ids (reference: physicsnemo/models/layers/activations.py:173-199) */
+enum {
+  MGN_ACT_NONE = 0,
+  MGN_ACT_RELU = 1,
+  MGN_ACT_SILU = 2,
+  MGN_ACT_TANH = 3,
+  MGN_ACT_SIGMOID = 4,
+  MGN_ACT_GELU = 5,
+  MGN_ACT_LEAKY_RELU = 6,
+  MGN_ACT_ELU = 7
+};
+
+int mgn_version(void);
+const char* mgn_error_string(int code);
+
+/* ------------------------------------------------------------------------------------------
+ * Graph plan: CSC -> CSR transpose (the structure the backward scatter walks).
+ * Replaces: cugraph-ops StaticCSC/BipartiteCSC(reverse_graph_bwd=True) built in
+ *           models/gnn_layers/graph.py:347-445 and DGL's reverse-graph formats used by
+ *           apply_edges/update_all backward (gnn_layers/utils.py:141-147, 370-372).
+ *   csc_dst[e]      destination of CSC edge e (expanded offsets; graph.py:462-471)
+ *   csr_offsets[u]  start of source u's out-edge list           [n_src+1]
+ *   csr_eids[j]     CSC edge position, ascending within a source [E]   (stable => bit-exact)
+ * ---------------------------------------------------------------------------------------- */
+size_t mgn_csr_workspace_bytes(int64_t n_src, int64_t n_dst, int64_t n_edges);
+int mgn_csr_from_csc(const int32_t* offsets, const int32_t* indices, int64_t n_src, int64_t n_dst,
+                     int64_t n_edges, int32_t* csc_dst, int32_t* csr_offsets, int32_t* csr_eids,
+                     void* workspace, size_t workspace_bytes, mgn_stream_t stream);
+
+/* Stable grouping of n items by integer key in [0, n_keys): offsets[n_keys+1] and ids[n] (item
+ * positions, ascending inside each key).  COO -> CSC is group_by(dst) and COO -> CSR is
+ * group_by(src); replaces DGL's adj_tensors("csc") used by CuGraphCSC.from_dgl
+ * (models/gnn_layers/graph.py:143-193) for graphs that arrive in edge-id order. */
+size_t mgn_group_by_key_workspace_bytes(int64_t n_keys);
+int mgn_group_by_key(const int32_t* keys, int64_t n, int64_t n_keys, int32_t* offsets, int32_t* ids,
+                     void* workspace, size_t workspace_bytes, mgn_stream_t stream);
+
+/* out[j] = s for j in [offsets[s], offsets[s+1])  (destination id of every CSC edge,
+ * graph.py:462-471 repeat_interleave) */
+int mgn_expand_offsets(const int32_t* offsets, int64_t n_segments, int32_t* out, mgn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Operator seam (models/gnn_layers/utils.py)
+ * ---------------------------------------------------------------------------------------- */
+/* concat_efeat forward, utils.py:151-229 / concat_message_function :94-109:
+ *   out[e] = [ efeat[e] | src_feat[src_idx[e]] | dst_feat[dst_idx[e]] ]      out: [E, De+Ds+Dd] */
+int mgn_concat_efeat_fwd(int dtype, const void* efeat, int64_t De, const void* src_feat, int64_t Ds,
+                         const void* dst_feat, int64_t Dd, const int32_t* src_idx,
+                         const int32_t* dst_idx, int64_t n_edges, void* out, mgn_stream_t stream);
+
+/* sum_efeat forward, utils.py:232-334:  out[e] = efeat[e] + src_feat[src_idx[e]] + dst_feat[dst_idx[e]] */
+int mgn_sum_efeat_fwd(int dtype, const void* efeat, const void* src_feat, const void* dst_feat,
+                      int64_t D, const int32_t* src_idx, const int32_t* dst_idx, int64_t n_edges,
+                      void* out, mgn_stream_t stream);
+
+/* Deterministic, atomic-free segmented sum (the reduction inside aggregate_and_concat,
+ * utils.py:337-427, and the backward of both gathers):
+ *   out[s, out_col0 : out_col0+D] (+)= scale_s * sum_{j in [offsets[s], offsets[s+1])}
+ *                                       in[ eids ? eids[j] : j , in_col0 : in_col0+D ]
+ * scale_s = 1 (sum) or 1/max(len_s,1) (mean).  accumulate != 0 adds to the existing out. */
+int mgn_segment_sum(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                    const int32_t* offsets, const int32_t* eids, int64_t n_segments, void* out,
+                    int64_t ld_out, int64_t out_col0, int mean, int accumulate,
+                    mgn_stream_t stream);
+
+/* Row gather into a column slice (backward of the segmented sum, halo packing):
+ *   out[r, out_col0 : out_col0+D] = scale_r * in[ idx ? idx[r] : r , in_col0 : in_col0+D ]
+ * inv_deg_offsets != NULL: scale_r = 1/max(deg(idx[r]),1) with deg from those CSC offsets. */
+int mgn_gather_rows(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                    const int32_t* idx, int64_t n_rows, void* out, int64_t ld_out,
+                    int64_t out_col0, const int32_t* inv_deg_offsets, mgn_stream_t stream);
+
+/* out[idx[r]] += in[r] for r in order, deterministic because idx_sorted_perm lists rows grouped by
+ * destination (backward of the halo gather; replaces index_add_ in distributed/utils.py:688-705).
+ * Implemented on top of mgn_segment_sum; see modulus_b200/distributed. */
+
+/* ------------------------------------------------------------------------------------------
+ * Dense pieces of MeshGraphMLP (models/gnn_layers/mesh_graph_mlp.py:142-203), fp32-accurate
+ * SIMT path used for fp32 models and as the on-device cross-check of the tensor-core path.
+ * ---------------------------------------------------------------------------------------- */
+/* y = x W^T + b ; h = act(y).  y_pre may be NULL (not stored); h may alias nothing. */
+int mgn_linear_fwd(int dtype, const void* x, int64_t ldx, int64_t M, int64_t K, const float* w,
+                   const float* b, int64_t N, int act, void* y_pre, void* h, int64_t ldh,
+                   mgn_stream_t stream);
+/* y = act(x) elementwise (the leading activation of MeshGraphEdgeMLPSum, mesh_graph_mlp.py:352) */
+int mgn_act_fwd(int dtype, const void* x, int act, void* y, int64_t n, mgn_stream_t stream);
+/* g_y = g_h * act'(y_pre)  (ReLU may pass the post-activation as y_pre) */
+int mgn_act_bwd(int dtype, const void* g_h, const void* y_pre, int act, void* g_y, int64_t n,
+                mgn_stream_t stream);
+/* g_x[M,K] = g_y[M,N] W[N,K] */
+int mgn_linear_bwd_data(int dtype, const void* g_y, int64_t M, int64_t N, const float* w, int64_t K,
+                        void* g_x, int64_t ldgx, mgn_stream_t stream);
+/* g_w[N,K] = g_y^T x ; g_b[N] = colsum(g_y)   (fp32 outputs, deterministic two-stage split-M) */
+size_t mgn_linear_bwd_weight_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int mgn_linear_bwd_weight(int dtype, const void* g_y, const void* x, int64_t ldx, int64_t M, int64_t N,
+                          int64_t K, float* g_w, float* g_b, void* workspace, size_t workspace_bytes,
+                          mgn_stream_t stream);
+/* out = LayerNorm(x) * gamma + beta (+ residual); eps as nn.LayerNorm (1e-5); mean/rstd fp32 [M] */
+int mgn_layernorm_fwd(int dtype, const void* x, int64_t M, int64_t D, const float* gamma,
+                      const float* beta, float eps, const void* residual, void* out, float* mean,
+                      float* rstd, mgn_stream_t stream);
+size_t mgn_layernorm_bwd_workspace_bytes(int64_t M, int64_t D);
+int mgn_layernorm_bwd(int dtype, const void* g_out, const void* x, const float* mean,
+                      const float* rstd, const float* gamma, int64_t M, int64_t D, void* g_x,
+                      float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
+                      mgn_stream_t stream);
+/* out = a + b (elementwise, n elements) */
+int mgn_add(int dtype, const void* a, const void* b, void* out, int64_t n, mgn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGN_B200_H_ */

@@ -1,0 +1,79 @@
+"""Build recipe for libmgn_b200.so (the C-ABI CUDA library) -- sm_100a only.
+
+`python -m modulus_b200.build` or `__graft_entry__.build()`.  nvcc cross-compiles without a
+GPU.  The shared object is written in-tree (modulus_b200/lib/) so it travels with the repo
+snapshot to the GPU box; it is git-ignored.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+CSRC = ROOT / "csrc"
+LIBDIR = ROOT / "lib"
+LIB = LIBDIR / "libmgn_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+    "--expt-relaxed-constexpr",
+]
+
+
+def sources():
+    return sorted(CSRC.glob("*.cu"))
+
+
+def _digest() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "mgn_b200.h"]):
+        h.update(p.name.encode())
+        h.update(p.read_bytes())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    LIBDIR.mkdir(exist_ok=True)
+    stamp = LIBDIR / "libmgn_b200.sha256"
+    dig = _digest()
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == dig:
+        return LIB
+    if not os.path.exists(nvcc):
+        if LIB.exists():  # GPU box without a toolchain mismatch: use the prebuilt library
+            return LIB
+        raise RuntimeError("nvcc not found and no prebuilt libmgn_b200.so present")
+    objs = []
+    procs = []
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+    for src in sources():
+        obj = objdir / (src.stem + ".o")
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    failed = False
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0 or verbose:
+            sys.stderr.write(f"--- nvcc {src.name} (rc={p.returncode})\n{out}\n")
+        failed |= p.returncode != 0
+    if failed:
+        raise RuntimeError("nvcc failed")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)]
+    subprocess.run(cmd, check=True)
+    stamp.write_text(dig)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,429 @@
+// mgn_gather.cu — the HBM-bound halves of the operator seam (gnn_layers/utils.py):
+// two-sided row gather (+concat / +sum), deterministic atomic-free segmented sum over a
+// CSC or CSR structure, and a generic indexed row gather.  All 128-bit vectorised with a
+// scalar fallback for feature widths that are not multiples of 16 bytes.
+#include "mgn_common.cuh"
+
+namespace mgn {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+__device__ __forceinline__ uint4 ldg16(const T* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// ---------------------------------------------------------------------------------------
+// concat_efeat forward: out[e] = [efeat[e] | src_feat[src[e]] | dst_feat[dst[e]]]
+// one warp owns kRows consecutive edges; lanes walk the 16-byte chunks of the output row
+// ---------------------------------------------------------------------------------------
+template <typename T, int kRows>
+__global__ void __launch_bounds__(256)
+concat_efeat_vec_kernel(const T* __restrict__ efeat, int ce, const T* __restrict__ sfeat, int cs,
+                        const T* __restrict__ dfeat, int cd, const int32_t* __restrict__ src,
+                        const int32_t* __restrict__ dst, int64_t E, T* __restrict__ out) {
+  constexpr int V = Num<T>::kVec;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int cpr = ce + cs + cd;
+  for (int64_t e0 = warp * kRows; e0 < E; e0 += nwarps * kRows) {
+    int32_t s[kRows], d[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int64_t e = e0 + r;
+      s[r] = e < E ? __ldg(src + e) : 0;
+      d[r] = e < E ? __ldg(dst + e) : 0;
+    }
+    for (int c = lane; c < cpr; c += 32) {
+      uint4 v[kRows];
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int64_t e = e0 + r;
+        if (e < E) {
+          const T* p;
+          if (c < ce) p = efeat + (e * ce + c) * V;
+          else if (c < ce + cs) p = sfeat + (static_cast<int64_t>(s[r]) * cs + (c - ce)) * V;
+          else p = dfeat + (static_cast<int64_t>(d[r]) * cd + (c - ce - cs)) * V;
+          v[r] = ldg16(p);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const int64_t e = e0 + r;
+        if (e < E) *reinterpret_cast<uint4*>(out + (e * cpr + c) * V) = v[r];
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void concat_efeat_scalar_kernel(const T* __restrict__ efeat, int De, const T* __restrict__ sfeat,
+                                           int Ds, const T* __restrict__ dfeat, int Dd,
+                                           const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                           int64_t E, T* __restrict__ out) {
+  const int D = De + Ds + Dd;
+  const int64_t total = E * D;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t e = i / D;
+    const int c = static_cast<int>(i - e * D);
+    T v;
+    if (c < De) v = efeat[e * De + c];
+    else if (c < De + Ds) v = sfeat[static_cast<int64_t>(src[e]) * Ds + (c - De)];
+    else v = dfeat[static_cast<int64_t>(dst[e]) * Dd + (c - De - Ds)];
+    out[i] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// sum_efeat forward: out[e] = efeat[e] + src_feat[src[e]] + dst_feat[dst[e]]  (fp32 add)
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+sum_efeat_vec_kernel(const T* __restrict__ efeat, const T* __restrict__ sfeat, const T* __restrict__ dfeat,
+                     int chunks, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int64_t E,
+                     T* __restrict__ out) {
+  constexpr int V = Num<T>::kVec;
+  const int64_t total = E * chunks;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t e = i / chunks;
+    const int c = static_cast<int>(i - e * chunks);
+    Vec16<T> a, b, d;
+    a.raw = ldg16(efeat + (e * chunks + c) * V);
+    b.raw = ldg16(sfeat + (static_cast<int64_t>(__ldg(src + e)) * chunks + c) * V);
+    d.raw = ldg16(dfeat + (static_cast<int64_t>(__ldg(dst + e)) * chunks + c) * V);
+    float fa[V], fb[V], fd[V];
+    a.unpack(fa); b.unpack(fb); d.unpack(fd);
+#pragma unroll
+    for (int k = 0; k < V; ++k) fa[k] = fa[k] + fb[k] + fd[k];
+    a.pack(fa);
+    *reinterpret_cast<uint4*>(out + (e * chunks + c) * V) = a.raw;
+  }
+}
+
+template <typename T>
+__global__ void sum_efeat_scalar_kernel(const T* __restrict__ efeat, const T* __restrict__ sfeat,
+                                        const T* __restrict__ dfeat, int D, const int32_t* __restrict__ src,
+                                        const int32_t* __restrict__ dst, int64_t E, T* __restrict__ out) {
+  const int64_t total = E * D;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t e = i / D;
+    const int c = static_cast<int>(i - e * D);
+    const float v = Num<T>::to_f(efeat[i]) + Num<T>::to_f(sfeat[static_cast<int64_t>(src[e]) * D + c]) +
+                    Num<T>::to_f(dfeat[static_cast<int64_t>(dst[e]) * D + c]);
+    out[i] = Num<T>::from_f(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Segmented sum.  One warp per segment; the warp is split into 32/G row groups of G lanes
+// (G = lanes needed for one row's 16-byte chunks), each group sums every (32/G)-th row in
+// fp32, then the groups are combined with a fixed xor-shuffle tree: no atomics, run-to-run
+// bit-identical.  Rows of a CSC segment are contiguous (eids == nullptr); CSR segments go
+// through the edge-id indirection.
+// ---------------------------------------------------------------------------------------
+template <typename T, int G>
+__global__ void __launch_bounds__(256)
+segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks,
+                       const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids, int64_t n_seg,
+                       T* __restrict__ out, int64_t ld_out, int64_t out_col0, int mean, int accumulate) {
+  constexpr int V = Num<T>::kVec;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / G, l = lane % G;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t s = warp; s < n_seg; s += nwarps) {
+    const int32_t b = __ldg(offsets + s), e = __ldg(offsets + s + 1);
+    const float scale = mean ? 1.f / static_cast<float>(max(e - b, 1)) : 1.f;
+    for (int cb = 0; cb < chunks; cb += G) {
+      const int c = cb + l;
+      const bool active = c < chunks;
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      int32_t j = b + g;
+      // 4 rows in flight per group
+      for (; j + 3 * R < e; j += 4 * R) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int64_t row = eids ? __ldg(eids + j + u * R) : (j + u * R);
+          if (active) v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+        }
+        if (active) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            Vec16<T> t;
+            t.raw = v[u];
+            float f[V];
+            t.unpack(f);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += f[k];
+          }
+        }
+      }
+      for (; j < e; j += R) {
+        const int64_t row = eids ? __ldg(eids + j) : j;
+        if (active) {
+          Vec16<T> t;
+          t.raw = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+          float f[V];
+          t.unpack(f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] += f[k];
+        }
+      }
+#pragma unroll
+      for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+      }
+      if (g == 0 && active) {
+        T* o = out + s * ld_out + out_col0 + static_cast<int64_t>(c) * V;
+        Vec16<T> t;
+        if (accumulate) {
+          t.raw = *reinterpret_cast<const uint4*>(o);
+          float f[V];
+          t.unpack(f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = f[k] + acc[k] * scale;
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] *= scale;
+        }
+        t.pack(acc);
+        *reinterpret_cast<uint4*>(o) = t.raw;
+      }
+    }
+  }
+}
+
+template <typename T>
+__global__ void segment_sum_scalar_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int D,
+                                          const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids,
+                                          int64_t n_seg, T* __restrict__ out, int64_t ld_out, int64_t out_col0,
+                                          int mean, int accumulate) {
+  const int64_t total = n_seg * D;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t s = i / D;
+    const int c = static_cast<int>(i - s * D);
+    const int32_t b = offsets[s], e = offsets[s + 1];
+    float acc = 0.f;
+    for (int32_t j = b; j < e; ++j) {
+      const int64_t row = eids ? eids[j] : j;
+      acc += Num<T>::to_f(in[row * ld_in + in_col0 + c]);
+    }
+    if (mean) acc /= static_cast<float>(max(e - b, 1));
+    T* o = out + s * ld_out + out_col0 + c;
+    if (accumulate) acc += Num<T>::to_f(*o);
+    *o = Num<T>::from_f(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// generic indexed row gather into a column slice
+// ---------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_rows_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks,
+                       const int32_t* __restrict__ idx, int64_t n_rows, T* __restrict__ out, int64_t ld_out,
+                       int64_t out_col0, const int32_t* __restrict__ deg_offsets) {
+  constexpr int V = Num<T>::kVec;
+  const int64_t total = n_rows * chunks;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / chunks;
+    const int c = static_cast<int>(i - r * chunks);
+    const int64_t row = idx ? __ldg(idx + r) : r;
+    Vec16<T> t;
+    t.raw = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+    if (deg_offsets) {
+      const float sc = 1.f / static_cast<float>(max(__ldg(deg_offsets + row + 1) - __ldg(deg_offsets + row), 1));
+      float f[V];
+      t.unpack(f);
+#pragma unroll
+      for (int k = 0; k < V; ++k) f[k] *= sc;
+      t.pack(f);
+    }
+    *reinterpret_cast<uint4*>(out + r * ld_out + out_col0 + static_cast<int64_t>(c) * V) = t.raw;
+  }
+}
+
+template <typename T>
+__global__ void gather_rows_scalar_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int D,
+                                          const int32_t* __restrict__ idx, int64_t n_rows, T* __restrict__ out,
+                                          int64_t ld_out, int64_t out_col0, const int32_t* __restrict__ deg_offsets) {
+  const int64_t total = n_rows * D;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / D;
+    const int c = static_cast<int>(i - r * D);
+    const int64_t row = idx ? idx[r] : r;
+    float v = Num<T>::to_f(in[row * ld_in + in_col0 + c]);
+    if (deg_offsets) v /= static_cast<float>(max(deg_offsets[row + 1] - deg_offsets[row], 1));
+    out[r * ld_out + out_col0 + c] = Num<T>::from_f(v);
+  }
+}
+
+static inline int grid_for(int64_t work_items, int threads_per_item_block = 256, int max_waves = 16) {
+  int64_t blocks = (work_items + threads_per_item_block - 1) / threads_per_item_block;
+  const int64_t cap = static_cast<int64_t>(num_sms()) * max_waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+template <typename T>
+static int concat_efeat_fwd_t(const void* efeat, int64_t De, const void* sfeat, int64_t Ds, const void* dfeat,
+                              int64_t Dd, const int32_t* src, const int32_t* dst, int64_t E, void* out,
+                              cudaStream_t st) {
+  constexpr int V = Num<T>::kVec;
+  if (E == 0) return MGN_OK;
+  const bool vec = De % V == 0 && Ds % V == 0 && Dd % V == 0 && aligned16(efeat) && aligned16(sfeat) &&
+                   aligned16(dfeat) && aligned16(out);
+  if (vec) {
+    constexpr int kRows = 4;
+    const int64_t warps = (E + kRows - 1) / kRows;
+    concat_efeat_vec_kernel<T, kRows><<<grid_for(warps * 32), 256, 0, st>>>(
+        static_cast<const T*>(efeat), static_cast<int>(De / V), static_cast<const T*>(sfeat),
+        static_cast<int>(Ds / V), static_cast<const T*>(dfeat), static_cast<int>(Dd / V), src, dst, E,
+        static_cast<T*>(out));
+  } else {
+    concat_efeat_scalar_kernel<T><<<grid_for(E * (De + Ds + Dd)), 256, 0, st>>>(
+        static_cast<const T*>(efeat), static_cast<int>(De), static_cast<const T*>(sfeat), static_cast<int>(Ds),
+        static_cast<const T*>(dfeat), static_cast<int>(Dd), src, dst, E, static_cast<T*>(out));
+  }
+  return mgn_launch_status();
+}
+
+template <typename T>
+static int sum_efeat_fwd_t(const void* efeat, const void* sfeat, const void* dfeat, int64_t D, const int32_t* src,
+                           const int32_t* dst, int64_t E, void* out, cudaStream_t st) {
+  constexpr int V = Num<T>::kVec;
+  if (E == 0) return MGN_OK;
+  const bool vec = D % V == 0 && aligned16(efeat) && aligned16(sfeat) && aligned16(dfeat) && aligned16(out);
+  if (vec)
+    sum_efeat_vec_kernel<T><<<grid_for(E * (D / V)), 256, 0, st>>>(
+        static_cast<const T*>(efeat), static_cast<const T*>(sfeat), static_cast<const T*>(dfeat),
+        static_cast<int>(D / V), src, dst, E, static_cast<T*>(out));
+  else
+    sum_efeat_scalar_kernel<T><<<grid_for(E * D), 256, 0, st>>>(
+        static_cast<const T*>(efeat), static_cast<const T*>(sfeat), static_cast<const T*>(dfeat),
+        static_cast<int>(D), src, dst, E, static_cast<T*>(out));
+  return mgn_launch_status();
+}
+
+template <typename T>
+static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t D, const int32_t* offsets,
+                         const int32_t* eids, int64_t n_seg, void* out, int64_t ld_out, int64_t out_col0, int mean,
+                         int accumulate, cudaStream_t st) {
+  constexpr int V = Num<T>::kVec;
+  if (n_seg == 0 || D == 0) return MGN_OK;
+  const bool vec = D % V == 0 && ld_in % V == 0 && in_col0 % V == 0 && ld_out % V == 0 && out_col0 % V == 0 &&
+                   aligned16(in) && aligned16(out);
+  const T* i_ = static_cast<const T*>(in);
+  T* o_ = static_cast<T*>(out);
+  if (vec) {
+    const int chunks = static_cast<int>(D / V);
+    const int grid = grid_for(n_seg * 32);
+#define MGN_SEG(G)                                                                                     \
+  segment_sum_vec_kernel<T, G><<<grid, 256, 0, st>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
+                                                     o_, ld_out, out_col0, mean, accumulate)
+    if (chunks <= 4) MGN_SEG(4);
+    else if (chunks <= 8) MGN_SEG(8);
+    else if (chunks <= 16) MGN_SEG(16);
+    else MGN_SEG(32);
+#undef MGN_SEG
+  } else {
+    segment_sum_scalar_kernel<T><<<grid_for(n_seg * D), 256, 0, st>>>(i_, ld_in, in_col0, static_cast<int>(D),
+                                                                      offsets, eids, n_seg, o_, ld_out, out_col0,
+                                                                      mean, accumulate);
+  }
+  return mgn_launch_status();
+}
+
+template <typename T>
+static int gather_rows_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t D, const int32_t* idx,
+                         int64_t n_rows, void* out, int64_t ld_out, int64_t out_col0, const int32_t* deg_offsets,
+                         cudaStream_t st) {
+  constexpr int V = Num<T>::kVec;
+  if (n_rows == 0 || D == 0) return MGN_OK;
+  const bool vec = D % V == 0 && ld_in % V == 0 && in_col0 % V == 0 && ld_out % V == 0 && out_col0 % V == 0 &&
+                   aligned16(in) && aligned16(out);
+  if (vec)
+    gather_rows_vec_kernel<T><<<grid_for(n_rows * (D / V)), 256, 0, st>>>(
+        static_cast<const T*>(in), ld_in, in_col0, static_cast<int>(D / V), idx, n_rows, static_cast<T*>(out),
+        ld_out, out_col0, deg_offsets);
+  else
+    gather_rows_scalar_kernel<T><<<grid_for(n_rows * D), 256, 0, st>>>(
+        static_cast<const T*>(in), ld_in, in_col0, static_cast<int>(D), idx, n_rows, static_cast<T*>(out), ld_out,
+        out_col0, deg_offsets);
+  return mgn_launch_status();
+}
+
+}  // namespace mgn
+
+using namespace mgn;
+
+extern "C" int mgn_concat_efeat_fwd(int dtype, const void* efeat, int64_t De, const void* src_feat, int64_t Ds,
+                                    const void* dst_feat, int64_t Dd, const int32_t* src_idx,
+                                    const int32_t* dst_idx, int64_t n_edges, void* out, mgn_stream_t stream) {
+  MGN_CHECK_ARG(n_edges >= 0 && De >= 0 && Ds >= 0 && Dd >= 0);
+  if (n_edges == 0) return MGN_OK;
+  MGN_CHECK_ARG(efeat && src_feat && dst_feat && src_idx && dst_idx && out);
+  if (dtype == MGN_F32)
+    return concat_efeat_fwd_t<float>(efeat, De, src_feat, Ds, dst_feat, Dd, src_idx, dst_idx, n_edges, out,
+                                     as_stream(stream));
+  if (dtype == MGN_BF16)
+    return concat_efeat_fwd_t<bf16>(efeat, De, src_feat, Ds, dst_feat, Dd, src_idx, dst_idx, n_edges, out,
+                                    as_stream(stream));
+  return MGN_EINVAL;
+}
+
+extern "C" int mgn_sum_efeat_fwd(int dtype, const void* efeat, const void* src_feat, const void* dst_feat,
+                                 int64_t D, const int32_t* src_idx, const int32_t* dst_idx, int64_t n_edges,
+                                 void* out, mgn_stream_t stream) {
+  MGN_CHECK_ARG(n_edges >= 0 && D >= 0);
+  if (n_edges == 0) return MGN_OK;
+  MGN_CHECK_ARG(efeat && src_feat && dst_feat && src_idx && dst_idx && out);
+  if (dtype == MGN_F32)
+    return sum_efeat_fwd_t<float>(efeat, src_feat, dst_feat, D, src_idx, dst_idx, n_edges, out, as_stream(stream));
+  if (dtype == MGN_BF16)
+    return sum_efeat_fwd_t<bf16>(efeat, src_feat, dst_feat, D, src_idx, dst_idx, n_edges, out, as_stream(stream));
+  return MGN_EINVAL;
+}
+
+extern "C" int mgn_segment_sum(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                               const int32_t* offsets, const int32_t* eids, int64_t n_segments, void* out,
+                               int64_t ld_out, int64_t out_col0, int mean, int accumulate, mgn_stream_t stream) {
+  MGN_CHECK_ARG(n_segments >= 0 && D >= 0 && ld_in >= 0 && ld_out >= 0 && in_col0 >= 0 && out_col0 >= 0);
+  if (n_segments == 0) return MGN_OK;
+  MGN_CHECK_ARG(offsets && out);
+  if (dtype == MGN_F32)
+    return segment_sum_t<float>(in, ld_in, in_col0, D, offsets, eids, n_segments, out, ld_out, out_col0, mean,
+                                accumulate, as_stream(stream));
+  if (dtype == MGN_BF16)
+    return segment_sum_t<bf16>(in, ld_in, in_col0, D, offsets, eids, n_segments, out, ld_out, out_col0, mean,
+                               accumulate, as_stream(stream));
+  return MGN_EINVAL;
+}
+
+extern "C" int mgn_gather_rows(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                               const int32_t* idx, int64_t n_rows, void* out, int64_t ld_out, int64_t out_col0,
+                               const int32_t* inv_deg_offsets, mgn_stream_t stream) {
+  MGN_CHECK_ARG(n_rows >= 0 && D >= 0 && ld_in >= 0 && ld_out >= 0 && in_col0 >= 0 && out_col0 >= 0);
+  if (n_rows == 0) return MGN_OK;
+  MGN_CHECK_ARG(in && out);
+  if (dtype == MGN_F32)
+    return gather_rows_t<float>(in, ld_in, in_col0, D, idx, n_rows, out, ld_out, out_col0, inv_deg_offsets,
+                                as_stream(stream));
+  if (dtype == MGN_BF16)
+    return gather_rows_t<bf16>(in, ld_in, in_col0, D, idx, n_rows, out, ld_out, out_col0, inv_deg_offsets,
+                               as_stream(stream));
+  return MGN_EINVAL;
+}

@@ -1,0 +1,235 @@
+"""MeshGraphNet on the B200 message-passing kernels.
+
+Drop-in for `physicsnemo.models.meshgraphnet.MeshGraphNet`
+(reference: physicsnemo/models/meshgraphnet/meshgraphnet.py:63-379): same constructor
+arguments, same sub-module names (`edge_encoder`, `node_encoder`, `node_decoder`,
+`processor.processor_layers.{i}`), same parameter shapes and construction order, hence an
+interchangeable `state_dict` and identical random init under a fixed seed.
+"""
+from __future__ import annotations
+
+from contextlib import nullcontext
+from dataclasses import dataclass
+from itertools import chain
+from typing import Callable, List, Tuple, Union
+from warnings import warn
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from ... import ops
+from ..gnn_layers.graph import CuGraphCSC
+from ..gnn_layers.mesh_edge_block import MeshEdgeBlock
+from ..gnn_layers.mesh_graph_mlp import MeshGraphMLP, compute_dtype
+from ..gnn_layers.mesh_node_block import MeshNodeBlock
+from ..gnn_layers.utils import graph_plan, set_checkpoint_fn
+from ..layers.activations import get_activation
+
+
+@dataclass
+class MetaData:
+    """Same flags as the reference's ModelMetaData for MeshGraphNet (meshgraphnet.py:47-60)."""
+
+    name: str = "MeshGraphNet"
+    jit: bool = False
+    cuda_graphs: bool = False
+    amp_cpu: bool = False
+    amp_gpu: bool = True
+    torch_fx: bool = False
+    onnx: bool = False
+    func_torch: bool = True
+    auto_grad: bool = True
+
+
+class MeshGraphNet(nn.Module):
+    """MeshGraphNet network architecture (Pfaff et al., arXiv:2010.03409).
+
+    Parameters are those of the reference constructor (meshgraphnet.py:128-150):
+    input_dim_nodes, input_dim_edges, output_dim, processor_size=15, mlp_activation_fn="relu",
+    num_layers_{node,edge}_processor=2, hidden_dim_processor=128, hidden_dim_*_{en,de}coder=128,
+    num_layers_*_{en,de}coder=2 (None => identity), aggregation="sum", do_concat_trick=False,
+    num_processor_checkpoint_segments=0, checkpoint_offloading=False, recompute_activation=False,
+    norm_type="LayerNorm".
+
+    forward(node_features [N, d_n], edge_features [E, d_e], graph) -> [N, output_dim]; `graph`
+    is a `CuGraphCSC` (edge rows in CSC order) or a DGL-like graph (edge rows in edge-id order).
+    """
+
+    def __init__(
+        self,
+        input_dim_nodes: int,
+        input_dim_edges: int,
+        output_dim: int,
+        processor_size: int = 15,
+        mlp_activation_fn: Union[str, List[str]] = "relu",
+        num_layers_node_processor: int = 2,
+        num_layers_edge_processor: int = 2,
+        hidden_dim_processor: int = 128,
+        hidden_dim_node_encoder: int = 128,
+        num_layers_node_encoder: Union[int, None] = 2,
+        hidden_dim_edge_encoder: int = 128,
+        num_layers_edge_encoder: Union[int, None] = 2,
+        hidden_dim_node_decoder: int = 128,
+        num_layers_node_decoder: Union[int, None] = 2,
+        aggregation: str = "sum",
+        do_concat_trick: bool = False,
+        num_processor_checkpoint_segments: int = 0,
+        checkpoint_offloading: bool = False,
+        recompute_activation: bool = False,
+        norm_type="LayerNorm",
+    ):
+        super().__init__()
+        self.meta = MetaData()
+        # reference's Module base registers this buffer; keep it so state_dicts interchange
+        self.register_buffer("device_buffer", torch.empty(0))
+
+        activation_fn = get_activation(mlp_activation_fn)
+
+        if norm_type not in ["LayerNorm", "TELayerNorm"]:
+            raise ValueError("Norm type should be either 'LayerNorm' or 'TELayerNorm'")
+
+        if not torch.cuda.is_available() and norm_type == "TELayerNorm":
+            warn("TELayerNorm is not supported on CPU. Switching to LayerNorm.")
+            norm_type = "LayerNorm"
+
+        self.edge_encoder = MeshGraphMLP(
+            input_dim_edges,
+            output_dim=hidden_dim_processor,
+            hidden_dim=hidden_dim_edge_encoder,
+            hidden_layers=num_layers_edge_encoder,
+            activation_fn=activation_fn,
+            norm_type=norm_type,
+            recompute_activation=recompute_activation,
+        )
+        self.node_encoder = MeshGraphMLP(
+            input_dim_nodes,
+            output_dim=hidden_dim_processor,
+            hidden_dim=hidden_dim_node_encoder,
+            hidden_layers=num_layers_node_encoder,
+            activation_fn=activation_fn,
+            norm_type=norm_type,
+            recompute_activation=recompute_activation,
+        )
+        self.node_decoder = MeshGraphMLP(
+            hidden_dim_processor,
+            output_dim=output_dim,
+            hidden_dim=hidden_dim_node_decoder,
+            hidden_layers=num_layers_node_decoder,
+            activation_fn=activation_fn,
+            norm_type=None,
+            recompute_activation=recompute_activation,
+        )
+        self.processor = MeshGraphNetProcessor(
+            processor_size=processor_size,
+            input_dim_node=hidden_dim_processor,
+            input_dim_edge=hidden_dim_processor,
+            num_layers_node=num_layers_node_processor,
+            num_layers_edge=num_layers_edge_processor,
+            aggregation=aggregation,
+            norm_type=norm_type,
+            activation_fn=activation_fn,
+            do_concat_trick=do_concat_trick,
+            num_processor_checkpoint_segments=num_processor_checkpoint_segments,
+            checkpoint_offloading=checkpoint_offloading,
+        )
+
+    @property
+    def device(self) -> torch.device:
+        return self.device_buffer.device
+
+    def forward(self, node_features: Tensor, edge_features: Tensor, graph, **kwargs) -> Tensor:
+        ops.require_cuda(node_features, edge_features)
+        if isinstance(graph, (list, tuple)):
+            raise NotImplementedError("lists of graphs (neighbor-sampling blocks) are not supported")
+        edge_features = self.edge_encoder(edge_features)
+        node_features = self.node_encoder(node_features)
+        x = self.processor(node_features, edge_features, graph)
+        x = self.node_decoder(x)
+        return x
+
+
+class MeshGraphNetProcessor(nn.Module):
+    """processor_size x (MeshEdgeBlock, MeshNodeBlock), interleaved (meshgraphnet.py:220-379).
+    Activation checkpointing over segments and CPU offload keep their reference switches."""
+
+    def __init__(
+        self,
+        processor_size: int = 15,
+        input_dim_node: int = 128,
+        input_dim_edge: int = 128,
+        num_layers_node: int = 2,
+        num_layers_edge: int = 2,
+        aggregation: str = "sum",
+        norm_type: str = "LayerNorm",
+        activation_fn: nn.Module = nn.ReLU(),
+        do_concat_trick: bool = False,
+        num_processor_checkpoint_segments: int = 0,
+        checkpoint_offloading: bool = False,
+    ):
+        super().__init__()
+        self.processor_size = processor_size
+        self.num_processor_checkpoint_segments = num_processor_checkpoint_segments
+        self.checkpoint_offloading = (
+            checkpoint_offloading if (num_processor_checkpoint_segments > 0) else False
+        )
+
+        edge_block_invars = (
+            input_dim_node, input_dim_edge, input_dim_edge, input_dim_edge, num_layers_edge,
+            activation_fn, norm_type, do_concat_trick, False,
+        )
+        node_block_invars = (
+            aggregation, input_dim_node, input_dim_edge, input_dim_edge, input_dim_edge, num_layers_node,
+            activation_fn, norm_type, False,
+        )
+        # all edge blocks are constructed before all node blocks: this fixes the init RNG order
+        edge_blocks = [MeshEdgeBlock(*edge_block_invars) for _ in range(self.processor_size)]
+        node_blocks = [MeshNodeBlock(*node_block_invars) for _ in range(self.processor_size)]
+        layers = list(chain(*zip(edge_blocks, node_blocks)))
+
+        self.processor_layers = nn.ModuleList(layers)
+        self.num_processor_layers = len(self.processor_layers)
+        self.set_checkpoint_segments(self.num_processor_checkpoint_segments)
+        self.set_checkpoint_offload_ctx(self.checkpoint_offloading)
+
+    def set_checkpoint_offload_ctx(self, enabled: bool):
+        if enabled:
+            self.checkpoint_offload_ctx = torch.autograd.graph.save_on_cpu(pin_memory=True)
+        else:
+            self.checkpoint_offload_ctx = nullcontext()
+
+    def set_checkpoint_segments(self, checkpoint_segments: int):
+        if checkpoint_segments > 0:
+            if self.num_processor_layers % checkpoint_segments != 0:
+                raise ValueError("Processor layers must be a multiple of checkpoint_segments")
+            segment_size = self.num_processor_layers // checkpoint_segments
+            self.checkpoint_segments = []
+            for i in range(0, self.num_processor_layers, segment_size):
+                self.checkpoint_segments.append((i, i + segment_size))
+            self.checkpoint_fn = set_checkpoint_fn(True)
+        else:
+            self.checkpoint_fn = set_checkpoint_fn(False)
+            self.checkpoint_segments = [(0, self.num_processor_layers)]
+
+    def run_function(self, segment_start: int, segment_end: int) -> Callable:
+        segment = self.processor_layers[segment_start:segment_end]
+
+        def custom_forward(node_features: Tensor, edge_features: Tensor, graph) -> Tuple[Tensor, Tensor]:
+            for module in segment:
+                edge_features, node_features = module(edge_features, node_features, graph)
+            return edge_features, node_features
+
+        return custom_forward
+
+    def forward(self, node_features: Tensor, edge_features: Tensor, graph) -> Tensor:
+        with self.checkpoint_offload_ctx:
+            for segment_start, segment_end in self.checkpoint_segments:
+                edge_features, node_features = self.checkpoint_fn(
+                    self.run_function(segment_start, segment_end),
+                    node_features,
+                    edge_features,
+                    graph,
+                    use_reentrant=False,
+                    preserve_rng_state=False,
+                )
+        return node_features

@@ -1,0 +1,414 @@
+"""Autograd-aware operators over libmgn_b200.so.
+
+Three layers, bottom-up:
+  * `GraphPlan`        int32 CSC/CSR structures precomputed once per graph on the device
+  * raw op wrappers    tensors -> pointers -> C ABI (allocation of outputs/workspaces only)
+  * autograd Functions concat_efeat / sum_efeat / aggregate_and_concat / fused MLP
+
+Everything requires CUDA tensors; there is no CPU path (reference semantics are restated for
+tests in oracle/, which this module never imports).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import ACT_IDS, MGN_BF16, MGN_F32, call
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------
+def _dt(t: Tensor) -> int:
+    if t.dtype == torch.float32:
+        return MGN_F32
+    if t.dtype == torch.bfloat16:
+        return MGN_BF16
+    raise TypeError(f"modulus_b200 kernels support float32 and bfloat16 features, got {t.dtype}")
+
+
+def _p(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_cuda(*tensors: Optional[Tensor]) -> None:
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "modulus_b200: the MeshGraphNet operators run on CUDA (sm_100a) only; got a "
+                f"{t.device} tensor and there is no CPU fallback"
+            )
+
+
+def _c(t: Tensor) -> Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _f32(t: Tensor) -> Tensor:
+    """Parameters are consumed as fp32 in place; anything else is a usage error we surface."""
+    if t.dtype != torch.float32:
+        raise TypeError(f"modulus_b200: parameters must be float32 (got {t.dtype})")
+    return _c(t)
+
+
+# ----------------------------------------------------------------------------------------
+# graph plan
+# ----------------------------------------------------------------------------------------
+def _group_by_key(keys: Tensor, n_keys: int) -> Tuple[Tensor, Tensor]:
+    n = keys.numel()
+    dev = keys.device
+    offsets = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+    ids = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ws_bytes = _lib.load().mgn_group_by_key_workspace_bytes(n_keys)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("mgn_group_by_key", _p(keys), n, n_keys, _p(offsets), _p(ids), _p(ws), ws_bytes, _stream())
+    return offsets, ids[:n]
+
+
+class GraphPlan:
+    """Device-side index structures for one (bipartite) graph.
+
+    Edge rows of every edge-feature table follow `src`/`dst` order.  For a CuGraphCSC that order
+    is the CSC order (`csc_eids is None`, destination segments are contiguous row ranges); a
+    graph that arrives as COO (DGL edge-id order) keeps its order and gets `csc_eids`.
+
+      src, dst        [E] int32   endpoints per edge row          (gnn_layers/graph.py:462-471)
+      csc_offsets     [n_dst+1]   in-edge segments by destination (CuGraphCSC.offsets)
+      csr_offsets     [n_src+1]   out-edge segments by source
+      csr_eids        [E]         edge rows grouped by source, ascending (backward scatter)
+    """
+
+    def __init__(self, src, dst, csc_offsets, csc_eids, csr_offsets, csr_eids, n_src, n_dst):
+        self.src, self.dst = src, dst
+        self.csc_offsets, self.csc_eids = csc_offsets, csc_eids
+        self.csr_offsets, self.csr_eids = csr_offsets, csr_eids
+        self.n_src, self.n_dst = int(n_src), int(n_dst)
+        self.n_edges = int(src.numel())
+        self.device = src.device
+        self.extra = {}  # per-plan caches of the fused kernels (tile schedules, ...)
+
+    @property
+    def is_csc_ordered(self) -> bool:
+        return self.csc_eids is None
+
+    @staticmethod
+    def from_csc(offsets: Tensor, indices: Tensor, n_src: int, n_dst: int) -> "GraphPlan":
+        require_cuda(offsets, indices)
+        if offsets.numel() != n_dst + 1:
+            raise ValueError(f"offsets has {offsets.numel()} entries, expected num_dst_nodes+1 = {n_dst + 1}")
+        E = int(indices.numel())
+        if E >= 2**31:
+            raise ValueError("graphs with >= 2^31 edges per rank are not supported")
+        off32 = _c(offsets.to(torch.int32))
+        src = _c(indices.to(torch.int32))
+        dev = off32.device
+        dst = torch.empty(E, dtype=torch.int32, device=dev)
+        call("mgn_expand_offsets", _p(off32), n_dst, _p(dst), _stream())
+        csr_offsets, csr_eids = _group_by_key(src, n_src)
+        return GraphPlan(src, dst, off32, None, csr_offsets, csr_eids, n_src, n_dst)
+
+    @staticmethod
+    def from_coo(src: Tensor, dst: Tensor, n_src: int, n_dst: int) -> "GraphPlan":
+        require_cuda(src, dst)
+        src = _c(src.to(torch.int32))
+        dst = _c(dst.to(torch.int32))
+        csc_offsets, csc_eids = _group_by_key(dst, n_dst)
+        csr_offsets, csr_eids = _group_by_key(src, n_src)
+        return GraphPlan(src, dst, csc_offsets, csc_eids, csr_offsets, csr_eids, n_src, n_dst)
+
+
+# ----------------------------------------------------------------------------------------
+# raw wrappers
+# ----------------------------------------------------------------------------------------
+def segment_sum(inp: Tensor, in_col0: int, D: int, offsets: Tensor, eids: Optional[Tensor], n_seg: int,
+                out: Optional[Tensor] = None, out_col0: int = 0, mean: bool = False,
+                accumulate: bool = False) -> Tensor:
+    if out is None:
+        out = torch.empty((n_seg, D), dtype=inp.dtype, device=inp.device)
+    call("mgn_segment_sum", _dt(inp), _p(inp), inp.stride(0) if inp.dim() == 2 else D, in_col0, D,
+         _p(offsets), _p(eids), n_seg, _p(out), out.stride(0), out_col0, int(mean), int(accumulate), _stream())
+    return out
+
+
+def gather_rows(inp: Tensor, in_col0: int, D: int, idx: Optional[Tensor], n_rows: int,
+                out: Optional[Tensor] = None, out_col0: int = 0,
+                inv_deg_offsets: Optional[Tensor] = None) -> Tensor:
+    if out is None:
+        out = torch.empty((n_rows, D), dtype=inp.dtype, device=inp.device)
+    call("mgn_gather_rows", _dt(inp), _p(inp), inp.stride(0), in_col0, D, _p(idx), n_rows, _p(out),
+         out.stride(0), out_col0, _p(inv_deg_offsets), _stream())
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# operator seam
+# ----------------------------------------------------------------------------------------
+class ConcatEfeatFn(torch.autograd.Function):
+    """concat_efeat (gnn_layers/utils.py:151-229): fwd two-sided gather + concat; bwd slice copy,
+    in-segment CSC sum for the dst rows and CSR (transposed) sum for the src rows."""
+
+    @staticmethod
+    def forward(ctx, efeat, src_feat, dst_feat, plan: GraphPlan):
+        require_cuda(efeat, src_feat, dst_feat)
+        efeat, src_feat, dst_feat = _c(efeat), _c(src_feat), _c(dst_feat)
+        E = plan.n_edges
+        De, Ds, Dd = efeat.shape[1], src_feat.shape[1], dst_feat.shape[1]
+        if efeat.shape[0] != E or src_feat.shape[0] < plan.n_src or dst_feat.shape[0] < plan.n_dst:
+            raise ValueError(
+                f"concat_efeat: feature rows ({efeat.shape[0]}, {src_feat.shape[0]}, {dst_feat.shape[0]}) do not "
+                f"match the graph (E={E}, n_src={plan.n_src}, n_dst={plan.n_dst})")
+        if not (efeat.dtype == src_feat.dtype == dst_feat.dtype):
+            raise TypeError("concat_efeat: all feature tables must share one dtype")
+        out = torch.empty((E, De + Ds + Dd), dtype=efeat.dtype, device=efeat.device)
+        call("mgn_concat_efeat_fwd", _dt(efeat), _p(efeat), De, _p(src_feat), Ds, _p(dst_feat), Dd,
+             _p(plan.src), _p(plan.dst), E, _p(out), _stream())
+        ctx.plan = plan
+        ctx.dims = (De, Ds, Dd, src_feat.shape[0], dst_feat.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: GraphPlan = ctx.plan
+        De, Ds, Dd, ns, nd = ctx.dims
+        g = _c(g)
+        ge = gs = gd = None
+        if ctx.needs_input_grad[0]:
+            ge = gather_rows(g, 0, De, None, plan.n_edges)
+        if ctx.needs_input_grad[1]:
+            gs = g.new_zeros((ns, Ds)) if ns != plan.n_src else None
+            gs = segment_sum(g, De, Ds, plan.csr_offsets, plan.csr_eids, plan.n_src, out=gs)
+        if ctx.needs_input_grad[2]:
+            gd = g.new_zeros((nd, Dd)) if nd != plan.n_dst else None
+            gd = segment_sum(g, De + Ds, Dd, plan.csc_offsets, plan.csc_eids, plan.n_dst, out=gd)
+        return ge, gs, gd, None
+
+
+class SumEfeatFn(torch.autograd.Function):
+    """sum_efeat (gnn_layers/utils.py:232-334)."""
+
+    @staticmethod
+    def forward(ctx, efeat, src_feat, dst_feat, plan: GraphPlan):
+        require_cuda(efeat, src_feat, dst_feat)
+        efeat, src_feat, dst_feat = _c(efeat), _c(src_feat), _c(dst_feat)
+        E, D = plan.n_edges, efeat.shape[1]
+        if efeat.shape[0] != E or src_feat.shape[1] != D or dst_feat.shape[1] != D:
+            raise ValueError("sum_efeat: shape mismatch")
+        out = torch.empty_like(efeat)
+        call("mgn_sum_efeat_fwd", _dt(efeat), _p(efeat), _p(src_feat), _p(dst_feat), D, _p(plan.src), _p(plan.dst),
+             E, _p(out), _stream())
+        ctx.plan = plan
+        ctx.dims = (D, src_feat.shape[0], dst_feat.shape[0])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: GraphPlan = ctx.plan
+        D, ns, nd = ctx.dims
+        g = _c(g)
+        gs = gd = None
+        if ctx.needs_input_grad[1]:
+            gs = g.new_zeros((ns, D)) if ns != plan.n_src else None
+            gs = segment_sum(g, 0, D, plan.csr_offsets, plan.csr_eids, plan.n_src, out=gs)
+        if ctx.needs_input_grad[2]:
+            gd = g.new_zeros((nd, D)) if nd != plan.n_dst else None
+            gd = segment_sum(g, 0, D, plan.csc_offsets, plan.csc_eids, plan.n_dst, out=gd)
+        return (g if ctx.needs_input_grad[0] else None), gs, gd, None
+
+
+class AggConcatFn(torch.autograd.Function):
+    """aggregate_and_concat (gnn_layers/utils.py:337-427): deterministic CSC segmented sum/mean of
+    edge rows by destination, concatenated with the destination rows."""
+
+    @staticmethod
+    def forward(ctx, efeat, nfeat, plan: GraphPlan, mean: bool):
+        require_cuda(efeat, nfeat)
+        efeat, nfeat = _c(efeat), _c(nfeat)
+        De, Dn = efeat.shape[1], nfeat.shape[1]
+        if efeat.shape[0] != plan.n_edges or nfeat.shape[0] != plan.n_dst:
+            raise ValueError(
+                f"aggregate_and_concat: got {efeat.shape[0]} edge rows / {nfeat.shape[0]} node rows for a graph "
+                f"with E={plan.n_edges}, n_dst={plan.n_dst}")
+        if efeat.dtype != nfeat.dtype:
+            raise TypeError("aggregate_and_concat: efeat and nfeat must share one dtype")
+        out = torch.empty((plan.n_dst, De + Dn), dtype=efeat.dtype, device=efeat.device)
+        segment_sum(efeat, 0, De, plan.csc_offsets, plan.csc_eids, plan.n_dst, out=out, out_col0=0, mean=mean)
+        gather_rows(nfeat, 0, Dn, None, plan.n_dst, out=out, out_col0=De)
+        ctx.plan, ctx.mean, ctx.dims = plan, mean, (De, Dn)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        plan: GraphPlan = ctx.plan
+        De, Dn = ctx.dims
+        g = _c(g)
+        ge = gn = None
+        if ctx.needs_input_grad[0]:
+            ge = gather_rows(g, 0, De, plan.dst, plan.n_edges,
+                             inv_deg_offsets=plan.csc_offsets if ctx.mean else None)
+        if ctx.needs_input_grad[1]:
+            gn = gather_rows(g, De, Dn, None, plan.n_dst)
+        return ge, gn, None, None
+
+
+# ----------------------------------------------------------------------------------------
+# MeshGraphMLP on the fp32-accurate SIMT kernels (any width, fp32 or bf16 activations)
+# ----------------------------------------------------------------------------------------
+def _linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int, want_pre: bool):
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"linear: input has {K} features but the weight expects {w.shape[1]}")
+    h = torch.empty((M, N), dtype=x.dtype, device=x.device)
+    pre = torch.empty_like(h) if want_pre else None
+    call("mgn_linear_fwd", _dt(x), _p(x), x.stride(0), M, K, _p(w), _p(b), N, act, _p(pre), _p(h), N, _stream())
+    return h, pre
+
+
+def _linear_bwd_weight(g_y: Tensor, x: Tensor, N: int, K: int, want_bias: bool):
+    M = x.shape[0]
+    g_w = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    g_b = torch.empty((N,), dtype=torch.float32, device=x.device) if want_bias else None
+    ws_bytes = _lib.load().mgn_linear_bwd_weight_workspace_bytes(M, N, K)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    call("mgn_linear_bwd_weight", _dt(x), _p(g_y), _p(x), x.stride(0), M, N, K, _p(g_w), _p(g_b), _p(ws), ws_bytes,
+         _stream())
+    return g_w, g_b
+
+
+def _linear_bwd_data(g_y: Tensor, w: Tensor) -> Tensor:
+    M, N = g_y.shape
+    K = w.shape[1]
+    g_x = torch.empty((M, K), dtype=g_y.dtype, device=g_y.device)
+    call("mgn_linear_bwd_data", _dt(g_y), _p(g_y), M, N, _p(w), K, _p(g_x), K, _stream())
+    return g_x
+
+
+class MLPFn(torch.autograd.Function):
+    """MeshGraphMLP.forward (mesh_graph_mlp.py:142-203) + optional residual add of the blocks
+    (mesh_edge_block.py:95, mesh_node_block.py:91):
+
+        out = [LayerNorm]( Linear_L( act( ... act( Linear_0(x) ) ) ) ) [+ residual]
+
+    args: x, residual|None, act_id, n_linear, has_norm, has_bias, eps, *params
+          params = w0, b0, ..., w_{L}, b_{L} [, gamma, beta]   (fp32, read in place)
+    """
+
+    @staticmethod
+    def forward(ctx, x, residual, act: int, n_linear: int, has_norm: bool, eps: float, *params):
+        require_cuda(x, residual, *params)
+        x = _c(x)
+        ws = [_f32(params[2 * i]) for i in range(n_linear)]
+        bs = [None if params[2 * i + 1] is None else _f32(params[2 * i + 1]) for i in range(n_linear)]
+        gamma = beta = None
+        if has_norm:
+            gamma, beta = _f32(params[2 * n_linear]), _f32(params[2 * n_linear + 1])
+        need_pre = act not in (ACT_IDS["relu"], ACT_IDS[None])
+        inputs: List[Tensor] = [x]
+        pres: List[Optional[Tensor]] = []
+        h = x
+        for i in range(n_linear - 1):
+            h, pre = _linear_fwd(h, ws[i], bs[i], act, need_pre)
+            inputs.append(h)
+            pres.append(pre)
+        y, _ = _linear_fwd(h, ws[-1], bs[-1], ACT_IDS[None], False)
+        mean = rstd = None
+        if has_norm:
+            M, D = y.shape
+            out = torch.empty_like(y)
+            mean = torch.empty(M, dtype=torch.float32, device=y.device)
+            rstd = torch.empty(M, dtype=torch.float32, device=y.device)
+            res = None if residual is None else _c(residual)
+            call("mgn_layernorm_fwd", _dt(y), _p(y), M, D, _p(gamma), _p(beta), eps, _p(res), _p(out), _p(mean),
+                 _p(rstd), _stream())
+        elif residual is not None:
+            out = torch.empty_like(y)
+            call("mgn_add", _dt(y), _p(y), _p(_c(residual)), _p(out), y.numel(), _stream())
+        else:
+            out = y
+        ctx.cfg = (act, n_linear, has_norm, need_pre, residual is not None)
+        ctx.params = (ws, bs, gamma)
+        ctx.acts = (inputs, pres, y, mean, rstd)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        act, n_linear, has_norm, need_pre, has_res = ctx.cfg
+        ws, bs, gamma = ctx.params
+        inputs, pres, y, mean, rstd = ctx.acts
+        g = _c(g)
+        grads: List[Optional[Tensor]] = [None] * (2 * n_linear + (2 if has_norm else 0))
+        g_res = g if (has_res and ctx.needs_input_grad[1]) else None
+        if has_norm:
+            M, D = y.shape
+            g_y = torch.empty_like(y)
+            g_gamma = torch.empty(D, dtype=torch.float32, device=y.device)
+            g_beta = torch.empty(D, dtype=torch.float32, device=y.device)
+            ws_bytes = _lib.load().mgn_layernorm_bwd_workspace_bytes(M, D)
+            wsb = torch.empty(ws_bytes, dtype=torch.uint8, device=y.device)
+            call("mgn_layernorm_bwd", _dt(y), _p(g), _p(y), _p(mean), _p(rstd), _p(gamma), M, D, _p(g_y),
+                 _p(g_gamma), _p(g_beta), _p(wsb), ws_bytes, _stream())
+            grads[2 * n_linear], grads[2 * n_linear + 1] = g_gamma, g_beta
+        else:
+            g_y = g
+        g_x = None
+        for i in range(n_linear - 1, -1, -1):
+            N, K = ws[i].shape
+            g_w, g_b = _linear_bwd_weight(g_y, inputs[i], N, K, bs[i] is not None)
+            grads[2 * i], grads[2 * i + 1] = g_w, g_b
+            if i > 0 or ctx.needs_input_grad[0]:
+                g_in = _linear_bwd_data(g_y, ws[i])
+                if i > 0:
+                    ref = pres[i - 1] if need_pre else inputs[i]
+                    if act != ACT_IDS[None]:
+                        g_y = torch.empty_like(g_in)
+                        call("mgn_act_bwd", _dt(g_in), _p(g_in), _p(ref), act, _p(g_y), g_in.numel(), _stream())
+                    else:
+                        g_y = g_in
+                else:
+                    g_x = g_in
+        return (g_x, g_res, None, None, None, None, *grads)
+
+
+def mlp_forward(x: Tensor, params: Sequence[Optional[Tensor]], n_linear: int, act: str, has_norm: bool,
+                residual: Optional[Tensor] = None, eps: float = 1e-5) -> Tensor:
+    if act not in ACT_IDS:
+        raise NotImplementedError(f"activation '{act}' has no modulus_b200 kernel")
+    return MLPFn.apply(x, residual, ACT_IDS[act], n_linear, has_norm, eps, *params)
+
+
+class ActFn(torch.autograd.Function):
+    """Standalone activation (leading activation of MeshGraphEdgeMLPSum, mesh_graph_mlp.py:352)."""
+
+    @staticmethod
+    def forward(ctx, x, act: int):
+        require_cuda(x)
+        x = _c(x)
+        y = torch.empty_like(x)
+        call("mgn_act_fwd", _dt(x), _p(x), act, _p(y), x.numel(), _stream())
+        ctx.act = act
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = _c(g)
+        gx = torch.empty_like(g)
+        call("mgn_act_bwd", _dt(g), _p(g), _p(x), ctx.act, _p(gx), g.numel(), _stream())
+        return gx, None
+
+
+def activation(x: Tensor, act: str) -> Tensor:
+    if act not in ACT_IDS:
+        raise NotImplementedError(f"activation '{act}' has no modulus_b200 kernel")
+    if ACT_IDS[act] == 0:
+        return x
+    return ActFn.apply(x, ACT_IDS[act])

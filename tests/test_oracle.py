@@ -1,0 +1,97 @@
+"""Pins the CPU oracle (oracle/mgn_oracle.py) against the reference:
+  * the reference's own golden vector (test/models/data/meshgraphnet_output.pth)
+  * outputs and gradients of the unmodified reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mgn_oracle as O
+
+
+def _coo(offsets, indices):
+    return O.coo_from_csc(offsets, indices)
+
+
+def test_kat1_reference_golden_vector():
+    """Replay test/models/meshgraphnet/test_meshgraphnet.py:41-65 with the oracle."""
+    g = load_golden("kat1_meshgraphnet_output.pt")
+    torch.manual_seed(0)
+    np.random.seed(0)
+    sd = O.make_state_dict(4, 3, 2)  # consumes the RNG exactly like MeshGraphNet(4, 3, 2)
+    graphs = []
+    off = 0
+    srcs, dsts = [], []
+    for _ in range(2):
+        src = torch.tensor([np.random.randint(20) for _ in range(10)])
+        dst = torch.tensor([np.random.randint(20) for _ in range(10)])
+        n = int(max(src.max(), dst.max())) + 1
+        srcs.append(src + off)
+        dsts.append(dst + off)
+        off += n
+    src, dst = torch.cat(srcs), torch.cat(dsts)
+    assert torch.equal(src, g["src"]) and torch.equal(dst, g["dst"])
+    nf = torch.randn(40, 4)
+    ef = torch.randn(20, 3)
+    with torch.no_grad():
+        out = O.meshgraphnet_forward(sd, nf, ef, src, dst)
+    # the reference's own tolerance is 1e-3 (test/models/common/fwdaccuracy.py:68-73)
+    assert torch.allclose(out, g["output"], rtol=1e-5, atol=2e-6), (out - g["output"]).abs().max()
+
+
+@pytest.mark.parametrize("case", ["relu_sum", "relu_mean", "silu_sum", "concat_trick"])
+def test_oracle_matches_reference_outputs_and_grads(case):
+    g = load_golden(f"ref_mgn_{case}.pt")
+    kw = g["kwargs"]
+    src, dst = _coo(g["offsets"], g["indices"])
+    pred, loss, grads = O.step_fwd_bwd(
+        g["state_dict"], g["node_features"], g["edge_features"], src, dst, g["target"],
+        processor_size=kw["processor_size"], act=kw.get("mlp_activation_fn", "relu"),
+        aggregation=kw.get("aggregation", "sum"), concat_trick=kw.get("do_concat_trick", False))
+    assert torch.allclose(pred, g["output"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(loss, g["loss"], rtol=1e-5)
+    for k, v in g["grads"].items():
+        assert torch.allclose(grads[k], v, rtol=1e-4, atol=1e-6), (k, (grads[k] - v).abs().max())
+    assert torch.allclose(grads["__node_features"], g["grad_node_features"], rtol=1e-4, atol=1e-7)
+    assert torch.allclose(grads["__edge_features"], g["grad_edge_features"], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("L", [1, 15])
+def test_oracle_default_size_model_from_seed(L):
+    """hidden 128: weights regenerated from the seed must be the reference's (same RNG stream)."""
+    g = load_golden(f"ref_mgn_h128_L{L}.pt")
+    torch.manual_seed(g["seed"])
+    sd = O.make_state_dict(6, 3, 3, processor_size=L)
+    nf = torch.randn(g["n_nodes"], 6)
+    ef = torch.randn(g["indices"].numel(), 3)
+    target = torch.randn(g["n_nodes"], 3)
+    assert torch.equal(nf, g["node_features"]) and torch.equal(ef, g["edge_features"])
+    chk = float(sum(v.double().sum() for v in sd.values()))
+    assert abs(chk - g["weight_checksum"]) < 1e-9
+    src, dst = _coo(g["offsets"], g["indices"])
+    pred, loss, grads = O.step_fwd_bwd(sd, nf, ef, src, dst, target, processor_size=L)
+    assert torch.allclose(pred, g["output"], rtol=1e-4, atol=1e-5)
+    for k, v in g["grads_selected"].items():
+        assert torch.allclose(grads[k], v, rtol=1e-3, atol=1e-6), k
+    for k, nrm in g["grad_norms"].items():
+        assert abs(float(grads[k].double().norm()) - nrm) <= 1e-3 * max(nrm, 1e-8), k
+
+
+def test_csr_from_csc_is_stable_transpose():
+    off, idx = torch.tensor([0, 2, 4, 6, 8]), torch.tensor([0, 3, 2, 1, 1, 0, 1, 2])
+    co, ce, cd = O.csr_from_csc(off, idx, 4)
+    assert co.tolist() == [0, 2, 5, 7, 8]
+    assert ce.tolist() == [0, 5, 3, 4, 6, 2, 7, 1]
+    assert cd.tolist() == [0, 2, 1, 2, 3, 1, 3, 0]
+
+
+def test_aggregate_mean_and_isolated_nodes():
+    ef = torch.arange(12, dtype=torch.float32).view(4, 3)
+    nf = torch.zeros(3, 2)
+    dst = torch.tensor([0, 0, 2, 2])
+    s = O.aggregate_and_concat(ef, nf, dst, "sum")
+    m = O.aggregate_and_concat(ef, nf, dst, "mean")
+    assert torch.equal(s[1, :3], torch.zeros(3)) and torch.equal(m[1, :3], torch.zeros(3))
+    assert torch.allclose(m[0, :3], (ef[0] + ef[1]) / 2)
+    with pytest.raises(RuntimeError):
+        O.aggregate_and_concat(ef, nf, dst, "max")
