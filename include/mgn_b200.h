@@ -146,6 +146,25 @@ int mgn_layernorm_bwd(int dtype, const void* g_out, const void* x, const float* 
 /* out = a + b (elementwise, n elements) */
 int mgn_add(int dtype, const void* a, const void* b, void* out, int64_t n, mgn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Fused tensor-core path (bf16 storage, hidden width 128, ReLU): tcgen05.mma + TMEM.
+ * ---------------------------------------------------------------------------------------- */
+/* Fused MeshGraphMLP forward over 128-row tiles:
+ *     A   = [ tab0[idx0[r]] | tab1[idx1[r]] | tab2[idx2[r]] ]   (n_tab tables of [*,128] bf16; idxK NULL = row r)
+ *           or, encoder mode (small_in > 0), the raw [M, small_in] features zero-padded to 64 columns
+ *     out = [LayerNorm]( W3 relu(W2 relu(W1 A + b1) + b2) + b3 ) [* gamma + beta] [+ residual]
+ * Replaces MeshEdgeBlock.forward (mesh_edge_block.py:88-96 = concat_efeat utils.py:151 + MeshGraphMLP
+ * mesh_graph_mlp.py:200-203 + residual), the MLP half of MeshNodeBlock.forward (mesh_node_block.py:88-91)
+ * and the encoder/decoder MLPs (meshgraphnet.py:213-216).  gamma == NULL: no LayerNorm (decoder).
+ * h1_save / h2_save (nullable): hidden activations [M,128] bf16 kept for the backward kernels.
+ * status (nullable, device int): OR-ed with a nonzero code if the kernel detected an internal timeout. */
+int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
+                    const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
+                    int small_is_f32, int64_t M, const float* w1, const float* b1, const float* w2,
+                    const float* b2, const float* w3, const float* b3, const float* gamma,
+                    const float* beta, int n_out, float eps, const void* residual, void* out,
+                    int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

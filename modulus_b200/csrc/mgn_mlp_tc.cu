@@ -1,0 +1,452 @@
+// mgn_mlp_tc.cu — fused MeshGraphMLP forward on the 5th-gen tensor cores (tcgen05 / TMEM).
+//
+// One persistent CTA per SM computes, for 128-row tiles,
+//
+//     A      = [ tab0[idx0[r]] | tab1[idx1[r]] | tab2[idx2[r]] ]        (gather + concat, never in HBM)
+//     H1     = relu(A  W1^T + b1)        GEMM1: A from smem (K-major, SW128), W1 resident in smem
+//     H2     = relu(H1 W2^T + b2)        GEMM2: H1 read from TMEM (packed bf16), W2 resident
+//     Y      =      H2 W3^T + b3         GEMM3: H2 from TMEM, W3 resident
+//     out    = LayerNorm(Y) * gamma + beta + residual                    (fp32 statistics, epilogue)
+//
+// which is MeshEdgeBlock.forward (tables = efeat, nfeat[src], nfeat[dst]; mesh_edge_block.py:88-96
+// with concat_efeat utils.py:94-109), MeshNodeBlock.forward after the aggregation (tables = agg,
+// nfeat; mesh_node_block.py:82-92) and the encoder / decoder MeshGraphMLPs
+// (mesh_graph_mlp.py:142-203).  Accumulators live in TMEM, hidden activations never leave the SM
+// (TMEM -> registers -> TMEM), weights are converted fp32 -> bf16 once per CTA from the optimizer's
+// own tensors.
+//
+// Warp roles (416 threads): warp 0 = MMA issuer (one elected lane) + TMEM owner,
+// warps 1-4 = loaders (cp.async row gather into the swizzled smem ring),
+// warps 5-8 / 9-12 = epilogue for even / odd tiles (thread = tile row = TMEM lane).
+// Two tiles are in flight (two TMEM accumulator sets) so the tensor pipe works on one tile while
+// the epilogue warps drain the other.
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+
+namespace mgn {
+
+constexpr int kTileM = 128;
+constexpr int kPanelBytes = 16384;  // 128 rows x 64 bf16
+constexpr int kFwdThreads = 416;
+constexpr int kH = 128;
+
+struct MlpFwdParams {
+  const bf16* tab[3];
+  const int32_t* idx[3];
+  const void* small_x;  // encoder mode: [M, small_in] raw features (fp32 or bf16), zero-padded to K=64
+  int small_in;
+  int small_is_f32;
+  long long M;
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *gamma, *beta;
+  int k1_true;  // columns of w1 (128 * n_tab, or small_in)
+  int n_out;    // rows of w3 (<= 128)
+  float eps;
+  const bf16* residual;
+  bf16* out;
+  long long ld_out;
+  bf16* h1_save;
+  bf16* h2_save;
+  int* status;
+};
+
+enum { kStatusTimeout = 1, kStatusSmem = 2 };
+
+// fp32 [n_rows, k_true] (nn.Linear layout) -> bf16 K-major SW128 panels [n_panels][128][64], zero padded
+__device__ __forceinline__ void stage_weight(uint8_t* dst, const float* __restrict__ w, int n_rows, int k_true,
+                                             int n_panels, int tid, int nthreads) {
+  const int per_row = n_panels * 8;
+  for (int item = tid; item < kTileM * per_row; item += nthreads) {
+    const int row = item / per_row;
+    const int rem = item - row * per_row;
+    const int panel = rem >> 3, chunk = rem & 7;
+    const int k0 = panel * 64 + chunk * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      f[j] = (row < n_rows && (k0 + j) < k_true) ? __ldg(w + static_cast<long long>(row) * k_true + k0 + j) : 0.f;
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]);
+    v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]);
+    v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + panel * kPanelBytes + sw128_offset(row, chunk)) = v;
+  }
+}
+
+template <int NP1, int NSLOT>
+struct FwdSmem {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = NP1 * kPanelBytes;
+  static constexpr int kW3 = kW2 + 2 * kPanelBytes;
+  static constexpr int kRing = kW3 + 2 * kPanelBytes;
+  static constexpr int kPar = kRing + NSLOT * kPanelBytes;  // b1,b2,b3,gamma,beta
+  static constexpr int kBars = kPar + 5 * kH * 4;
+  static constexpr int kNumBars = 2 * NSLOT + 6;
+  static constexpr int kTmemSlot = kBars + kNumBars * 8;
+  static constexpr int kTotal = kTmemSlot + 16;
+  static constexpr int kAlloc = kTotal + 1024;  // slack for manual 1024-byte alignment
+};
+
+template <int NP1, int NSLOT>
+__global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFwdParams p) {
+  using L = FwdSmem<NP1, NSLOT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sW1 = smem + L::kW1;
+  uint8_t* sW2 = smem + L::kW2;
+  uint8_t* sW3 = smem + L::kW3;
+  uint8_t* sRing = smem + L::kRing;
+  float* sPar = reinterpret_cast<float*>(smem + L::kPar);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint64_t* empty = full + NSLOT;
+  uint64_t* acc_full = empty + NSLOT;
+  uint64_t* h_ready = acc_full + 2;
+  uint64_t* acc_free = h_ready + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool has_ln = p.gamma != nullptr;
+
+  // ---------------- one-time setup ----------------
+  stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads);
+  stage_weight(sW2, p.w2, kH, kH, 2, tid, kFwdThreads);
+  stage_weight(sW3, p.w3, p.n_out, kH, 2, tid, kFwdThreads);
+  for (int i = tid; i < kH; i += kFwdThreads) {
+    sPar[i] = p.b1 ? p.b1[i] : 0.f;
+    sPar[kH + i] = p.b2 ? p.b2[i] : 0.f;
+    sPar[2 * kH + i] = (p.b3 && i < p.n_out) ? p.b3[i] : 0.f;
+    sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
+    sPar[4 * kH + i] = (has_ln && p.beta) ? p.beta[i] : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      mbar_init(&full[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&h_ready[b], 128);
+      mbar_init(&acc_free[b], 128);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+
+  const long long n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+  bool timed_out = false;
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      uint32_t ph_h[2] = {0, 0};
+      const uint32_t ring_addr = smem_u32(sRing);
+      const uint32_t w1_addr = smem_u32(sW1), w2_addr = smem_u32(sW2), w3_addr = smem_u32(sW3);
+      for (int j = 0; j < n_my; j += 2) {
+        const int nt = (n_my - j) < 2 ? (n_my - j) : 2;
+        for (int b = 0; b < nt; ++b) {  // GEMM1 of both tiles
+          const int i = j + b;
+          timed_out |= !mbar_wait(&acc_free[b], ((i >> 1) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t d = tmem + b * 256;
+#pragma unroll
+          for (int pnl = 0; pnl < NP1; ++pnl, ++cnt) {
+            const uint32_t slot = cnt % NSLOT;
+            timed_out |= !mbar_wait(&full[slot], (cnt / NSLOT) & 1);
+            tc_fence_after_sync();
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_ss(d, umma_desc_kmajor(ring_addr + slot * kPanelBytes, k),
+                      umma_desc_kmajor(w1_addr + pnl * kPanelBytes, k), idesc, (pnl | k) != 0);
+            umma_commit(&empty[slot]);
+          }
+          umma_commit(&acc_full[b]);
+        }
+#pragma unroll
+        for (int layer = 0; layer < 2; ++layer) {  // GEMM2 then GEMM3, A operand = hidden in TMEM
+          const uint32_t w_addr = layer == 0 ? w2_addr : w3_addr;
+          for (int b = 0; b < nt; ++b) {
+            timed_out |= !mbar_wait(&h_ready[b], ph_h[b]);
+            ph_h[b] ^= 1;
+            tc_fence_after_sync();
+            const uint32_t d = tmem + b * 256;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              umma_ts(d, d + 128 + k * 8, umma_desc_kmajor(w_addr + (k >> 2) * kPanelBytes, k & 3), idesc, k != 0);
+            umma_commit(&acc_full[b]);
+          }
+        }
+      }
+    }
+  } else if (warp <= 4) {
+    // =========================== loaders ===========================
+    const int lw = warp - 1;
+    uint32_t cnt = 0;
+    int prev_slot = -1;
+    const uint32_t ring_addr = smem_u32(sRing);
+    for (int i = 0; i < n_my; ++i) {
+      const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * kTileM;
+      const long long my_row = row0 + lw * 32 + lane;
+      int32_t ix[3] = {0, 0, 0};
+      if (p.small_in == 0) {
+#pragma unroll
+        for (int k = 0; k < (NP1 + 1) / 2; ++k)
+          if (p.idx[k] != nullptr && my_row < p.M) ix[k] = __ldg(p.idx[k] + my_row);
+      }
+#pragma unroll
+      for (int pnl = 0; pnl < NP1; ++pnl, ++cnt) {
+        const uint32_t slot = cnt % NSLOT;
+        timed_out |= !mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
+        const uint32_t sbase = ring_addr + slot * kPanelBytes;
+        if (p.small_in > 0) {
+          // raw features, zero padded to 64 columns (encoders)
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r_local = it * 4 + (lane >> 3), chunk = lane & 7;
+            const int row_in_tile = lw * 32 + r_local;
+            const long long grow = row0 + row_in_tile;
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int col = chunk * 8 + q;
+              float v = 0.f;
+              if (grow < p.M && col < p.small_in) {
+                v = p.small_is_f32 ? __ldg(static_cast<const float*>(p.small_x) + grow * p.small_in + col)
+                                   : __bfloat162float(static_cast<const bf16*>(p.small_x)[grow * p.small_in + col]);
+              }
+              f[q] = v;
+            }
+            uint4 v4;
+            v4.x = pack_bf16x2(f[0], f[1]);
+            v4.y = pack_bf16x2(f[2], f[3]);
+            v4.z = pack_bf16x2(f[4], f[5]);
+            v4.w = pack_bf16x2(f[6], f[7]);
+            *reinterpret_cast<uint4*>(sRing + slot * kPanelBytes + sw128_offset(row_in_tile, chunk)) = v4;
+          }
+        } else {
+          const int k = pnl >> 1, half = pnl & 1;
+          const bf16* tab = p.tab[k];
+          const bool indexed = p.idx[k] != nullptr;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r_local = it * 4 + (lane >> 3), chunk = lane & 7;
+            const int row_in_tile = lw * 32 + r_local;
+            const long long grow = row0 + row_in_tile;
+            const int32_t gi = __shfl_sync(0xffffffffu, ix[k], r_local);
+            const bool v = grow < p.M;
+            const long long srow = v ? (indexed ? static_cast<long long>(gi) : grow) : 0;
+            cp_async16_zfill(sbase + sw128_offset(row_in_tile, chunk), tab + srow * kH + half * 64 + chunk * 8, v);
+          }
+        }
+        cp_async_commit();
+        if (prev_slot >= 0) {  // publish the previous panel while this one is in flight
+          cp_async_wait<1>();
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[prev_slot]);
+        }
+        prev_slot = static_cast<int>(slot);
+      }
+    }
+    if (prev_slot >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[prev_slot]);
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int b = (warp - 5) >> 2;  // tile parity served by this warp group
+    const int q = warp & 3;         // TMEM lane quarter this warp may touch
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_acc = tmem + b * 256 + (static_cast<uint32_t>(q * 32) << 16);
+    const uint32_t t_h = t_acc + 128;
+    uint32_t ph = 0;
+    for (int i = b; i < n_my; i += 2) {
+      const long long grow =
+          (static_cast<long long>(blockIdx.x) + static_cast<long long>(i) * gridDim.x) * kTileM + row_in_tile;
+      const bool valid = grow < p.M;
+      // ---- hidden layers: bias + ReLU, write back to TMEM as packed bf16 (A operand of the next GEMM)
+#pragma unroll 1
+      for (int layer = 0; layer < 2; ++layer) {
+        timed_out |= !mbar_wait(&acc_full[b], ph);
+        ph ^= 1;
+        tc_fence_after_sync();
+        const float* bias = sPar + layer * kH;
+        bf16* save = layer == 0 ? p.h1_save : p.h2_save;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float a0 = fmaxf(__uint_as_float(v[2 * jj]) + bias[g * 32 + 2 * jj], 0.f);
+            const float a1 = fmaxf(__uint_as_float(v[2 * jj + 1]) + bias[g * 32 + 2 * jj + 1], 0.f);
+            pk[jj] = pack_bf16x2(a0, a1);
+          }
+          tmem_st16(t_h + g * 16, pk);
+          if (save != nullptr && valid) {
+            uint4* dst = reinterpret_cast<uint4*>(save + grow * kH + g * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) dst[u] = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive(&h_ready[b]);
+      }
+      // ---- output layer: bias (+ LayerNorm + residual), store
+      timed_out |= !mbar_wait(&acc_full[b], ph);
+      ph ^= 1;
+      tc_fence_after_sync();
+      const float* b3 = sPar + 2 * kH;
+      float mu = 0.f, rstd = 1.f;
+      if (has_ln) {
+        float s = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) s += __uint_as_float(v[jj]) + b3[g * 32 + jj];
+        }
+        mu = s * (1.f / kH);
+        float qv = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const float d = __uint_as_float(v[jj]) + b3[g * 32 + jj] - mu;
+            qv = fmaf(d, d, qv);
+          }
+        }
+        rstd = rsqrtf(qv * (1.f / kH) + p.eps);
+      }
+      const float* gam = sPar + 3 * kH;
+      const float* bet = sPar + 4 * kH;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + g * 32, v);
+        tmem_ld_wait();
+        float y[32];
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const float x = __uint_as_float(v[jj]) + b3[g * 32 + jj];
+          y[jj] = has_ln ? ((x - mu) * rstd * gam[g * 32 + jj] + bet[g * 32 + jj]) : x;
+        }
+        if (valid) {
+          if (p.residual != nullptr) {
+            const uint4* rs = reinterpret_cast<const uint4*>(p.residual + grow * kH + g * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const uint4 rv = __ldg(rs + u);
+              const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = unpack_bf16x2(w[e]);
+                y[u * 8 + 2 * e] += f.x;
+                y[u * 8 + 2 * e + 1] += f.y;
+              }
+            }
+          }
+          if (p.n_out == kH) {
+            uint4* dst = reinterpret_cast<uint4*>(p.out + grow * p.ld_out + g * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              dst[u] = make_uint4(pack_bf16x2(y[8 * u], y[8 * u + 1]), pack_bf16x2(y[8 * u + 2], y[8 * u + 3]),
+                                  pack_bf16x2(y[8 * u + 4], y[8 * u + 5]), pack_bf16x2(y[8 * u + 6], y[8 * u + 7]));
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj)
+              if (g * 32 + jj < p.n_out) p.out[grow * p.ld_out + g * 32 + jj] = __float2bfloat16_rn(y[jj]);
+          }
+        }
+      }
+      tc_fence_before_sync();
+      mbar_arrive(&acc_free[b]);
+    }
+  }
+
+  if (timed_out && p.status != nullptr) atomicOr(p.status, kStatusTimeout);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int NP1, int NSLOT>
+static int launch_fwd(const MlpFwdParams& p, cudaStream_t st) {
+  using L = FwdSmem<NP1, NSLOT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp3_fwd_tc_kernel<NP1, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kAlloc);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const long long n_tiles = (p.M + kTileM - 1) / kTileM;
+  const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+  mlp3_fwd_tc_kernel<NP1, NSLOT><<<grid, kFwdThreads, L::kAlloc, st>>>(p);
+  return mgn_launch_status();
+}
+
+}  // namespace mgn
+
+using namespace mgn;
+
+extern "C" int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
+                               const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
+                               int small_is_f32, int64_t M, const float* w1, const float* b1, const float* w2,
+                               const float* b2, const float* w3, const float* b3, const float* gamma,
+                               const float* beta, int n_out, float eps, const void* residual, void* out,
+                               int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= kH && ld_out >= n_out);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(out != nullptr);
+  MlpFwdParams p{};
+  p.tab[0] = static_cast<const bf16*>(tab0);
+  p.tab[1] = static_cast<const bf16*>(tab1);
+  p.tab[2] = static_cast<const bf16*>(tab2);
+  p.idx[0] = idx0;
+  p.idx[1] = idx1;
+  p.idx[2] = idx2;
+  p.small_x = small_x;
+  p.small_in = small_in;
+  p.small_is_f32 = small_is_f32;
+  p.M = M;
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
+  p.gamma = gamma; p.beta = beta;
+  p.n_out = n_out;
+  p.eps = eps;
+  p.residual = static_cast<const bf16*>(residual);
+  p.out = static_cast<bf16*>(out);
+  p.ld_out = ld_out;
+  p.h1_save = static_cast<bf16*>(h1_save);
+  p.h2_save = static_cast<bf16*>(h2_save);
+  p.status = status;
+  cudaStream_t st = as_stream(stream);
+  if (small_in > 0) {
+    MGN_CHECK_ARG(small_x != nullptr && small_in <= 64);
+    p.k1_true = small_in;
+    return launch_fwd<1, 4>(p, st);
+  }
+  MGN_CHECK_ARG(n_tab >= 1 && n_tab <= 3);
+  for (int k = 0; k < n_tab; ++k) MGN_CHECK_ARG(p.tab[k] != nullptr);
+  p.k1_true = kH * n_tab;
+  if (n_tab == 1) return launch_fwd<2, 4>(p, st);
+  if (n_tab == 2) return launch_fwd<4, 4>(p, st);
+  return launch_fwd<6, 3>(p, st);
+}

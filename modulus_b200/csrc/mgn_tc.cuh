@@ -213,7 +213,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   return true;
 #else
-  for (uint32_t it = 0; it < (1u << 22); ++it)
+  for (uint32_t it = 0; it < (1u << 20); ++it)
     if (mbar_try_wait(bar, parity)) return true;
   return false;
 #endif

@@ -412,3 +412,45 @@ def activation(x: Tensor, act: str) -> Tensor:
     if ACT_IDS[act] == 0:
         return x
     return ActFn.apply(x, ACT_IDS[act])
+
+
+# ----------------------------------------------------------------------------------------
+# tensor-core (tcgen05) path: bf16 storage, hidden width 128, ReLU
+# ----------------------------------------------------------------------------------------
+TC_HIDDEN = 128
+_STATUS = {}
+
+
+def tc_status(device) -> Tensor:
+    """Device int the fused kernels OR an error code into (internal pipeline timeout).  Checked by
+    `tc_check()`; never read on the hot path."""
+    key = torch.device(device).index or 0
+    if key not in _STATUS:
+        _STATUS[key] = torch.zeros(1, dtype=torch.int32, device=device)
+    return _STATUS[key]
+
+
+def tc_check(device="cuda") -> None:
+    code = int(tc_status(device).item())
+    if code != 0:
+        tc_status(device).zero_()
+        raise _lib.MGNError(f"libmgn_b200: fused tensor-core kernel reported internal status {code}")
+
+
+def mlp3_fwd_tc(tabs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]], M: int,
+                w1, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
+                residual: Optional[Tensor] = None, n_out: int = TC_HIDDEN,
+                small_x: Optional[Tensor] = None, save_hidden: bool = False):
+    """Raw call of the fused forward kernel (see include/mgn_b200.h: mgn_mlp3_fwd_tc)."""
+    dev = (small_x if small_x is not None else tabs[0]).device
+    out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
+    h1 = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if save_hidden else None
+    h2 = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if save_hidden else None
+    t = list(tabs) + [None] * (3 - len(tabs))
+    ix = list(idxs) + [None] * (3 - len(idxs))
+    small_in = 0 if small_x is None else small_x.shape[1]
+    small_f32 = int(small_x is not None and small_x.dtype == torch.float32)
+    call("mgn_mlp3_fwd_tc", _p(t[0]), _p(ix[0]), _p(t[1]), _p(ix[1]), _p(t[2]), _p(ix[2]), len(tabs),
+         _p(small_x), small_in, small_f32, M, _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta),
+         n_out, eps, _p(residual), _p(out), n_out, _p(h1), _p(h2), _p(tc_status(dev)), _stream())
+    return out, h1, h2
