@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- MeshGraphNet fwd+bwd edges/s on B200 (BASELINE.json metric) with roofline evidence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3] [--impl b200|reference]
+
+One "step" = zero_grad -> forward -> MSE loss -> backward of a 15-layer, hidden-128 MeshGraphNet
+(examples/cfd/vortex_shedding_mgn/train.py:151-166 of the reference; optimizer excluded)
+on a synthetic mesh.  N=1 default workload is BASELINE.json configs[1] (2-D triangle mesh, 100k
+nodes / ~600k edges, bf16).  With N>1 ranks (torchrun) the mesh grows N-fold and is partitioned
+with DistributedGraph (weak scaling, halo exchange = NCCL all-to-all); value = global edges / max
+over ranks of the device time.
+
+The JSON line carries: value (inputs resident in HBM), e2e (host buffers, H2D + loss D2H inside
+the timed region), roofline (dominant kernel, CUDA-event durations recorded inside the timed
+region against algorithmic bytes/flops), cpu_baseline (oracle port on the host cores, bounded
+sample), clocks, gpu_launches.
+
+--impl reference times the CPU implementation of the same path (oracle/mgn_oracle.py: the
+reference's algorithm restated in plain torch, pinned to the reference's golden vectors in
+tests/test_oracle.py; /root/reference itself is not present on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MGN fwd+bwd edges/s"
+UNIT = "edges/s"
+H = 128
+L = 15
+
+WORKLOADS = {
+    # name: (generator, args, d_node, d_edge, d_out, dtype)
+    "c1": ("triangle_grid_mesh", (42, 45), 6, 3, 3, "f32"),     # ~1.9k nodes (vortex_shedding_mgn size)
+    "c2": ("triangle_grid_mesh", (316, 317), 6, 3, 3, "bf16"),   # 100k nodes / ~600k edges
+    "c3": ("torus_surface_mesh", (1000, 1000), 11, 4, 4, "bf16"),  # 1M nodes / 6M edges
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------------
+# algorithmic work (SURVEY 8d / BASELINE.md section 3)
+# ------------------------------------------------------------------------------------------
+def step_flops(N, E, d_n, d_e, d_out):
+    f_l = 10 * H * H * E + 8 * H * H * N
+    f_encdec = 2 * (d_e * H + 2 * H * H) * E + 2 * (d_n * H + 2 * H * H) * N + 2 * (2 * H * H + H * d_out) * N
+    return 3 * (L * f_l + f_encdec)
+
+
+def step_bytes(N, E, b):
+    return L * (9 * E + 13 * N) * H * b + L * (24 * E + 12 * N)
+
+
+class ClockSampler:
+    """nvidia-smi sampling of SM clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------
+# CPU arm (oracle port) -- the reference's algorithm on the host cores
+# ------------------------------------------------------------------------------------------
+def cpu_step_rate(sample_nx: int, sample_ny: int, d_n, d_e, d_out, reps: int, warmup: int, threads: int):
+    import torch
+    from modulus_b200.mesh import triangle_grid_mesh
+    from oracle import mgn_oracle as O  # CPU baseline leg only
+
+    torch.set_num_threads(threads)
+    mesh = triangle_grid_mesh(sample_nx, sample_ny)
+    n, E = mesh["num_nodes"], int(mesh["indices"].numel())
+    src, dst = O.coo_from_csc(mesh["offsets"], mesh["indices"])
+    torch.manual_seed(0)
+    sd = O.make_state_dict(d_n, d_e, d_out, processor_size=L, hidden=H)
+    nf, tgt = torch.randn(n, d_n), torch.randn(n, d_out)
+    ef = mesh["edge_features"][:, :d_e].contiguous() if mesh["edge_features"].shape[1] >= d_e else torch.randn(E, d_e)
+    times = []
+    for i in range(warmup + reps):
+        t0 = time.perf_counter()
+        O.step_fwd_bwd(sd, nf, ef, src, dst, tgt, processor_size=L)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    t = sum(times) / len(times)
+    return E / t, t, n, E
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[args.workload]
+    threads = os.cpu_count() or 1
+    # bounded sample of the workload: a 100x100 triangle mesh (10k nodes, ~59k edges) per step
+    nx, ny = (42, 45) if args.workload == "c1" else (100, 100)
+    rate, t, n, E = cpu_step_rate(nx, ny, d_n, d_e, d_out, reps=max(args.steps, 1), warmup=min(args.warmup, 1),
+                                  threads=threads)
+    sample = f"triangle_grid_mesh({nx},{ny}): {n} nodes / {E} edges, 15 layers, hidden 128, fp32, torch CPU"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, 1), "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w, world):
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[w]
+    return (f"{w}: MeshGraphNet({d_n},{d_e},{d_out}) 15 layers hidden 128 on {gen}{gargs}"
+            + (f" x{world} ranks (rows scaled, DistributedGraph nodewise partition)" if world > 1 else ""))
+
+
+# ------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from modulus_b200 import _lib, ops
+    from modulus_b200 import mesh as meshgen
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[args.workload]
+    gargs = (gargs[0] * world, gargs[1])  # weak scaling: more rows, same row length
+    mesh = getattr(meshgen, gen)(*gargs, device=dev)
+    n_glob, E_glob = mesh["num_nodes"], int(mesh["indices"].numel())
+
+    torch.manual_seed(0)
+    model = MeshGraphNet(d_n, d_e, d_out).to(dev)
+    g = torch.Generator().manual_seed(1)
+    if world > 1:
+        from modulus_b200.distributed import DistributedManager, mark_module_as_shared
+        DistributedManager.initialize()
+        dm = DistributedManager()
+        dm.create_process_subgroup("graph_partition", world)
+        graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n_glob, n_glob, partition_size=world,
+                           partition_group_name="graph_partition")
+        mark_module_as_shared(model, "graph_partition")
+        gp = graph.dist_graph.graph_partition
+        n_loc, E_loc = gp.num_local_dst_nodes, gp.num_local_indices
+        halo_rows = int(gp.num_local_src_nodes - gp.sizes[rank][rank])
+        ef_all = mesh["edge_features"][:, :d_e]
+        ef_host = graph.get_edge_features_in_partition(ef_all).float().cpu().contiguous()
+    else:
+        graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n_glob, n_glob)
+        n_loc, E_loc, halo_rows = n_glob, E_glob, 0
+        ef_src = mesh["edge_features"]
+        ef_host = (ef_src[:, :d_e] if ef_src.shape[1] >= d_e else
+                   torch.cat([ef_src, ef_src[:, :1].expand(-1, d_e - ef_src.shape[1])], 1)).float().cpu().contiguous()
+    nf_host = torch.randn(n_loc, d_n, generator=g)
+    tgt_host = torch.randn(n_loc, d_out, generator=g)
+    nf_host, ef_host, tgt_host = nf_host.pin_memory(), ef_host.pin_memory(), tgt_host.pin_memory()
+    del mesh
+    graph.b200_plan()
+
+    use_bf16 = dtype == "bf16"
+
+    def step(nf, ef, tgt):
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_bf16):
+            pred = model(nf, ef, graph)
+        loss = torch.nn.functional.mse_loss(pred.float(), tgt)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    nf_d, ef_d, tgt_d = nf_host.to(dev), ef_host.to(dev), tgt_host.to(dev)
+
+    # ---- warm-up (also the profiling pass that finds the dominant C-ABI entry point)
+    for _ in range(max(args.warmup - 1, 2)):
+        step(nf_d, ef_d, tgt_d)
+    torch.cuda.synchronize()
+    _lib.PROFILE.start(all_symbols=True, n_edges=E_loc)
+    step(nf_d, ef_d, tgt_d)
+    torch.cuda.synchronize()
+    shares = _lib.PROFILE.stop()
+    top = max(shares.items(), key=lambda kv: kv[1]["ms"])[0] if shares else None
+
+    # ---- timed region A: inputs resident in HBM
+    clocks = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                          int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]) if
+                          os.environ["CUDA_VISIBLE_DEVICES"].replace(",", "").isdigit() else local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    clocks.start()
+    l0 = lib.mgn_launch_count()
+    _lib.PROFILE.start(all_symbols=False, only=top, n_edges=E_loc)
+    ev0.record()
+    for _ in range(args.steps):
+        step(nf_d, ef_d, tgt_d)
+    ev1.record()
+    barrier()
+    top_prof = _lib.PROFILE.stop()
+    launches = (lib.mgn_launch_count() - l0) // max(args.steps, 1)
+    t_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)  # ms
+    clk = clocks.stop()
+    ops.tc_check(dev)
+
+    # ---- timed region B: end to end from pinned host buffers, loss read back every step
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = 0.0
+    for _ in range(args.steps):
+        nf = nf_host.to(dev, non_blocking=True)
+        ef = ef_host.to(dev, non_blocking=True)
+        tg = tgt_host.to(dev, non_blocking=True)
+        last = float(step(nf, ef, tg).item())
+    e1.record()
+    barrier()
+    t_e2e = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    h2d = (nf_host.numel() + ef_host.numel() + tgt_host.numel()) * 4
+    if last != last:
+        raise RuntimeError("bench.py: loss is NaN")
+
+    if rank != 0:
+        return
+    b = 2 if use_bf16 else 4
+    N1, E1 = n_glob // world, E_glob // world  # per-rank work (weak scaling)
+    flops, bytes_ = step_flops(N1, E1, d_n, d_e, d_out), step_bytes(N1, E1, b)
+    roof = None
+    if top is not None and top in top_prof and top_prof[top]["calls"]:
+        avg_ms = top_prof[top]["ms"] / top_prof[top]["calls"]
+        if top_prof[top]["bound"] is not None:
+            # algorithmic bytes (or useful flops) per call of the entry point, averaged over its calls
+            kind, amount = top_prof[top]["bound"], top_prof[top]["work"] / top_prof[top]["calls"]
+            if kind == "hbm":
+                ach = amount / (avg_ms * 1e-3) / 1e9
+                roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm"], "traffic": None}
+            else:
+                ach = amount / (avg_ms * 1e-3) / 1e12
+                roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tc_sust"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tc_sust"], "traffic": None}
+            roof["avg_launch_ms"] = avg_ms
+            roof["share_of_step"] = shares[top]["ms"] / max(sum(v["ms"] for v in shares.values()), 1e-9)
+            roof["peak_source"] = peaks["src"]
+    # whole-step fractions (report both)
+    whole = {
+        "hbm_frac": bytes_ / (t_step * 1e-3) / 1e9 / peaks["hbm"],
+        "tensor_frac": flops / (t_step * 1e-3) / 1e12 / peaks["tc_sust"],
+        "algorithmic_GB_per_step": bytes_ / 1e9, "algorithmic_TFLOP_per_step": flops / 1e12,
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, t, n_s, E_s = cpu_step_rate(100, 100, d_n, d_e, d_out, reps=3, warmup=1, threads=threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle step on triangle_grid_mesh(100,100): {n_s} nodes / {E_s} edges, fp32, "
+                         f"3 reps after 1 warm-up, {t:.2f} s per step"}
+    line = {
+        "metric": METRIC, "value": E_glob / (t_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, world), "nodes": n_glob, "edges": E_glob,
+                   "halo_rows_rank0": halo_rows,
+                   "l2": "per-step working set (edge table alone %.0f MB) exceeds the 126 MB L2; no explicit flush"
+                         % (E1 * H * b / 1e6) if E1 * H * b > 126e6 else
+                         "working set smaller than L2: numbers are L2-warm (c1 is launch-bound by construction)"},
+        "e2e": {"value": E_glob / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "clocks": clk,
+        "kernel_shares": {k: round(v["ms"], 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"bench.py: --gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+    if world > 1:
+        import torch.distributed as dist
+        import torch
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            if dist.is_initialized():
+                dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

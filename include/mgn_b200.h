@@ -51,6 +51,8 @@ enum {
 
 int mgn_version(void);
 const char* mgn_error_string(int code);
+/* kernels launched by this library since it was loaded (all streams, all entry points) */
+int64_t mgn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Graph plan: CSC -> CSR transpose (the structure the backward scatter walks).

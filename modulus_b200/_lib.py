@@ -34,7 +34,7 @@ def _parse_header(text: str):
     binding cannot drift from include/mgn_b200.h."""
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\n\s*(const\s+char\s*\*|size_t|int)\s+(mgn_\w+)\s*\(([^;{]*?)\)\s*;", text):
+    for m in re.finditer(r"\n\s*(const\s+char\s*\*|size_t|int64_t|int)\s+(mgn_\w+)\s*\(([^;{]*?)\)\s*;", text):
         ret, name, args = m.group(1), m.group(2), m.group(3)
         restype = c_char_p if "char" in ret else _CTYPE[ret.strip()]
         argtypes = []
@@ -92,4 +92,102 @@ def check(rc: int, what: str = "") -> None:
 
 
 def call(name: str, *args) -> None:
+    if PROFILE.active and (PROFILE.only is None or PROFILE.only == name):
+        PROFILE.record(name, args)
+        return
     check(getattr(load(), name)(*args), name)
+
+
+# ----------------------------------------------------------------------------------------
+# measurement hooks (bench.py): CUDA-event bracketing of C-ABI calls on the calling stream
+# ----------------------------------------------------------------------------------------
+_DT_BYTES = {MGN_F32: 4, MGN_BF16: 2}
+
+
+def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
+    """(bound, amount) of ONE call from its arguments: ("hbm", algorithmic bytes) for the
+    gather / scatter / elementwise entry points, ("tensor", useful flops) for the dense ones.
+    Formulas: DESIGN.md section 'Kernels and their rooflines' (SURVEY 8d)."""
+    if name == "mgn_mlp3_fwd_tc":
+        n_tab, small_in, M, n_out = a[6], a[8], a[10], a[19]
+        k1 = small_in if small_in > 0 else 128 * n_tab
+        return "tensor", 2.0 * M * (k1 * 128 + 128 * 128 + 128 * n_out)
+    if name == "mgn_mlp3_bwd_tc":
+        n_tab, small_in, M, n_out = a[6], a[8], a[10], a[19]
+        k1 = small_in if small_in > 0 else 128 * n_tab
+        return "tensor", 4.0 * M * (k1 * 128 + 128 * 128 + 128 * n_out)
+    if name == "mgn_linear_fwd":
+        M, K, N = a[3], a[4], a[7]
+        return "tensor", 2.0 * M * K * N
+    if name == "mgn_linear_bwd_data":
+        M, N, K = a[2], a[3], a[5]
+        return "tensor", 2.0 * M * K * N
+    if name == "mgn_linear_bwd_weight":
+        M, N, K = a[4], a[5], a[6]
+        return "tensor", 2.0 * M * K * N
+    if name == "mgn_segment_sum":
+        b, D, n_seg = _DT_BYTES[a[0]], a[4], a[7]
+        return "hbm", None if PROFILE.n_edges is None else (PROFILE.n_edges + n_seg) * D * b + 4.0 * n_seg
+    if name == "mgn_gather_rows":
+        b, D, rows = _DT_BYTES[a[0]], a[4], a[6]
+        return "hbm", 2.0 * rows * D * b
+    if name == "mgn_concat_efeat_fwd":
+        b, De, Ds, Dd, E = _DT_BYTES[a[0]], a[2], a[4], a[6], a[9]
+        return "hbm", E * (De + De + Ds + Dd) * b + 8.0 * E  # + one pass over the node tables (not known here)
+    if name == "mgn_layernorm_fwd":
+        b, M, D = _DT_BYTES[a[0]], a[2], a[3]
+        return "hbm", (3.0 if a[7] else 2.0) * M * D * b
+    if name == "mgn_layernorm_bwd":
+        b, M, D = _DT_BYTES[a[0]], a[6], a[7]
+        return "hbm", 3.0 * M * D * b
+    if name in ("mgn_act_bwd", "mgn_add"):
+        b, n = _DT_BYTES[a[0]], (a[5] if name == "mgn_act_bwd" else a[4])
+        return "hbm", 3.0 * n * b
+    return None
+
+
+class _Profile:
+    def __init__(self):
+        self.active = False
+        self.only = None
+        self.n_edges = None
+        self._ev = []
+
+    def start(self, all_symbols: bool = True, only: "str | None" = None, n_edges: "int | None" = None) -> None:
+        self.only = None if all_symbols else only
+        if not all_symbols and only is None:
+            return
+        self.n_edges = n_edges
+        self._ev = []
+        self.active = True
+
+    def record(self, name, args) -> None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(load(), name)(*args)
+        e1.record()
+        check(rc, name)
+        self._ev.append((name, e0, e1, algorithmic_work(name, args)))
+
+    def stop(self) -> dict:
+        import torch
+
+        if not self.active:
+            return {}
+        self.active = False
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1, work in self._ev:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "bound": None, "work": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+            if work is not None and work[1] is not None:
+                d["bound"] = work[0]
+                d["work"] += work[1]
+        self._ev = []
+        return out
+
+
+PROFILE = _Profile()

@@ -23,6 +23,15 @@ static inline int mgn_launch_status() {
 
 static inline cudaStream_t as_stream(mgn_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// number of kernels launched by this library since load (bench.py reports the delta over its timed
+// region as "gpu_launches"); every launch site passes its stream through MGN_ST()
+extern unsigned long long g_mgn_launches;
+static inline cudaStream_t count_launch(cudaStream_t s) {
+  __atomic_fetch_add(&g_mgn_launches, 1ull, __ATOMIC_RELAXED);
+  return s;
+}
+#define MGN_ST(s) ::mgn::count_launch(s)
+
 static inline int num_sms() {
   static int n = 0;
   if (n == 0) {

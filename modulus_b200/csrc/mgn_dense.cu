@@ -310,7 +310,7 @@ static int linear_fwd_t(const void* x, int64_t ldx, int64_t M, int64_t K, const 
                         int act, void* y_pre, void* h, int64_t ldh, cudaStream_t st) {
   if (M == 0 || N == 0) return MGN_OK;
   dim3 grid(static_cast<unsigned>((N + GB_N - 1) / GB_N), static_cast<unsigned>((M + GB_M - 1) / GB_M), 1);
-  linear_fwd_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ldx, w, b, M, N, K, act,
+  linear_fwd_kernel<T><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const T*>(x), ldx, w, b, M, N, K, act,
                                              static_cast<T*>(y_pre), static_cast<T*>(h), ldh);
   return mgn_launch_status();
 }
@@ -339,10 +339,10 @@ extern "C" int mgn_act_bwd(int dtype, const void* g_h, const void* y_pre, int ac
   MGN_CHECK_ARG(g_h && y_pre && g_y && act >= MGN_ACT_NONE && act <= MGN_ACT_ELU);
   cudaStream_t st = as_stream(stream);
   if (dtype == MGN_F32)
-    act_bwd_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(g_h), static_cast<const float*>(y_pre),
+    act_bwd_kernel<float><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const float*>(g_h), static_cast<const float*>(y_pre),
                                                       act, static_cast<float*>(g_y), n);
   else if (dtype == MGN_BF16)
-    act_bwd_kernel<bf16><<<ew_grid(n), 256, 0, st>>>(static_cast<const bf16*>(g_h), static_cast<const bf16*>(y_pre),
+    act_bwd_kernel<bf16><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(g_h), static_cast<const bf16*>(y_pre),
                                                      act, static_cast<bf16*>(g_y), n);
   else
     return MGN_EINVAL;
@@ -355,9 +355,9 @@ extern "C" int mgn_act_fwd(int dtype, const void* x, int act, void* y, int64_t n
   MGN_CHECK_ARG(x && y && act >= MGN_ACT_NONE && act <= MGN_ACT_ELU);
   cudaStream_t st = as_stream(stream);
   if (dtype == MGN_F32)
-    act_fwd_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(x), act, static_cast<float*>(y), n);
+    act_fwd_kernel<float><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const float*>(x), act, static_cast<float*>(y), n);
   else if (dtype == MGN_BF16)
-    act_fwd_kernel<bf16><<<ew_grid(n), 256, 0, st>>>(static_cast<const bf16*>(x), act, static_cast<bf16*>(y), n);
+    act_fwd_kernel<bf16><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(x), act, static_cast<bf16*>(y), n);
   else
     return MGN_EINVAL;
   return mgn_launch_status();
@@ -369,10 +369,10 @@ extern "C" int mgn_add(int dtype, const void* a, const void* b, void* out, int64
   MGN_CHECK_ARG(a && b && out);
   cudaStream_t st = as_stream(stream);
   if (dtype == MGN_F32)
-    add_kernel<float><<<ew_grid(n), 256, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b),
+    add_kernel<float><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const float*>(a), static_cast<const float*>(b),
                                                   static_cast<float*>(out), n);
   else if (dtype == MGN_BF16)
-    add_kernel<bf16><<<ew_grid(n), 256, 0, st>>>(static_cast<const bf16*>(a), static_cast<const bf16*>(b),
+    add_kernel<bf16><<<ew_grid(n), 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(a), static_cast<const bf16*>(b),
                                                  static_cast<bf16*>(out), n);
   else
     return MGN_EINVAL;
@@ -390,10 +390,10 @@ extern "C" int mgn_linear_bwd_data(int dtype, const void* g_y, int64_t M, int64_
   dim3 grid(static_cast<unsigned>((K + GB_N - 1) / GB_N), static_cast<unsigned>((M + GB_M - 1) / GB_M), 1);
   // C[m,k] = sum_n g_y[m,n] W[n,k]:  A(i=m, r=n) = g_y[m*N+n],  B(r=n, j=k) = W[n*K+k]
   if (dtype == MGN_F32)
-    gemm_simt_kernel<float, float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(g_y), N, 1, w, K, 1, M, K,
+    gemm_simt_kernel<float, float, float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const float*>(g_y), N, 1, w, K, 1, M, K,
                                                                 N, N, static_cast<float*>(g_x), ldgx);
   else if (dtype == MGN_BF16)
-    gemm_simt_kernel<bf16, float, bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(g_y), N, 1, w, K, 1, M, K, N,
+    gemm_simt_kernel<bf16, float, bf16><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(g_y), N, 1, w, K, 1, M, K, N,
                                                               N, static_cast<bf16*>(g_x), ldgx);
   else
     return MGN_EINVAL;
@@ -431,24 +431,24 @@ extern "C" int mgn_linear_bwd_weight(int dtype, const void* g_y, const void* x, 
             static_cast<unsigned>(splits));
   // C[n,k] = sum_m g_y[m,n] x[m,k]:  A(i=n, r=m) = g_y[m*N+n],  B(r=m, j=k) = x[m*ldx+k]
   if (dtype == MGN_F32)
-    gemm_simt_kernel<float, float, float><<<grid, 256, 0, st>>>(static_cast<const float*>(g_y), 1, N,
+    gemm_simt_kernel<float, float, float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const float*>(g_y), 1, N,
                                                          static_cast<const float*>(x), ldx, 1, N, K, M, r_chunk,
                                                          part_w, K);
   else if (dtype == MGN_BF16)
-    gemm_simt_kernel<bf16, bf16, float><<<grid, 256, 0, st>>>(static_cast<const bf16*>(g_y), 1, N,
+    gemm_simt_kernel<bf16, bf16, float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(g_y), 1, N,
                                                        static_cast<const bf16*>(x), ldx, 1, N, K, M, r_chunk, part_w,
                                                        K);
   else
     return MGN_EINVAL;
-  reduce_partials_kernel<float><<<ew_grid(N * K), 256, 0, st>>>(part_w, N * K, static_cast<int>(splits), g_w);
+  reduce_partials_kernel<float><<<ew_grid(N * K), 256, 0, MGN_ST(st)>>>(part_w, N * K, static_cast<int>(splits), g_w);
   if (g_b) {
     if (dtype == MGN_F32)
-      colsum_partial_kernel<float><<<static_cast<unsigned>(splits), 128, 0, st>>>(static_cast<const float*>(g_y), M, N,
+      colsum_partial_kernel<float><<<static_cast<unsigned>(splits), 128, 0, MGN_ST(st)>>>(static_cast<const float*>(g_y), M, N,
                                                                                   r_chunk, part_b);
     else
-      colsum_partial_kernel<bf16><<<static_cast<unsigned>(splits), 128, 0, st>>>(static_cast<const bf16*>(g_y), M, N,
+      colsum_partial_kernel<bf16><<<static_cast<unsigned>(splits), 128, 0, MGN_ST(st)>>>(static_cast<const bf16*>(g_y), M, N,
                                                                                  r_chunk, part_b);
-    reduce_partials_kernel<float><<<ew_grid(N), 256, 0, st>>>(part_b, N, static_cast<int>(splits), g_b);
+    reduce_partials_kernel<float><<<ew_grid(N), 256, 0, MGN_ST(st)>>>(part_b, N, static_cast<int>(splits), g_b);
   }
   return mgn_launch_status();
 }
@@ -462,11 +462,11 @@ extern "C" int mgn_layernorm_fwd(int dtype, const void* x, int64_t M, int64_t D,
   cudaStream_t st = as_stream(stream);
   const int grid = ew_grid(M * 32);
   if (dtype == MGN_F32)
-    layernorm_fwd_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(x), M, static_cast<int>(D), gamma,
+    layernorm_fwd_kernel<float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const float*>(x), M, static_cast<int>(D), gamma,
                                                       beta, eps, static_cast<const float*>(residual),
                                                       static_cast<float*>(out), mean, rstd);
   else if (dtype == MGN_BF16)
-    layernorm_fwd_kernel<bf16><<<grid, 256, 0, st>>>(static_cast<const bf16*>(x), M, static_cast<int>(D), gamma, beta,
+    layernorm_fwd_kernel<bf16><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const bf16*>(x), M, static_cast<int>(D), gamma, beta,
                                                      eps, static_cast<const bf16*>(residual), static_cast<bf16*>(out),
                                                      mean, rstd);
   else
@@ -509,16 +509,16 @@ extern "C" int mgn_layernorm_bwd(int dtype, const void* g_out, const void* x, co
   nb = (M + rows_per_block - 1) / rows_per_block;
   float* partial = static_cast<float*>(workspace);
   if (dtype == MGN_F32)
-    layernorm_bwd_kernel<float><<<static_cast<unsigned>(nb), 256, 0, st>>>(
+    layernorm_bwd_kernel<float><<<static_cast<unsigned>(nb), 256, 0, MGN_ST(st)>>>(
         static_cast<const float*>(g_out), static_cast<const float*>(x), mean, rstd, gamma, M, static_cast<int>(D),
         rows_per_block, static_cast<float*>(g_x), partial);
   else if (dtype == MGN_BF16)
-    layernorm_bwd_kernel<bf16><<<static_cast<unsigned>(nb), 256, 0, st>>>(
+    layernorm_bwd_kernel<bf16><<<static_cast<unsigned>(nb), 256, 0, MGN_ST(st)>>>(
         static_cast<const bf16*>(g_out), static_cast<const bf16*>(x), mean, rstd, gamma, M, static_cast<int>(D),
         rows_per_block, static_cast<bf16*>(g_x), partial);
   else
     return MGN_EINVAL;
-  ln_reduce2_kernel<<<static_cast<unsigned>((2 * D + 255) / 256), 256, 0, st>>>(partial, D, static_cast<int>(nb), g_gamma,
+  ln_reduce2_kernel<<<static_cast<unsigned>((2 * D + 255) / 256), 256, 0, MGN_ST(st)>>>(partial, D, static_cast<int>(nb), g_gamma,
                                                                              g_beta);
   return mgn_launch_status();
 }

@@ -289,12 +289,12 @@ static int concat_efeat_fwd_t(const void* efeat, int64_t De, const void* sfeat, 
   if (vec) {
     constexpr int kRows = 4;
     const int64_t warps = (E + kRows - 1) / kRows;
-    concat_efeat_vec_kernel<T, kRows><<<grid_for(warps * 32), 256, 0, st>>>(
+    concat_efeat_vec_kernel<T, kRows><<<grid_for(warps * 32), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(efeat), static_cast<int>(De / V), static_cast<const T*>(sfeat),
         static_cast<int>(Ds / V), static_cast<const T*>(dfeat), static_cast<int>(Dd / V), src, dst, E,
         static_cast<T*>(out));
   } else {
-    concat_efeat_scalar_kernel<T><<<grid_for(E * (De + Ds + Dd)), 256, 0, st>>>(
+    concat_efeat_scalar_kernel<T><<<grid_for(E * (De + Ds + Dd)), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(efeat), static_cast<int>(De), static_cast<const T*>(sfeat), static_cast<int>(Ds),
         static_cast<const T*>(dfeat), static_cast<int>(Dd), src, dst, E, static_cast<T*>(out));
   }
@@ -308,11 +308,11 @@ static int sum_efeat_fwd_t(const void* efeat, const void* sfeat, const void* dfe
   if (E == 0) return MGN_OK;
   const bool vec = D % V == 0 && aligned16(efeat) && aligned16(sfeat) && aligned16(dfeat) && aligned16(out);
   if (vec)
-    sum_efeat_vec_kernel<T><<<grid_for(E * (D / V)), 256, 0, st>>>(
+    sum_efeat_vec_kernel<T><<<grid_for(E * (D / V)), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(efeat), static_cast<const T*>(sfeat), static_cast<const T*>(dfeat),
         static_cast<int>(D / V), src, dst, E, static_cast<T*>(out));
   else
-    sum_efeat_scalar_kernel<T><<<grid_for(E * D), 256, 0, st>>>(
+    sum_efeat_scalar_kernel<T><<<grid_for(E * D), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(efeat), static_cast<const T*>(sfeat), static_cast<const T*>(dfeat),
         static_cast<int>(D), src, dst, E, static_cast<T*>(out));
   return mgn_launch_status();
@@ -332,7 +332,7 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
     const int chunks = static_cast<int>(D / V);
     const int grid = grid_for(n_seg * 32);
 #define MGN_SEG(G)                                                                                     \
-  segment_sum_vec_kernel<T, G><<<grid, 256, 0, st>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
+  segment_sum_vec_kernel<T, G><<<grid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
                                                      o_, ld_out, out_col0, mean, accumulate)
     if (chunks <= 4) MGN_SEG(4);
     else if (chunks <= 8) MGN_SEG(8);
@@ -340,7 +340,7 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
     else MGN_SEG(32);
 #undef MGN_SEG
   } else {
-    segment_sum_scalar_kernel<T><<<grid_for(n_seg * D), 256, 0, st>>>(i_, ld_in, in_col0, static_cast<int>(D),
+    segment_sum_scalar_kernel<T><<<grid_for(n_seg * D), 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, static_cast<int>(D),
                                                                       offsets, eids, n_seg, o_, ld_out, out_col0,
                                                                       mean, accumulate);
   }
@@ -356,11 +356,11 @@ static int gather_rows_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
   const bool vec = D % V == 0 && ld_in % V == 0 && in_col0 % V == 0 && ld_out % V == 0 && out_col0 % V == 0 &&
                    aligned16(in) && aligned16(out);
   if (vec)
-    gather_rows_vec_kernel<T><<<grid_for(n_rows * (D / V)), 256, 0, st>>>(
+    gather_rows_vec_kernel<T><<<grid_for(n_rows * (D / V)), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(in), ld_in, in_col0, static_cast<int>(D / V), idx, n_rows, static_cast<T*>(out),
         ld_out, out_col0, deg_offsets);
   else
-    gather_rows_scalar_kernel<T><<<grid_for(n_rows * D), 256, 0, st>>>(
+    gather_rows_scalar_kernel<T><<<grid_for(n_rows * D), 256, 0, MGN_ST(st)>>>(
         static_cast<const T*>(in), ld_in, in_col0, static_cast<int>(D), idx, n_rows, static_cast<T*>(out), ld_out,
         out_col0, deg_offsets);
   return mgn_launch_status();

@@ -196,15 +196,15 @@ extern "C" int mgn_group_by_key(const int32_t* keys, int64_t n, int64_t n_keys, 
   cudaMemsetAsync(cursor, 0, n1 * sizeof(int32_t), st);
   cudaMemsetAsync(long_count, 0, sizeof(int32_t), st);
   const int grid = num_sms() * 8;
-  if (n > 0) count_keys_kernel<<<grid, 256, 0, st>>>(keys, n, offsets);
+  if (n > 0) count_keys_kernel<<<grid, 256, 0, MGN_ST(st)>>>(keys, n, offsets);
   // offsets holds counts[0..n_keys) and 0 at [n_keys]; exclusive scan over n_keys+1 entries
-  scan_blocks_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(offsets, n1, block_sums);
-  scan_sums_kernel<<<1, kScanBlock, 0, st>>>(block_sums, nb);
-  scan_add_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, st>>>(offsets, n1, block_sums);
+  scan_blocks_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, MGN_ST(st)>>>(offsets, n1, block_sums);
+  scan_sums_kernel<<<1, kScanBlock, 0, MGN_ST(st)>>>(block_sums, nb);
+  scan_add_kernel<<<static_cast<unsigned>(nb), kScanBlock, 0, MGN_ST(st)>>>(offsets, n1, block_sums);
   if (n > 0) {
-    csr_fill_kernel<<<grid, 256, 0, st>>>(keys, n, offsets, cursor, ids);
-    csr_sort_short_kernel<<<grid, 256, 0, st>>>(offsets, n_keys, ids, long_list, long_count);
-    csr_sort_long_kernel<<<num_sms() * 2, 256, 0, st>>>(offsets, ids, long_list, long_count);
+    csr_fill_kernel<<<grid, 256, 0, MGN_ST(st)>>>(keys, n, offsets, cursor, ids);
+    csr_sort_short_kernel<<<grid, 256, 0, MGN_ST(st)>>>(offsets, n_keys, ids, long_list, long_count);
+    csr_sort_long_kernel<<<num_sms() * 2, 256, 0, MGN_ST(st)>>>(offsets, ids, long_list, long_count);
   }
   return mgn_launch_status();
 }
@@ -213,7 +213,7 @@ extern "C" int mgn_expand_offsets(const int32_t* offsets, int64_t n_segments, in
   MGN_CHECK_ARG(n_segments >= 0);
   if (n_segments == 0) return MGN_OK;
   MGN_CHECK_ARG(offsets && out);
-  expand_offsets_kernel<<<num_sms() * 8, 256, 0, as_stream(stream)>>>(offsets, n_segments, out);
+  expand_offsets_kernel<<<num_sms() * 8, 256, 0, MGN_ST(as_stream(stream))>>>(offsets, n_segments, out);
   return mgn_launch_status();
 }
 

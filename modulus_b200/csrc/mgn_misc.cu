@@ -1,7 +1,15 @@
 // mgn_misc.cu — version / error strings of the C ABI.
 #include "mgn_common.cuh"
 
-extern "C" int mgn_version(void) { return 100; }
+namespace mgn {
+unsigned long long g_mgn_launches = 0;
+}
+
+extern "C" int mgn_version(void) { return 101; }
+
+extern "C" int64_t mgn_launch_count(void) {
+  return static_cast<int64_t>(__atomic_load_n(&mgn::g_mgn_launches, __ATOMIC_RELAXED));
+}
 
 extern "C" const char* mgn_error_string(int code) {
   switch (code) {

@@ -399,7 +399,7 @@ static int launch_fwd(const MlpFwdParams& p, cudaStream_t st) {
   }
   const long long n_tiles = (p.M + kTileM - 1) / kTileM;
   const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
-  mlp3_fwd_tc_kernel<NP1, NSLOT><<<grid, kFwdThreads, L::kAlloc, st>>>(p);
+  mlp3_fwd_tc_kernel<NP1, NSLOT><<<grid, kFwdThreads, L::kAlloc, MGN_ST(st)>>>(p);
   return mgn_launch_status();
 }
 
