@@ -167,6 +167,45 @@ int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, con
                     const float* beta, int n_out, float eps, const void* residual, void* out,
                     int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream);
 
+/* Same fused forward with the first Linear split the way the reference's "concat trick" does
+ * (MeshGraphEdgeMLPSum, mesh_graph_mlp.py:278-458: per-node partial products gathered and summed per edge):
+ *     z1  = A W1^T + G + b1,   A = a_tab[a_idx[r]] [*,128],   G = g1_tab[g1_idx[r]] (+ g2_tab[g2_idx[r]])
+ *     out = [LayerNorm]( W3 relu(W2 relu(z1) + b2) + b3 ) [+ residual]
+ * g*_tab rows are [*, g*_ld] bf16 read from column g*_col0 (128 columns); w1 is read with row stride ld_w1.
+ * Edge block:  A = efeat, G = P[src][0:128] + P[dst][128:256] with P = nfeat [W1_src; W1_dst]^T.
+ * Node block:  A = agg,   G = P[r][256:384]                   with P = nfeat W1_nfeat^T. */
+int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const void* g1_tab, const int32_t* g1_idx,
+                      int64_t g1_ld, int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx,
+                      int64_t g2_ld, int64_t g2_col0, int64_t M, const float* w1, int64_t ld_w1,
+                      const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                      const float* gamma, const float* beta, int n_out, float eps, const void* residual,
+                      void* out, int64_t ld_out, int* status, mgn_stream_t stream);
+
+/* Fused MeshGraphMLP backward over 128-row tiles (forward hiddens are recomputed, nothing but the
+ * layer inputs is read back):
+ *     z1 = A W1^T + G + b1,  A = a_tab[a_idx[r]] (or raw small_x),  G = g1_tab[g1_idx[r]] (+ g2_tab[g2_idx[r]])
+ *     g_out = go1[go1_idx[r]] (+ go2[go2_idx[r]])             incoming gradient of the block output (idx NULL = r)
+ *   outputs
+ *     g_a   [M,128] bf16 = dL/dA (+ g_out when add_gout: the residual connection)      (nullable)
+ *     g_z1  [M,128] bf16 (row stride g_z1_ld) = dL/dz1 (= dL/dG rows; reduced per node by mgn_segment_sum) (nullable)
+ *     g_w1 [128, k1] (row stride ld_gw1), g_w2, g_w3 [n_out,128], g_b1..3, g_gamma, g_beta   fp32, nullable
+ * Replaces the autograd backward of MeshEdgeBlock.forward (mesh_edge_block.py:88-96), MeshNodeBlock.forward
+ * (mesh_node_block.py:82-92) and MeshGraphMLP.forward (mesh_graph_mlp.py:200-203): cuBLAS dgrad/wgrad GEMMs,
+ * native_layer_norm_backward, threshold_backward and the index_add_ scatter of the gathered rows.
+ * w1 is read with row stride ld_w1 (a column block of the [128, 3*128] first Linear).  gamma == NULL:
+ * no LayerNorm (decoder; then n_out may be < 128 and go1 is a dense [M, n_out] bf16 matrix). */
+size_t mgn_mlp3_bwd_tc_workspace_bytes(int64_t M);
+int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+                    int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
+                    int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
+                    int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
+                    const int32_t* go2_idx, int64_t M,
+                    const float* w1, int64_t ld_w1, const float* b1, const float* w2, const float* b2,
+                    const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
+                    int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
+                    float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
+                    size_t workspace_bytes, int* status, mgn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,862 @@
+// mgn_mlp_bwd_tc.cu — fused MeshGraphMLP backward on tcgen05 / TMEM (bf16 storage, hidden 128, ReLU).
+//
+// One persistent CTA per SM.  For every 128-row tile the kernel RECOMPUTES the forward hidden
+// activations (nothing but the layer inputs is kept from the forward pass) and then walks the
+// chain backwards, all GEMMs on the tensor cores with operands staged in shared memory:
+//
+//   fwd recompute   z1 = A W1^T + G + b1 ; h1 = relu(z1)        (G = optional additive gathered rows)
+//                   h2 = relu(h1 W2^T + b2) ; y = h2 W3^T + b3
+//   LayerNorm bwd   g_y  = rstd * (ghat - mean(ghat) - xhat * mean(ghat * xhat)),  ghat = g_out * gamma
+//   layer 3         gW3 += g_y^T  h2      g_h2 = g_y  W3     g_z2 = g_h2 * (h2 > 0)
+//   layer 2         gW2 += g_z2^T h1      g_h1 = g_z2 W2     g_z1 = g_h1 * (h1 > 0)
+//   layer 1         gW1 += g_z1^T A       g_A  = g_z1 W1 (+ g_out for the residual connection)
+//
+// The three weight-gradient accumulators stay resident in TMEM (3 x 128 columns) for the whole life
+// of the CTA and are written once, as per-CTA fp32 partials that a second kernel sums in a fixed
+// order (deterministic, no atomics).  One smem copy of each operand serves every GEMM that touches
+// it: the same swizzled [rows][64]-bf16 panels are read K-major (forward / dgrad A operand) and
+// MN-major (wgrad operands, dgrad B operand) -- layouts verified on hardware by tools/probe_tc.cu.
+//
+// This is the backward of MeshEdgeBlock / MeshNodeBlock / the encoder+decoder MeshGraphMLPs of the
+// reference (physicsnemo/models/gnn_layers/mesh_graph_mlp.py:142-203, mesh_edge_block.py:88-96,
+// mesh_node_block.py:82-92), which the reference leaves to autograd over cuBLAS + ATen kernels.
+//
+// Warp roles (288 threads): warp 0 = MMA issuer (one lane) + TMEM owner; warps 1-4 = movers
+// (stage tiles global->smem with 128-bit coalesced loads incl. the row gathers, write result
+// tiles smem->global coalesced, bias-gradient column sums); warps 5-8 = epilogue (thread = tile
+// row = TMEM lane).
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+
+namespace mgn {
+
+namespace bwd {
+
+constexpr int kRows = 128;       // tile rows
+constexpr int kPB = 16384;       // bytes per panel: 128 rows x 64 bf16
+constexpr int kThreads = 288;
+constexpr int kH = 128;
+
+struct RowSrc {  // row r of the tile source lives at tab[(idx ? idx[r] : r) * ld + col0 ...]
+  const bf16* tab;
+  const int32_t* idx;
+  long long ld;
+  long long col0;
+};
+
+struct Params {
+  RowSrc a;             // layer-1 input rows [*,128]                       (KP == 2)
+  const void* small_x;  // raw [M, small_in] features zero-padded to K=64    (KP == 1)
+  int small_in;
+  int small_is_f32;
+  RowSrc g1, g2;        // additive rows of layer 1 (tab == nullptr: absent)
+  RowSrc go1, go2;      // incoming gradient rows, summed (go2 optional)
+  int go_small;         // go1 is a dense [M, n_out] bf16 matrix with n_out < 128
+  long long M;
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *gamma;
+  long long ld_w1;
+  int k1_true;
+  int n_out;
+  float eps;
+  bf16* g_a;            // [M,128] gradient w.r.t. the layer-1 input rows (nullable)
+  int add_gout;         // g_a += g_out (residual connection on the A rows)
+  bf16* g_z1;           // [M,128] gradient w.r.t. the layer-1 pre-activation (nullable), row stride g_z1_ld
+  long long g_z1_ld;
+  float* partials;      // [gridDim.x][part_floats]
+  long long part_floats;
+  int* status;
+};
+
+enum { kStatusTimeout = 1, kStatusSmem = 2 };
+
+// barrier indices
+enum { B_AG = 0, B_GO = 1, B_A2 = 2, B_MMA1 = 3, B_E1 = 9, B_NUM = 15 };
+
+template <int KP>
+struct Smem {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = KP * kPB;
+  static constexpr int kW3 = kW2 + 2 * kPB;
+  static constexpr int kA = kW3 + 2 * kPB;
+  static constexpr int kX = kA + 2 * kPB;
+  static constexpr int kH1 = kX + 2 * kPB;
+  static constexpr int kH2 = kH1 + 2 * kPB;
+  static constexpr int kPar = kH2 + 2 * kPB;  // b1, b2, b3, gamma
+  static constexpr int kBars = kPar + 4 * kH * 4;
+  static constexpr int kTmemSlot = kBars + 16 * 8;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+
+// per-CTA partial layout (floats)
+template <int KP>
+struct Part {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = kH * 64 * KP;
+  static constexpr int kW3 = kW2 + kH * kH;
+  static constexpr int kB1 = kW3 + kH * kH;
+  static constexpr int kB2 = kB1 + kH;
+  static constexpr int kB3 = kB2 + kH;
+  static constexpr int kGamma = kB3 + kH;
+  static constexpr int kBeta = kGamma + kH;
+  static constexpr int kTotal = kBeta + kH;
+};
+
+__device__ __forceinline__ bool wait_clk(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s: a wrong descriptor must not hang the box
+  }
+  return true;
+}
+
+__device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+__device__ __forceinline__ uint4 add_bf16x8(uint4 a, uint4 b) {
+  const uint32_t x[4] = {a.x, a.y, a.z, a.w}, y[4] = {b.x, b.y, b.z, b.w};
+  uint32_t r[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 fa = unpack_bf16x2(x[i]), fb = unpack_bf16x2(y[i]);
+    r[i] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+  }
+  return make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+// fp32 [n_rows, k_true] (row stride ld) -> bf16 K-major SW128 panels [n_panels][128][64], zero padded
+__device__ __forceinline__ void stage_weight_ld(uint8_t* dst, const float* __restrict__ w, long long ld, int n_rows,
+                                                int k_true, int n_panels, int tid, int nthreads) {
+  const int per_row = n_panels * 8;
+  for (int item = tid; item < kRows * per_row; item += nthreads) {
+    const int row = item / per_row;
+    const int rem = item - row * per_row;
+    const int panel = rem >> 3, chunk = rem & 7;
+    const int k0 = panel * 64 + chunk * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (row < n_rows && (k0 + j) < k_true) ? __ldg(w + row * ld + k0 + j) : 0.f;
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]);
+    v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]);
+    v.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(dst + panel * kPB + sw128_offset(row, chunk)) = v;
+  }
+}
+
+// movers: stage NP panels of rows [row0, row0+128): v = s1[row] (+ s2[row]); rows >= M are zero
+template <int NP>
+__device__ __forceinline__ void stage_rows(uint8_t* buf, const RowSrc& s1, const RowSrc& s2, long long row0,
+                                           long long M, int mt) {
+  constexpr int CH = NP * 8;
+  const int chunk = mt % CH;
+  const int rsub = mt / CH;
+  constexpr int RSTEP = 128 / CH;
+  const bool two = s2.tab != nullptr;
+#pragma unroll
+  for (int base = 0; base < CH; base += 8) {
+    uint4 v1[8], v2[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = (base + u) * RSTEP + rsub;
+      const long long grow = row0 + row;
+      v1[u] = make_uint4(0, 0, 0, 0);
+      v2[u] = make_uint4(0, 0, 0, 0);
+      if (grow < M) {
+        const long long r1 = s1.idx ? static_cast<long long>(__ldg(s1.idx + grow)) : grow;
+        v1[u] = ldg128(s1.tab + r1 * s1.ld + s1.col0 + chunk * 8);
+        if (two) {
+          const long long r2 = s2.idx ? static_cast<long long>(__ldg(s2.idx + grow)) : grow;
+          v2[u] = ldg128(s2.tab + r2 * s2.ld + s2.col0 + chunk * 8);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int row = (base + u) * RSTEP + rsub;
+      const uint4 v = two ? add_bf16x8(v1[u], v2[u]) : v1[u];
+      *reinterpret_cast<uint4*>(buf + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7)) = v;
+    }
+  }
+}
+
+// movers: raw [M, n_in] features (fp32 or bf16), zero padded to one 64-column panel
+__device__ __forceinline__ void stage_small(uint8_t* buf, const void* x, int n_in, int is_f32, long long row0,
+                                            long long M, int mt) {
+  const int chunk = mt & 7, rsub = mt >> 3;
+#pragma unroll 4
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 16 + rsub;
+    const long long grow = row0 + row;
+    float f[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int col = chunk * 8 + q;
+      float v = 0.f;
+      if (grow < M && col < n_in)
+        v = is_f32 ? __ldg(static_cast<const float*>(x) + grow * n_in + col)
+                   : __bfloat162float(static_cast<const bf16*>(x)[grow * n_in + col]);
+      f[q] = v;
+    }
+    uint4 v4;
+    v4.x = pack_bf16x2(f[0], f[1]);
+    v4.y = pack_bf16x2(f[2], f[3]);
+    v4.z = pack_bf16x2(f[4], f[5]);
+    v4.w = pack_bf16x2(f[6], f[7]);
+    *reinterpret_cast<uint4*>(buf + sw128_offset(row, chunk)) = v4;
+  }
+}
+
+// movers: smem tile (2 panels) -> global rows [row0, ...) of a dense [M,128] bf16 matrix, coalesced
+__device__ __forceinline__ void store_rows(const uint8_t* buf, bf16* dst, long long ld, long long row0, long long M,
+                                           int mt) {
+  const int chunk = mt & 15, rsub = mt >> 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = i * 8 + rsub;
+    const long long grow = row0 + row;
+    if (grow < M) {
+      const uint4 v = *reinterpret_cast<const uint4*>(buf + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7));
+      *reinterpret_cast<uint4*>(dst + grow * ld + chunk * 8) = v;
+    }
+  }
+}
+
+// movers: acc[j] += sum over this thread's rows of tile[row][chunk*8 + j]
+__device__ __forceinline__ void colsum_tile(const uint8_t* buf, int mt, float (&acc)[8]) {
+  const int chunk = mt & 15, rsub = mt >> 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = i * 8 + rsub;
+    const uint4 v = *reinterpret_cast<const uint4*>(buf + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_bf16x2(w[e]);
+      acc[2 * e] += f.x;
+      acc[2 * e + 1] += f.y;
+    }
+  }
+}
+
+// epilogue: 32 bf16 of this thread's row (column group g) <-> registers
+__device__ __forceinline__ void row_load32(const uint8_t* buf, int row, int g, float (&f)[32]) {
+  const uint8_t* base = buf + (g >> 1) * kPB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + sw128_offset(row, (g & 1) * 4 + u));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16x2(w[e]);
+      f[u * 8 + 2 * e] = t.x;
+      f[u * 8 + 2 * e + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void row_store32(uint8_t* buf, int row, int g, const float (&f)[32]) {
+  uint8_t* base = buf + (g >> 1) * kPB;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    uint4 v;
+    v.x = pack_bf16x2(f[u * 8 + 0], f[u * 8 + 1]);
+    v.y = pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]);
+    v.z = pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]);
+    v.w = pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]);
+    *reinterpret_cast<uint4*>(base + sw128_offset(row, (g & 1) * 4 + u)) = v;
+  }
+}
+
+// warp transpose-reduce: on return lane L holds sum over the 32 lanes of their v[L]   (31 shuffles)
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p) {
+  using L = Smem<KP>;
+  using PT = Part<KP>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {  // uniform: the swizzled panels need 1024-byte alignment
+    if (tid == 0 && p.status) atomicOr(p.status, kStatusSmem);
+    return;
+  }
+  uint8_t* sW1 = smem + L::kW1;
+  uint8_t* sW2 = smem + L::kW2;
+  uint8_t* sW3 = smem + L::kW3;
+  uint8_t* bA = smem + L::kA;
+  uint8_t* bX = smem + L::kX;
+  uint8_t* bH1 = smem + L::kH1;
+  uint8_t* bH2 = smem + L::kH2;
+  float* sPar = reinterpret_cast<float*>(smem + L::kPar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+  const bool has_ln = p.gamma != nullptr;
+  const bool has_g = p.g1.tab != nullptr;
+  const bool need_ga = p.g_a != nullptr;
+  constexpr int N1 = 64 * KP;  // width of the layer-1 input
+
+  // ---------------- one-time setup ----------------
+  stage_weight_ld(sW1, p.w1, p.ld_w1, kH, p.k1_true, KP, tid, kThreads);
+  stage_weight_ld(sW2, p.w2, kH, kH, kH, 2, tid, kThreads);
+  stage_weight_ld(sW3, p.w3, kH, p.n_out, kH, 2, tid, kThreads);
+  for (int i = tid; i < kH; i += kThreads) {
+    sPar[i] = p.b1 ? p.b1[i] : 0.f;
+    sPar[kH + i] = p.b2 ? p.b2[i] : 0.f;
+    sPar[2 * kH + i] = (p.b3 && i < p.n_out) ? p.b3[i] : 0.f;
+    sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], (b >= B_MMA1 && b < B_E1) ? 1 : 4);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tAcc = tmem, tW1 = tmem + 128, tW2 = tmem + 256, tW3 = tmem + 384;
+
+  const long long n_tiles = (p.M + kRows - 1) / kRows;
+  const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  bool timed_out = false;
+
+  // mover-side running column sums (fixed columns per thread) and epilogue-side gamma gradient
+  float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
+        cs_beta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float gg[4] = {0.f, 0.f, 0.f, 0.f};
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t aA = smem_u32(bA), aX = smem_u32(bX), aH1 = smem_u32(bH1), aH2 = smem_u32(bH2);
+      const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+      (void)aX;
+      const uint32_t id_nt = umma_idesc_bf16(128, 128, 0, 0);   // D = A(K-major) * B(K-major)^T
+      const uint32_t id_tn = umma_idesc_bf16(128, 128, 1, 1);   // D = A(MN)^T * B(MN)          (wgrad)
+      const uint32_t id_nn = umma_idesc_bf16(128, 128, 0, 1);   // D = A(K-major) * B(MN)       (dgrad)
+      const uint32_t id_tn1 = umma_idesc_bf16(128, N1, 1, 1);
+      const uint32_t id_nn1 = umma_idesc_bf16(128, N1, 0, 1);
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = it & 1;
+#define MGN_W(b, ph)                         \
+  if (!wait_clk(&bars[b], ph)) {             \
+    timed_out = true;                        \
+    break;                                   \
+  }
+        // ---- GEMM1: acc = A W1^T
+        MGN_W(B_AG, par);
+        if (it > 0) MGN_W(B_E1 + 5, par ^ 1);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < KP * 4; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3),
+                  id_nt, k != 0);
+        umma_commit(&bars[B_MMA1 + 0]);
+        // ---- GEMM2: acc = h1 W2^T
+        MGN_W(B_E1 + 0, par);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH1 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW2 + (k >> 2) * kPB, k & 3),
+                  id_nt, k != 0);
+        umma_commit(&bars[B_MMA1 + 1]);
+        // ---- GEMM3: acc = h2 W3^T
+        MGN_W(B_E1 + 1, par);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW3 + (k >> 2) * kPB, k & 3),
+                  id_nt, k != 0);
+        umma_commit(&bars[B_MMA1 + 2]);
+        // ---- layer 3: gW3 += g_y^T h2 ; acc = g_y W3          (g_y in bA)
+        MGN_W(B_E1 + 2, par);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA1 + 3]);
+        // ---- layer 2: gW2 += g_z2^T h1 ; acc = g_z2 W2        (g_z2 in bH2)
+        MGN_W(B_E1 + 3, par);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA1 + 4]);
+        // ---- layer 1: gW1 += g_z1^T A ; acc = g_z1 W1          (g_z1 in bH1, A re-staged in bA)
+        MGN_W(B_E1 + 4, par);
+        MGN_W(B_A2, par);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW1, umma_desc_mnmajor(aH1, j, kPB), umma_desc_mnmajor(aA, j, kPB), id_tn1, (it | j) != 0);
+        if (need_ga) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_ss(tAcc, umma_desc_kmajor(aH1 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW1, k, kPB), id_nn1,
+                    k != 0);
+        }
+        umma_commit(&bars[B_MMA1 + 5]);
+#undef MGN_W
+      }
+    }
+  } else if (warp <= 4) {
+    // =========================== movers ===========================
+    const int mt = tid - 32;
+    const RowSrc none{nullptr, nullptr, 0, 0};
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_PUBLISH(b)        \
+  fence_proxy_async_smem();   \
+  __syncwarp();               \
+  if (lane == 0) mbar_arrive(&bars[b]);
+#define MGN_MOVER_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+      // A (and G) tiles
+      if (KP == 2) stage_rows<2>(bA, p.a, none, row0, p.M, mt);
+      else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      if (has_g) stage_rows<2>(bX, p.g1, p.g2, row0, p.M, mt);
+      MGN_PUBLISH(B_AG);
+      // incoming gradient, once the epilogue has consumed G
+      MGN_W(B_E1 + 0, par);
+      if (!p.go_small) {
+        stage_rows<2>(bX, p.go1, p.go2, row0, p.M, mt);
+      } else {
+        const int chunk = mt & 15, rsub = mt >> 4;
+        for (int i = 0; i < 16; ++i) {
+          const int row = i * 8 + rsub;
+          const long long grow = row0 + row;
+          float f[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int col = chunk * 8 + q;
+            f[q] = (grow < p.M && col < p.n_out) ? __bfloat162float(p.go1.tab[grow * p.go1.ld + col]) : 0.f;
+          }
+          uint4 v4;
+          v4.x = pack_bf16x2(f[0], f[1]);
+          v4.y = pack_bf16x2(f[2], f[3]);
+          v4.z = pack_bf16x2(f[4], f[5]);
+          v4.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(bX + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7)) = v4;
+        }
+      }
+      MGN_PUBLISH(B_GO);
+      MGN_MOVER_SYNC();
+      colsum_tile(bX, mt, cs_beta);
+      // g_y (in bA): bias-3 gradient, then re-stage A once the layer-3 MMAs have consumed g_y
+      MGN_W(B_E1 + 2, par);
+      colsum_tile(bA, mt, cs_b3);
+      MGN_W(B_MMA1 + 3, par);
+      MGN_MOVER_SYNC();
+      if (KP == 2) stage_rows<2>(bA, p.a, none, row0, p.M, mt);
+      else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      MGN_PUBLISH(B_A2);
+      MGN_W(B_E1 + 3, par);
+      colsum_tile(bH2, mt, cs_b2);
+      MGN_W(B_E1 + 4, par);
+      colsum_tile(bH1, mt, cs_b1);
+      if (p.g_z1) store_rows(bH1, p.g_z1, p.g_z1_ld, row0, p.M, mt);
+      MGN_W(B_E1 + 5, par);
+      if (need_ga) store_rows(bX, p.g_a, kH, row0, p.M, mt);
+      MGN_MOVER_SYNC();
+    }
+#undef MGN_W
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t t_acc = tAcc + (static_cast<uint32_t>(q * 32) << 16);
+    const float* b1 = sPar;
+    const float* b2 = sPar + kH;
+    const float* b3 = sPar + 2 * kH;
+    const float* gam = sPar + 3 * kH;
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_EPI_DONE(b)       \
+  fence_proxy_async_smem();   \
+  tc_fence_before_sync();     \
+  __syncwarp();               \
+  if (lane == 0) mbar_arrive(&bars[b]);
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      // ---- E1: h1 = relu(acc + b1 + G) -> bH1
+      MGN_W(B_MMA1 + 0, par);
+      MGN_W(B_AG, par);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + g * 32, v);
+        float f[32];
+        if (has_g) row_load32(bX, row, g, f);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float z = __uint_as_float(v[j]) + b1[g * 32 + j];
+          if (has_g) z += f[j];
+          f[j] = fmaxf(z, 0.f);
+        }
+        row_store32(bH1, row, g, f);
+      }
+      MGN_EPI_DONE(B_E1 + 0);
+      // ---- E2: h2 = relu(acc + b2) -> bH2
+      MGN_W(B_MMA1 + 1, par);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + g * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + b2[g * 32 + j], 0.f);
+        row_store32(bH2, row, g, f);
+      }
+      MGN_EPI_DONE(B_E1 + 1);
+      // ---- E3: LayerNorm backward: g_y -> bA   (g_out in bX)
+      MGN_W(B_MMA1 + 2, par);
+      MGN_W(B_GO, par);
+      tc_fence_after_sync();
+      if (has_ln) {
+        float s = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + b3[g * 32 + j];
+        }
+        const float mu = s * (1.f / kH);
+        float qv = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          float go[32];
+          row_load32(bX, row, g, go);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float d = __uint_as_float(v[j]) + b3[g * 32 + j] - mu;
+            const float gh = go[j] * gam[g * 32 + j];
+            qv = fmaf(d, d, qv);
+            s1 += gh;
+            s2 = fmaf(gh, d, s2);
+          }
+        }
+        const float rstd = rsqrtf(qv * (1.f / kH) + p.eps);
+        const float m1 = s1 * (1.f / kH);
+        const float m2 = s2 * rstd * (1.f / kH);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          float go[32];
+          row_load32(bX, row, g, go);
+          tmem_ld_wait();
+          float gy[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float xhat = (__uint_as_float(v[j]) + b3[g * 32 + j] - mu) * rstd;
+            const float gh = go[j] * gam[g * 32 + j];
+            gy[j] = rstd * (gh - m1 - xhat * m2);
+            go[j] *= xhat;  // gamma-gradient contribution of this row
+          }
+          row_store32(bA, row, g, gy);
+          gg[g] += warp_colsum32(go, lane);
+        }
+      } else {
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          float go[32];
+          row_load32(bX, row, g, go);
+          row_store32(bA, row, g, go);
+        }
+      }
+      MGN_EPI_DONE(B_E1 + 2);
+      // ---- E4: g_z2 = acc * (h2 > 0), in place in bH2
+      MGN_W(B_MMA1 + 3, par);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + g * 32, v);
+        float h[32];
+        row_load32(bH2, row, g, h);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
+        row_store32(bH2, row, g, h);
+      }
+      MGN_EPI_DONE(B_E1 + 3);
+      // ---- E5: g_z1 = acc * (h1 > 0), in place in bH1
+      MGN_W(B_MMA1 + 4, par);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + g * 32, v);
+        float h[32];
+        row_load32(bH1, row, g, h);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
+        row_store32(bH1, row, g, h);
+      }
+      MGN_EPI_DONE(B_E1 + 4);
+      // ---- E6: g_A = acc (+ g_out), in place in bX
+      MGN_W(B_MMA1 + 5, par);
+      tc_fence_after_sync();
+      if (need_ga) {
+#pragma unroll 1
+        for (int g = 0; g < N1 / 32; ++g) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + g * 32, v);
+          float go[32];
+          if (p.add_gout) row_load32(bX, row, g, go);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) go[j] = __uint_as_float(v[j]) + (p.add_gout ? go[j] : 0.f);
+          row_store32(bX, row, g, go);
+        }
+      }
+      MGN_EPI_DONE(B_E1 + 5);
+    }
+#undef MGN_W
+  }
+
+  if (timed_out && p.status != nullptr) atomicOr(p.status, kStatusTimeout);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  // ---------------- write this CTA's partial gradients ----------------
+  float* part = p.partials + static_cast<long long>(blockIdx.x) * p.part_floats;
+  float* scratch = reinterpret_cast<float*>(bX);  // tile buffers are free now
+  if (warp >= 5) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;  // TMEM lane = output-feature row of the weight gradient
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+#pragma unroll 1
+    for (int w = 0; w < 3; ++w) {
+      const uint32_t t = (w == 0 ? tW1 : (w == 1 ? tW2 : tW3)) + lane_off;
+      const int ncol = (w == 0) ? N1 : kH;
+      float* dst = part + (w == 0 ? PT::kW1 : (w == 1 ? PT::kW2 : PT::kW3)) + row * ncol;
+#pragma unroll 1
+      for (int g = 0; g < ncol / 32; ++g) {
+        uint32_t v[32];
+        tmem_ld32(t + g * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          reinterpret_cast<float4*>(dst + g * 32)[u] =
+              make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                          __uint_as_float(v[4 * u + 3]));
+      }
+    }
+    // gamma gradient: lane holds column g*32+lane summed over this warp's 32 rows
+#pragma unroll
+    for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + g * 32 + lane] = gg[g];
+  } else if (warp >= 1) {
+    const int mt = tid - 32;
+    const int chunk = mt & 15, rsub = mt >> 4;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      scratch[(0 * 8 + rsub) * kH + chunk * 8 + j] = cs_b1[j];
+      scratch[(1 * 8 + rsub) * kH + chunk * 8 + j] = cs_b2[j];
+      scratch[(2 * 8 + rsub) * kH + chunk * 8 + j] = cs_b3[j];
+      scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (tid < kH) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += scratch[(k * 8 + r) * kH + tid];
+    }
+    float sg = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) sg += scratch[4 * 8 * kH + w * kH + tid];
+    part[PT::kB1 + tid] = s[0];
+    part[PT::kB2 + tid] = s[1];
+    part[PT::kB3 + tid] = s[2];
+    part[PT::kBeta + tid] = s[3];
+    part[PT::kGamma + tid] = sg;
+  }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// second stage: out[r, c] = sum over CTAs of partial[cta][off + r * cols + c]   (fixed order)
+// ------------------------------------------------------------------------------------------------
+struct ReduceSeg {
+  float* dst;
+  long long ld_dst;
+  int rows, cols;
+  int src_off;
+  int src_ld;
+};
+struct ReduceParams {
+  const float* partials;
+  long long stride;
+  int n_parts;
+  int n_seg;
+  ReduceSeg seg[8];
+};
+
+__global__ void reduce_bwd_partials_kernel(const ReduceParams rp) {
+  const ReduceSeg sg = rp.seg[blockIdx.y];
+  if (sg.dst == nullptr) return;
+  const int n = sg.rows * sg.cols;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int r = i / sg.cols, c = i - r * sg.cols;
+    const float* src = rp.partials + sg.src_off + r * sg.src_ld + c;
+    float s = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < rp.n_parts; ++k) s += src[static_cast<long long>(k) * rp.stride];
+    sg.dst[r * sg.ld_dst + c] = s;
+  }
+}
+
+template <int KP>
+static int launch(Params& p, int grid, cudaStream_t st) {
+  using L = Smem<KP>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp3_bwd_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  p.part_floats = Part<KP>::kTotal;
+  mlp3_bwd_tc_kernel<KP><<<grid, kThreads, L::kTotal, MGN_ST(st)>>>(p);
+  return mgn_launch_status();
+}
+
+}  // namespace bwd
+}  // namespace mgn
+
+using namespace mgn;
+
+static int bwd_grid(int64_t M) {
+  const long long n_tiles = (M + bwd::kRows - 1) / bwd::kRows;
+  return static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+}
+
+extern "C" size_t mgn_mlp3_bwd_tc_workspace_bytes(int64_t M) {
+  if (M <= 0) return 0;
+  return static_cast<size_t>(bwd_grid(M)) * bwd::Part<2>::kTotal * sizeof(float);
+}
+
+extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+                               int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
+                               int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
+                               int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
+                               const int32_t* go2_idx, int64_t M,
+                               const float* w1, int64_t ld_w1, const float* b1, const float* w2, const float* b2,
+                               const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
+                               int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
+                               float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
+                               size_t workspace_bytes, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= bwd::kH && go1 != nullptr);
+  MGN_CHECK_ARG(gamma == nullptr || n_out == bwd::kH);
+  if (M == 0) return MGN_OK;  // caller zero-fills gradients of an empty batch
+  MGN_CHECK_ARG(workspace != nullptr);
+  if (workspace_bytes < mgn_mlp3_bwd_tc_workspace_bytes(M)) return MGN_EWORKSPACE;
+  bwd::Params p{};
+  p.a = bwd::RowSrc{static_cast<const bf16*>(a_tab), a_idx, bwd::kH, 0};
+  p.small_x = small_x;
+  p.small_in = small_in;
+  p.small_is_f32 = small_is_f32;
+  p.g1 = bwd::RowSrc{static_cast<const bf16*>(g1_tab), g1_idx, g1_ld, g1_col0};
+  p.g2 = bwd::RowSrc{static_cast<const bf16*>(g2_tab), g2_idx, g2_ld, g2_col0};
+  p.go1 = bwd::RowSrc{static_cast<const bf16*>(go1), go1_idx, n_out, 0};
+  p.go2 = bwd::RowSrc{static_cast<const bf16*>(go2), go2_idx, bwd::kH, 0};
+  p.go_small = n_out < bwd::kH;
+  MGN_CHECK_ARG(!(p.go_small && (go2 != nullptr || go1_idx != nullptr)));
+  if (g1_tab) MGN_CHECK_ARG(g1_ld % 8 == 0 && g1_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g1_tab) & 15) == 0);
+  if (g2_tab) MGN_CHECK_ARG(g1_tab && g2_ld % 8 == 0 && g2_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g2_tab) & 15) == 0);
+  p.M = M;
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.gamma = gamma;
+  p.ld_w1 = ld_w1;
+  p.n_out = n_out;
+  p.eps = eps;
+  p.g_a = static_cast<bf16*>(g_a);
+  p.add_gout = add_gout;
+  p.g_z1 = static_cast<bf16*>(g_z1);
+  p.g_z1_ld = g_z1_ld > 0 ? g_z1_ld : bwd::kH;
+  if (g_z1) MGN_CHECK_ARG(p.g_z1_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g_z1) & 15) == 0);
+  p.partials = static_cast<float*>(workspace);
+  p.status = status;
+  cudaStream_t st = as_stream(stream);
+  const int grid = bwd_grid(M);
+  int rc;
+  int n1;
+  if (small_in > 0) {
+    MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && g_a == nullptr && ld_w1 >= small_in);
+    p.k1_true = small_in;
+    n1 = small_in;
+    rc = bwd::launch<1>(p, grid, st);
+  } else {
+    MGN_CHECK_ARG(a_tab != nullptr && ld_w1 >= bwd::kH && (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0);
+    p.k1_true = bwd::kH;
+    n1 = bwd::kH;
+    rc = bwd::launch<2>(p, grid, st);
+  }
+  if (rc != MGN_OK) return rc;
+  bwd::ReduceParams rp{};
+  rp.partials = p.partials;
+  rp.stride = p.part_floats;
+  rp.n_parts = grid;
+  const int kp = small_in > 0 ? 1 : 2;
+  const int oW2 = bwd::kH * 64 * kp, oW3 = oW2 + bwd::kH * bwd::kH, oB1 = oW3 + bwd::kH * bwd::kH;
+  int ns = 0;
+  // gW1: the TMEM accumulator is [128][64*kp]; only the first n1 columns are real
+  rp.seg[ns++] = bwd::ReduceSeg{g_w1, ld_gw1, bwd::kH, n1, 0, 64 * kp};
+  rp.seg[ns++] = bwd::ReduceSeg{g_w2, bwd::kH, bwd::kH, bwd::kH, oW2, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_w3, bwd::kH, n_out, bwd::kH, oW3, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_b1, bwd::kH, 1, bwd::kH, oB1, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_b2, bwd::kH, 1, bwd::kH, oB1 + bwd::kH, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_b3, bwd::kH, 1, n_out, oB1 + 2 * bwd::kH, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_gamma, bwd::kH, 1, bwd::kH, oB1 + 3 * bwd::kH, bwd::kH};
+  rp.seg[ns++] = bwd::ReduceSeg{g_beta, bwd::kH, 1, bwd::kH, oB1 + 4 * bwd::kH, bwd::kH};
+  rp.n_seg = ns;
+  bwd::reduce_bwd_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
+  return mgn_launch_status();
+}

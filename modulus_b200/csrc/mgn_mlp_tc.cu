@@ -30,9 +30,19 @@ constexpr int kPanelBytes = 16384;  // 128 rows x 64 bf16
 constexpr int kFwdThreads = 416;
 constexpr int kH = 128;
 
+struct GRows {  // additive rows of layer 1: row r -> tab[(idx ? idx[r] : r) * ld + col0 ...]
+  const bf16* tab;
+  const int32_t* idx;
+  long long ld;
+  long long col0;
+};
+
 struct MlpFwdParams {
   const bf16* tab[3];
   const int32_t* idx[3];
+  GRows g1, g2;   // z1 += g1[row] (+ g2[row]): staged as the LAST two panels, multiplied by an identity block
+  int g_tab;      // table slot (pnl >> 1) the G panels occupy; -1: none
+  long long ld_w1;
   const void* small_x;  // encoder mode: [M, small_in] raw features (fp32 or bf16), zero-padded to K=64
   int small_in;
   int small_is_f32;
@@ -53,8 +63,10 @@ enum { kStatusTimeout = 1, kStatusSmem = 2 };
 
 // fp32 [n_rows, k_true] (nn.Linear layout) -> bf16 K-major SW128 panels [n_panels][128][64], zero padded
 __device__ __forceinline__ void stage_weight(uint8_t* dst, const float* __restrict__ w, int n_rows, int k_true,
-                                             int n_panels, int tid, int nthreads) {
+                                             int n_panels, int tid, int nthreads, long long ld = -1,
+                                             int ident_k0 = 1 << 30) {
   const int per_row = n_panels * 8;
+  if (ld < 0) ld = k_true;
   for (int item = tid; item < kTileM * per_row; item += nthreads) {
     const int row = item / per_row;
     const int rem = item - row * per_row;
@@ -62,8 +74,12 @@ __device__ __forceinline__ void stage_weight(uint8_t* dst, const float* __restri
     const int k0 = panel * 64 + chunk * 8;
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      f[j] = (row < n_rows && (k0 + j) < k_true) ? __ldg(w + static_cast<long long>(row) * k_true + k0 + j) : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + j;
+      // columns >= ident_k0 hold an identity block: the G panels pass through the GEMM unchanged
+      f[j] = k >= ident_k0 ? (k - ident_k0 == row ? 1.f : 0.f)
+                           : ((row < n_rows && k < k_true) ? __ldg(w + static_cast<long long>(row) * ld + k) : 0.f);
+    }
     uint4 v;
     v.x = pack_bf16x2(f[0], f[1]);
     v.y = pack_bf16x2(f[2], f[3]);
@@ -108,7 +124,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
   const bool has_ln = p.gamma != nullptr;
 
   // ---------------- one-time setup ----------------
-  stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads);
+  stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads, p.ld_w1, p.g_tab >= 0 ? p.g_tab * kH : (1 << 30));
   stage_weight(sW2, p.w2, kH, kH, 2, tid, kFwdThreads);
   stage_weight(sW3, p.w3, p.n_out, kH, 2, tid, kFwdThreads);
   for (int i = tid; i < kH; i += kFwdThreads) {
@@ -229,6 +245,44 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
             v4.z = pack_bf16x2(f[4], f[5]);
             v4.w = pack_bf16x2(f[6], f[7]);
             *reinterpret_cast<uint4*>(sRing + slot * kPanelBytes + sw128_offset(row_in_tile, chunk)) = v4;
+          }
+        } else if ((pnl >> 1) == p.g_tab) {
+          // G panels: bf16(g1[row] + g2[row]) with 128-bit loads, summed in fp32
+          const int half = pnl & 1;
+          const bool two = p.g2.tab != nullptr;
+          uint4 v1[8], v2[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r_local = it * 4 + (lane >> 3), chunk = lane & 7;
+            const long long grow = row0 + lw * 32 + r_local;
+            v1[it] = make_uint4(0, 0, 0, 0);
+            v2[it] = make_uint4(0, 0, 0, 0);
+            if (grow < p.M) {
+              const long long r1 = p.g1.idx ? static_cast<long long>(__ldg(p.g1.idx + grow)) : grow;
+              v1[it] = __ldg(reinterpret_cast<const uint4*>(p.g1.tab + r1 * p.g1.ld + p.g1.col0 + half * 64 + chunk * 8));
+              if (two) {
+                const long long r2 = p.g2.idx ? static_cast<long long>(__ldg(p.g2.idx + grow)) : grow;
+                v2[it] = __ldg(reinterpret_cast<const uint4*>(p.g2.tab + r2 * p.g2.ld + p.g2.col0 + half * 64 + chunk * 8));
+              }
+            }
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r_local = it * 4 + (lane >> 3), chunk = lane & 7;
+            const int row_in_tile = lw * 32 + r_local;
+            uint4 v = v1[it];
+            if (two) {
+              const uint32_t x[4] = {v1[it].x, v1[it].y, v1[it].z, v1[it].w};
+              const uint32_t y[4] = {v2[it].x, v2[it].y, v2[it].z, v2[it].w};
+              uint32_t r[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 fa = unpack_bf16x2(x[e]), fb = unpack_bf16x2(y[e]);
+                r[e] = pack_bf16x2(fa.x + fb.x, fa.y + fb.y);
+              }
+              v = make_uint4(r[0], r[1], r[2], r[3]);
+            }
+            *reinterpret_cast<uint4*>(sRing + slot * kPanelBytes + sw128_offset(row_in_tile, chunk)) = v;
           }
         } else {
           const int k = pnl >> 1, half = pnl & 1;
@@ -407,12 +461,13 @@ static int launch_fwd(const MlpFwdParams& p, cudaStream_t st) {
 
 using namespace mgn;
 
-extern "C" int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
-                               const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
-                               int small_is_f32, int64_t M, const float* w1, const float* b1, const float* w2,
-                               const float* b2, const float* w3, const float* b3, const float* gamma,
-                               const float* beta, int n_out, float eps, const void* residual, void* out,
-                               int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream) {
+static int mlp3_fwd_common(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
+                           const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
+                           int small_is_f32, const GRows& g1, const GRows& g2, int64_t M, const float* w1,
+                           int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                           const float* b3, const float* gamma, const float* beta, int n_out, float eps,
+                           const void* residual, void* out, int64_t ld_out, void* h1_save, void* h2_save,
+                           int* status, mgn_stream_t stream) {
   MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= kH && ld_out >= n_out);
   if (M == 0) return MGN_OK;
   MGN_CHECK_ARG(out != nullptr);
@@ -423,6 +478,9 @@ extern "C" int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void
   p.idx[0] = idx0;
   p.idx[1] = idx1;
   p.idx[2] = idx2;
+  p.g1 = g1;
+  p.g2 = g2;
+  p.g_tab = -1;
   p.small_x = small_x;
   p.small_in = small_in;
   p.small_is_f32 = small_is_f32;
@@ -439,14 +497,51 @@ extern "C" int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void
   p.status = status;
   cudaStream_t st = as_stream(stream);
   if (small_in > 0) {
-    MGN_CHECK_ARG(small_x != nullptr && small_in <= 64);
+    MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && g1.tab == nullptr);
     p.k1_true = small_in;
+    p.ld_w1 = ld_w1 > 0 ? ld_w1 : small_in;
     return launch_fwd<1, 4>(p, st);
   }
   MGN_CHECK_ARG(n_tab >= 1 && n_tab <= 3);
   for (int k = 0; k < n_tab; ++k) MGN_CHECK_ARG(p.tab[k] != nullptr);
   p.k1_true = kH * n_tab;
-  if (n_tab == 1) return launch_fwd<2, 4>(p, st);
-  if (n_tab == 2) return launch_fwd<4, 4>(p, st);
+  p.ld_w1 = ld_w1 > 0 ? ld_w1 : p.k1_true;
+  MGN_CHECK_ARG(p.ld_w1 >= p.k1_true);
+  int slots = n_tab;
+  if (g1.tab != nullptr) {
+    MGN_CHECK_ARG(n_tab <= 2 && g1.ld % 8 == 0 && g1.col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g1.tab) & 15) == 0);
+    if (g2.tab) MGN_CHECK_ARG(g2.ld % 8 == 0 && g2.col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g2.tab) & 15) == 0);
+    p.g_tab = n_tab;
+    slots = n_tab + 1;
+  } else {
+    MGN_CHECK_ARG(g2.tab == nullptr);
+  }
+  if (slots == 1) return launch_fwd<2, 4>(p, st);
+  if (slots == 2) return launch_fwd<4, 4>(p, st);
   return launch_fwd<6, 3>(p, st);
+}
+
+extern "C" int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
+                               const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
+                               int small_is_f32, int64_t M, const float* w1, const float* b1, const float* w2,
+                               const float* b2, const float* w3, const float* b3, const float* gamma,
+                               const float* beta, int n_out, float eps, const void* residual, void* out,
+                               int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream) {
+  const GRows none{nullptr, nullptr, 0, 0};
+  return mlp3_fwd_common(tab0, idx0, tab1, idx1, tab2, idx2, n_tab, small_x, small_in, small_is_f32, none, none, M,
+                         w1, -1, b1, w2, b2, w3, b3, gamma, beta, n_out, eps, residual, out, ld_out, h1_save, h2_save,
+                         status, stream);
+}
+
+extern "C" int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const void* g1_tab, const int32_t* g1_idx,
+                                 int64_t g1_ld, int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx,
+                                 int64_t g2_ld, int64_t g2_col0, int64_t M, const float* w1, int64_t ld_w1,
+                                 const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
+                                 const float* gamma, const float* beta, int n_out, float eps, const void* residual,
+                                 void* out, int64_t ld_out, int* status, mgn_stream_t stream) {
+  const GRows g1{static_cast<const bf16*>(g1_tab), g1_idx, g1_ld, g1_col0};
+  const GRows g2{static_cast<const bf16*>(g2_tab), g2_idx, g2_ld, g2_col0};
+  return mlp3_fwd_common(a_tab, a_idx, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0, 0, g1, g2, M, w1, ld_w1, b1,
+                         w2, b2, w3, b3, gamma, beta, n_out, eps, residual, out, ld_out, nullptr, nullptr, status,
+                         stream);
 }

@@ -454,3 +454,51 @@ def mlp3_fwd_tc(tabs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]], M: int
          _p(small_x), small_in, small_f32, M, _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta),
          n_out, eps, _p(residual), _p(out), n_out, _p(h1), _p(h2), _p(tc_status(dev)), _stream())
     return out, h1, h2
+
+
+def _ws(nbytes: int, dev) -> Tensor:
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+def mlp3_fwd_tc_g(a: Tensor, a_idx: Optional[Tensor], g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
+                  g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int, M: int,
+                  w1: Tensor, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
+                  residual: Optional[Tensor] = None, n_out: int = TC_HIDDEN, out: Optional[Tensor] = None) -> Tensor:
+    """Fused forward with additive gathered rows (include/mgn_b200.h: mgn_mlp3_fwd_tc_g).  `w1` may be a
+    column-block view of the full first-layer weight (row stride = w1.stride(0))."""
+    dev = a.device
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
+    call("mgn_mlp3_fwd_tc_g", _p(a), _p(a_idx), _p(g1), _p(g1_idx), 0 if g1 is None else g1.stride(0), g1_col0,
+         _p(g2), _p(g2_idx), 0 if g2 is None else g2.stride(0), g2_col0, M, _p(w1), w1.stride(0), _p(b1), _p(w2),
+         _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), n_out, eps, _p(residual), _p(out), out.stride(0),
+         _p(tc_status(dev)), _stream())
+    return out
+
+
+def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
+                g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
+                g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int,
+                go1: Tensor, go2: Optional[Tensor], go2_idx: Optional[Tensor], M: int,
+                w1: Tensor, b1, w2, b2, w3, b3, gamma, n_out: int, eps: float,
+                want_ga: bool, add_gout: bool, want_gz1: bool,
+                g_w1: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta,
+                go1_idx: Optional[Tensor] = None, g_z1_out: Optional[Tensor] = None):
+    """Fused backward (include/mgn_b200.h: mgn_mlp3_bwd_tc).  Gradient tensors are caller-allocated fp32
+    (g_w1 may be a column-block view); returns (g_a, g_z1) bf16 [M,128] or None."""
+    dev = go1.device
+    g_a = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if want_ga else None
+    g_z1 = g_z1_out
+    if want_gz1 and g_z1 is None:
+        g_z1 = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    nbytes = _lib.load().mgn_mlp3_bwd_tc_workspace_bytes(M)
+    ws = _ws(nbytes, dev)
+    small_in = 0 if small_x is None else small_x.shape[1]
+    small_f32 = int(small_x is not None and small_x.dtype == torch.float32)
+    call("mgn_mlp3_bwd_tc", _p(a), _p(a_idx), _p(small_x), small_in, small_f32,
+         _p(g1), _p(g1_idx), 0 if g1 is None else g1.stride(0), g1_col0,
+         _p(g2), _p(g2_idx), 0 if g2 is None else g2.stride(0), g2_col0,
+         _p(go1), _p(go1_idx), _p(go2), _p(go2_idx), M, _p(w1), w1.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma),
+         n_out, eps, _p(g_a), int(add_gout), _p(g_z1), 0 if g_z1 is None else g_z1.stride(0), _p(g_w1), g_w1.stride(0), _p(g_b1), _p(g_w2), _p(g_b2),
+         _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes, _p(tc_status(dev)), _stream())
+    return g_a, g_z1

@@ -96,3 +96,128 @@ def test_node_and_plain_and_decoder_fwd_tc(M):
     torch.cuda.synchronize()
     ops.tc_check(DEV)
     assert rel_err(out, ref) < 1e-2
+
+
+# ----------------------------------------------------------------------------------------
+# "concat trick" forward (additive gathered rows) and the fused backward kernel
+# ----------------------------------------------------------------------------------------
+def st_round(x):
+    """bf16 rounding with a straight-through gradient."""
+    return x + (bf(x.detach().float()).to(x.dtype) - x.detach())
+
+
+def _trick_case(M, seed, n_nodes=None):
+    g = torch.Generator().manual_seed(seed)
+    Nn = n_nodes or max(M // 5, 3)
+    A = bf(torch.randn(M, 128, generator=g))
+    P = bf(torch.randn(Nn, 384, generator=g) * 0.5)
+    src = torch.randint(0, Nn, (M,), generator=g)
+    dst = torch.sort(torch.randint(0, Nn, (M,), generator=g)).values
+    go1 = bf(torch.randn(M, 128, generator=g))
+    go2 = bf(torch.randn(Nn, 128, generator=g))
+    p = make_params(384, seed=seed + 1)
+    return A, P, src, dst, go1, go2, p
+
+
+def _ref_trick(A, P, src, dst, p, dtype=torch.float64, round_hidden=False):
+    """z1 = A W1e^T + P[src][:, :128] + P[dst][:, 128:256] + b1, then the rest of the MLP + LN + residual A."""
+    c = lambda t: t.to(dtype)
+    w1e = c(bf(p["w1"][:, :128]))
+    Gs = c(bf(P[src][:, :128] + P[dst][:, 128:256]))  # the kernel rounds the gathered sum to bf16
+    z1 = c(A) @ w1e.T + Gs + c(p["b1"])
+    h1 = F.relu(z1)
+    if round_hidden:
+        h1 = c(bf(h1.float()))
+    h2 = F.relu(h1 @ c(bf(p["w2"])).T + c(p["b2"]))
+    if round_hidden:
+        h2 = c(bf(h2.float()))
+    y = h2 @ c(bf(p["w3"])).T + c(p["b3"])
+    out = F.layer_norm(y, (128,), c(p["gamma"]), c(p["beta"]), 1e-5) + c(A)
+    return out, z1
+
+
+@pytest.mark.parametrize("M", [1, 130, 1000, 50021])
+def test_mlp3_fwd_tc_g(M):
+    from modulus_b200 import ops
+
+    A, P, src, dst, go1, go2, p = _trick_case(M, seed=M)
+    ref, _ = _ref_trick(A, P, src, dst, p, dtype=torch.float32, round_hidden=True)
+    d = dev_params(p)
+    Ad, Pd = A.to(DEV).bfloat16(), P.to(DEV).bfloat16()
+    out = ops.mlp3_fwd_tc_g(Ad, None, Pd, src.to(DEV).int(), 0, Pd, dst.to(DEV).int(), 128, M,
+                            d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"],
+                            residual=Ad)
+    ops.tc_check(DEV)
+    assert rel_err(out.float(), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("M", [1, 130, 1000, 50021])
+def test_mlp3_bwd_tc_edge_form(M):
+    """Edge-block form: A = efeat, G = P[src] + P[dst], g_out = go1 + go2[dst], residual on A."""
+    from modulus_b200 import ops
+
+    A, P, src, dst, go1, go2, p = _trick_case(M, seed=100 + M)
+    # fp64 autograd reference on the bf16-rounded operands
+    leaves = {k: bf(v).double().requires_grad_(True) if k in ("w1", "w2", "w3") else v.double().requires_grad_(True)
+              for k, v in p.items()}
+    A64 = A.double().requires_grad_(True)
+    w1e = leaves["w1"][:, :128]
+    Gs = bf(P[src][:, :128] + P[dst][:, 128:256]).double().requires_grad_(True)
+    z1 = A64 @ w1e.T + Gs + leaves["b1"]
+    h1 = st_round(F.relu(z1))  # the kernel keeps hidden activations in bf16 (ReLU masks follow them)
+    h2 = st_round(F.relu(h1 @ leaves["w2"].T + leaves["b2"]))
+    y = h2 @ leaves["w3"].T + leaves["b3"]
+    out = F.layer_norm(y, (128,), leaves["gamma"], leaves["beta"], 1e-5) + A64
+    gout = bf(go1 + go2[dst]).double()
+    (out * gout).sum().backward()
+
+    d = dev_params(p)
+    Ad, Pd = A.to(DEV).bfloat16(), P.to(DEV).bfloat16()
+    gw1 = torch.zeros(128, 384, device=DEV)
+    gw2, gw3 = torch.empty(128, 128, device=DEV), torch.empty(128, 128, device=DEV)
+    gb1, gb2, gb3, gga, gbe = (torch.empty(128, device=DEV) for _ in range(5))
+    g_a, g_z1 = ops.mlp3_bwd_tc(Ad, None, None, Pd, src.to(DEV).int(), 0, Pd, dst.to(DEV).int(), 128,
+                                go1.to(DEV).bfloat16(), go2.to(DEV).bfloat16(), dst.to(DEV).int(), M,
+                                d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], 128, 1e-5,
+                                True, True, True, gw1[:, :128], gb1, gw2, gb2, gw3, gb3, gga, gbe)
+    ops.tc_check(DEV)
+    tol = 2e-2
+
+    def rows_ok(got, ref):
+        # a ReLU pre-activation within rounding distance of zero may flip its mask between the fp32-accumulating
+        # kernel and the fp64 reference: allow a 1e-3 fraction of such rows, everything else must match
+        err = (got.double().cpu() - ref).abs().max(dim=1).values / ref.abs().max()
+        return float((err > tol).double().mean()) <= 1e-3
+
+    assert rows_ok(g_a.float(), A64.grad)
+    assert rows_ok(g_z1.float(), Gs.grad)
+    assert rel_err(gw1[:, :128], leaves["w1"].grad[:, :128]) < tol
+    assert float(gw1[:, 128:].abs().max()) == 0.0
+    assert rel_err(gw2, leaves["w2"].grad) < tol
+    assert rel_err(gw3, leaves["w3"].grad) < tol
+    assert rel_err(gb1, leaves["b1"].grad) < tol
+    assert rel_err(gb2, leaves["b2"].grad) < tol
+    assert rel_err(gb3, leaves["b3"].grad) < tol
+    assert rel_err(gga, leaves["gamma"].grad) < tol
+    assert rel_err(gbe, leaves["beta"].grad) < tol
+
+
+def test_mlp3_bwd_tc_is_deterministic():
+    from modulus_b200 import ops
+
+    M = 40000
+    A, P, src, dst, go1, go2, p = _trick_case(M, seed=7)
+    d = dev_params(p)
+    Ad, Pd = A.to(DEV).bfloat16(), P.to(DEV).bfloat16()
+    outs = []
+    for _ in range(2):
+        gw1, gw2, gw3 = (torch.empty(128, 128, device=DEV) for _ in range(3))
+        gb1, gb2, gb3, gga, gbe = (torch.empty(128, device=DEV) for _ in range(5))
+        g_a, g_z1 = ops.mlp3_bwd_tc(Ad, None, None, Pd, src.to(DEV).int(), 0, Pd, dst.to(DEV).int(), 128,
+                                    go1.to(DEV).bfloat16(), None, None, M, d["w1"][:, :128], d["b1"], d["w2"],
+                                    d["b2"], d["w3"], d["b3"], d["gamma"], 128, 1e-5, True, False, True,
+                                    gw1, gb1, gw2, gb2, gw3, gb3, gga, gbe)
+        outs.append([t.clone() for t in (g_a, g_z1, gw1, gw2, gw3, gb1, gb2, gb3, gga, gbe)])
+    ops.tc_check(DEV)
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
