@@ -112,10 +112,17 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
         n_tab, small_in, M, n_out = a[6], a[8], a[10], a[19]
         k1 = small_in if small_in > 0 else 128 * n_tab
         return "tensor", 2.0 * M * (k1 * 128 + 128 * 128 + 128 * n_out)
+    if name == "mgn_mlp3_fwd_tc_g":
+        M, g2 = a[10], a[6]
+        return "tensor", (10.0 if g2 else 8.0) * 128 * 128 * M  # useful flops of the concat formulation
     if name == "mgn_mlp3_bwd_tc":
-        n_tab, small_in, M, n_out = a[6], a[8], a[10], a[19]
-        k1 = small_in if small_in > 0 else 128 * n_tab
-        return "tensor", 4.0 * M * (k1 * 128 + 128 * 128 + 128 * n_out)
+        small_in, g1, g2, M = a[3], a[5], a[9], a[17]
+        if g2:
+            return "tensor", 20.0 * 128 * 128 * M  # edge block: dgrad + wgrad = 2 x forward
+        if g1:
+            return "tensor", 16.0 * 128 * 128 * M  # node block
+        k1 = small_in if small_in > 0 else 128
+        return "tensor", 4.0 * M * (k1 * 128 + 2 * 128 * 128)
     if name == "mgn_linear_fwd":
         M, K, N = a[3], a[4], a[7]
         return "tensor", 2.0 * M * K * N

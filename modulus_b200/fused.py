@@ -1,0 +1,246 @@
+"""Fast path of the MeshGraphNet hot loop on the tcgen05 kernels (bf16 storage, hidden 128, ReLU,
+LayerNorm, "sum" aggregation, CSC-ordered edges).
+
+Two autograd Functions drive libmgn_b200.so directly, with hand-managed buffers:
+
+  * `FusedProcessorFn`  the L x (MeshEdgeBlock, MeshNodeBlock) loop of MeshGraphNetProcessor
+                         (reference: models/meshgraphnet/meshgraphnet.py:353-379)
+  * `FusedMLPFn`        a stand-alone MeshGraphMLP: encoders / decoder (meshgraphnet.py:213-216)
+
+Algebra.  The first Linear of both block MLPs is split by input block, the way the reference's own
+"concat trick" does for the edge MLP (MeshGraphEdgeMLPSum, mesh_graph_mlp.py:278-458) -- here applied
+internally, parameters keep the plain `Linear(3H, H)` / `Linear(2H, H)` layout:
+
+    edge:  z1[e] = efeat[e] W1[:, :H]^T  + P[src[e], 0:H] + P[dst[e], H:2H] + b1
+    node:  z1[v] = agg[v]   W1n[:, :H]^T + P[v, 2H:3H] + b1n
+    P = nfeat [W1[:, H:2H]; W1[:, 2H:3H]; W1n[:, H:2H]]^T              one node-level GEMM per layer
+
+so the per-edge tensor work is three 128-wide GEMMs, the gathered operands are per-node rows that
+stay L2-resident, and in backward the per-edge gradient of the gathered rows is just g_z1, reduced to
+nodes by the deterministic CSC / CSR segmented sums BEFORE it meets a weight:
+
+    T = [ csr_sum(g_z1_edge) | csc_sum(g_z1_edge) | g_z1_node ]   [N, 3H]
+    g_nfeat += T Wp,        g_Wp = T^T nfeat
+
+Backward recomputes hidden activations inside the kernels; only layer inputs (efeat_l, nfeat_l), the
+aggregate and P are kept from the forward pass.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from ._lib import ACT_IDS, MGN_BF16, call
+from .ops import GraphPlan, TC_HIDDEN, _p, _stream
+
+Tensor = torch.Tensor
+ENABLED = True  # tests flip this to compare against the generic (unfused) kernels
+H = TC_HIDDEN
+BF16 = torch.bfloat16
+
+
+# ----------------------------------------------------------------------------------------
+# node-level dense helpers (plain GEMMs on [N, *] tables)
+# ----------------------------------------------------------------------------------------
+def _node_linear(x: Tensor, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """out[M, Nout] = x[M, K] w[Nout, K]^T   (bf16 rows, fp32 weights)."""
+    return ops.linear_tc(x, w, out=out)
+
+
+def _node_wgrad(g: Tensor, x: Tensor) -> Tensor:
+    """[Ng, K] fp32 = g[M, Ng]^T x[M, K]."""
+    return ops.wgrad_tc(g, x)
+
+
+# ----------------------------------------------------------------------------------------
+# processor
+# ----------------------------------------------------------------------------------------
+class FusedProcessorFn(torch.autograd.Function):
+    """args: nfeat [N,H] bf16, efeat [E,H] bf16, plan, L, then 16 parameters per layer:
+    edge (w1 [H,3H], b1, w2, b2, w3, b3, gamma, beta), node (w1 [H,2H], b1, w2, b2, w3, b3, gamma, beta)."""
+
+    @staticmethod
+    def forward(ctx, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, L: int, eps: float, *params: Tensor):
+        E, N = plan.n_edges, plan.n_dst
+        src, dst = plan.src, plan.dst
+        nfeat, efeat = nfeat.contiguous(), efeat.contiguous()
+        saved: List[Tensor] = []
+        for l in range(L):
+            ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
+            wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
+            P = _node_linear(nfeat, wp)  # [N, 3H]
+            efeat_new = ops.mlp3_fwd_tc_g(efeat, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2], ew[3],
+                                          ew[4], ew[5], ew[6], ew[7], eps=eps, residual=efeat)
+            agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
+            nfeat_new = ops.mlp3_fwd_tc_g(agg, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
+                                          nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
+            saved += [efeat, nfeat, agg, P]
+            efeat, nfeat = efeat_new, nfeat_new
+        ctx.plan, ctx.L, ctx.eps = plan, L, eps
+        ctx.save_for_backward(*saved, *params)
+        ctx.n_saved = len(saved)
+        return nfeat
+
+    @staticmethod
+    def backward(ctx, g_n: Tensor):
+        plan: GraphPlan = ctx.plan
+        L, eps = ctx.L, ctx.eps
+        E, N = plan.n_edges, plan.n_dst
+        src, dst = plan.src, plan.dst
+        saved = ctx.saved_tensors[:ctx.n_saved]
+        params = ctx.saved_tensors[ctx.n_saved:]
+        dev = g_n.device
+        g_n = g_n.contiguous().to(BF16)
+        g_e: Optional[Tensor] = None
+        grads: List[Optional[Tensor]] = [None] * len(params)
+        f32 = dict(dtype=torch.float32, device=dev)
+        for l in range(L - 1, -1, -1):
+            efeat, nfeat, agg, P = saved[4 * l: 4 * l + 4]
+            ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
+            gew1, gnw1 = torch.empty((H, 3 * H), **f32), torch.empty((H, 2 * H), **f32)
+            ge = [gew1] + [torch.empty_like(t, dtype=torch.float32) for t in ew[1:]]
+            gn = [gnw1] + [torch.empty_like(t, dtype=torch.float32) for t in nw[1:]]
+            T = torch.empty((N, 3 * H), dtype=BF16, device=dev)
+            # ---- node block: g_agg = dL/d agg, g_z1 (node) -> T[:, 2H:3H]
+            g_agg, _ = ops.mlp3_bwd_tc(agg, None, None, P, None, 2 * H, None, None, 0, g_n, None, None, N,
+                                       nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6], H, eps,
+                                       True, False, True, gnw1[:, :H], gn[1], gn[2], gn[3], gn[4], gn[5], gn[6], gn[7],
+                                       g_z1_out=T[:, 2 * H:])
+            # ---- edge block: g_out = g_e + g_agg[dst]
+            if g_e is None:
+                go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
+            else:
+                go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
+            g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, P, src, 0, P, dst, H, go1, go2, go2_idx, E,
+                                         ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
+                                         True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6], ge[7],
+                                         go1_idx=go1_idx)
+            # ---- per-node reductions of the gathered-row gradient, then the node-level GEMMs
+            ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
+            ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+            wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
+            g_n = ops.linear_tc(T, wp.t().contiguous(), residual=g_n)  # g_n + T wp
+            gwp = _node_wgrad(T, nfeat)  # [3H, H]
+            gew1[:, H:2 * H] = gwp[:H]
+            gew1[:, 2 * H:] = gwp[H:2 * H]
+            gnw1[:, H:] = gwp[2 * H:]
+            grads[16 * l: 16 * l + 8] = ge
+            grads[16 * l + 8: 16 * l + 16] = gn
+        return (g_n, g_e, None, None, None, *grads)
+
+
+def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPlan, dt: torch.dtype) -> bool:
+    """Conditions under which the fused tcgen05 path computes exactly what the generic path does."""
+    from .models.gnn_layers.mesh_graph_mlp import MeshGraphEdgeMLPConcat
+    from .models.layers.activations import activation_name
+
+    if dt != BF16 or not plan.is_csc_ordered or plan.n_src != plan.n_dst or plan.n_edges == 0:
+        return False
+    if getattr(graph, "is_distributed", False):
+        return False
+    if nfeat.shape[1] != H or efeat.shape[1] != H or nfeat.shape[0] != plan.n_dst:
+        return False
+    for i, layer in enumerate(proc.processor_layers):
+        mlp = layer.edge_mlp if i % 2 == 0 else layer.node_mlp
+        if i % 2 == 0 and not isinstance(mlp, MeshGraphEdgeMLPConcat):
+            return False
+        if i % 2 == 1 and layer.aggregation != "sum":
+            return False
+        if mlp.hidden_layers != 2 or mlp.norm_type is None or mlp.hidden_dim != H or mlp.output_dim != H:
+            return False
+        try:
+            if activation_name(mlp.activation_fn) != "relu":
+                return False
+        except NotImplementedError:
+            return False
+        if any(q.dtype != torch.float32 or not q.is_cuda for q in mlp.parameters()):
+            return False
+    return True
+
+
+def processor_forward(proc, nfeat: Tensor, efeat: Tensor, plan: GraphPlan) -> Tensor:
+    params: List[Tensor] = []
+    eps = 1e-5
+    for i, layer in enumerate(proc.processor_layers):
+        mlp = layer.edge_mlp if i % 2 == 0 else layer.node_mlp
+        params += mlp._flat_params()
+        eps = mlp._norm().eps
+    return FusedProcessorFn.apply(nfeat.to(BF16), efeat.to(BF16), plan, proc.processor_size, eps, *params)
+
+
+# ----------------------------------------------------------------------------------------
+# stand-alone MLP (encoders / decoder)
+# ----------------------------------------------------------------------------------------
+class FusedMLPFn(torch.autograd.Function):
+    """x -> [LayerNorm]( W3 relu(W2 relu(W1 x + b1) + b2) + b3 ).  x is either raw features [M, d <= 64]
+    (fp32 or bf16; encoders) or a bf16 [M, 128] table (decoder).  args: x, eps, w1, b1, w2, b2, w3, b3[, gamma, beta]."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, eps: float, *params: Tensor):
+        w1, b1, w2, b2, w3, b3 = params[:6]
+        gamma, beta = (params[6], params[7]) if len(params) == 8 else (None, None)
+        M, d_in = x.shape
+        n_out = w3.shape[0]
+        small = d_in != H
+        if small:
+            x = x.contiguous()
+            if x.dtype not in (torch.float32, BF16):
+                x = x.float()
+            out, _, _ = ops.mlp3_fwd_tc([], [], M, w1, b1, w2, b2, w3, b3, gamma, beta, eps=eps, n_out=n_out, small_x=x)
+        else:
+            x = x.contiguous().to(BF16)
+            out, _, _ = ops.mlp3_fwd_tc([x], [None], M, w1, b1, w2, b2, w3, b3, gamma, beta, eps=eps, n_out=n_out)
+        ctx.save_for_backward(x, *params)
+        ctx.eps, ctx.small = eps, small
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        x, *params = ctx.saved_tensors
+        w1, b1, w2, b2, w3, b3 = params[:6]
+        gamma = params[6] if len(params) == 8 else None
+        M = x.shape[0]
+        n_out = w3.shape[0]
+        dev = g.device
+        g = g.contiguous().to(BF16)
+        gs = [torch.empty_like(t, dtype=torch.float32) for t in params]
+        if gamma is None:
+            gg = gb = None
+        else:
+            gg, gb = gs[6], gs[7]
+        need_gx = ctx.needs_input_grad[0]
+        g_x = None
+        if ctx.small:
+            _, g_z1 = ops.mlp3_bwd_tc(None, None, x, None, None, 0, None, None, 0, g, None, None, M, w1, b1, w2, b2, w3,
+                                      b3, gamma, n_out, ctx.eps, False, False, need_gx, gs[0], gs[1], gs[2], gs[3],
+                                      gs[4], gs[5], gg, gb)
+            if need_gx:
+                g_x = ops._linear_bwd_data(g_z1, w1).to(x.dtype)
+        else:
+            g_x, _ = ops.mlp3_bwd_tc(x, None, None, None, None, 0, None, None, 0, g, None, None, M, w1, b1, w2, b2, w3,
+                                     b3, gamma, n_out, ctx.eps, need_gx, False, False, gs[0], gs[1], gs[2], gs[3],
+                                     gs[4], gs[5], gg, gb)
+        return (g_x, None, *gs)
+
+
+def mlp_eligible(mlp, x: Tensor, dt: torch.dtype) -> bool:
+    from .models.layers.activations import activation_name
+
+    if dt != BF16 or mlp.hidden_layers != 2 or mlp.hidden_dim != H or x.dim() != 2 or x.shape[0] == 0:
+        return False
+    d_in, d_out = mlp.input_dim, mlp.output_dim
+    if not (d_in == H or d_in <= 64) or d_out > H or (mlp.norm_type is not None and d_out != H):
+        return False
+    try:
+        if activation_name(mlp.activation_fn) != "relu":
+            return False
+    except NotImplementedError:
+        return False
+    return all(q.dtype == torch.float32 and q.is_cuda for q in mlp.parameters())
+
+
+def mlp_forward(mlp, x: Tensor) -> Tensor:
+    nrm = mlp._norm()
+    return FusedMLPFn.apply(x, nrm.eps if nrm is not None else 1e-5, *mlp._flat_params())

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from ... import ops
+from ... import fused, ops
 from ..layers.activations import activation_name
 from .graph import CuGraphCSC
 from .utils import _split, graph_plan, sum_efeat
@@ -105,6 +105,8 @@ class MeshGraphMLP(nn.Module):
         if self.hidden_layers is None:
             return x if residual is None else x + residual
         dt = compute_dtype(x)
+        if residual is None and fused.ENABLED and fused.mlp_eligible(self, x, dt):
+            return fused.mlp_forward(self, x)  # tcgen05 path: encoders / decoder
         x = x.to(dt)
         if residual is not None:
             residual = residual.to(dt)

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
-from ... import ops
+from ... import fused, ops
 from ..gnn_layers.graph import CuGraphCSC
 from ..gnn_layers.mesh_edge_block import MeshEdgeBlock
 from ..gnn_layers.mesh_graph_mlp import MeshGraphMLP, compute_dtype
@@ -222,6 +222,13 @@ class MeshGraphNetProcessor(nn.Module):
         return custom_forward
 
     def forward(self, node_features: Tensor, edge_features: Tensor, graph) -> Tensor:
+        if fused.ENABLED and node_features.is_cuda:
+            dt = compute_dtype(node_features)
+            plan = graph_plan(graph, node_features.device)
+            if fused.processor_eligible(self, node_features, edge_features, graph, plan, dt):
+                # bf16 / hidden 128 / ReLU / sum: fused tcgen05 kernels with in-kernel recompute (checkpoint
+                # segments only trade memory for recompute in the reference; nothing to do here)
+                return fused.processor_forward(self, node_features, edge_features, plan)
         with self.checkpoint_offload_ctx:
             for segment_start, segment_end in self.checkpoint_segments:
                 edge_features, node_features = self.checkpoint_fn(

@@ -502,3 +502,25 @@ def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[
          n_out, eps, _p(g_a), int(add_gout), _p(g_z1), 0 if g_z1 is None else g_z1.stride(0), _p(g_w1), g_w1.stride(0), _p(g_b1), _p(g_w2), _p(g_b2),
          _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes, _p(tc_status(dev)), _stream())
     return g_a, g_z1
+
+
+# ----------------------------------------------------------------------------------------
+# node-level plain GEMMs of the fused path (bf16 rows, fp32 weights)
+# ----------------------------------------------------------------------------------------
+def linear_tc(x: Tensor, w: Tensor, out: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
+    """out[M, Nout] = x[M, K] w[Nout, K]^T (+ residual)."""
+    h, _ = _linear_fwd(x, _f32(w), None, ACT_IDS[None], False)
+    if residual is not None:
+        o = torch.empty_like(h) if out is None else out
+        call("mgn_add", _dt(h), _p(h), _p(_c(residual)), _p(o), h.numel(), _stream())
+        return o
+    if out is not None:
+        out.copy_(h)
+        return out
+    return h
+
+
+def wgrad_tc(g: Tensor, x: Tensor) -> Tensor:
+    """[Ng, K] fp32 = g[M, Ng]^T x[M, K]  (deterministic two-stage reduction)."""
+    g_w, _ = _linear_bwd_weight(_c(g), _c(x), g.shape[1], x.shape[1], False)
+    return g_w
