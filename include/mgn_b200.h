@@ -206,6 +206,24 @@ int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x
                     float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
                     size_t workspace_bytes, int* status, mgn_stream_t stream);
 
+/* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):
+ *   mgn_linear_tc : out[M,128] (row stride ld_out) = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual[M,128])
+ *                   x_k are [M,128] column blocks with row stride ld_k; W is [128, 128*n_tab] with row stride ld_w
+ *   mgn_wgrad_tc  : out[128*n_blocks, 128] (fp32, row stride ld_out) = G[M, 128*n_blocks]^T X[M,128]
+ * They replace the cuBLAS GEMMs autograd runs for the node-row column blocks of the first Linear
+ * (mesh_graph_mlp.py:142-168 / the lin_src, lin_dst products of MeshGraphEdgeMLPSum :396-405). */
+int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_t ld1, const void* x2, int64_t ld2,
+                  int n_tab, int64_t M, const float* w, int64_t ld_w, const float* bias,
+                  const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
+size_t mgn_wgrad_tc_workspace_bytes(int64_t M, int n_blocks);
+int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const void* x, int64_t ld_x, int64_t M,
+                 float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, int* status,
+                 mgn_stream_t stream);
+
+/* Debug hook (not part of the drop-in surface): dev_buf = 96 x int64 that CTA 0 of subsequent
+ * mgn_mlp3_bwd_tc launches fills with per-role, per-phase cycle counts; NULL disables. */
+int mgn_debug_set_bwd_timing(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,6 +123,12 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
             return "tensor", 16.0 * 128 * 128 * M  # node block
         k1 = small_in if small_in > 0 else 128
         return "tensor", 4.0 * M * (k1 * 128 + 2 * 128 * 128)
+    if name == "mgn_linear_tc":
+        n_tab, M = a[6], a[7]
+        return "tensor", 2.0 * M * 128 * 128 * n_tab
+    if name == "mgn_wgrad_tc":
+        jb, M = a[2], a[5]
+        return "tensor", 2.0 * M * 128 * 128 * jb
     if name == "mgn_linear_fwd":
         M, K, N = a[3], a[4], a[7]
         return "tensor", 2.0 * M * K * N

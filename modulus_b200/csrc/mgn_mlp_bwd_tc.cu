@@ -27,6 +27,7 @@
 // row = TMEM lane).
 #include "mgn_common.cuh"
 #include "mgn_tc.cuh"
+#include "mgn_reduce.cuh"
 
 namespace mgn {
 
@@ -65,9 +66,17 @@ struct Params {
   float* partials;      // [gridDim.x][part_floats]
   long long part_floats;
   int* status;
+  long long* timing;    // debug: [3 roles][32] cycle counters of CTA 0 (nullable)
 };
 
 enum { kStatusTimeout = 1, kStatusSmem = 2 };
+
+#define MGN_T(i)                      \
+  if (tm_on) {                        \
+    const long long t_ = clock64();   \
+    tm[i] += t_ - tlast;              \
+    tlast = t_;                       \
+  }
 
 // barrier indices
 enum { B_AG = 0, B_GO = 1, B_A2 = 2, B_MMA1 = 3, B_E1 = 9, B_NUM = 15 };
@@ -333,6 +342,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   bool timed_out = false;
+  long long tm[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) tm[i] = 0;
+  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 5);
+  long long tlast = clock64();
 
   // mover-side running column sums (fixed columns per thread) and epilogue-side gamma gradient
   float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
@@ -360,30 +374,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         // ---- GEMM1: acc = A W1^T
         MGN_W(B_AG, par);
         if (it > 0) MGN_W(B_E1 + 5, par ^ 1);
+        MGN_T(0);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < KP * 4; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3),
                   id_nt, k != 0);
         umma_commit(&bars[B_MMA1 + 0]);
+        MGN_T(1);
         // ---- GEMM2: acc = h1 W2^T
         MGN_W(B_E1 + 0, par);
+        MGN_T(2);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH1 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW2 + (k >> 2) * kPB, k & 3),
                   id_nt, k != 0);
         umma_commit(&bars[B_MMA1 + 1]);
+        MGN_T(3);
         // ---- GEMM3: acc = h2 W3^T
         MGN_W(B_E1 + 1, par);
+        MGN_T(4);
         tc_fence_after_sync();
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW3 + (k >> 2) * kPB, k & 3),
                   id_nt, k != 0);
         umma_commit(&bars[B_MMA1 + 2]);
+        MGN_T(5);
         // ---- layer 3: gW3 += g_y^T h2 ; acc = g_y W3          (g_y in bA)
         MGN_W(B_E1 + 2, par);
+        MGN_T(6);
         tc_fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -392,8 +413,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
         umma_commit(&bars[B_MMA1 + 3]);
+        MGN_T(7);
         // ---- layer 2: gW2 += g_z2^T h1 ; acc = g_z2 W2        (g_z2 in bH2)
         MGN_W(B_E1 + 3, par);
+        MGN_T(8);
         tc_fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -402,9 +425,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
         umma_commit(&bars[B_MMA1 + 4]);
+        MGN_T(9);
         // ---- layer 1: gW1 += g_z1^T A ; acc = g_z1 W1          (g_z1 in bH1, A re-staged in bA)
         MGN_W(B_E1 + 4, par);
+        MGN_T(10);
         MGN_W(B_A2, par);
+        MGN_T(11);
         tc_fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -416,6 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
                     k != 0);
         }
         umma_commit(&bars[B_MMA1 + 5]);
+        MGN_T(12);
 #undef MGN_W
       }
     }
@@ -444,8 +471,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
       if (has_g) stage_rows<2>(bX, p.g1, p.g2, row0, p.M, mt);
       MGN_PUBLISH(B_AG);
+      MGN_T(0);
       // incoming gradient, once the epilogue has consumed G
       MGN_W(B_E1 + 0, par);
+      MGN_T(1);
       if (!p.go_small) {
         stage_rows<2>(bX, p.go1, p.go2, row0, p.M, mt);
       } else {
@@ -468,24 +497,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         }
       }
       MGN_PUBLISH(B_GO);
+      MGN_T(2);
       MGN_MOVER_SYNC();
       colsum_tile(bX, mt, cs_beta);
+      MGN_T(3);
       // g_y (in bA): bias-3 gradient, then re-stage A once the layer-3 MMAs have consumed g_y
       MGN_W(B_E1 + 2, par);
+      MGN_T(4);
       colsum_tile(bA, mt, cs_b3);
+      MGN_T(5);
       MGN_W(B_MMA1 + 3, par);
       MGN_MOVER_SYNC();
+      MGN_T(6);
       if (KP == 2) stage_rows<2>(bA, p.a, none, row0, p.M, mt);
       else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
       MGN_PUBLISH(B_A2);
+      MGN_T(7);
       MGN_W(B_E1 + 3, par);
+      MGN_T(8);
       colsum_tile(bH2, mt, cs_b2);
+      MGN_T(9);
       MGN_W(B_E1 + 4, par);
+      MGN_T(10);
       colsum_tile(bH1, mt, cs_b1);
       if (p.g_z1) store_rows(bH1, p.g_z1, p.g_z1_ld, row0, p.M, mt);
+      MGN_T(11);
       MGN_W(B_E1 + 5, par);
+      MGN_T(12);
       if (need_ga) store_rows(bX, p.g_a, kH, row0, p.M, mt);
       MGN_MOVER_SYNC();
+      MGN_T(13);
     }
 #undef MGN_W
   } else {
@@ -515,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       // ---- E1: h1 = relu(acc + b1 + G) -> bH1
       MGN_W(B_MMA1 + 0, par);
       MGN_W(B_AG, par);
+      MGN_T(0);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -532,8 +574,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         row_store32(bH1, row, g, f);
       }
       MGN_EPI_DONE(B_E1 + 0);
+      MGN_T(1);
       // ---- E2: h2 = relu(acc + b2) -> bH2
       MGN_W(B_MMA1 + 1, par);
+      MGN_T(2);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -546,9 +590,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         row_store32(bH2, row, g, f);
       }
       MGN_EPI_DONE(B_E1 + 1);
+      MGN_T(3);
       // ---- E3: LayerNorm backward: g_y -> bA   (g_out in bX)
       MGN_W(B_MMA1 + 2, par);
+      MGN_T(4);
       MGN_W(B_GO, par);
+      MGN_T(5);
       tc_fence_after_sync();
       if (has_ln) {
         float s = 0.f;
@@ -608,8 +655,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         }
       }
       MGN_EPI_DONE(B_E1 + 2);
+      MGN_T(6);
       // ---- E4: g_z2 = acc * (h2 > 0), in place in bH2
       MGN_W(B_MMA1 + 3, par);
+      MGN_T(7);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -623,8 +672,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         row_store32(bH2, row, g, h);
       }
       MGN_EPI_DONE(B_E1 + 3);
+      MGN_T(8);
       // ---- E5: g_z1 = acc * (h1 > 0), in place in bH1
       MGN_W(B_MMA1 + 4, par);
+      MGN_T(9);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
@@ -638,8 +689,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         row_store32(bH1, row, g, h);
       }
       MGN_EPI_DONE(B_E1 + 4);
+      MGN_T(10);
       // ---- E6: g_A = acc (+ g_out), in place in bX
       MGN_W(B_MMA1 + 5, par);
+      MGN_T(11);
       tc_fence_after_sync();
       if (need_ga) {
 #pragma unroll 1
@@ -655,8 +708,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         }
       }
       MGN_EPI_DONE(B_E1 + 5);
+      MGN_T(12);
     }
 #undef MGN_W
+  }
+  if (tm_on) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    for (int i = 0; i < 32; ++i) p.timing[role * 32 + i] = tm[i];
   }
 
   if (timed_out && p.status != nullptr) atomicOr(p.status, kStatusTimeout);
@@ -723,38 +781,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// ------------------------------------------------------------------------------------------------
-// second stage: out[r, c] = sum over CTAs of partial[cta][off + r * cols + c]   (fixed order)
-// ------------------------------------------------------------------------------------------------
-struct ReduceSeg {
-  float* dst;
-  long long ld_dst;
-  int rows, cols;
-  int src_off;
-  int src_ld;
-};
-struct ReduceParams {
-  const float* partials;
-  long long stride;
-  int n_parts;
-  int n_seg;
-  ReduceSeg seg[8];
-};
-
-__global__ void reduce_bwd_partials_kernel(const ReduceParams rp) {
-  const ReduceSeg sg = rp.seg[blockIdx.y];
-  if (sg.dst == nullptr) return;
-  const int n = sg.rows * sg.cols;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int r = i / sg.cols, c = i - r * sg.cols;
-    const float* src = rp.partials + sg.src_off + r * sg.src_ld + c;
-    float s = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < rp.n_parts; ++k) s += src[static_cast<long long>(k) * rp.stride];
-    sg.dst[r * sg.ld_dst + c] = s;
-  }
-}
-
 template <int KP>
 static int launch(Params& p, int grid, cudaStream_t st) {
   using L = Smem<KP>;
@@ -777,6 +803,13 @@ using namespace mgn;
 static int bwd_grid(int64_t M) {
   const long long n_tiles = (M + bwd::kRows - 1) / bwd::kRows;
   return static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+}
+
+static long long* g_bwd_timing = nullptr;
+/* debug hook: device buffer of 96 int64 that CTA 0 of the next backward launches fills with per-phase cycles */
+extern "C" int mgn_debug_set_bwd_timing(void* dev_buf) {
+  g_bwd_timing = static_cast<long long*>(dev_buf);
+  return MGN_OK;
 }
 
 extern "C" size_t mgn_mlp3_bwd_tc_workspace_bytes(int64_t M) {
@@ -824,6 +857,7 @@ extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const vo
   if (g_z1) MGN_CHECK_ARG(p.g_z1_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(g_z1) & 15) == 0);
   p.partials = static_cast<float*>(workspace);
   p.status = status;
+  p.timing = g_bwd_timing;
   cudaStream_t st = as_stream(stream);
   const int grid = bwd_grid(M);
   int rc;
@@ -840,7 +874,7 @@ extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const vo
     rc = bwd::launch<2>(p, grid, st);
   }
   if (rc != MGN_OK) return rc;
-  bwd::ReduceParams rp{};
+  ReduceParams rp{};
   rp.partials = p.partials;
   rp.stride = p.part_floats;
   rp.n_parts = grid;
@@ -848,15 +882,15 @@ extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const vo
   const int oW2 = bwd::kH * 64 * kp, oW3 = oW2 + bwd::kH * bwd::kH, oB1 = oW3 + bwd::kH * bwd::kH;
   int ns = 0;
   // gW1: the TMEM accumulator is [128][64*kp]; only the first n1 columns are real
-  rp.seg[ns++] = bwd::ReduceSeg{g_w1, ld_gw1, bwd::kH, n1, 0, 64 * kp};
-  rp.seg[ns++] = bwd::ReduceSeg{g_w2, bwd::kH, bwd::kH, bwd::kH, oW2, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_w3, bwd::kH, n_out, bwd::kH, oW3, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_b1, bwd::kH, 1, bwd::kH, oB1, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_b2, bwd::kH, 1, bwd::kH, oB1 + bwd::kH, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_b3, bwd::kH, 1, n_out, oB1 + 2 * bwd::kH, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_gamma, bwd::kH, 1, bwd::kH, oB1 + 3 * bwd::kH, bwd::kH};
-  rp.seg[ns++] = bwd::ReduceSeg{g_beta, bwd::kH, 1, bwd::kH, oB1 + 4 * bwd::kH, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_w1, ld_gw1, bwd::kH, n1, 0, 64 * kp};
+  rp.seg[ns++] = ReduceSeg{g_w2, bwd::kH, bwd::kH, bwd::kH, oW2, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_w3, bwd::kH, n_out, bwd::kH, oW3, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_b1, bwd::kH, 1, bwd::kH, oB1, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_b2, bwd::kH, 1, bwd::kH, oB1 + bwd::kH, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_b3, bwd::kH, 1, n_out, oB1 + 2 * bwd::kH, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_gamma, bwd::kH, 1, bwd::kH, oB1 + 3 * bwd::kH, bwd::kH};
+  rp.seg[ns++] = ReduceSeg{g_beta, bwd::kH, 1, bwd::kH, oB1 + 4 * bwd::kH, bwd::kH};
   rp.n_seg = ns;
-  bwd::reduce_bwd_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
+  reduce_cta_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
   return mgn_launch_status();
 }

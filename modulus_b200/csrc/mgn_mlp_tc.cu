@@ -40,6 +40,9 @@ struct GRows {  // additive rows of layer 1: row r -> tab[(idx ? idx[r] : r) * l
 struct MlpFwdParams {
   const bf16* tab[3];
   const int32_t* idx[3];
+  long long tab_ld[3];    // row stride / first column of each A table (default 128 / 0)
+  long long tab_col0[3];
+  int single;             // 1: out = A W1^T + b3 (+ residual), one GEMM only (node-level projections)
   GRows g1, g2;   // z1 += g1[row] (+ g2[row]): staged as the LAST two panels, multiplied by an identity block
   int g_tab;      // table slot (pnl >> 1) the G panels occupy; -1: none
   long long ld_w1;
@@ -125,8 +128,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
 
   // ---------------- one-time setup ----------------
   stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads, p.ld_w1, p.g_tab >= 0 ? p.g_tab * kH : (1 << 30));
-  stage_weight(sW2, p.w2, kH, kH, 2, tid, kFwdThreads);
-  stage_weight(sW3, p.w3, p.n_out, kH, 2, tid, kFwdThreads);
+  if (!p.single) {
+    stage_weight(sW2, p.w2, kH, kH, 2, tid, kFwdThreads);
+    stage_weight(sW3, p.w3, p.n_out, kH, 2, tid, kFwdThreads);
+  }
   for (int i = tid; i < kH; i += kFwdThreads) {
     sPar[i] = p.b1 ? p.b1[i] : 0.f;
     sPar[kH + i] = p.b2 ? p.b2[i] : 0.f;
@@ -185,6 +190,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
           }
           umma_commit(&acc_full[b]);
         }
+        if (p.single) continue;
 #pragma unroll
         for (int layer = 0; layer < 2; ++layer) {  // GEMM2 then GEMM3, A operand = hidden in TMEM
           const uint32_t w_addr = layer == 0 ? w2_addr : w3_addr;
@@ -251,19 +257,29 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
           const int half = pnl & 1;
           const bool two = p.g2.tab != nullptr;
           uint4 v1[8], v2[8];
+          long long r1[8], r2[8];
+          const int chunk_g = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {  // row indices first (rows past M are clamped, zeroed below)
+            const long long grow = row0 + lw * 32 + it * 4 + (lane >> 3);
+            const long long gc = grow < p.M ? grow : p.M - 1;
+            r1[it] = p.g1.idx ? static_cast<long long>(__ldg(p.g1.idx + gc)) : gc;
+            r2[it] = (two && p.g2.idx) ? static_cast<long long>(__ldg(p.g2.idx + gc)) : gc;
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it)  // all row loads in flight together
+            v1[it] = __ldg(reinterpret_cast<const uint4*>(p.g1.tab + r1[it] * p.g1.ld + p.g1.col0 + half * 64 + chunk_g * 8));
+          if (two) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              v2[it] = __ldg(reinterpret_cast<const uint4*>(p.g2.tab + r2[it] * p.g2.ld + p.g2.col0 + half * 64 + chunk_g * 8));
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int r_local = it * 4 + (lane >> 3), chunk = lane & 7;
-            const long long grow = row0 + lw * 32 + r_local;
-            v1[it] = make_uint4(0, 0, 0, 0);
-            v2[it] = make_uint4(0, 0, 0, 0);
-            if (grow < p.M) {
-              const long long r1 = p.g1.idx ? static_cast<long long>(__ldg(p.g1.idx + grow)) : grow;
-              v1[it] = __ldg(reinterpret_cast<const uint4*>(p.g1.tab + r1 * p.g1.ld + p.g1.col0 + half * 64 + chunk * 8));
-              if (two) {
-                const long long r2 = p.g2.idx ? static_cast<long long>(__ldg(p.g2.idx + grow)) : grow;
-                v2[it] = __ldg(reinterpret_cast<const uint4*>(p.g2.tab + r2 * p.g2.ld + p.g2.col0 + half * 64 + chunk * 8));
-              }
+            const long long grow = row0 + lw * 32 + it * 4 + (lane >> 3);
+            if (grow >= p.M) {
+              v1[it] = make_uint4(0, 0, 0, 0);
+              v2[it] = make_uint4(0, 0, 0, 0);
             }
           }
 #pragma unroll
@@ -296,7 +312,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
             const int32_t gi = __shfl_sync(0xffffffffu, ix[k], r_local);
             const bool v = grow < p.M;
             const long long srow = v ? (indexed ? static_cast<long long>(gi) : grow) : 0;
-            cp_async16_zfill(sbase + sw128_offset(row_in_tile, chunk), tab + srow * kH + half * 64 + chunk * 8, v);
+            cp_async16_zfill(sbase + sw128_offset(row_in_tile, chunk),
+                             tab + srow * p.tab_ld[k] + p.tab_col0[k] + half * 64 + chunk * 8, v);
           }
         }
         cp_async_commit();
@@ -329,7 +346,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
       const bool valid = grow < p.M;
       // ---- hidden layers: bias + ReLU, write back to TMEM as packed bf16 (A operand of the next GEMM)
 #pragma unroll 1
-      for (int layer = 0; layer < 2; ++layer) {
+      for (int layer = 0; layer < (p.single ? 0 : 2); ++layer) {
         timed_out |= !mbar_wait(&acc_full[b], ph);
         ph ^= 1;
         tc_fence_after_sync();
@@ -481,6 +498,11 @@ static int mlp3_fwd_common(const void* tab0, const int32_t* idx0, const void* ta
   p.g1 = g1;
   p.g2 = g2;
   p.g_tab = -1;
+  for (int k = 0; k < 3; ++k) {
+    p.tab_ld[k] = kH;
+    p.tab_col0[k] = 0;
+  }
+  p.single = 0;
   p.small_x = small_x;
   p.small_in = small_in;
   p.small_is_f32 = small_is_f32;
@@ -544,4 +566,41 @@ extern "C" int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const 
   return mlp3_fwd_common(a_tab, a_idx, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0, 0, g1, g2, M, w1, ld_w1, b1,
                          w2, b2, w3, b3, gamma, beta, n_out, eps, residual, out, ld_out, nullptr, nullptr, status,
                          stream);
+}
+
+// out[M,128] = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual): one GEMM through the same pipeline
+// (node-level projections of the fused path: P = nfeat Wp^T and g_nfeat += T Wp)
+extern "C" int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_t ld1, const void* x2, int64_t ld2,
+                             int n_tab, int64_t M, const float* w, int64_t ld_w, const float* bias,
+                             const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(M >= 0 && w && n_tab >= 1 && n_tab <= 3 && ld_out >= kH && ld_w >= kH * n_tab);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(out != nullptr && x0 != nullptr);
+  MlpFwdParams p{};
+  const void* xs[3] = {x0, x1, x2};
+  const int64_t lds[3] = {ld0, ld1, ld2};
+  for (int k = 0; k < 3; ++k) {
+    p.tab[k] = static_cast<const bf16*>(xs[k]);
+    p.idx[k] = nullptr;
+    p.tab_ld[k] = lds[k] > 0 ? lds[k] : kH;
+    p.tab_col0[k] = 0;
+    if (k < n_tab) MGN_CHECK_ARG(xs[k] != nullptr && p.tab_ld[k] % 8 == 0 && (reinterpret_cast<uintptr_t>(xs[k]) & 15) == 0);
+  }
+  p.g_tab = -1;
+  p.single = 1;
+  p.M = M;
+  p.w1 = w;
+  p.ld_w1 = ld_w;
+  p.k1_true = kH * n_tab;
+  p.b3 = bias;
+  p.n_out = kH;
+  p.eps = 0.f;
+  p.residual = static_cast<const bf16*>(residual);
+  p.out = static_cast<bf16*>(out);
+  p.ld_out = ld_out;
+  p.status = status;
+  cudaStream_t st = as_stream(stream);
+  if (n_tab == 1) return launch_fwd<2, 4>(p, st);
+  if (n_tab == 2) return launch_fwd<4, 4>(p, st);
+  return launch_fwd<6, 3>(p, st);
 }

@@ -508,19 +508,45 @@ def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[
 # node-level plain GEMMs of the fused path (bf16 rows, fp32 weights)
 # ----------------------------------------------------------------------------------------
 def linear_tc(x: Tensor, w: Tensor, out: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
-    """out[M, Nout] = x[M, K] w[Nout, K]^T (+ residual)."""
-    h, _ = _linear_fwd(x, _f32(w), None, ACT_IDS[None], False)
-    if residual is not None:
-        o = torch.empty_like(h) if out is None else out
-        call("mgn_add", _dt(h), _p(h), _p(_c(residual)), _p(o), h.numel(), _stream())
-        return o
-    if out is not None:
-        out.copy_(h)
-        return out
-    return h
+    """out[M, Nout] = x[M, K] w[Nout, K]^T (+ residual); K, Nout multiples of 128 (K <= 384).  tcgen05 GEMM
+    (include/mgn_b200.h: mgn_linear_tc), one launch per 128 output columns."""
+    M, K = x.shape
+    n_out = w.shape[0]
+    if K % TC_HIDDEN or n_out % TC_HIDDEN or K > 3 * TC_HIDDEN or w.shape[1] != K or x.dtype != torch.bfloat16:
+        raise ValueError(f"linear_tc: unsupported shapes x{tuple(x.shape)} w{tuple(w.shape)} {x.dtype}")
+    if residual is not None and n_out != TC_HIDDEN:
+        raise ValueError("linear_tc: residual needs a 128-wide output")
+    w = _f32(w)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
+    n_tab = K // TC_HIDDEN
+    xs = [x[:, TC_HIDDEN * k: TC_HIDDEN * (k + 1)] for k in range(n_tab)] + [None] * (3 - n_tab)
+    st = tc_status(x.device)
+    for j in range(n_out // TC_HIDDEN):
+        wj = w[TC_HIDDEN * j: TC_HIDDEN * (j + 1)]
+        oj = out[:, TC_HIDDEN * j: TC_HIDDEN * (j + 1)]
+        call("mgn_linear_tc", _p(xs[0]), x.stride(0), _p(xs[1]), x.stride(0), _p(xs[2]), x.stride(0), n_tab, M,
+             _p(wj), wj.stride(0), None, _p(None if residual is None else _c(residual)), _p(oj), out.stride(0),
+             _p(st), _stream())
+    return out
 
 
 def wgrad_tc(g: Tensor, x: Tensor) -> Tensor:
-    """[Ng, K] fp32 = g[M, Ng]^T x[M, K]  (deterministic two-stage reduction)."""
-    g_w, _ = _linear_bwd_weight(_c(g), _c(x), g.shape[1], x.shape[1], False)
-    return g_w
+    """[Ng, 128] fp32 = g[M, Ng]^T x[M, 128], Ng in {128, 256, 384} (include/mgn_b200.h: mgn_wgrad_tc)."""
+    M, ng = g.shape
+    if ng % TC_HIDDEN or ng > 3 * TC_HIDDEN or x.shape != (M, TC_HIDDEN) or g.dtype != torch.bfloat16:
+        raise ValueError(f"wgrad_tc: unsupported shapes g{tuple(g.shape)} x{tuple(x.shape)}")
+    if g.stride(1) != 1:
+        g = g.contiguous()
+    x = _c(x)
+    out = torch.empty((ng, TC_HIDDEN), dtype=torch.float32, device=g.device)
+    if M == 0:
+        return out.zero_()
+    jb = ng // TC_HIDDEN
+    nbytes = _lib.load().mgn_wgrad_tc_workspace_bytes(M, jb)
+    ws = _ws(nbytes, g.device)
+    call("mgn_wgrad_tc", _p(g), g.stride(0), jb, _p(x), x.stride(0), M, _p(out), out.stride(0), _p(ws), nbytes,
+         _p(tc_status(g.device)), _stream())
+    return out

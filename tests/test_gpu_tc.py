@@ -221,3 +221,34 @@ def test_mlp3_bwd_tc_is_deterministic():
     ops.tc_check(DEV)
     for a, b in zip(*outs):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("M", [1, 129, 20000])
+@pytest.mark.parametrize("K,N", [(128, 384), (384, 128), (256, 128)])
+def test_linear_tc(M, K, N):
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(M + K)
+    x = bf(torch.randn(M, K, generator=g))
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    res = bf(torch.randn(M, N, generator=g)) if N == 128 else None
+    ref = x @ bf(w).T + (res if res is not None else 0)
+    out = ops.linear_tc(x.to(DEV).bfloat16(), w.to(DEV), residual=None if res is None else res.to(DEV).bfloat16())
+    ops.tc_check(DEV)
+    assert rel_err(out.float(), ref) < 1e-2
+
+
+@pytest.mark.parametrize("M", [1, 129, 20000, 100172])
+@pytest.mark.parametrize("JB", [1, 3])
+def test_wgrad_tc(M, JB):
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(M + JB)
+    G = bf(torch.randn(M, 128 * JB, generator=g))
+    x = bf(torch.randn(M, 128, generator=g))
+    ref = G.double().T @ x.double()
+    out = ops.wgrad_tc(G.to(DEV).bfloat16(), x.to(DEV).bfloat16())
+    out2 = ops.wgrad_tc(G.to(DEV).bfloat16(), x.to(DEV).bfloat16())
+    ops.tc_check(DEV)
+    assert rel_err(out, ref) < 1e-4
+    assert torch.equal(out, out2)

@@ -1,0 +1,66 @@
+"""Stand-alone launches of the fused edge-block kernels at the c2 size (for ncu captures and timing)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from modulus_b200 import ops
+from modulus_b200.mesh import triangle_grid_mesh
+
+DEV = "cuda:0"
+nx, ny = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (316, 317)
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+mesh = triangle_grid_mesh(nx, ny, device=DEV)
+N, E = mesh["num_nodes"], int(mesh["indices"].numel())
+plan = ops.GraphPlan.from_csc(mesh["offsets"], mesh["indices"], N, N)
+g = torch.Generator(device=DEV).manual_seed(0)
+r = lambda *s: torch.randn(*s, generator=g, device=DEV)
+efeat, P = r(E, 128).bfloat16(), (r(N, 384) * 0.5).bfloat16()
+g_e, g_agg = r(E, 128).bfloat16(), r(N, 128).bfloat16()
+w1, w2, w3 = r(128, 384) / 20, r(128, 128) / 11, r(128, 128) / 11
+b1, b2, b3, gamma, beta = r(128) * .1, r(128) * .1, r(128) * .1, 1 + .1 * r(128), .1 * r(128)
+gw1 = torch.empty(128, 384, device=DEV); gw2 = torch.empty(128, 128, device=DEV); gw3 = torch.empty(128, 128, device=DEV)
+gb = [torch.empty(128, device=DEV) for _ in range(5)]
+
+def fwd():
+    return ops.mlp3_fwd_tc_g(efeat, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta,
+                             residual=efeat)
+
+def bwd():
+    return ops.mlp3_bwd_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, g_e, g_agg, plan.dst, E,
+                           w1[:, :128], b1, w2, b2, w3, b3, gamma, 128, 1e-5, True, True, True,
+                           gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4])
+
+def agg():
+    return ops.segment_sum(efeat, 0, 128, plan.csc_offsets, None, N)
+
+def csr():
+    return ops.segment_sum(efeat, 0, 128, plan.csr_offsets, plan.csr_eids, N)
+
+for name, fn in (("fwd_g edge", fwd), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr)):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    print(f"{name:12s} N={N} E={E}: {ms:.3f} ms  ({E / ms / 1e3:.1f} M edges/s)", flush=True)
+ops.tc_check(DEV)
+
+# per-phase cycle breakdown of CTA 0 of the backward kernel
+from modulus_b200 import _lib
+tbuf = torch.zeros(96, dtype=torch.int64, device=DEV)
+_lib.call("mgn_debug_set_bwd_timing", tbuf.data_ptr())
+bwd(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_bwd_timing", None)
+t = tbuf.cpu().view(3, 32)
+n_tiles = (E + 127) // 128
+per_cta = -(-n_tiles // 148)
+names = {0: "MMA  : wAG+E6 | g1 | wE1 | g2 | wE2 | g3 | wE3 | g4 | wE4 | g5 | wE5 | wA2 | g6",
+         1: "MOVER: stageAG | wE1 | stageGO | csX | wE3 | csA | wMMA4 | stageA2 | wE4 | csH2 | wE5 | csH1+st | wE6 | stGA",
+         2: "EPI  : wMMA1 | E1 | wMMA2 | E2 | wMMA3 | wGO | E3 | wMMA4 | E4 | wMMA5 | E5 | wMMA6 | E6"}
+for r in range(3):
+    print(names[r])
+    print("   cycles/tile:", [int(v) // per_cta for v in t[r, :14].tolist()], " total/tile:", int(t[r].sum()) // per_cta)
