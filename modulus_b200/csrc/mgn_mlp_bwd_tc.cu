@@ -35,7 +35,7 @@ namespace bwd {
 
 constexpr int kRows = 128;       // tile rows
 constexpr int kPB = 16384;       // bytes per panel: 128 rows x 64 bf16
-constexpr int kThreads = 288;
+constexpr int kThreads = 416;  // warp 0: MMA, warps 1-4: movers, warps 5-12: epilogue
 constexpr int kH = 128;
 
 struct RowSrc {  // row r of the tile source lives at tab[(idx ? idx[r] : r) * ld + col0 ...]
@@ -76,7 +76,7 @@ enum { kStatusTimeout = 1, kStatusSmem = 2 };
     const long long t_ = clock64();   \
     tm[i] += t_ - tlast;              \
     tlast = t_;                       \
-  }
+  }  // tm lives in shared memory: the counters must not cost registers
 
 // barrier indices
 enum { B_AG = 0, B_GO = 1, B_A2 = 2, B_MMA1 = 3, B_E1 = 9, B_NUM = 15 };
@@ -93,7 +93,8 @@ struct Smem {
   static constexpr int kPar = kH2 + 2 * kPB;  // b1, b2, b3, gamma
   static constexpr int kBars = kPar + 4 * kH * 4;
   static constexpr int kTmemSlot = kBars + 16 * 8;
-  static constexpr int kTotal = kTmemSlot + 16;
+  static constexpr int kTiming = kTmemSlot + 16;  // 3 roles x 16 x int64 (debug)
+  static constexpr int kTotal = kTiming + 3 * 16 * 8;
 };
 
 // per-CTA partial layout (floats)
@@ -153,39 +154,66 @@ __device__ __forceinline__ void stage_weight_ld(uint8_t* dst, const float* __res
   }
 }
 
-// movers: stage NP panels of rows [row0, row0+128): v = s1[row] (+ s2[row]); rows >= M are zero
-template <int NP>
-__device__ __forceinline__ void stage_rows(uint8_t* buf, const RowSrc& s1, const RowSrc& s2, long long row0,
-                                           long long M, int mt) {
-  constexpr int CH = NP * 8;
-  const int chunk = mt % CH;
-  const int rsub = mt / CH;
-  constexpr int RSTEP = 128 / CH;
+// movers: stage 2 panels of rows [row0, row0+128): v = s1[row] (+ s2[row]); rows >= M are zero.
+// Row indices are fetched first, then all row loads of a batch are in flight together (a dependent
+// idx -> row chain per row would serialise ~1 us round trips).
+__device__ __forceinline__ void stage_rows_sum(uint8_t* buf, const RowSrc& s1, const RowSrc& s2, long long row0,
+                                               long long M, int mt) {
+  const int chunk = mt & 15, rsub = mt >> 4;
   const bool two = s2.tab != nullptr;
+  int32_t r1[16], r2[16];
 #pragma unroll
-  for (int base = 0; base < CH; base += 8) {
+  for (int i = 0; i < 16; ++i) {
+    const long long grow = row0 + i * 8 + rsub;
+    const long long gc = grow < M ? grow : M - 1;
+    r1[i] = s1.idx ? __ldg(s1.idx + gc) : static_cast<int32_t>(gc);
+    r2[i] = (two && s2.idx) ? __ldg(s2.idx + gc) : static_cast<int32_t>(gc);
+  }
+#pragma unroll
+  for (int base = 0; base < 16; base += 8) {
     uint4 v1[8], v2[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int row = (base + u) * RSTEP + rsub;
-      const long long grow = row0 + row;
-      v1[u] = make_uint4(0, 0, 0, 0);
-      v2[u] = make_uint4(0, 0, 0, 0);
-      if (grow < M) {
-        const long long r1 = s1.idx ? static_cast<long long>(__ldg(s1.idx + grow)) : grow;
-        v1[u] = ldg128(s1.tab + r1 * s1.ld + s1.col0 + chunk * 8);
-        if (two) {
-          const long long r2 = s2.idx ? static_cast<long long>(__ldg(s2.idx + grow)) : grow;
-          v2[u] = ldg128(s2.tab + r2 * s2.ld + s2.col0 + chunk * 8);
-        }
-      }
+    for (int u = 0; u < 8; ++u)
+      v1[u] = ldg128(s1.tab + static_cast<long long>(r1[base + u]) * s1.ld + s1.col0 + chunk * 8);
+    if (two) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v2[u] = ldg128(s2.tab + static_cast<long long>(r2[base + u]) * s2.ld + s2.col0 + chunk * 8);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
-      const int row = (base + u) * RSTEP + rsub;
-      const uint4 v = two ? add_bf16x8(v1[u], v2[u]) : v1[u];
+      const int row = (base + u) * 8 + rsub;
+      uint4 v = two ? add_bf16x8(v1[u], v2[u]) : v1[u];
+      if (row0 + row >= M) v = make_uint4(0, 0, 0, 0);
       *reinterpret_cast<uint4*>(buf + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7)) = v;
     }
+  }
+}
+
+// movers: row ids of this thread's 16 rows (rows i*8 + rsub) of the tile starting at row0.  Issued EARLY (one
+// tile ahead): the L1TEX queue returns loads in order, so an index load issued behind a batch of cp.async
+// gathers only comes back after them -- a dependent idx -> gather chain costs a full memory round trip each.
+__device__ __forceinline__ void fetch_row_ids(const int32_t* __restrict__ idx, long long row0, long long M, int rsub,
+                                              int32_t (&r)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const long long grow = row0 + i * 8 + rsub;
+    const long long gc = grow < M ? grow : M - 1;
+    r[i] = idx ? __ldg(idx + gc) : static_cast<int32_t>(gc);
+  }
+}
+
+// movers: stage 2 panels asynchronously (cp.async.cg: L1-bypassing 16-byte requests, zero fill past M) from the
+// rows r[]; the caller commits / waits before publishing the tile
+__device__ __forceinline__ void stage_rows_async(uint8_t* buf, const RowSrc& s, const int32_t (&r)[16], long long row0,
+                                                 long long M, int mt) {
+  const int chunk = mt & 15, rsub = mt >> 4;
+  const uint32_t base = smem_u32(buf) + (chunk >> 3) * kPB;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int row = i * 8 + rsub;
+    cp_async16_zfill(base + sw128_offset(row, chunk & 7), s.tab + static_cast<long long>(r[i]) * s.ld + s.col0 + chunk * 8,
+                     row0 + row < M);
   }
 }
 
@@ -276,6 +304,51 @@ __device__ __forceinline__ void row_store32(uint8_t* buf, int row, int g, const 
   }
 }
 
+// 16 bf16 of this thread's row starting at column col (multiple of 16) <-> registers
+__device__ __forceinline__ void row_load16(const uint8_t* buf, int row, int col, float (&f)[16]) {
+  const uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + sw128_offset(row, c8 + u));
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 t = unpack_bf16x2(w[e]);
+      f[u * 8 + 2 * e] = t.x;
+      f[u * 8 + 2 * e + 1] = t.y;
+    }
+  }
+}
+__device__ __forceinline__ void row_store16(uint8_t* buf, int row, int col, const float (&f)[16]) {
+  uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    uint4 v;
+    v.x = pack_bf16x2(f[u * 8 + 0], f[u * 8 + 1]);
+    v.y = pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]);
+    v.z = pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]);
+    v.w = pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]);
+    *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + u)) = v;
+  }
+}
+
+// warp transpose-reduce of 16 columns: on return lane L holds the sum over all 32 lanes of their v[L & 15]
+__device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int off = 8; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 16);
+}
+
 // warp transpose-reduce: on return lane L holds sum over the 32 lanes of their v[L]   (31 shuffles)
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
@@ -314,6 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
 
   const bool has_ln = p.gamma != nullptr;
   const bool has_g = p.g1.tab != nullptr;
+  const bool has_g2 = p.g2.tab != nullptr;
+  const bool has_go2 = p.go2.tab != nullptr;
   const bool need_ga = p.g_a != nullptr;
   constexpr int N1 = 64 * KP;  // width of the layer-1 input
 
@@ -328,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
   }
   if (tid == 0) {
-    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], (b >= B_MMA1 && b < B_E1) ? 1 : 4);
+    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], b < B_MMA1 ? 4 : (b < B_E1 ? 1 : 8));
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -342,10 +417,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   bool timed_out = false;
-  long long tm[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) tm[i] = 0;
   const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 5);
+  long long* tm = reinterpret_cast<long long*>(smem + L::kTiming) + (warp == 0 ? 0 : (warp == 1 ? 16 : 32));
+  if (tm_on) {
+    for (int i = 0; i < 16; ++i) tm[i] = 0;
+  }
   long long tlast = clock64();
 
   // mover-side running column sums (fixed columns per thread) and epilogue-side gamma gradient
@@ -449,7 +525,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   } else if (warp <= 4) {
     // =========================== movers ===========================
     const int mt = tid - 32;
-    const RowSrc none{nullptr, nullptr, 0, 0};
 #define MGN_W(b, ph)                                                      \
   {                                                                       \
     const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
@@ -463,20 +538,51 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   __syncwarp();               \
   if (lane == 0) mbar_arrive(&bars[b]);
 #define MGN_MOVER_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
+    const int rsub_m = mt >> 4;
+    const bool go2_shares_g2 = has_go2 && p.go2.idx == p.g2.idx && p.go2.idx != nullptr;
+    int32_t r_g1[16], r_g2[16], r_tmp[16];
+    {
+      const long long row00 = static_cast<long long>(blockIdx.x) * kRows;
+      fetch_row_ids(has_g ? p.g1.idx : nullptr, row00, p.M, rsub_m, r_g1);
+      fetch_row_ids(has_g2 ? p.g2.idx : (has_go2 ? p.go2.idx : nullptr), row00, p.M, rsub_m, r_g2);
+    }
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
       const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+      const long long row0n = row0 + static_cast<long long>(gridDim.x) * kRows;  // next tile of this CTA
       // A (and G) tiles
-      if (KP == 2) stage_rows<2>(bA, p.a, none, row0, p.M, mt);
-      else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
-      if (has_g) stage_rows<2>(bX, p.g1, p.g2, row0, p.M, mt);
+      if (KP == 2) {
+        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_tmp);
+        stage_rows_async(bA, p.a, r_tmp, row0, p.M, mt);
+      } else {
+        stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      }
+      MGN_T(14);
+      if (has_g) {  // additive rows: g1 -> bX, g2 -> bH2 (free until the epilogue writes h2); summed in E1
+        stage_rows_async(bX, p.g1, r_g1, row0, p.M, mt);
+        MGN_T(15);
+        if (has_g2) stage_rows_async(bH2, p.g2, r_g2, row0, p.M, mt);
+        MGN_T(3);
+      }
+      cp_async_commit();
+      if (has_g && it + 1 < n_my) fetch_row_ids(p.g1.idx, row0n, p.M, rsub_m, r_g1);  // used one tile later
+      cp_async_wait<0>();
       MGN_PUBLISH(B_AG);
       MGN_T(0);
       // incoming gradient, once the epilogue has consumed G
       MGN_W(B_E1 + 0, par);
       MGN_T(1);
-      if (!p.go_small) {
-        stage_rows<2>(bX, p.go1, p.go2, row0, p.M, mt);
+      if (!p.go_small) {  // go1 -> bX, go2 -> bA (A was consumed by GEMM1); summed in E3
+        fetch_row_ids(p.go1.idx, row0, p.M, rsub_m, r_tmp);
+        stage_rows_async(bX, p.go1, r_tmp, row0, p.M, mt);
+        if (has_go2) {
+          if (!go2_shares_g2) fetch_row_ids(p.go2.idx, row0, p.M, rsub_m, r_g2);
+          stage_rows_async(bA, p.go2, r_g2, row0, p.M, mt);
+        }
+        cp_async_commit();
+        if (it + 1 < n_my && (has_g2 || go2_shares_g2))
+          fetch_row_ids(has_g2 ? p.g2.idx : p.go2.idx, row0n, p.M, rsub_m, r_g2);  // used one tile later
+        cp_async_wait<0>();
       } else {
         const int chunk = mt & 15, rsub = mt >> 4;
         for (int i = 0; i < 16; ++i) {
@@ -498,19 +604,25 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       }
       MGN_PUBLISH(B_GO);
       MGN_T(2);
-      MGN_MOVER_SYNC();
-      colsum_tile(bX, mt, cs_beta);
       MGN_T(3);
-      // g_y (in bA): bias-3 gradient, then re-stage A once the layer-3 MMAs have consumed g_y
+      // after E3: bX = g_out (summed), bA = g_y.  Bias / beta gradients, then re-stage A once the layer-3
+      // MMAs have consumed g_y
       MGN_W(B_E1 + 2, par);
       MGN_T(4);
+      colsum_tile(bX, mt, cs_beta);
       colsum_tile(bA, mt, cs_b3);
       MGN_T(5);
       MGN_W(B_MMA1 + 3, par);
       MGN_MOVER_SYNC();
       MGN_T(6);
-      if (KP == 2) stage_rows<2>(bA, p.a, none, row0, p.M, mt);
-      else stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      if (KP == 2) {
+        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_tmp);
+        stage_rows_async(bA, p.a, r_tmp, row0, p.M, mt);
+        cp_async_commit();
+        cp_async_wait<0>();
+      } else {
+        stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      }
       MGN_PUBLISH(B_A2);
       MGN_T(7);
       MGN_W(B_E1 + 3, par);
@@ -530,14 +642,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     }
 #undef MGN_W
   } else {
-    // =========================== epilogue ===========================
+    // =========================== epilogue (8 warps) ===========================
+    // two warps per TMEM lane quarter: warp (q, ch) owns tile rows [32q, 32q+32) (thread = row = TMEM lane)
+    // and columns [64 ch, 64 ch + 64), processed in 16-column chunks
     const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
     const int row = q * 32 + lane;
-    const uint32_t t_acc = tAcc + (static_cast<uint32_t>(q * 32) << 16);
-    const float* b1 = sPar;
-    const float* b2 = sPar + kH;
-    const float* b3 = sPar + 2 * kH;
-    const float* gam = sPar + 3 * kH;
+    const int c0 = ch * 64;
+    const uint32_t t_acc = tAcc + (static_cast<uint32_t>(q * 32) << 16) + c0;
+    const float* b1 = sPar + c0;
+    const float* b2 = sPar + kH + c0;
+    const float* b3 = sPar + 2 * kH + c0;
+    const float* gam = sPar + 3 * kH + c0;
+    float4* xch = reinterpret_cast<float4*>(bA);  // LayerNorm row-sum exchange between the two column halves
 #define MGN_W(b, ph)                                                      \
   {                                                                       \
     const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
@@ -551,27 +668,30 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   tc_fence_before_sync();     \
   __syncwarp();               \
   if (lane == 0) mbar_arrive(&bars[b]);
+#define MGN_EPI_SYNC() asm volatile("bar.sync 2, 256;" ::: "memory")
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
-      // ---- E1: h1 = relu(acc + b1 + G) -> bH1
+      // ---- E1: h1 = relu(acc + b1 + g1 rows + g2 rows) -> bH1
       MGN_W(B_MMA1 + 0, par);
       MGN_W(B_AG, par);
       MGN_T(0);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + g * 32, v);
-        float f[32];
-        if (has_g) row_load32(bX, row, g, f);
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        float f[16], f2[16];
+        if (has_g) row_load16(bX, row, c0 + g * 16, f);
+        if (has_g2) row_load16(bH2, row, c0 + g * 16, f2);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float z = __uint_as_float(v[j]) + b1[g * 32 + j];
+        for (int j = 0; j < 16; ++j) {
+          float z = __uint_as_float(v[j]) + b1[g * 16 + j];
           if (has_g) z += f[j];
+          if (has_g2) z += f2[j];
           f[j] = fmaxf(z, 0.f);
         }
-        row_store32(bH1, row, g, f);
+        row_store16(bH1, row, c0 + g * 16, f);
       }
       MGN_EPI_DONE(B_E1 + 0);
       MGN_T(1);
@@ -581,77 +701,90 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + g * 32, v);
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
         tmem_ld_wait();
-        float f[32];
+        float f[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + b2[g * 32 + j], 0.f);
-        row_store32(bH2, row, g, f);
+        for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + b2[g * 16 + j], 0.f);
+        row_store16(bH2, row, c0 + g * 16, f);
       }
       MGN_EPI_DONE(B_E1 + 1);
       MGN_T(3);
-      // ---- E3: LayerNorm backward: g_y -> bA   (g_out in bX)
+      // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> bX ; g_y -> bA
       MGN_W(B_MMA1 + 2, par);
       MGN_T(4);
       MGN_W(B_GO, par);
       MGN_T(5);
       tc_fence_after_sync();
-      if (has_ln) {
-        float s = 0.f;
+      if (has_go2) {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + g * 32, v);
-          tmem_ld_wait();
+          float a[16], b[16];
+          row_load16(bX, row, c0 + g * 16, a);
+          row_load16(bA, row, c0 + g * 16, b);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) s += __uint_as_float(v[j]) + b3[g * 32 + j];
+          for (int j = 0; j < 16; ++j) a[j] += b[j];
+          row_store16(bX, row, c0 + g * 16, a);
         }
-        const float mu = s * (1.f / kH);
-        float qv = 0.f, s1 = 0.f, s2 = 0.f;
+        MGN_EPI_SYNC();  // every go2 row has been read: bA may now carry the row-sum exchange
+      }
+      if (has_ln) {
+        float s_y = 0.f, s_yy = 0.f, s_g = 0.f, s_gy = 0.f;
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + g * 32, v);
-          float go[32];
-          row_load32(bX, row, g, go);
+          uint32_t v[16];
+          tmem_ld16(t_acc + g * 16, v);
+          float go[16];
+          row_load16(bX, row, c0 + g * 16, go);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float d = __uint_as_float(v[j]) + b3[g * 32 + j] - mu;
-            const float gh = go[j] * gam[g * 32 + j];
-            qv = fmaf(d, d, qv);
-            s1 += gh;
-            s2 = fmaf(gh, d, s2);
+          for (int j = 0; j < 16; ++j) {
+            const float y = __uint_as_float(v[j]) + b3[g * 16 + j];
+            const float gh = go[j] * gam[g * 16 + j];
+            s_y += y;
+            s_yy = fmaf(y, y, s_yy);
+            s_g += gh;
+            s_gy = fmaf(gh, y, s_gy);
           }
         }
-        const float rstd = rsqrtf(qv * (1.f / kH) + p.eps);
-        const float m1 = s1 * (1.f / kH);
-        const float m2 = s2 * rstd * (1.f / kH);
+        xch[row * 2 + ch] = make_float4(s_y, s_yy, s_g, s_gy);
+        MGN_EPI_SYNC();
+        const float4 o = xch[row * 2 + (ch ^ 1)];
+        MGN_EPI_SYNC();  // both halves have read before g_y overwrites bA
+        s_y += o.x;
+        s_yy += o.y;
+        s_g += o.z;
+        s_gy += o.w;
+        const float mu = s_y * (1.f / kH);
+        const float var = fmaxf(s_yy * (1.f / kH) - mu * mu, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const float m1 = s_g * (1.f / kH);
+        const float m2 = (s_gy - mu * s_g) * rstd * (1.f / kH);  // mean(ghat * xhat)
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + g * 32, v);
-          float go[32];
-          row_load32(bX, row, g, go);
+          uint32_t v[16];
+          tmem_ld16(t_acc + g * 16, v);
+          float go[16];
+          row_load16(bX, row, c0 + g * 16, go);
           tmem_ld_wait();
-          float gy[32];
+          float gy[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float xhat = (__uint_as_float(v[j]) + b3[g * 32 + j] - mu) * rstd;
-            const float gh = go[j] * gam[g * 32 + j];
+          for (int j = 0; j < 16; ++j) {
+            const float xhat = (__uint_as_float(v[j]) + b3[g * 16 + j] - mu) * rstd;
+            const float gh = go[j] * gam[g * 16 + j];
             gy[j] = rstd * (gh - m1 - xhat * m2);
             go[j] *= xhat;  // gamma-gradient contribution of this row
           }
-          row_store32(bA, row, g, gy);
-          gg[g] += warp_colsum32(go, lane);
+          row_store16(bA, row, c0 + g * 16, gy);
+          gg[g] += warp_colsum16(go, lane);
         }
       } else {
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
-          float go[32];
-          row_load32(bX, row, g, go);
-          row_store32(bA, row, g, go);
+          float go[16];
+          row_load16(bX, row, c0 + g * 16, go);
+          row_store16(bA, row, c0 + g * 16, go);
         }
       }
       MGN_EPI_DONE(B_E1 + 2);
@@ -662,14 +795,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + g * 32, v);
-        float h[32];
-        row_load32(bH2, row, g, h);
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        float h[16];
+        row_load16(bH2, row, c0 + g * 16, h);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
-        row_store32(bH2, row, g, h);
+        for (int j = 0; j < 16; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
+        row_store16(bH2, row, c0 + g * 16, h);
       }
       MGN_EPI_DONE(B_E1 + 3);
       MGN_T(8);
@@ -679,14 +812,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       tc_fence_after_sync();
 #pragma unroll 1
       for (int g = 0; g < 4; ++g) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + g * 32, v);
-        float h[32];
-        row_load32(bH1, row, g, h);
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        float h[16];
+        row_load16(bH1, row, c0 + g * 16, h);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
-        row_store32(bH1, row, g, h);
+        for (int j = 0; j < 16; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
+        row_store16(bH1, row, c0 + g * 16, h);
       }
       MGN_EPI_DONE(B_E1 + 4);
       MGN_T(10);
@@ -696,15 +829,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       tc_fence_after_sync();
       if (need_ga) {
 #pragma unroll 1
-        for (int g = 0; g < N1 / 32; ++g) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + g * 32, v);
-          float go[32];
-          if (p.add_gout) row_load32(bX, row, g, go);
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + g * 16, v);
+          float go[16];
+          if (p.add_gout) row_load16(bX, row, c0 + g * 16, go);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) go[j] = __uint_as_float(v[j]) + (p.add_gout ? go[j] : 0.f);
-          row_store32(bX, row, g, go);
+          for (int j = 0; j < 16; ++j) go[j] = __uint_as_float(v[j]) + (p.add_gout ? go[j] : 0.f);
+          row_store16(bX, row, c0 + g * 16, go);
         }
       }
       MGN_EPI_DONE(B_E1 + 5);
@@ -714,7 +847,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   }
   if (tm_on) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
-    for (int i = 0; i < 32; ++i) p.timing[role * 32 + i] = tm[i];
+    for (int i = 0; i < 16; ++i) p.timing[role * 32 + i] = tm[i];
   }
 
   if (timed_out && p.status != nullptr) atomicOr(p.status, kStatusTimeout);
@@ -727,6 +860,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   float* scratch = reinterpret_cast<float*>(bX);  // tile buffers are free now
   if (warp >= 5) {
     const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
     const int row = q * 32 + lane;  // TMEM lane = output-feature row of the weight gradient
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
 #pragma unroll 1
@@ -735,7 +869,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       const int ncol = (w == 0) ? N1 : kH;
       float* dst = part + (w == 0 ? PT::kW1 : (w == 1 ? PT::kW2 : PT::kW3)) + row * ncol;
 #pragma unroll 1
-      for (int g = 0; g < ncol / 32; ++g) {
+      for (int g = ch * (ncol / 64); g < (ch + 1) * (ncol / 64); ++g) {  // this warp's half of the columns
         uint32_t v[32];
         tmem_ld32(t + g * 32, v);
         tmem_ld_wait();
@@ -746,9 +880,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
                           __uint_as_float(v[4 * u + 3]));
       }
     }
-    // gamma gradient: lane holds column g*32+lane summed over this warp's 32 rows
+    // gamma gradient: lane (< 16) holds column 64 ch + 16 g + lane summed over this warp's 32 rows
+    if (lane < 16) {
 #pragma unroll
-    for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + g * 32 + lane] = gg[g];
+      for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + ch * 64 + g * 16 + lane] = gg[g];
+    }
   } else if (warp >= 1) {
     const int mt = tid - 32;
     const int chunk = mt & 15, rsub = mt >> 4;

@@ -43,6 +43,7 @@ struct MlpFwdParams {
   long long tab_ld[3];    // row stride / first column of each A table (default 128 / 0)
   long long tab_col0[3];
   int single;             // 1: out = A W1^T + b3 (+ residual), one GEMM only (node-level projections)
+  int ident_k0;           // W1 columns >= ident_k0 are staged as repeating 128x128 identity blocks (0: none)
   GRows g1, g2;   // z1 += g1[row] (+ g2[row]): staged as the LAST two panels, multiplied by an identity block
   int g_tab;      // table slot (pnl >> 1) the G panels occupy; -1: none
   long long ld_w1;
@@ -60,9 +61,17 @@ struct MlpFwdParams {
   bf16* h1_save;
   bf16* h2_save;
   int* status;
+  long long* timing;  // debug: [3 roles][32] cycle counters of CTA 0 (nullable)
 };
 
 enum { kStatusTimeout = 1, kStatusSmem = 2 };
+
+#define MGN_T(i)                      \
+  if (tm_on) {                        \
+    const long long t_ = clock64();   \
+    tm[i] += t_ - tlast;              \
+    tlast = t_;                       \
+  }
 
 // fp32 [n_rows, k_true] (nn.Linear layout) -> bf16 K-major SW128 panels [n_panels][128][64], zero padded
 __device__ __forceinline__ void stage_weight(uint8_t* dst, const float* __restrict__ w, int n_rows, int k_true,
@@ -80,7 +89,7 @@ __device__ __forceinline__ void stage_weight(uint8_t* dst, const float* __restri
     for (int j = 0; j < 8; ++j) {
       const int k = k0 + j;
       // columns >= ident_k0 hold an identity block: the G panels pass through the GEMM unchanged
-      f[j] = k >= ident_k0 ? (k - ident_k0 == row ? 1.f : 0.f)
+      f[j] = k >= ident_k0 ? (((k - ident_k0) & (kH - 1)) == row ? 1.f : 0.f)
                            : ((row < n_rows && k < k_true) ? __ldg(w + static_cast<long long>(row) * ld + k) : 0.f);
     }
     uint4 v;
@@ -102,7 +111,8 @@ struct FwdSmem {
   static constexpr int kBars = kPar + 5 * kH * 4;
   static constexpr int kNumBars = 2 * NSLOT + 6;
   static constexpr int kTmemSlot = kBars + kNumBars * 8;
-  static constexpr int kTotal = kTmemSlot + 16;
+  static constexpr int kTiming = kTmemSlot + 16;  // 3 roles x 16 x int64 (debug)
+  static constexpr int kTotal = kTiming + 3 * 16 * 8;
   static constexpr int kAlloc = kTotal + 1024;  // slack for manual 1024-byte alignment
 };
 
@@ -127,7 +137,8 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
   const bool has_ln = p.gamma != nullptr;
 
   // ---------------- one-time setup ----------------
-  stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads, p.ld_w1, p.g_tab >= 0 ? p.g_tab * kH : (1 << 30));
+  stage_weight(sW1, p.w1, kH, p.k1_true, NP1, tid, kFwdThreads, p.ld_w1,
+               p.ident_k0 > 0 ? p.ident_k0 : (p.g_tab >= 0 ? p.g_tab * kH : (1 << 30)));
   if (!p.single) {
     stage_weight(sW2, p.w2, kH, kH, 2, tid, kFwdThreads);
     stage_weight(sW3, p.w3, p.n_out, kH, 2, tid, kFwdThreads);
@@ -162,6 +173,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
   bool timed_out = false;
+  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 5);
+  long long* tm = reinterpret_cast<long long*>(smem + L::kTiming) + (warp == 0 ? 0 : (warp == 1 ? 16 : 32));
+  if (tm_on) {
+    for (int i = 0; i < 16; ++i) tm[i] = 0;
+  }
+  long long tlast = clock64();
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
@@ -175,18 +192,21 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
         for (int b = 0; b < nt; ++b) {  // GEMM1 of both tiles
           const int i = j + b;
           timed_out |= !mbar_wait(&acc_free[b], ((i >> 1) & 1) ^ 1);
+          MGN_T(0);
           tc_fence_after_sync();
           const uint32_t d = tmem + b * 256;
 #pragma unroll
           for (int pnl = 0; pnl < NP1; ++pnl, ++cnt) {
             const uint32_t slot = cnt % NSLOT;
             timed_out |= !mbar_wait(&full[slot], (cnt / NSLOT) & 1);
+            MGN_T(1);
             tc_fence_after_sync();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_ss(d, umma_desc_kmajor(ring_addr + slot * kPanelBytes, k),
                       umma_desc_kmajor(w1_addr + pnl * kPanelBytes, k), idesc, (pnl | k) != 0);
             umma_commit(&empty[slot]);
+            MGN_T(2);
           }
           umma_commit(&acc_full[b]);
         }
@@ -197,12 +217,14 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
           for (int b = 0; b < nt; ++b) {
             timed_out |= !mbar_wait(&h_ready[b], ph_h[b]);
             ph_h[b] ^= 1;
+            MGN_T(3 + layer);
             tc_fence_after_sync();
             const uint32_t d = tmem + b * 256;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
               umma_ts(d, d + 128 + k * 8, umma_desc_kmajor(w_addr + (k >> 2) * kPanelBytes, k & 3), idesc, k != 0);
             umma_commit(&acc_full[b]);
+            MGN_T(5);
           }
         }
       }
@@ -225,7 +247,9 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
 #pragma unroll
       for (int pnl = 0; pnl < NP1; ++pnl, ++cnt) {
         const uint32_t slot = cnt % NSLOT;
+        MGN_T(1);
         timed_out |= !mbar_wait(&empty[slot], ((cnt / NSLOT) & 1) ^ 1);
+        MGN_T(0);
         const uint32_t sbase = ring_addr + slot * kPanelBytes;
         if (p.small_in > 0) {
           // raw features, zero padded to 64 columns (encoders)
@@ -347,8 +371,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
       // ---- hidden layers: bias + ReLU, write back to TMEM as packed bf16 (A operand of the next GEMM)
 #pragma unroll 1
       for (int layer = 0; layer < (p.single ? 0 : 2); ++layer) {
+        MGN_T(5);
         timed_out |= !mbar_wait(&acc_full[b], ph);
         ph ^= 1;
+        MGN_T(layer);
         tc_fence_after_sync();
         const float* bias = sPar + layer * kH;
         bf16* save = layer == 0 ? p.h1_save : p.h2_save;
@@ -374,10 +400,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
         tmem_st_wait();
         tc_fence_before_sync();
         mbar_arrive(&h_ready[b]);
+        MGN_T(2 + layer);
       }
       // ---- output layer: bias (+ LayerNorm + residual), store
+      MGN_T(5);
       timed_out |= !mbar_wait(&acc_full[b], ph);
       ph ^= 1;
+      MGN_T(4);
       tc_fence_after_sync();
       const float* b3 = sPar + 2 * kH;
       float mu = 0.f, rstd = 1.f;
@@ -406,6 +435,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
         }
         rstd = rsqrtf(qv * (1.f / kH) + p.eps);
       }
+      MGN_T(6);
       const float* gam = sPar + 3 * kH;
       const float* bet = sPar + 4 * kH;
 #pragma unroll 1
@@ -449,7 +479,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
       }
       tc_fence_before_sync();
       mbar_arrive(&acc_free[b]);
+      MGN_T(7);
     }
+  }
+  if (tm_on) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    for (int i = 0; i < 16; ++i) p.timing[role * 32 + i] = tm[i];
   }
 
   if (timed_out && p.status != nullptr) atomicOr(p.status, kStatusTimeout);
@@ -458,8 +493,12 @@ __global__ void __launch_bounds__(kFwdThreads, 1) mlp3_fwd_tc_kernel(const MlpFw
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+static long long* g_fwd_timing = nullptr;
+
 template <int NP1, int NSLOT>
-static int launch_fwd(const MlpFwdParams& p, cudaStream_t st) {
+static int launch_fwd(const MlpFwdParams& p_in, cudaStream_t st) {
+  MlpFwdParams p = p_in;
+  p.timing = g_fwd_timing;
   using L = FwdSmem<NP1, NSLOT>;
   static bool configured = false;
   if (!configured) {
@@ -561,11 +600,47 @@ extern "C" int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const 
                                  const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
                                  const float* gamma, const float* beta, int n_out, float eps, const void* residual,
                                  void* out, int64_t ld_out, int* status, mgn_stream_t stream) {
-  const GRows g1{static_cast<const bf16*>(g1_tab), g1_idx, g1_ld, g1_col0};
-  const GRows g2{static_cast<const bf16*>(g2_tab), g2_idx, g2_ld, g2_col0};
-  return mlp3_fwd_common(a_tab, a_idx, nullptr, nullptr, nullptr, nullptr, 1, nullptr, 0, 0, g1, g2, M, w1, ld_w1, b1,
-                         w2, b2, w3, b3, gamma, beta, n_out, eps, residual, out, ld_out, nullptr, nullptr, status,
-                         stream);
+  // The additive rows ride through GEMM1 as extra K panels against identity blocks:
+  //   z1 = [A | g1 rows | g2 rows] [W1 | I | I]^T
+  // so every operand row is fetched by cp.async (L1-bypassing, fully asynchronous gathers); products with the
+  // identity are exact in bf16 x bf16 -> fp32.
+  MGN_CHECK_ARG(M >= 0 && a_tab && w1 && w2 && w3 && n_out >= 1 && n_out <= kH && ld_out >= n_out && ld_w1 >= kH);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(out != nullptr && (g1_tab != nullptr || g2_tab == nullptr));
+  MlpFwdParams p{};
+  const void* tabs[3] = {a_tab, g1_tab, g2_tab};
+  const int32_t* idxs[3] = {a_idx, g1_idx, g2_idx};
+  const int64_t lds[3] = {kH, g1_ld, g2_ld};
+  const int64_t cols[3] = {0, g1_col0, g2_col0};
+  int n_tab = 0;
+  for (int k = 0; k < 3; ++k) {
+    p.tab[k] = static_cast<const bf16*>(tabs[k]);
+    p.idx[k] = idxs[k];
+    p.tab_ld[k] = lds[k];
+    p.tab_col0[k] = cols[k];
+    if (tabs[k] != nullptr) {
+      MGN_CHECK_ARG(lds[k] % 8 == 0 && cols[k] % 8 == 0 && (reinterpret_cast<uintptr_t>(tabs[k]) & 15) == 0);
+      n_tab = k + 1;
+    }
+  }
+  p.g_tab = -1;
+  p.ident_k0 = kH;  // W1' columns >= 128 are identity blocks
+  p.single = 0;
+  p.M = M;
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
+  p.gamma = gamma; p.beta = beta;
+  p.k1_true = kH;
+  p.ld_w1 = ld_w1;
+  p.n_out = n_out;
+  p.eps = eps;
+  p.residual = static_cast<const bf16*>(residual);
+  p.out = static_cast<bf16*>(out);
+  p.ld_out = ld_out;
+  p.status = status;
+  cudaStream_t st = as_stream(stream);
+  if (n_tab == 1) return launch_fwd<2, 4>(p, st);
+  if (n_tab == 2) return launch_fwd<4, 4>(p, st);
+  return launch_fwd<6, 3>(p, st);
 }
 
 // out[M,128] = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual): one GEMM through the same pipeline
@@ -603,4 +678,10 @@ extern "C" int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_
   if (n_tab == 1) return launch_fwd<2, 4>(p, st);
   if (n_tab == 2) return launch_fwd<4, 4>(p, st);
   return launch_fwd<6, 3>(p, st);
+}
+
+/* debug hook: see mgn_debug_set_bwd_timing */
+extern "C" int mgn_debug_set_fwd_timing(void* dev_buf) {
+  g_fwd_timing = static_cast<long long*>(dev_buf);
+  return MGN_OK;
 }

@@ -123,7 +123,7 @@ def _ref_trick(A, P, src, dst, p, dtype=torch.float64, round_hidden=False):
     """z1 = A W1e^T + P[src][:, :128] + P[dst][:, 128:256] + b1, then the rest of the MLP + LN + residual A."""
     c = lambda t: t.to(dtype)
     w1e = c(bf(p["w1"][:, :128]))
-    Gs = c(bf(P[src][:, :128] + P[dst][:, 128:256]))  # the kernel rounds the gathered sum to bf16
+    Gs = c(P[src][:, :128]) + c(P[dst][:, 128:256])  # bf16 rows, summed in fp32 by the kernel
     z1 = c(A) @ w1e.T + Gs + c(p["b1"])
     h1 = F.relu(z1)
     if round_hidden:
@@ -162,10 +162,11 @@ def test_mlp3_bwd_tc_edge_form(M):
               for k, v in p.items()}
     A64 = A.double().requires_grad_(True)
     w1e = leaves["w1"][:, :128]
-    Gs = bf(P[src][:, :128] + P[dst][:, 128:256]).double().requires_grad_(True)
+    Gs = (P[src][:, :128].double() + P[dst][:, 128:256].double()).requires_grad_(True)
     z1 = A64 @ w1e.T + Gs + leaves["b1"]
     h1 = st_round(F.relu(z1))  # the kernel keeps hidden activations in bf16 (ReLU masks follow them)
-    h2 = st_round(F.relu(h1 @ leaves["w2"].T + leaves["b2"]))
+    z2 = h1 @ leaves["w2"].T + leaves["b2"]
+    h2 = st_round(F.relu(z2))
     y = h2 @ leaves["w3"].T + leaves["b3"]
     out = F.layer_norm(y, (128,), leaves["gamma"], leaves["beta"], 1e-5) + A64
     gout = bf(go1 + go2[dst]).double()
@@ -183,11 +184,14 @@ def test_mlp3_bwd_tc_edge_form(M):
     ops.tc_check(DEV)
     tol = 2e-2
 
+    # a ReLU pre-activation within rounding distance of zero may flip its mask between the fp32-accumulating
+    # kernel and the fp64 reference: rows without such an element must match, of the others at most 5% may differ
+    amb = (z1.detach().abs().min(dim=1).values < 2e-3) | (z2.detach().abs().min(dim=1).values < 2e-3)
+
     def rows_ok(got, ref):
-        # a ReLU pre-activation within rounding distance of zero may flip its mask between the fp32-accumulating
-        # kernel and the fp64 reference: allow a 1e-3 fraction of such rows, everything else must match
         err = (got.double().cpu() - ref).abs().max(dim=1).values / ref.abs().max()
-        return float((err > tol).double().mean()) <= 1e-3
+        bad = err > tol
+        return not bool((bad & ~amb).any()) and float((bad & amb).double().sum()) <= max(1.0, 0.05 * float(amb.sum()))
 
     assert rows_ok(g_a.float(), A64.grad)
     assert rows_ok(g_z1.float(), Gs.grad)

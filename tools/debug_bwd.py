@@ -12,7 +12,7 @@ def run(M, use_go2=True, add_gout=True):
               for k, v in p.items()}
     A64 = A.double().requires_grad_(True)
     w1e = leaves["w1"][:, :128]
-    Gs = bf(P[src][:, :128] + P[dst][:, 128:256]).double().requires_grad_(True)
+    Gs = (P[src][:, :128].double() + P[dst][:, 128:256].double()).requires_grad_(True)
     z1 = A64 @ w1e.T + Gs + leaves["b1"]
     h1 = st_round(F.relu(z1)); h1.retain_grad()
     z2 = h1 @ leaves["w2"].T + leaves["b2"]

@@ -59,8 +59,21 @@ t = tbuf.cpu().view(3, 32)
 n_tiles = (E + 127) // 128
 per_cta = -(-n_tiles // 148)
 names = {0: "MMA  : wAG+E6 | g1 | wE1 | g2 | wE2 | g3 | wE3 | g4 | wE4 | g5 | wE5 | wA2 | g6",
-         1: "MOVER: stageAG | wE1 | stageGO | csX | wE3 | csA | wMMA4 | stageA2 | wE4 | csH2 | wE5 | csH1+st | wE6 | stGA",
+         1: "MOVER [14]=issueA [15]=idx+issue g1 [3]=idx+issue g2 [0]=wait: stageAG | wE1 | stageGO | csX | wE3 | csA | wMMA4 | stageA2 | wE4 | csH2 | wE5 | csH1+st | wE6 | stGA",
          2: "EPI  : wMMA1 | E1 | wMMA2 | E2 | wMMA3 | wGO | E3 | wMMA4 | E4 | wMMA5 | E5 | wMMA6 | E6"}
 for r in range(3):
     print(names[r])
-    print("   cycles/tile:", [int(v) // per_cta for v in t[r, :14].tolist()], " total/tile:", int(t[r].sum()) // per_cta)
+    print("   cycles/tile:", [int(v) // per_cta for v in t[r, :16].tolist()], " total/tile:", int(t[r].sum()) // per_cta)
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd_timing", tbuf.data_ptr())
+fwd(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd_timing", None)
+t = tbuf.cpu().view(3, 32)
+print("FWD kernel, CTA 0, cycles per tile")
+print(" MMA   : wait acc_free | wait full (sum) | issue GEMM1 | wait h_ready L2 | wait h_ready L3 | issue L2/L3")
+print("   ", [int(v) // per_cta for v in t[0, :6].tolist()], "total", int(t[0].sum()) // per_cta)
+print(" LOADER: wait empty (sum) | issue+publish (sum)")
+print("   ", [int(v) // per_cta for v in t[1, :2].tolist()], "total", int(t[1].sum()) // per_cta)
+print(" EPI(one of two groups; per its tile): wait L1 | wait L2 | epi L1 | epi L2 | wait out | (gap) | LN stats | store")
+print("   ", [int(v) // max(per_cta // 2, 1) for v in t[2, :8].tolist()], "total", int(t[2].sum()) // max(per_cta // 2, 1))
