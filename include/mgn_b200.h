@@ -181,6 +181,22 @@ int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const void* g1_ta
                       const float* gamma, const float* beta, int n_out, float eps, const void* residual,
                       void* out, int64_t ld_out, int* status, mgn_stream_t stream);
 
+/* Second-generation fused forward (same maths as mgn_mlp3_fwd_tc_g; all operand rows staged by cp.async, output
+ * tile leaves through coalesced stores, next tile prefetched while the current one computes):
+ *     z1  = A W1^T + b1 + g1_tab[g1_idx[r]] + g2_tab[g2_idx[r]]     (A = a_tab[a_idx[r]] or raw small_x)
+ *     out = [LayerNorm]( W3 relu(W2 relu(z1) + b2) + b3 ) + residual
+ * residual: res_is_a != 0 -> the A rows themselves (MeshEdgeBlock: efeat' = mlp(...) + efeat,
+ * mesh_edge_block.py:95); res_tab != NULL -> rows of another [M,128] table (MeshNodeBlock: + nfeat,
+ * mesh_node_block.py:91; excludes g2_tab). */
+int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+                     int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
+                     int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
+                     int64_t g2_col0, const void* res_tab, int res_is_a, int64_t M, const float* w1,
+                     int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                     const float* b3, const float* gamma, const float* beta, int n_out, float eps, void* out,
+                     int64_t ld_out, int* status, mgn_stream_t stream);
+int mgn_debug_set_fwd2_timing(void* dev_buf);
+
 /* Fused MeshGraphMLP backward over 128-row tiles (forward hiddens are recomputed, nothing but the
  * layer inputs is read back):
  *     z1 = A W1^T + G + b1,  A = a_tab[a_idx[r]] (or raw small_x),  G = g1_tab[g1_idx[r]] (+ g2_tab[g2_idx[r]])
@@ -215,6 +231,10 @@ int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x
 int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_t ld1, const void* x2, int64_t ld2,
                   int n_tab, int64_t M, const float* w, int64_t ld_w, const float* bias,
                   const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
+/* out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); second-generation
+ * pipeline (cp.async staging, coalesced stores).  Wider products are issued per 128-column block. */
+int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,
+                     const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
 size_t mgn_wgrad_tc_workspace_bytes(int64_t M, int n_blocks);
 int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const void* x, int64_t ld_x, int64_t M,
                  float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, int* status,

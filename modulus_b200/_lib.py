@@ -123,6 +123,16 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
             return "tensor", 16.0 * 128 * 128 * M  # node block
         k1 = small_in if small_in > 0 else 128
         return "tensor", 4.0 * M * (k1 * 128 + 2 * 128 * 128)
+    if name == "mgn_mlp3_fwd2_tc":
+        small_in, g1, g2, M = a[3], a[5], a[9], a[15]
+        if g2:
+            return "tensor", 10.0 * 128 * 128 * M
+        if g1:
+            return "tensor", 8.0 * 128 * 128 * M
+        k1 = small_in if small_in > 0 else 128
+        return "tensor", 2.0 * M * (k1 * 128 + 2 * 128 * 128)
+    if name == "mgn_linear128_tc":
+        return "tensor", 2.0 * a[2] * 128 * 128
     if name == "mgn_linear_tc":
         n_tab, M = a[6], a[7]
         return "tensor", 2.0 * M * 128 * 128 * n_tab

@@ -1,0 +1,559 @@
+// mgn_mlp_fwd2_tc.cu — fused MeshGraphMLP forward, second generation (tcgen05 / TMEM, bf16, hidden 128, ReLU).
+//
+//     z1  = A W1^T + b1 + G1[r] + G2[r]        A: 128-row tile of layer-input rows, G*: additive gathered rows
+//     h1  = relu(z1) ; h2 = relu(h1 W2^T + b2) ; y = h2 W3^T + b3
+//     out = [LayerNorm(y) * gamma + beta] [+ residual]
+//
+// = MeshEdgeBlock.forward / MeshNodeBlock.forward / encoder+decoder MeshGraphMLP of the reference
+// (physicsnemo/models/gnn_layers/mesh_edge_block.py:88-96, mesh_node_block.py:82-92, mesh_graph_mlp.py:142-203)
+// with the first Linear split per input block (see modulus_b200/fused.py).
+//
+// Data movement rules learnt from the first-generation kernel (profiles/r01_*):
+//   * every global->shared byte moves by cp.async (16-byte, L1-bypassing): with > 200 KB of shared memory the L1
+//     is a few KB and LDG-based staging collapses to a handful of lines in flight;
+//   * row indices are fetched one tile ahead (the L1TEX queue returns loads in order behind the gathers);
+//   * epilogue threads (thread = row = TMEM lane) touch TMEM and shared memory only; the output tile is written
+//     in place over the A tile (the residual is read from shared memory, never re-fetched) and leaves the SM
+//     through coalesced 16-byte stores issued by the mover warps;
+//   * hidden activations go back to TMEM as packed bf16 and feed the next GEMM as the A operand.
+//
+// Warp roles (416 threads): warp 0 = MMA issuer + TMEM owner, warps 1-4 = movers, warps 5-12 = epilogue
+// (two warps per TMEM lane quarter, 64 columns each; LayerNorm row sums are exchanged through spare TMEM columns).
+// Shared memory: W1, W2, W3 (96 KB, converted fp32 -> bf16 once per CTA from the optimizer's tensors),
+// two A buffers (the next tile's rows stream in while the current tile computes), one G1 and one G2 buffer.
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+#include "mgn_tile.cuh"
+
+namespace mgn {
+namespace fwd2 {
+
+using namespace tile;
+constexpr int kThreads = 416;
+constexpr int kH = 128;
+
+struct Params {
+  RowSrc a;             // layer-1 input rows [*,128]                      (KP == 2)
+  const void* small_x;  // raw [M, small_in] features zero-padded to K=64   (KP == 1)
+  int small_in;
+  int small_is_f32;
+  RowSrc g1, g2;        // additive rows of layer 1 (tab == nullptr: absent)
+  RowSrc res;           // residual rows [*,128] (tab == nullptr: none); res_is_a: the A rows themselves
+  int res_is_a;
+  int single;           // 1: out = A W1^T + b3 (+ residual): one GEMM (node-level projections)
+  long long M;
+  const float *w1, *b1, *w2, *b2, *w3, *b3, *gamma, *beta;
+  long long ld_w1;
+  int k1_true;
+  int n_out;
+  float eps;
+  bf16* out;
+  long long ld_out;
+  int* status;
+  long long* timing;
+};
+
+enum { B_IN = 0, B_M1 = 1, B_M2 = 2, B_M3 = 3, B_H1 = 4, B_H2 = 5, B_OUT = 6, B_NUM = 7 };
+
+template <int KP>
+struct Smem {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = KP * kPB;
+  static constexpr int kW3 = kW2 + 2 * kPB;
+  static constexpr int kA = kW3 + 2 * kPB;   // 2 buffers x 2 panels
+  static constexpr int kG1 = kA + 4 * kPB;
+  static constexpr int kG2 = kG1 + 2 * kPB;
+  static constexpr int kPar = kG2 + 2 * kPB;  // b1, b2, b3, gamma, beta
+  static constexpr int kBars = kPar + 5 * kH * 4;
+  static constexpr int kTmemSlot = kBars + 8 * 8;
+  static constexpr int kTiming = kTmemSlot + 16;  // 3 roles x 8 x int64
+  static constexpr int kTotal = kTiming + 3 * 8 * 8;
+};
+
+#define MGN_T(i)                      \
+  if (tm_on) {                        \
+    const long long t_ = clock64();   \
+    tm[i] += t_ - tlast;              \
+    tlast = t_;                       \
+  }
+
+template <int KP>
+__global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params p) {
+  using L = Smem<KP>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0 && p.status) atomicOr(p.status, 2);
+    return;
+  }
+  uint8_t* sW1 = smem + L::kW1;
+  uint8_t* sW2 = smem + L::kW2;
+  uint8_t* sW3 = smem + L::kW3;
+  uint8_t* bA0 = smem + L::kA;
+  uint8_t* bG1 = smem + L::kG1;
+  uint8_t* bG2 = smem + L::kG2;
+  float* sPar = reinterpret_cast<float*>(smem + L::kPar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+
+  const bool has_ln = p.gamma != nullptr;
+  const bool has_g1 = p.g1.tab != nullptr;
+  const bool has_g2 = p.g2.tab != nullptr;
+  const bool res_g2 = p.res.tab != nullptr && !p.res_is_a;  // residual rows travel in the G2 buffer
+  const bool direct_out = p.n_out < kH;                      // narrow outputs (decoder) are stored by the epilogue
+
+  // ---------------- one-time setup ----------------
+  stage_weight_ld(sW1, p.w1, p.ld_w1, kH, p.k1_true, KP, tid, kThreads);
+  if (!p.single) {
+    stage_weight_ld(sW2, p.w2, kH, kH, kH, 2, tid, kThreads);
+    stage_weight_ld(sW3, p.w3, kH, p.n_out, kH, 2, tid, kThreads);
+  }
+  for (int i = tid; i < kH; i += kThreads) {
+    sPar[i] = p.b1 ? p.b1[i] : 0.f;
+    sPar[kH + i] = p.b2 ? p.b2[i] : 0.f;
+    sPar[2 * kH + i] = (p.b3 && i < p.n_out) ? p.b3[i] : 0.f;
+    sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
+    sPar[4 * kH + i] = (has_ln && p.beta) ? p.beta[i] : 0.f;
+  }
+  if (tid == 0) {
+    mbar_init(&bars[B_IN], 4);
+    mbar_init(&bars[B_M1], 1);
+    mbar_init(&bars[B_M2], 1);
+    mbar_init(&bars[B_M3], 1);
+    mbar_init(&bars[B_H1], 8);
+    mbar_init(&bars[B_H2], 8);
+    mbar_init(&bars[B_OUT], 8);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tAcc = tmem, tH = tmem + 128, tX = tmem + 192;
+
+  const long long n_tiles = (p.M + kRows - 1) / kRows;
+  const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  bool timed_out = false;
+  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 5);
+  long long* tm = reinterpret_cast<long long*>(smem + L::kTiming) + (warp == 0 ? 0 : (warp == 1 ? 8 : 16));
+  if (tm_on) {
+    for (int i = 0; i < 8; ++i) tm[i] = 0;
+  }
+  long long tlast = clock64();
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t aA0 = smem_u32(bA0);
+      const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = it & 1;
+        const uint32_t aA = aA0 + (it & 1) * 2 * kPB;
+#define MGN_W(b, ph)             \
+  if (!wait_clk(&bars[b], ph)) { \
+    timed_out = true;            \
+    break;                       \
+  }
+        MGN_W(B_IN, par);
+        if (it > 0) MGN_W(B_OUT, par ^ 1);  // previous tile's epilogue has drained the accumulator
+        MGN_T(0);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < KP * 4; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3), idesc,
+                  k != 0);
+        umma_commit(&bars[B_M1]);
+        MGN_T(1);
+        if (p.single) continue;
+        MGN_W(B_H1, par);
+        MGN_T(2);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tAcc, tH + k * 8, umma_desc_kmajor(aW2 + (k >> 2) * kPB, k & 3), idesc, k != 0);
+        umma_commit(&bars[B_M2]);
+        MGN_W(B_H2, par);
+        MGN_T(3);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ts(tAcc, tH + k * 8, umma_desc_kmajor(aW3 + (k >> 2) * kPB, k & 3), idesc, k != 0);
+        umma_commit(&bars[B_M3]);
+        MGN_T(4);
+#undef MGN_W
+      }
+    }
+  } else if (warp <= 4) {
+    // =========================== movers ===========================
+    const int mt = tid - 32;
+    const int rsub_m = mt >> 4;
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_MOVER_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
+    int32_t r_a[16], r_g1[16], r_g2[16];
+    const RowSrc& g2src = res_g2 ? p.res : p.g2;
+    const bool use_g2buf = has_g2 || res_g2;
+    const long long stride = static_cast<long long>(gridDim.x) * kRows;
+    long long row0 = static_cast<long long>(blockIdx.x) * kRows;
+    // prologue: tile 0
+    if (n_my > 0) {
+      if (KP == 2) {
+        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_a);
+        stage_rows_async(bA0, p.a, r_a, row0, p.M, mt);
+      } else {
+        stage_small(bA0, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+      }
+      if (has_g1) {
+        fetch_row_ids(p.g1.idx, row0, p.M, rsub_m, r_g1);
+        stage_rows_async(bG1, p.g1, r_g1, row0, p.M, mt);
+      }
+      if (use_g2buf) {
+        fetch_row_ids(g2src.idx, row0, p.M, rsub_m, r_g2);
+        stage_rows_async(bG2, g2src, r_g2, row0, p.M, mt);
+      }
+      cp_async_commit();
+      if (n_my > 1) {  // row ids of tile 1
+        if (KP == 2) fetch_row_ids(p.a.idx, row0 + stride, p.M, rsub_m, r_a);
+        if (has_g1) fetch_row_ids(p.g1.idx, row0 + stride, p.M, rsub_m, r_g1);
+        if (use_g2buf) fetch_row_ids(g2src.idx, row0 + stride, p.M, rsub_m, r_g2);
+      }
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_IN]);
+    }
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      const bool more = it + 1 < n_my;
+      const long long row1 = row0 + stride;  // next tile of this CTA
+      uint8_t* bAcur = bA0 + (it & 1) * 2 * kPB;
+      uint8_t* bAnext = bA0 + ((it + 1) & 1) * 2 * kPB;
+      // next tile's A rows stream into the other A buffer right away (its previous output was stored last iteration)
+      if (more) {
+        if (KP == 2) stage_rows_async(bAnext, p.a, r_a, row1, p.M, mt);
+        else stage_small(bAnext, p.small_x, p.small_in, p.small_is_f32, row1, p.M, mt);
+      }
+      MGN_T(0);
+      // the additive-row buffers are free once the layer-1 epilogue has consumed them
+      if (!p.single) MGN_W(B_H1, par);
+      MGN_T(1);
+      if (more && has_g1) stage_rows_async(bG1, p.g1, r_g1, row1, p.M, mt);
+      if (more && use_g2buf && !res_g2) stage_rows_async(bG2, g2src, r_g2, row1, p.M, mt);
+      // (single-GEMM mode has no layer-1 epilogue to order against: publishing early could run two barrier phases
+      //  ahead of a waiter, which a parity wait cannot distinguish)
+      const bool late_publish = res_g2 || p.single;
+      if (more && !late_publish) {  // next tile is complete: publish it now, long before this tile's output is due
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_IN]);
+      }
+      // output tile (written in place over the A tile) -> global, coalesced
+      MGN_W(B_OUT, par);
+      MGN_T(2);
+      if (more && late_publish) {  // the residual rows in bG2 were needed until now
+        if (res_g2) stage_rows_async(bG2, g2src, r_g2, row1, p.M, mt);
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_IN]);
+      }
+      if (!direct_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
+      if (more && it + 2 < n_my) {  // row ids two tiles ahead of the running one
+        if (KP == 2) fetch_row_ids(p.a.idx, row1 + stride, p.M, rsub_m, r_a);
+        if (has_g1) fetch_row_ids(p.g1.idx, row1 + stride, p.M, rsub_m, r_g1);
+        if (use_g2buf) fetch_row_ids(g2src.idx, row1 + stride, p.M, rsub_m, r_g2);
+      }
+      MGN_T(3);
+      MGN_MOVER_SYNC();  // all movers have finished reading bAcur before it is refilled (tile it + 2)
+      MGN_T(4);
+      row0 = row1;
+    }
+#undef MGN_W
+  } else {
+    // =========================== epilogue (8 warps) ===========================
+    const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = ch * 64;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t t_acc = tAcc + lane_off + c0;
+    const uint32_t t_h = tH + lane_off + ch * 32;
+    const uint32_t t_x = tX + lane_off;
+    const float* b1 = sPar + c0;
+    const float* b2 = sPar + kH + c0;
+    const float* b3 = sPar + 2 * kH + c0;
+    const float* gam = sPar + 3 * kH + c0;
+    const float* bet = sPar + 4 * kH + c0;
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_EPI_SYNC()                               \
+  tc_fence_before_sync();                            \
+  asm volatile("bar.sync 2, 256;" ::: "memory");     \
+  tc_fence_after_sync()
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      uint8_t* bAcur = bA0 + (it & 1) * 2 * kPB;
+      const long long grow = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows + row;
+      // ---- E1: h1 = relu(acc + b1 + G1 + G2) -> TMEM (packed bf16)
+      MGN_W(B_M1, par);
+      MGN_W(B_IN, par);
+      MGN_T(0);
+      tc_fence_after_sync();
+      if (!p.single) {
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        float f[16], f2[16];
+        if (has_g1) row_load16(bG1, row, c0 + g * 16, f);
+        if (has_g2) row_load16(bG2, row, c0 + g * 16, f2);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float z0 = __uint_as_float(v[2 * j]) + b1[g * 16 + 2 * j];
+          float z1 = __uint_as_float(v[2 * j + 1]) + b1[g * 16 + 2 * j + 1];
+          if (has_g1) {
+            z0 += f[2 * j];
+            z1 += f[2 * j + 1];
+          }
+          if (has_g2) {
+            z0 += f2[2 * j];
+            z1 += f2[2 * j + 1];
+          }
+          pk[j] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+        }
+        tmem_st8(t_h + g * 8, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_H1]);
+      MGN_T(1);
+      // ---- E2: h2 = relu(acc + b2) -> TMEM
+      MGN_W(B_M2, par);
+      MGN_T(2);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[g * 16 + 2 * j], 0.f),
+                              fmaxf(__uint_as_float(v[2 * j + 1]) + b2[g * 16 + 2 * j + 1], 0.f));
+        tmem_st8(t_h + g * 8, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_H2]);
+      MGN_T(3);
+      // ---- E3: y = acc + b3 ; LayerNorm ; + residual ; -> output tile (in place over the A tile) or global
+      MGN_W(B_M3, par);
+      }  // !single
+      MGN_T(4);
+      tc_fence_after_sync();
+      float mu = 0.f, rstd = 1.f;
+      if (has_ln) {
+        float s = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) s += __uint_as_float(v[j]) + b3[g * 16 + j];
+        }
+        // exchange the partial row sums of the two column halves through spare TMEM columns
+        tmem_st2(t_x + ch * 2, __float_as_uint(s), 0u);
+        tmem_st_wait();
+        MGN_EPI_SYNC();
+        uint32_t o0, o1;
+        tmem_ld2(t_x + (ch ^ 1) * 2, o0, o1);
+        tmem_ld_wait();
+        mu = (s + __uint_as_float(o0)) * (1.f / kH);
+        float qv = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          uint32_t v[16];
+          tmem_ld16(t_acc + g * 16, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d = __uint_as_float(v[j]) + b3[g * 16 + j] - mu;
+            qv = fmaf(d, d, qv);
+          }
+        }
+        MGN_EPI_SYNC();  // partner has read the first exchange
+        tmem_st2(t_x + ch * 2, __float_as_uint(qv), 0u);
+        tmem_st_wait();
+        MGN_EPI_SYNC();
+        tmem_ld2(t_x + (ch ^ 1) * 2, o0, o1);
+        tmem_ld_wait();
+        rstd = rsqrtf((qv + __uint_as_float(o0)) * (1.f / kH) + p.eps);
+      }
+      const uint8_t* rbuf = p.res_is_a ? bAcur : bG2;
+      const bool has_res = p.res.tab != nullptr || p.res_is_a;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t v[16];
+        tmem_ld16(t_acc + g * 16, v);
+        float r[16];
+        if (has_res) row_load16(rbuf, row, c0 + g * 16, r);
+        tmem_ld_wait();
+        float y[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float x = __uint_as_float(v[j]) + b3[g * 16 + j];
+          y[j] = has_ln ? ((x - mu) * rstd * gam[g * 16 + j] + bet[g * 16 + j]) : x;
+          if (has_res) y[j] += r[j];
+        }
+        if (!direct_out) {
+          row_store16(bAcur, row, c0 + g * 16, y);
+        } else if (grow < p.M) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (c0 + g * 16 + j < p.n_out) p.out[grow * p.ld_out + c0 + g * 16 + j] = __float2bfloat16_rn(y[j]);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_OUT]);
+      MGN_T(5);
+    }
+#undef MGN_W
+  }
+  if (tm_on) {
+    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    for (int i = 0; i < 8; ++i) p.timing[role * 32 + i] = tm[i];
+  }
+  if (timed_out && p.status != nullptr) atomicOr(p.status, 1);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static long long* g_timing = nullptr;
+
+template <int KP>
+static int launch(Params& p, cudaStream_t st) {
+  using L = Smem<KP>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(mlp3_fwd2_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const long long n_tiles = (p.M + kRows - 1) / kRows;
+  const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+  p.timing = g_timing;
+  mlp3_fwd2_tc_kernel<KP><<<grid, kThreads, L::kTotal, MGN_ST(st)>>>(p);
+  return mgn_launch_status();
+}
+
+}  // namespace fwd2
+}  // namespace mgn
+
+using namespace mgn;
+
+extern "C" int mgn_debug_set_fwd2_timing(void* dev_buf) {
+  fwd2::g_timing = static_cast<long long*>(dev_buf);
+  return MGN_OK;
+}
+
+extern "C" int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+                                int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
+                                int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
+                                int64_t g2_col0, const void* res_tab, int res_is_a, int64_t M, const float* w1,
+                                int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                                const float* b3, const float* gamma, const float* beta, int n_out, float eps, void* out,
+                                int64_t ld_out, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= fwd2::kH && ld_out >= n_out);
+  MGN_CHECK_ARG(gamma == nullptr || n_out == fwd2::kH);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(out != nullptr);
+  fwd2::Params p{};
+  p.a = tile::RowSrc{static_cast<const bf16*>(a_tab), a_idx, fwd2::kH, 0};
+  p.small_x = small_x;
+  p.small_in = small_in;
+  p.small_is_f32 = small_is_f32;
+  p.g1 = tile::RowSrc{static_cast<const bf16*>(g1_tab), g1_idx, g1_ld, g1_col0};
+  p.g2 = tile::RowSrc{static_cast<const bf16*>(g2_tab), g2_idx, g2_ld, g2_col0};
+  p.res = tile::RowSrc{static_cast<const bf16*>(res_tab), nullptr, fwd2::kH, 0};
+  p.res_is_a = res_is_a;
+  p.single = 0;
+  if (g1_tab) MGN_CHECK_ARG(g1_ld % 8 == 0 && g1_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g1_tab) & 15) == 0);
+  if (g2_tab) MGN_CHECK_ARG(g1_tab && g2_ld % 8 == 0 && g2_col0 % 8 == 0 && (reinterpret_cast<uintptr_t>(g2_tab) & 15) == 0);
+  // the residual either is the A tile itself or rides in the (then unused) second additive-row buffer
+  MGN_CHECK_ARG(!(res_is_a && (small_in > 0 || res_tab != nullptr)));
+  MGN_CHECK_ARG(!(res_tab != nullptr && g2_tab != nullptr));
+  if (res_tab) MGN_CHECK_ARG((reinterpret_cast<uintptr_t>(res_tab) & 15) == 0 && n_out == fwd2::kH);
+  if (n_out == fwd2::kH) MGN_CHECK_ARG(ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  p.M = M;
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.gamma = gamma; p.beta = beta;
+  p.ld_w1 = ld_w1;
+  p.n_out = n_out;
+  p.eps = eps;
+  p.out = static_cast<bf16*>(out);
+  p.ld_out = ld_out;
+  p.status = status;
+  cudaStream_t st = as_stream(stream);
+  if (small_in > 0) {
+    MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && ld_w1 >= small_in && g1_tab == nullptr);
+    p.k1_true = small_in;
+    return fwd2::launch<1>(p, st);
+  }
+  MGN_CHECK_ARG(a_tab != nullptr && ld_w1 >= fwd2::kH && (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0);
+  p.k1_true = fwd2::kH;
+  return fwd2::launch<2>(p, st);
+}
+
+// out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); W [128, >=128] fp32
+// with row stride ld_w.  Node-level projections of the fused path (P = nfeat Wp^T, g_nfeat += T Wp).
+extern "C" int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,
+                                const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(M >= 0 && w && ld_w >= fwd2::kH && ld_x >= fwd2::kH && ld_out >= fwd2::kH);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(x && out && ld_x % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  if (residual) MGN_CHECK_ARG((reinterpret_cast<uintptr_t>(residual) & 15) == 0);
+  fwd2::Params p{};
+  p.a = tile::RowSrc{static_cast<const bf16*>(x), nullptr, ld_x, 0};
+  p.res = tile::RowSrc{static_cast<const bf16*>(residual), nullptr, fwd2::kH, 0};
+  p.res_is_a = 0;
+  p.single = 1;
+  p.M = M;
+  p.w1 = w;
+  p.ld_w1 = ld_w;
+  p.k1_true = fwd2::kH;
+  // W2 / W3 are not used by the single-GEMM mode; the staging code still reads 128x128 floats from them
+  p.w2 = w;
+  p.w3 = w;
+  p.b3 = bias;
+  p.n_out = fwd2::kH;
+  p.out = static_cast<bf16*>(out);
+  p.ld_out = ld_out;
+  p.status = status;
+  return fwd2::launch<2>(p, as_stream(stream));
+}

@@ -71,11 +71,11 @@ class FusedProcessorFn(torch.autograd.Function):
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
             P = _node_linear(nfeat, wp)  # [N, 3H]
-            efeat_new = ops.mlp3_fwd_tc_g(efeat, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2], ew[3],
-                                          ew[4], ew[5], ew[6], ew[7], eps=eps, residual=efeat)
+            efeat_new = ops.mlp3_fwd2_tc(efeat, None, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2], ew[3],
+                                         ew[4], ew[5], ew[6], ew[7], eps=eps, res_is_a=True)
             agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
-            nfeat_new = ops.mlp3_fwd_tc_g(agg, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
-                                          nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
+            nfeat_new = ops.mlp3_fwd2_tc(agg, None, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
+                                         nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
             saved += [efeat, nfeat, agg, P]
             efeat, nfeat = efeat_new, nfeat_new
         ctx.plan, ctx.L, ctx.eps = plan, L, eps
@@ -188,10 +188,12 @@ class FusedMLPFn(torch.autograd.Function):
             x = x.contiguous()
             if x.dtype not in (torch.float32, BF16):
                 x = x.float()
-            out, _, _ = ops.mlp3_fwd_tc([], [], M, w1, b1, w2, b2, w3, b3, gamma, beta, eps=eps, n_out=n_out, small_x=x)
+            out = ops.mlp3_fwd2_tc(None, None, x, None, None, 0, None, None, 0, M, w1, b1, w2, b2, w3, b3, gamma, beta,
+                                   eps=eps, n_out=n_out)
         else:
             x = x.contiguous().to(BF16)
-            out, _, _ = ops.mlp3_fwd_tc([x], [None], M, w1, b1, w2, b2, w3, b3, gamma, beta, eps=eps, n_out=n_out)
+            out = ops.mlp3_fwd2_tc(x, None, None, None, None, 0, None, None, 0, M, w1, b1, w2, b2, w3, b3, gamma, beta,
+                                   eps=eps, n_out=n_out)
         ctx.save_for_backward(x, *params)
         ctx.eps, ctx.small = eps, small
         return out

@@ -476,6 +476,26 @@ def mlp3_fwd_tc_g(a: Tensor, a_idx: Optional[Tensor], g1: Optional[Tensor], g1_i
     return out
 
 
+def mlp3_fwd2_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
+                 g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
+                 g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int, M: int,
+                 w1: Tensor, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
+                 residual: Optional[Tensor] = None, res_is_a: bool = False, n_out: int = TC_HIDDEN,
+                 out: Optional[Tensor] = None) -> Tensor:
+    """Second-generation fused forward (include/mgn_b200.h: mgn_mlp3_fwd2_tc)."""
+    dev = (small_x if small_x is not None else a).device
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
+    small_in = 0 if small_x is None else small_x.shape[1]
+    small_f32 = int(small_x is not None and small_x.dtype == torch.float32)
+    call("mgn_mlp3_fwd2_tc", _p(a), _p(a_idx), _p(small_x), small_in, small_f32,
+         _p(g1), _p(g1_idx), 0 if g1 is None else g1.stride(0), g1_col0,
+         _p(g2), _p(g2_idx), 0 if g2 is None else g2.stride(0), g2_col0,
+         _p(residual), int(res_is_a), M, _p(w1), w1.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
+         _p(gamma), _p(beta), n_out, eps, _p(out), out.stride(0), _p(tc_status(dev)), _stream())
+    return out
+
+
 def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
                 g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
                 g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int,
@@ -521,15 +541,19 @@ def linear_tc(x: Tensor, w: Tensor, out: Optional[Tensor] = None, residual: Opti
         x = x.contiguous()
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.bfloat16, device=x.device)
-    n_tab = K // TC_HIDDEN
-    xs = [x[:, TC_HIDDEN * k: TC_HIDDEN * (k + 1)] for k in range(n_tab)] + [None] * (3 - n_tab)
     st = tc_status(x.device)
+    kb = K // TC_HIDDEN
+    res = None if residual is None else _c(residual)
     for j in range(n_out // TC_HIDDEN):
-        wj = w[TC_HIDDEN * j: TC_HIDDEN * (j + 1)]
         oj = out[:, TC_HIDDEN * j: TC_HIDDEN * (j + 1)]
-        call("mgn_linear_tc", _p(xs[0]), x.stride(0), _p(xs[1]), x.stride(0), _p(xs[2]), x.stride(0), n_tab, M,
-             _p(wj), wj.stride(0), None, _p(None if residual is None else _c(residual)), _p(oj), out.stride(0),
-             _p(st), _stream())
+        for k in range(kb):  # K blocks accumulate through the residual input
+            xk = x[:, TC_HIDDEN * k: TC_HIDDEN * (k + 1)]
+            wjk = w[TC_HIDDEN * j: TC_HIDDEN * (j + 1), TC_HIDDEN * k: TC_HIDDEN * (k + 1)]
+            # in place is safe: a tile's residual rows are staged in shared memory before the same tile's output
+            # rows are written, and tiles own disjoint rows
+            r = res if k == 0 else oj
+            call("mgn_linear128_tc", _p(xk), x.stride(0), M, _p(wjk), w.stride(0), None, _p(r),
+                 _p(oj), out.stride(0), _p(st), _stream())
     return out
 
 

@@ -227,7 +227,7 @@ def test_mlp3_bwd_tc_is_deterministic():
         assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("M", [1, 129, 20000])
+@pytest.mark.parametrize("M", [1, 129, 20000, 100172])
 @pytest.mark.parametrize("K,N", [(128, 384), (384, 128), (256, 128)])
 def test_linear_tc(M, K, N):
     from modulus_b200 import ops
@@ -256,3 +256,57 @@ def test_wgrad_tc(M, JB):
     ops.tc_check(DEV)
     assert rel_err(out, ref) < 1e-4
     assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("M", [1, 130, 1000, 50021])
+def test_mlp3_fwd2_tc_edge_and_node_forms(M):
+    from modulus_b200 import ops
+
+    A, P, src, dst, go1, go2, p = _trick_case(M, seed=M)
+    d = dev_params(p)
+    Ad, Pd = A.to(DEV).bfloat16(), P.to(DEV).bfloat16()
+    # edge form: two gathered additive rows, residual = A
+    ref, _ = _ref_trick(A, P, src, dst, p, dtype=torch.float32, round_hidden=True)
+    out = ops.mlp3_fwd2_tc(Ad, None, None, Pd, src.to(DEV).int(), 0, Pd, dst.to(DEV).int(), 128, M,
+                           d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"],
+                           res_is_a=True)
+    ops.tc_check(DEV)
+    assert rel_err(out.float(), ref) < 1.5e-2
+    # node form: one additive table read row by row, residual from another table
+    Nn = P.shape[0]
+    agg = bf(torch.randn(Nn, 128, generator=torch.Generator().manual_seed(3)))
+    nfe = bf(torch.randn(Nn, 128, generator=torch.Generator().manual_seed(4)))
+    h1 = bf(F.relu(agg @ bf(p["w1"][:, :128]).T + P[:, 256:384] + p["b1"]))
+    h2 = bf(F.relu(h1 @ bf(p["w2"]).T + p["b2"]))
+    refn = F.layer_norm(h2 @ bf(p["w3"]).T + p["b3"], (128,), p["gamma"], p["beta"], 1e-5) + nfe
+    outn = ops.mlp3_fwd2_tc(agg.to(DEV).bfloat16(), None, None, Pd, None, 256, None, None, 0, Nn,
+                            d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"],
+                            residual=nfe.to(DEV).bfloat16())
+    ops.tc_check(DEV)
+    assert rel_err(outn.float(), refn) < 1.5e-2
+
+
+@pytest.mark.parametrize("M", [77, 30000])
+def test_mlp3_fwd2_tc_encoder_and_decoder_forms(M):
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(M)
+    # encoder: raw fp32 features, 6 -> 128 -> 128 -> 128 + LN
+    x = torch.randn(M, 6, generator=g)
+    p = make_params(6, seed=5)
+    ref, _, _ = ref_mlp(bf(x), p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], p["gamma"], p["beta"], None)
+    d = dev_params(p)
+    out = ops.mlp3_fwd2_tc(None, None, x.to(DEV), None, None, 0, None, None, 0, M, d["w1"], d["b1"], d["w2"], d["b2"],
+                           d["w3"], d["b3"], d["gamma"], d["beta"])
+    ops.tc_check(DEV)
+    assert rel_err(out.float(), ref) < 1.5e-2
+    # decoder: 128 -> 128 -> 128 -> 3, no LayerNorm
+    xn = bf(torch.randn(M, 128, generator=g))
+    p = make_params(128, n_out=3, seed=6)
+    ref, _, _ = ref_mlp(xn, p["w1"], p["b1"], p["w2"], p["b2"], p["w3"], p["b3"], None, None, None)
+    d = dev_params(p)
+    out = ops.mlp3_fwd2_tc(xn.to(DEV).bfloat16(), None, None, None, None, 0, None, None, 0, M, d["w1"], d["b1"],
+                           d["w2"], d["b2"], d["w3"], d["b3"], None, None, n_out=3)
+    ops.tc_check(DEV)
+    assert out.shape == (M, 3)
+    assert rel_err(out.float(), ref) < 1.5e-2

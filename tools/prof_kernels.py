@@ -24,6 +24,10 @@ def fwd():
     return ops.mlp3_fwd_tc_g(efeat, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta,
                              residual=efeat)
 
+def fwd2():
+    return ops.mlp3_fwd2_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3,
+                            gamma, beta, res_is_a=True)
+
 def bwd():
     return ops.mlp3_bwd_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, g_e, g_agg, plan.dst, E,
                            w1[:, :128], b1, w2, b2, w3, b3, gamma, 128, 1e-5, True, True, True,
@@ -35,7 +39,7 @@ def agg():
 def csr():
     return ops.segment_sum(efeat, 0, 128, plan.csr_offsets, plan.csr_eids, N)
 
-for name, fn in (("fwd_g edge", fwd), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr)):
+for name, fn in (("fwd_g edge", fwd), ("fwd2 edge", fwd2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr)):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -77,3 +81,13 @@ print(" LOADER: wait empty (sum) | issue+publish (sum)")
 print("   ", [int(v) // per_cta for v in t[1, :2].tolist()], "total", int(t[1].sum()) // per_cta)
 print(" EPI(one of two groups; per its tile): wait L1 | wait L2 | epi L1 | epi L2 | wait out | (gap) | LN stats | store")
 print("   ", [int(v) // max(per_cta // 2, 1) for v in t[2, :8].tolist()], "total", int(t[2].sum()) // max(per_cta // 2, 1))
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
+fwd2(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd2_timing", None)
+t = tbuf.cpu().view(3, 32)
+print("FWD2 kernel, CTA 0, cycles per tile")
+print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // per_cta for v in t[0, :5].tolist()], "total", int(t[0].sum()) // per_cta)
+print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // per_cta for v in t[1, :5].tolist()], "total", int(t[1].sum()) // per_cta)
+print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 :", [int(v) // per_cta for v in t[2, :6].tolist()], "total", int(t[2].sum()) // per_cta)
