@@ -55,6 +55,87 @@ def _node_wgrad(g: Tensor, x: Tensor) -> Tensor:
 
 
 # ----------------------------------------------------------------------------------------
+# halo exchange of the source-row projections (partitioned graphs)
+# ----------------------------------------------------------------------------------------
+class HaloContext:
+    """Per-graph state of the fused path on a partitioned graph (reference: DistributedGraph
+    .get_src_node_features_in_local_graph, distributed_graph.py:999-1011 -> indexed_all_to_all_v).
+
+    What travels is the source projection P[:, 0:H] = nfeat W1[:, H:2H]^T (the reference's concat-trick order:
+    per-node products BEFORE the exchange, mesh_graph_mlp.py:396-405).  Edges whose source row is owned by this
+    rank ("interior") do not wait for the exchange: with a locality-preserving partition they form one long
+    run of CSC edge rows, which is launched while the all-to-all is in flight; the boundary runs follow."""
+
+    def __init__(self, graph, plan: GraphPlan):
+        from .distributed import utils as du
+
+        dg = graph.dist_graph
+        gp = dg.graph_partition
+        self.group = dg.process_group
+        rank = gp.partition_rank
+        self.xplan = du._halo_plan(gp.scatter_indices, gp.sizes, rank)
+        self.n_part = int(gp.num_src_nodes_in_each_partition[rank])  # rows of the partitioned (owned) table
+        self.n_src_local = int(gp.num_local_src_nodes)
+        own_off = int(sum(gp.sizes[r][rank] for r in range(rank)))
+        own_cnt = int(gp.sizes[rank][rank])
+        src = plan.src.long()
+        owned = (src >= own_off) & (src < own_off + own_cnt)
+        E = int(src.numel())
+        # longest run of interior edges
+        bpos = torch.nonzero(~owned).flatten()
+        if bpos.numel() == 0:
+            e0, e1 = 0, E
+        else:
+            edges = torch.cat([bpos.new_tensor([-1]), bpos, bpos.new_tensor([E])])
+            gaps = edges[1:] - edges[:-1] - 1
+            k = int(torch.argmax(gaps))
+            e0, e1 = int(edges[k]) + 1, int(edges[k + 1])
+        if e1 - e0 < E // 2:
+            e0 = e1 = 0  # no useful interior run: everything waits for the exchange
+        self.e0, self.e1 = e0, e1
+        # interior edges read their source projection straight from the local P table
+        own_rows = gp.scatter_indices[rank].to(device=src.device, dtype=torch.int64)
+        self.src_own = None
+        if e1 > e0:
+            self.src_own = own_rows[src[e0:e1] - own_off].to(torch.int32).contiguous()
+        self.halo_rows = self.n_src_local - own_cnt
+
+    # forward: pack -> all-to-all (async) ; returns (work, recv buffer [n_src_local, H], packed keep-alive)
+    def start_fwd(self, P: Tensor):
+        from .distributed import utils as du
+        import torch.distributed as dist
+
+        xp = self.xplan
+        packed = ops.gather_rows(P, 0, H, xp.send_idx, xp.send_idx.numel())
+        if du._backend_has_alltoall(self.group):
+            recv = packed.new_empty((int(sum(xp.recv_splits)), H))
+            work = dist.all_to_all_single(recv, packed, list(xp.recv_splits), list(xp.send_splits), group=self.group,
+                                          async_op=True)
+            return work, recv, packed
+        recv = du.all_to_all_rows(packed, xp.send_splits, xp.recv_splits, group=self.group)
+        return None, recv, packed
+
+    # backward: gradients of the received rows travel back and are summed (fixed order) into out[:, col0:col0+H]
+    def start_bwd(self, g_rows: Tensor):
+        from .distributed import utils as du
+        import torch.distributed as dist
+
+        xp = self.xplan
+        if du._backend_has_alltoall(self.group):
+            recv = g_rows.new_empty((int(sum(xp.send_splits)), H))
+            work = dist.all_to_all_single(recv, g_rows, list(xp.send_splits), list(xp.recv_splits), group=self.group,
+                                          async_op=True)
+            return work, recv
+        return None, du.all_to_all_rows(g_rows, xp.recv_splits, xp.send_splits, group=self.group)
+
+    def finish_bwd(self, work, recv: Tensor, out: Tensor, out_col0: int):
+        if work is not None:
+            work.wait()
+        offsets, ids = self.xplan.acc_structs(self.n_part)
+        ops.segment_sum(recv, 0, H, offsets, ids, self.n_part, out=out, out_col0=out_col0)
+
+
+# ----------------------------------------------------------------------------------------
 # processor
 # ----------------------------------------------------------------------------------------
 class FusedProcessorFn(torch.autograd.Function):
@@ -62,7 +143,7 @@ class FusedProcessorFn(torch.autograd.Function):
     edge (w1 [H,3H], b1, w2, b2, w3, b3, gamma, beta), node (w1 [H,2H], b1, w2, b2, w3, b3, gamma, beta)."""
 
     @staticmethod
-    def forward(ctx, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, L: int, eps: float, *params: Tensor):
+    def forward(ctx, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, halo, L: int, eps: float, *params: Tensor):
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         nfeat, efeat = nfeat.contiguous(), efeat.contiguous()
@@ -71,14 +152,31 @@ class FusedProcessorFn(torch.autograd.Function):
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
             P = _node_linear(nfeat, wp)  # [N, 3H]
-            efeat_new = ops.mlp3_fwd2_tc(efeat, None, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2], ew[3],
-                                         ew[4], ew[5], ew[6], ew[7], eps=eps, res_is_a=True)
+            if halo is None:
+                efeat_new = ops.mlp3_fwd2_tc(efeat, None, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2],
+                                             ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps, res_is_a=True)
+            else:
+                efeat_new = torch.empty_like(efeat)
+                work, Ps, keep = halo.start_fwd(P)  # all-to-all of the source projections, in flight
+
+                def run(lo, hi, g1, g1_idx):
+                    if hi > lo:
+                        ops.mlp3_fwd2_tc(efeat[lo:hi], None, None, g1, g1_idx, 0, P, dst[lo:hi], H, hi - lo,
+                                         ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps,
+                                         res_is_a=True, out=efeat_new[lo:hi])
+
+                run(halo.e0, halo.e1, P, halo.src_own)  # interior edges overlap the exchange
+                if work is not None:
+                    work.wait()
+                run(0, halo.e0, Ps, src[:halo.e0])
+                run(halo.e1, E, Ps, src[halo.e1:])
+                del keep
             agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
             nfeat_new = ops.mlp3_fwd2_tc(agg, None, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
                                          nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
-            saved += [efeat, nfeat, agg, P]
+            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
-        ctx.plan, ctx.L, ctx.eps = plan, L, eps
+        ctx.plan, ctx.L, ctx.eps, ctx.halo = plan, L, eps, halo
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
         return nfeat
@@ -86,7 +184,8 @@ class FusedProcessorFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_n: Tensor):
         plan: GraphPlan = ctx.plan
-        L, eps = ctx.L, ctx.eps
+        L, eps, halo = ctx.L, ctx.eps, ctx.halo
+        ns = 4 if halo is None else 5
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         saved = ctx.saved_tensors[:ctx.n_saved]
@@ -97,7 +196,7 @@ class FusedProcessorFn(torch.autograd.Function):
         grads: List[Optional[Tensor]] = [None] * len(params)
         f32 = dict(dtype=torch.float32, device=dev)
         for l in range(L - 1, -1, -1):
-            efeat, nfeat, agg, P = saved[4 * l: 4 * l + 4]
+            efeat, nfeat, agg, P = saved[ns * l: ns * l + 4]
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             gew1, gnw1 = torch.empty((H, 3 * H), **f32), torch.empty((H, 2 * H), **f32)
             ge = [gew1] + [torch.empty_like(t, dtype=torch.float32) for t in ew[1:]]
@@ -113,13 +212,22 @@ class FusedProcessorFn(torch.autograd.Function):
                 go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
             else:
                 go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
-            g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, P, src, 0, P, dst, H, go1, go2, go2_idx, E,
+            g1 = P if halo is None else saved[ns * l + 4]  # source projections: local table or exchanged rows
+            g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, g1, src, 0, P, dst, H, go1, go2, go2_idx, E,
                                          ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
                                          True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6], ge[7],
                                          go1_idx=go1_idx)
             # ---- per-node reductions of the gathered-row gradient, then the node-level GEMMs
-            ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
-            ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+            if halo is None:
+                ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
+                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+            else:
+                # gradient of every referenced source row (incl. halo rows) goes back to its owner while the
+                # destination-side sum runs; owners accumulate in a fixed order
+                s_src = ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src)
+                work, recv = halo.start_bwd(s_src)
+                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+                halo.finish_bwd(work, recv, T, 0)
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
             g_n = ops.linear_tc(T, wp.t().contiguous(), residual=g_n)  # g_n + T wp
             gwp = _node_wgrad(T, nfeat)  # [3H, H]
@@ -128,7 +236,7 @@ class FusedProcessorFn(torch.autograd.Function):
             gnw1[:, H:] = gwp[2 * H:]
             grads[16 * l: 16 * l + 8] = ge
             grads[16 * l + 8: 16 * l + 16] = gn
-        return (g_n, g_e, None, None, None, *grads)
+        return (g_n, g_e, None, None, None, None, *grads)
 
 
 def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPlan, dt: torch.dtype) -> bool:
@@ -136,9 +244,15 @@ def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPla
     from .models.gnn_layers.mesh_graph_mlp import MeshGraphEdgeMLPConcat
     from .models.layers.activations import activation_name
 
-    if dt != BF16 or not plan.is_csc_ordered or plan.n_src != plan.n_dst or plan.n_edges == 0:
+    if dt != BF16 or not plan.is_csc_ordered or plan.n_edges == 0:
         return False
     if getattr(graph, "is_distributed", False):
+        gp = graph.dist_graph.graph_partition
+        r = gp.partition_rank
+        # square graphs partitioned identically on both id spaces: one owned node table serves src and dst
+        if int(gp.num_src_nodes_in_each_partition[r]) != int(gp.num_dst_nodes_in_each_partition[r]):
+            return False
+    elif plan.n_src != plan.n_dst:
         return False
     if nfeat.shape[1] != H or efeat.shape[1] != H or nfeat.shape[0] != plan.n_dst:
         return False
@@ -160,14 +274,19 @@ def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPla
     return True
 
 
-def processor_forward(proc, nfeat: Tensor, efeat: Tensor, plan: GraphPlan) -> Tensor:
+def processor_forward(proc, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, graph=None) -> Tensor:
     params: List[Tensor] = []
     eps = 1e-5
     for i, layer in enumerate(proc.processor_layers):
         mlp = layer.edge_mlp if i % 2 == 0 else layer.node_mlp
         params += mlp._flat_params()
         eps = mlp._norm().eps
-    return FusedProcessorFn.apply(nfeat.to(BF16), efeat.to(BF16), plan, proc.processor_size, eps, *params)
+    halo = None
+    if graph is not None and getattr(graph, "is_distributed", False):
+        halo = plan.extra.get("halo")
+        if halo is None:
+            halo = plan.extra["halo"] = HaloContext(graph, plan)
+    return FusedProcessorFn.apply(nfeat.to(BF16), efeat.to(BF16), plan, halo, proc.processor_size, eps, *params)
 
 
 # ----------------------------------------------------------------------------------------

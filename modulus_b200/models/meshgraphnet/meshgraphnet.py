@@ -228,7 +228,7 @@ class MeshGraphNetProcessor(nn.Module):
             if fused.processor_eligible(self, node_features, edge_features, graph, plan, dt):
                 # bf16 / hidden 128 / ReLU / sum: fused tcgen05 kernels with in-kernel recompute (checkpoint
                 # segments only trade memory for recompute in the reference; nothing to do here)
-                return fused.processor_forward(self, node_features, edge_features, plan)
+                return fused.processor_forward(self, node_features, edge_features, plan, graph)
         with self.checkpoint_offload_ctx:
             for segment_start, segment_end in self.checkpoint_segments:
                 edge_features, node_features = self.checkpoint_fn(
