@@ -35,7 +35,8 @@ namespace mgn {
 namespace bwd {
 
 using namespace tile;
-constexpr int kThreads = 416;  // warp 0: MMA, warps 1-4: movers, warps 5-12: epilogue
+constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, 64 columns each
+constexpr int kThreads = 32 * (1 + 4 + kEpiWarps);  // warp 0: MMA, warps 1-4: movers, warps 5-12: epilogue
 constexpr int kH = 128;
 
 struct Params {
@@ -71,21 +72,26 @@ enum { kStatusTimeout = 1, kStatusSmem = 2 };
     tlast = t_;                       \
   }  // tm lives in shared memory: the counters must not cost registers
 
-// barrier indices
-enum { B_AG = 0, B_GO = 1, B_A2 = 2, B_MMA1 = 3, B_E1 = 9, B_NUM = 15 };
+// barriers.  B_A / B_G: layer-1 input rows / additive rows of a tile are staged (published one tile ahead);
+// B_GO: incoming gradient rows staged; B_A2: layer-1 input rows staged again for the weight gradient;
+// B_MMA1 + k: k-th group of MMAs of the tile has completed; B_E1 + k: k-th epilogue phase has completed.
+enum { B_A = 0, B_G = 1, B_GO = 2, B_A2 = 3, B_MMA1 = 4, B_E1 = 11, B_NUM = 17 };
+
+// Four 32 KB tile buffers rotate roles from tile to tile so that the next tile's rows stream in while the current
+// tile is still in its backward half: role r of tile `it` lives in buffer (r - it) mod 4, i.e. the next tile's A
+// takes over this tile's H2 buffer (free after the layer-2 MMAs), its G1 this tile's A buffer and its G2 this
+// tile's H1 buffer (both free after the layer-1 MMAs).
+enum { R_A = 0, R_X = 1, R_H1 = 2, R_H2 = 3 };
 
 template <int KP>
 struct Smem {
   static constexpr int kW1 = 0;
   static constexpr int kW2 = KP * kPB;
   static constexpr int kW3 = kW2 + 2 * kPB;
-  static constexpr int kA = kW3 + 2 * kPB;
-  static constexpr int kX = kA + 2 * kPB;
-  static constexpr int kH1 = kX + 2 * kPB;
-  static constexpr int kH2 = kH1 + 2 * kPB;
-  static constexpr int kPar = kH2 + 2 * kPB;  // b1, b2, b3, gamma
+  static constexpr int kBuf = kW3 + 2 * kPB;   // 4 tile buffers x 2 panels
+  static constexpr int kPar = kBuf + 8 * kPB;  // b1, b2, b3, gamma
   static constexpr int kBars = kPar + 4 * kH * 4;
-  static constexpr int kTmemSlot = kBars + 16 * 8;
+  static constexpr int kTmemSlot = kBars + 24 * 8;
   static constexpr int kTiming = kTmemSlot + 16;  // 3 roles x 16 x int64 (debug)
   static constexpr int kTotal = kTiming + 3 * 16 * 8;
 };
@@ -104,6 +110,9 @@ struct Part {
   static constexpr int kTotal = kBeta + kH;
 };
 
+__device__ __forceinline__ bool bf_pos_lo(uint32_t w) { return static_cast<int32_t>(w << 16) > 0; }
+__device__ __forceinline__ bool bf_pos_hi(uint32_t w) { return static_cast<int32_t>(w & 0xFFFF0000u) > 0; }
+
 template <int KP>
 __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p) {
   using L = Smem<KP>;
@@ -117,13 +126,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   uint8_t* sW1 = smem + L::kW1;
   uint8_t* sW2 = smem + L::kW2;
   uint8_t* sW3 = smem + L::kW3;
-  uint8_t* bA = smem + L::kA;
-  uint8_t* bX = smem + L::kX;
-  uint8_t* bH1 = smem + L::kH1;
-  uint8_t* bH2 = smem + L::kH2;
+  uint8_t* buf0 = smem + L::kBuf;
   float* sPar = reinterpret_cast<float*>(smem + L::kPar);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
+#define MGN_BUF(role, it) (buf0 + ((((role) - (it)) & 3) * (2 * kPB)))
 
   const bool has_ln = p.gamma != nullptr;
   const bool has_g = p.g1.tab != nullptr;
@@ -143,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
   }
   if (tid == 0) {
-    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], b < B_MMA1 ? 4 : (b < B_E1 ? 1 : 8));
+    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], b < B_MMA1 ? 4 : (b < B_E1 ? 1 : kEpiWarps));
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -164,17 +171,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   }
   long long tlast = clock64();
 
-  // mover-side running column sums (fixed columns per thread) and epilogue-side gamma gradient
-  float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
-        cs_beta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float gg[4] = {0.f, 0.f, 0.f, 0.f};
+  // per-CTA reduction scratch (bias / beta column sums of the movers, gamma sums of the epilogue): the H2 buffer
+  // of this CTA's last tile, which nobody touches after that tile's layer-2 MMAs
+  float* scratch = reinterpret_cast<float*>(MGN_BUF(R_H2, n_my - 1));
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t aA = smem_u32(bA), aX = smem_u32(bX), aH1 = smem_u32(bH1), aH2 = smem_u32(bH2);
+      const uint32_t a0 = smem_u32(buf0);
       const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
-      (void)aX;
       const uint32_t id_nt = umma_idesc_bf16(128, 128, 0, 0);   // D = A(K-major) * B(K-major)^T
       const uint32_t id_tn = umma_idesc_bf16(128, 128, 1, 1);   // D = A(MN)^T * B(MN)          (wgrad)
       const uint32_t id_nn = umma_idesc_bf16(128, 128, 0, 1);   // D = A(K-major) * B(MN)       (dgrad)
@@ -182,14 +187,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       const uint32_t id_nn1 = umma_idesc_bf16(128, N1, 0, 1);
       for (int it = 0; it < n_my; ++it) {
         const uint32_t par = it & 1;
+        const uint32_t aA = a0 + ((R_A - it) & 3) * (2 * kPB);
+        const uint32_t aH1 = a0 + ((R_H1 - it) & 3) * (2 * kPB);
+        const uint32_t aH2 = a0 + ((R_H2 - it) & 3) * (2 * kPB);
 #define MGN_W(b, ph)                         \
   if (!wait_clk(&bars[b], ph)) {             \
     timed_out = true;                        \
     break;                                   \
   }
-        // ---- GEMM1: acc = A W1^T
-        MGN_W(B_AG, par);
-        if (it > 0) MGN_W(B_E1 + 5, par ^ 1);
+        // ---- GEMM1: acc = A W1^T   (A was staged during the previous tile)
+        MGN_W(B_A, par);
+        if (it > 0) MGN_W(B_E1 + 5, par ^ 1);  // the previous tile's last epilogue has drained the accumulator
         MGN_T(0);
         tc_fence_after_sync();
 #pragma unroll
@@ -218,39 +226,37 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
                   id_nt, k != 0);
         umma_commit(&bars[B_MMA1 + 2]);
         MGN_T(5);
-        // ---- layer 3: gW3 += g_y^T h2 ; acc = g_y W3          (g_y in bA)
+        // ---- layer 3: gW3 += g_y^T h2 ; acc = g_y W3          (g_y in the A buffer)
         MGN_W(B_E1 + 2, par);
         MGN_T(6);
         tc_fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
-#pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
         umma_commit(&bars[B_MMA1 + 3]);
         MGN_T(7);
-        // ---- layer 2: gW2 += g_z2^T h1 ; acc = g_z2 W2        (g_z2 in bH2)
+        // ---- layer 2: gW2 += g_z2^T h1 ; acc = g_z2 W2        (g_z2 in the H2 buffer)
         MGN_W(B_E1 + 3, par);
         MGN_T(8);
         tc_fence_after_sync();
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
-#pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
-        umma_commit(&bars[B_MMA1 + 4]);
-        MGN_T(9);
-        // ---- layer 1: gW1 += g_z1^T A ; acc = g_z1 W1          (g_z1 in bH1, A re-staged in bA)
-        MGN_W(B_E1 + 4, par);
-        MGN_T(10);
-        MGN_W(B_A2, par);
-        MGN_T(11);
-        tc_fence_after_sync();
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          umma_ss(tW1, umma_desc_mnmajor(aH1, j, kPB), umma_desc_mnmajor(aA, j, kPB), id_tn1, (it | j) != 0);
+          umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
+        umma_commit(&bars[B_MMA1 + 4]);
+        MGN_T(9);
+        // ---- layer 1: acc = g_z1 W1 (epilogue may start on it at once) ; gW1 += g_z1^T A
+        //      (g_z1 in the H1 buffer, A re-staged in the A buffer)
+        MGN_W(B_E1 + 4, par);
+        MGN_T(10);
+        // (waiting for the re-staged A here too orders every mover's column sums of X before E6 rewrites X)
+        MGN_W(B_A2, par);
+        tc_fence_after_sync();
         if (need_ga) {
 #pragma unroll
           for (int k = 0; k < 8; ++k)
@@ -258,6 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
                     k != 0);
         }
         umma_commit(&bars[B_MMA1 + 5]);
+        MGN_T(11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW1, umma_desc_mnmajor(aH1, j, kPB), umma_desc_mnmajor(aA, j, kPB), id_tn1, (it | j) != 0);
+        umma_commit(&bars[B_MMA1 + 6]);
         MGN_T(12);
 #undef MGN_W
       }
@@ -281,38 +292,44 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     const int rsub_m = mt >> 4;
     const bool go2_shares_g2 = has_go2 && p.go2.idx == p.g2.idx && p.go2.idx != nullptr;
     int32_t r_g1[16], r_g2[16], r_tmp[16];
-    {
+    // running column sums (fixed columns per thread) for the bias / beta gradients
+    float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
+          cs_beta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // prologue: tile 0 (A, then the additive rows; published separately so GEMM1 never waits for the gathers)
+    if (n_my > 0) {
       const long long row00 = static_cast<long long>(blockIdx.x) * kRows;
       fetch_row_ids(has_g ? p.g1.idx : nullptr, row00, p.M, rsub_m, r_g1);
       fetch_row_ids(has_g2 ? p.g2.idx : (has_go2 ? p.go2.idx : nullptr), row00, p.M, rsub_m, r_g2);
+      if (KP == 2) {
+        fetch_row_ids(p.a.idx, row00, p.M, rsub_m, r_tmp);
+        stage_rows_async(MGN_BUF(R_A, 0), p.a, r_tmp, row00, p.M, mt);
+      } else {
+        stage_small(MGN_BUF(R_A, 0), p.small_x, p.small_in, p.small_is_f32, row00, p.M, mt);
+      }
+      cp_async_commit();
+      if (has_g) stage_rows_async(MGN_BUF(R_X, 0), p.g1, r_g1, row00, p.M, mt);
+      if (has_g2) stage_rows_async(MGN_BUF(R_H2, 0), p.g2, r_g2, row00, p.M, mt);
+      cp_async_commit();
+      cp_async_wait<1>();
+      MGN_PUBLISH(B_A);
+      cp_async_wait<0>();
+      MGN_PUBLISH(B_G);
     }
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
+      const bool more = it + 1 < n_my;
       const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
       const long long row0n = row0 + static_cast<long long>(gridDim.x) * kRows;  // next tile of this CTA
-      // A (and G) tiles
-      if (KP == 2) {
-        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_tmp);
-        stage_rows_async(bA, p.a, r_tmp, row0, p.M, mt);
-      } else {
-        stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
-      }
-      MGN_T(14);
-      if (has_g) {  // additive rows: g1 -> bX, g2 -> bH2 (free until the epilogue writes h2); summed in E1
-        stage_rows_async(bX, p.g1, r_g1, row0, p.M, mt);
-        MGN_T(15);
-        if (has_g2) stage_rows_async(bH2, p.g2, r_g2, row0, p.M, mt);
-        MGN_T(3);
-      }
-      cp_async_commit();
-      if (has_g && it + 1 < n_my) fetch_row_ids(p.g1.idx, row0n, p.M, rsub_m, r_g1);  // used one tile later
-      cp_async_wait<0>();
-      MGN_PUBLISH(B_AG);
+      uint8_t* bA = MGN_BUF(R_A, it);
+      uint8_t* bX = MGN_BUF(R_X, it);
+      uint8_t* bH1 = MGN_BUF(R_H1, it);
+      uint8_t* bH2 = MGN_BUF(R_H2, it);
+      if (more && has_g) fetch_row_ids(p.g1.idx, row0n, p.M, rsub_m, r_g1);  // used at the end of this tile
       MGN_T(0);
-      // incoming gradient, once the epilogue has consumed G
+      // incoming gradient, once the layer-1 epilogue has consumed the additive rows (and GEMM1 the A rows)
       MGN_W(B_E1 + 0, par);
       MGN_T(1);
-      if (!p.go_small) {  // go1 -> bX, go2 -> bA (A was consumed by GEMM1); summed in E3
+      if (!p.go_small) {  // go1 -> X, go2 -> A; summed in E3
         fetch_row_ids(p.go1.idx, row0, p.M, rsub_m, r_tmp);
         stage_rows_async(bX, p.go1, r_tmp, row0, p.M, mt);
         if (has_go2) {
@@ -320,8 +337,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
           stage_rows_async(bA, p.go2, r_g2, row0, p.M, mt);
         }
         cp_async_commit();
-        if (it + 1 < n_my && (has_g2 || go2_shares_g2))
-          fetch_row_ids(has_g2 ? p.g2.idx : p.go2.idx, row0n, p.M, rsub_m, r_g2);  // used one tile later
+        if (more && (has_g2 || go2_shares_g2))
+          fetch_row_ids(has_g2 ? p.g2.idx : p.go2.idx, row0n, p.M, rsub_m, r_g2);  // used at the end of this tile
         cp_async_wait<0>();
       } else {
         const int chunk = mt & 15, rsub = mt >> 4;
@@ -344,17 +361,15 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       }
       MGN_PUBLISH(B_GO);
       MGN_T(2);
-      MGN_T(3);
-      // after E3: bX = g_out (summed), bA = g_y.  Bias / beta gradients, then re-stage A once the layer-3
-      // MMAs have consumed g_y
+      // after E3: X = g_out (summed), A = g_y.  Bias / beta gradients, then re-stage A once the layer-3 MMAs have
+      // consumed g_y
       MGN_W(B_E1 + 2, par);
-      MGN_T(4);
+      MGN_T(3);
       colsum_tile(bX, mt, cs_beta);
       colsum_tile(bA, mt, cs_b3);
-      MGN_T(5);
+      MGN_T(4);
       MGN_W(B_MMA1 + 3, par);
-      MGN_MOVER_SYNC();
-      MGN_T(6);
+      MGN_T(5);
       if (KP == 2) {
         fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_tmp);
         stage_rows_async(bA, p.a, r_tmp, row0, p.M, mt);
@@ -364,27 +379,65 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
       }
       MGN_PUBLISH(B_A2);
-      MGN_T(7);
+      MGN_T(6);
       MGN_W(B_E1 + 3, par);
-      MGN_T(8);
+      MGN_T(7);
       colsum_tile(bH2, mt, cs_b2);
+      MGN_T(8);
+      // the layer-2 MMAs have consumed g_z2: the next tile's A rows stream into this tile's H2 buffer
+      MGN_W(B_MMA1 + 4, par);
+      if (more) {
+        if (KP == 2) {
+          fetch_row_ids(p.a.idx, row0n, p.M, rsub_m, r_tmp);
+          stage_rows_async(bH2, p.a, r_tmp, row0n, p.M, mt);
+        } else {
+          stage_small(bH2, p.small_x, p.small_in, p.small_is_f32, row0n, p.M, mt);
+        }
+        cp_async_commit();
+      }
       MGN_T(9);
       MGN_W(B_E1 + 4, par);
       MGN_T(10);
+      if (more) {  // the next tile's A rows have had a whole epilogue phase to land: publish them before anything else
+        cp_async_wait<0>();
+        MGN_PUBLISH(B_A);
+      }
       colsum_tile(bH1, mt, cs_b1);
       if (p.g_z1) store_rows(bH1, p.g_z1, p.g_z1_ld, row0, p.M, mt);
       MGN_T(11);
-      MGN_W(B_E1 + 5, par);
+      // the layer-1 MMAs have consumed A and g_z1: the next tile's additive rows stream into those buffers
+      MGN_W(B_MMA1 + 6, par);
+      if (more) {
+        if (has_g) stage_rows_async(bA, p.g1, r_g1, row0n, p.M, mt);
+        if (has_g2) stage_rows_async(bH1, p.g2, r_g2, row0n, p.M, mt);
+        cp_async_commit();
+      }
       MGN_T(12);
-      if (need_ga) store_rows(bX, p.g_a, kH, row0, p.M, mt);
-      MGN_MOVER_SYNC();
+      MGN_W(B_E1 + 5, par);
       MGN_T(13);
+      if (need_ga) store_rows(bX, p.g_a, kH, row0, p.M, mt);
+      if (more) {
+        cp_async_wait<0>();
+        MGN_PUBLISH(B_G);  // also orders this warp's reads of X (g_A store) before the next tile's E1 writes h1 there
+      }
+      MGN_T(14);
     }
 #undef MGN_W
+    asm volatile("bar.sync 10, 384;" ::: "memory");  // movers + epilogue: nobody reads a tile buffer any more
+    {
+      const int chunk = mt & 15, rsub = mt >> 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        scratch[(0 * 8 + rsub) * kH + chunk * 8 + j] = cs_b1[j];
+        scratch[(1 * 8 + rsub) * kH + chunk * 8 + j] = cs_b2[j];
+        scratch[(2 * 8 + rsub) * kH + chunk * 8 + j] = cs_b3[j];
+        scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
+      }
+    }
   } else {
     // =========================== epilogue (8 warps) ===========================
     // two warps per TMEM lane quarter: warp (q, ch) owns tile rows [32q, 32q+32) (thread = row = TMEM lane)
-    // and columns [64 ch, 64 ch + 64), processed in 16-column chunks
+    // and columns [64 ch, 64 ch + 64) = panel ch of every tile buffer, processed as two 32-column halves
     const int q = warp & 3;
     const int ch = (warp - 5) >> 2;
     const int row = q * 32 + lane;
@@ -394,7 +447,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     const float* b2 = sPar + kH + c0;
     const float* b3 = sPar + 2 * kH + c0;
     const float* gam = sPar + 3 * kH + c0;
-    float4* xch = reinterpret_cast<float4*>(bA);  // LayerNorm row-sum exchange between the two column halves
+    // LayerNorm row-sum exchange slot of (row, column half): the first 16 bytes of this thread's own 128-byte span
+    // of the A buffer (only this thread reads that span in E3, so it may overwrite it as soon as it has)
+    const uint32_t xch_own = ch * kPB + sw128_offset(row, 0);
+    const uint32_t xch_other = (ch ^ 1) * kPB + sw128_offset(row, 0);
+    float gg[4] = {0.f, 0.f, 0.f, 0.f};  // gamma gradient: lane (< 16) holds column c0 + 16 g + lane over this warp's rows
 #define MGN_W(b, ph)                                                      \
   {                                                                       \
     const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
@@ -408,182 +465,230 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   tc_fence_before_sync();     \
   __syncwarp();               \
   if (lane == 0) mbar_arrive(&bars[b]);
-#define MGN_EPI_SYNC() asm volatile("bar.sync 2, 256;" ::: "memory")
+// the two warps that share tile rows (same TMEM lane quarter) synchronise on their own named barrier
+#define MGN_ROW_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory")
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
-      // ---- E1: h1 = relu(acc + b1 + g1 rows + g2 rows) -> bH1
+      uint8_t* bA = MGN_BUF(R_A, it);
+      uint8_t* bX = MGN_BUF(R_X, it);
+      uint8_t* bH1 = MGN_BUF(R_H1, it);
+      uint8_t* bH2 = MGN_BUF(R_H2, it);
+      // ---- E1: h1 = relu(acc + b1 + g1 rows + g2 rows) -> H1
       MGN_W(B_MMA1 + 0, par);
-      MGN_W(B_AG, par);
+      MGN_W(B_G, par);
       MGN_T(0);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
-        float f[16], f2[16];
-        if (has_g) row_load16(bX, row, c0 + g * 16, f);
-        if (has_g2) row_load16(bH2, row, c0 + g * 16, f2);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = c0 + 32 * hh;
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t ga[16], gb[16];
+        if (has_g) row_load32p(bX, row, cc, ga);
+        if (has_g2) row_load32p(bH2, row, cc, gb);
         tmem_ld_wait();
+        uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          float z = __uint_as_float(v[j]) + b1[g * 16 + j];
-          if (has_g) z += f[j];
-          if (has_g2) z += f2[j];
-          f[j] = fmaxf(z, 0.f);
+          float z0 = __uint_as_float(v[2 * j]) + b1[32 * hh + 2 * j];
+          float z1 = __uint_as_float(v[2 * j + 1]) + b1[32 * hh + 2 * j + 1];
+          if (has_g) {
+            z0 += bf_lo(ga[j]);
+            z1 += bf_hi(ga[j]);
+          }
+          if (has_g2) {
+            z0 += bf_lo(gb[j]);
+            z1 += bf_hi(gb[j]);
+          }
+          o[j] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
         }
-        row_store16(bH1, row, c0 + g * 16, f);
+        row_store32p(bH1, row, cc, o);
       }
       MGN_EPI_DONE(B_E1 + 0);
       MGN_T(1);
-      // ---- E2: h2 = relu(acc + b2) -> bH2
+      // ---- E2: h2 = relu(acc + b2) -> H2
       MGN_W(B_MMA1 + 1, par);
       MGN_T(2);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
         tmem_ld_wait();
-        float f[16];
+        uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = fmaxf(__uint_as_float(v[j]) + b2[g * 16 + j], 0.f);
-        row_store16(bH2, row, c0 + g * 16, f);
+        for (int j = 0; j < 16; ++j)
+          o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[32 * hh + 2 * j], 0.f),
+                             fmaxf(__uint_as_float(v[2 * j + 1]) + b2[32 * hh + 2 * j + 1], 0.f));
+        row_store32p(bH2, row, c0 + 32 * hh, o);
       }
       MGN_EPI_DONE(B_E1 + 1);
       MGN_T(3);
-      // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> bX ; g_y -> bA
+      // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> X ; g_y -> A
       MGN_W(B_MMA1 + 2, par);
       MGN_T(4);
       MGN_W(B_GO, par);
       MGN_T(5);
       tc_fence_after_sync();
-      if (has_go2) {
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          float a[16], b[16];
-          row_load16(bX, row, c0 + g * 16, a);
-          row_load16(bA, row, c0 + g * 16, b);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) a[j] += b[j];
-          row_store16(bX, row, c0 + g * 16, a);
-        }
-        MGN_EPI_SYNC();  // every go2 row has been read: bA may now carry the row-sum exchange
-      }
       if (has_ln) {
         float s_y = 0.f, s_yy = 0.f, s_g = 0.f, s_gy = 0.f;
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + g * 16, v);
-          float go[16];
-          row_load16(bX, row, c0 + g * 16, go);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          row_load32p(bX, row, cc, go);
+          if (has_go2) {
+            uint32_t g2[16];
+            row_load32p(bA, row, cc, g2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
+            row_store32p(bX, row, cc, go);
+          }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float y = __uint_as_float(v[j]) + b3[g * 16 + j];
-            const float gh = go[j] * gam[g * 16 + j];
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]) + b3[32 * hh + j];
+            const float gh = ((j & 1) ? bf_hi(go[j >> 1]) : bf_lo(go[j >> 1])) * gam[32 * hh + j];
             s_y += y;
             s_yy = fmaf(y, y, s_yy);
             s_g += gh;
             s_gy = fmaf(gh, y, s_gy);
           }
         }
-        xch[row * 2 + ch] = make_float4(s_y, s_yy, s_g, s_gy);
-        MGN_EPI_SYNC();
-        const float4 o = xch[row * 2 + (ch ^ 1)];
-        MGN_EPI_SYNC();  // both halves have read before g_y overwrites bA
-        s_y += o.x;
-        s_yy += o.y;
-        s_g += o.z;
-        s_gy += o.w;
+        *reinterpret_cast<float4*>(bA + xch_own) = make_float4(s_y, s_yy, s_g, s_gy);
+        MGN_ROW_SYNC();
+        {
+          const float4 t = *reinterpret_cast<const float4*>(bA + xch_other);
+          s_y += t.x;
+          s_yy += t.y;
+          s_g += t.z;
+          s_gy += t.w;
+        }
+        MGN_ROW_SYNC();  // both halves have read the exchange before g_y overwrites the A buffer
         const float mu = s_y * (1.f / kH);
         const float var = fmaxf(s_yy * (1.f / kH) - mu * mu, 0.f);
         const float rstd = rsqrtf(var + p.eps);
         const float m1 = s_g * (1.f / kH);
         const float m2 = (s_gy - mu * s_g) * rstd * (1.f / kH);  // mean(ghat * xhat)
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + g * 16, v);
-          float go[16];
-          row_load16(bX, row, c0 + g * 16, go);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          row_load32p(bX, row, cc, go);
           tmem_ld_wait();
-          float gy[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float xhat = (__uint_as_float(v[j]) + b3[g * 16 + j] - mu) * rstd;
-            const float gh = go[j] * gam[g * 16 + j];
-            gy[j] = rstd * (gh - m1 - xhat * m2);
-            go[j] *= xhat;  // gamma-gradient contribution of this row
+          for (int h = 0; h < 2; ++h) {
+            float t[16];
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 16 * h + 2 * j;  // column within this 32-column half
+              const float g0 = bf_lo(go[c >> 1]), g1v = bf_hi(go[c >> 1]);
+              const float x0 = (__uint_as_float(v[c]) + b3[32 * hh + c] - mu) * rstd;
+              const float x1 = (__uint_as_float(v[c + 1]) + b3[32 * hh + c + 1] - mu) * rstd;
+              const float y0 = rstd * (g0 * gam[32 * hh + c] - m1 - x0 * m2);
+              const float y1 = rstd * (g1v * gam[32 * hh + c + 1] - m1 - x1 * m2);
+              o[j] = pack_bf16x2(y0, y1);
+              t[2 * j] = g0 * x0;  // gamma-gradient contribution of this row
+              t[2 * j + 1] = g1v * x1;
+            }
+            uint8_t* base = bA + ch * kPB;
+            const int c8 = 4 * hh + 2 * h;
+            *reinterpret_cast<uint4*>(base + sw128_offset(row, c8)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+            const float cs = warp_colsum16(t, lane);
+            if (hh == 0) gg[h] += cs;
+            else gg[2 + h] += cs;
           }
-          row_store16(bA, row, c0 + g * 16, gy);
-          gg[g] += warp_colsum16(go, lane);
         }
       } else {
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          float go[16];
-          row_load16(bX, row, c0 + g * 16, go);
-          row_store16(bA, row, c0 + g * 16, go);
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t go[16];
+          row_load32p(bX, row, cc, go);
+          if (has_go2) {
+            uint32_t g2[16];
+            row_load32p(bA, row, cc, g2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
+            row_store32p(bX, row, cc, go);
+          }
+          row_store32p(bA, row, cc, go);
         }
       }
       MGN_EPI_DONE(B_E1 + 2);
       MGN_T(6);
-      // ---- E4: g_z2 = acc * (h2 > 0), in place in bH2
+      // ---- E4: g_z2 = acc * (h2 > 0), in place in H2
       MGN_W(B_MMA1 + 3, par);
       MGN_T(7);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
-        float h[16];
-        row_load16(bH2, row, c0 + g * 16, h);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t h[16];
+        row_load32p(bH2, row, c0 + 32 * hh, h);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
-        row_store16(bH2, row, c0 + g * 16, h);
+        for (int j = 0; j < 16; ++j)
+          h[j] = pack_bf16x2(bf_pos_lo(h[j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                             bf_pos_hi(h[j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        row_store32p(bH2, row, c0 + 32 * hh, h);
       }
       MGN_EPI_DONE(B_E1 + 3);
       MGN_T(8);
-      // ---- E5: g_z1 = acc * (h1 > 0), in place in bH1
+      // ---- E5: g_z1 = acc * (h1 > 0), in place in H1
       MGN_W(B_MMA1 + 4, par);
       MGN_T(9);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
-        float h[16];
-        row_load16(bH1, row, c0 + g * 16, h);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t h[16];
+        row_load32p(bH1, row, c0 + 32 * hh, h);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) h[j] = h[j] > 0.f ? __uint_as_float(v[j]) : 0.f;
-        row_store16(bH1, row, c0 + g * 16, h);
+        for (int j = 0; j < 16; ++j)
+          h[j] = pack_bf16x2(bf_pos_lo(h[j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                             bf_pos_hi(h[j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        row_store32p(bH1, row, c0 + 32 * hh, h);
       }
       MGN_EPI_DONE(B_E1 + 4);
       MGN_T(10);
-      // ---- E6: g_A = acc (+ g_out), in place in bX
+      // ---- E6: g_A = acc (+ g_out), in place in X (runs while the layer-1 weight-gradient MMAs execute)
       MGN_W(B_MMA1 + 5, par);
       MGN_T(11);
       tc_fence_after_sync();
       if (need_ga) {
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + g * 16, v);
-          float go[16];
-          if (p.add_gout) row_load16(bX, row, c0 + g * 16, go);
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          if (p.add_gout) row_load32p(bX, row, c0 + 32 * hh, go);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) go[j] = __uint_as_float(v[j]) + (p.add_gout ? go[j] : 0.f);
-          row_store16(bX, row, c0 + g * 16, go);
+          for (int j = 0; j < 16; ++j)
+            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + (p.add_gout ? bf_lo(go[j]) : 0.f),
+                                __uint_as_float(v[2 * j + 1]) + (p.add_gout ? bf_hi(go[j]) : 0.f));
+          row_store32p(bX, row, c0 + 32 * hh, go);
         }
       }
       MGN_EPI_DONE(B_E1 + 5);
       MGN_T(12);
     }
 #undef MGN_W
+    asm volatile("bar.sync 10, 384;" ::: "memory");  // movers + epilogue: nobody reads a tile buffer any more
+    if (lane < 16) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + c0 + g * 16 + lane] = gg[g];
+    }
   }
   if (tm_on) {
     const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
@@ -597,7 +702,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
 
   // ---------------- write this CTA's partial gradients ----------------
   float* part = p.partials + static_cast<long long>(blockIdx.x) * p.part_floats;
-  float* scratch = reinterpret_cast<float*>(bX);  // tile buffers are free now
   if (warp >= 5) {
     const int q = warp & 3;
     const int ch = (warp - 5) >> 2;
@@ -620,24 +724,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
                           __uint_as_float(v[4 * u + 3]));
       }
     }
-    // gamma gradient: lane (< 16) holds column 64 ch + 16 g + lane summed over this warp's 32 rows
-    if (lane < 16) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + ch * 64 + g * 16 + lane] = gg[g];
-    }
-  } else if (warp >= 1) {
-    const int mt = tid - 32;
-    const int chunk = mt & 15, rsub = mt >> 4;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      scratch[(0 * 8 + rsub) * kH + chunk * 8 + j] = cs_b1[j];
-      scratch[(1 * 8 + rsub) * kH + chunk * 8 + j] = cs_b2[j];
-      scratch[(2 * 8 + rsub) * kH + chunk * 8 + j] = cs_b3[j];
-      scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
-    }
   }
-  tc_fence_before_sync();
-  __syncthreads();
   if (tid < kH) {
     float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -654,6 +741,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     part[PT::kBeta + tid] = s[3];
     part[PT::kGamma + tid] = sg;
   }
+  tc_fence_before_sync();
+  __syncthreads();  // every tcgen05.ld of the dump above has completed
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

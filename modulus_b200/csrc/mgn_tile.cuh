@@ -243,6 +243,29 @@ __device__ __forceinline__ void row_store16(uint8_t* buf, int row, int col, cons
   }
 }
 
+// ---- packed variants (32 bf16 of this thread's row at column col, a multiple of 32, as 16 bf16x2 words) ----
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+__device__ __forceinline__ void row_load32p(const uint8_t* buf, int row, int col, uint32_t (&w)[16]) {
+  const uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 v = *reinterpret_cast<const uint4*>(base + sw128_offset(row, c8 + u));
+    w[4 * u] = v.x;
+    w[4 * u + 1] = v.y;
+    w[4 * u + 2] = v.z;
+    w[4 * u + 3] = v.w;
+  }
+}
+__device__ __forceinline__ void row_store32p(uint8_t* buf, int row, int col, const uint32_t (&w)[16]) {
+  uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + u)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
+}
+
 // warp transpose-reduce of 16 columns: on return lane L holds the sum over all 32 lanes of their v[L & 15]
 __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 #pragma unroll

@@ -62,9 +62,9 @@ _lib.call("mgn_debug_set_bwd_timing", None)
 t = tbuf.cpu().view(3, 32)
 n_tiles = (E + 127) // 128
 per_cta = -(-n_tiles // 148)
-names = {0: "MMA  : wAG+E6 | g1 | wE1 | g2 | wE2 | g3 | wE3 | g4 | wE4 | g5 | wE5 | wA2 | g6",
-         1: "MOVER [14]=issueA [15]=idx+issue g1 [3]=idx+issue g2 [0]=wait: stageAG | wE1 | stageGO | csX | wE3 | csA | wMMA4 | stageA2 | wE4 | csH2 | wE5 | csH1+st | wE6 | stGA",
-         2: "EPI  : wMMA1 | E1 | wMMA2 | E2 | wMMA3 | wGO | E3 | wMMA4 | E4 | wMMA5 | E5 | wMMA6 | E6"}
+names = {0: "MMA  : wA+E6prev | g1 | wE1 | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 | wE5 | dgrad1+wA2 | wgrad1",
+         1: "MOVER: ids | wE1 | stageGO | wE3 | csX,A | wMMA4 | stageA2 | wE4 | csH2 | wMMA5+issueA' | wE5 | csH1+st gz1 | wMMA7+issueG'+waitA' | wE6 | st gA+waitG'",
+         2: "EPI  : wMMA1+G | E1 | wMMA2 | E2 | wMMA3 | wGO | E3 | wMMA4 | E4 | wMMA5 | E5 | wMMA6 | E6"}
 for r in range(3):
     print(names[r])
     print("   cycles/tile:", [int(v) // per_cta for v in t[r, :16].tolist()], " total/tile:", int(t[r].sum()) // per_cta)
