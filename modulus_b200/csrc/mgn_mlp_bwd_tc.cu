@@ -29,6 +29,7 @@
 #include "mgn_tc.cuh"
 #include "mgn_reduce.cuh"
 #include "mgn_tile.cuh"
+#include "mgn_tma.cuh"
 
 namespace mgn {
 
@@ -36,7 +37,8 @@ namespace bwd {
 
 using namespace tile;
 constexpr int kEpiWarps = 8;                        // two per TMEM lane quarter, 64 columns each
-constexpr int kThreads = 32 * (1 + 4 + kEpiWarps);  // warp 0: MMA, warps 1-4: movers, warps 5-12: epilogue
+constexpr int kLoaderWarp = 5 + kEpiWarps;            // warp 13: TMA loads / stores
+constexpr int kThreads = 32 * (kLoaderWarp + 1);     // warp 0: MMA, warps 1-4: reducers, warps 5-12: epilogue
 constexpr int kH = 128;
 
 struct Params {
@@ -61,7 +63,11 @@ struct Params {
   long long part_floats;
   int* status;
   long long* timing;    // debug: [3 roles][32] cycle counters of CTA 0 (nullable)
+  // tensor maps (mgn_tma.cuh): a row source without idx uses a {64 x 128} box map, one with idx a {64 x 1} gather map
+  // whose row extent is kOobRow, so that the index kOobRow (rows past M) reads as zeros
+  alignas(64) CUtensorMap m_a, m_g1, m_g2, m_go1, m_go2, m_ga, m_gz1;
 };
+constexpr int kOobRow = 1 << 30;
 
 enum { kStatusTimeout = 1, kStatusSmem = 2 };
 
@@ -75,7 +81,31 @@ enum { kStatusTimeout = 1, kStatusSmem = 2 };
 // barriers.  B_A / B_G: layer-1 input rows / additive rows of a tile are staged (published one tile ahead);
 // B_GO: incoming gradient rows staged; B_A2: layer-1 input rows staged again for the weight gradient;
 // B_MMA1 + k: k-th group of MMAs of the tile has completed; B_E1 + k: k-th epilogue phase has completed.
-enum { B_A = 0, B_G = 1, B_GO = 2, B_A2 = 3, B_MMA1 = 4, B_E1 = 11, B_NUM = 17 };
+// B_CS + k: the reducer warps have finished the k-th column-sum pass (its buffers may be overwritten).
+// B_ST: the g_z1 result tile has left the H1 buffer.
+enum { B_A = 0, B_G = 1, B_GO = 2, B_A2 = 3, B_MMA1 = 4, B_E1 = 11, B_CS = 17, B_ST = 20, B_NUM = 21 };
+
+// loader warp: stage one 128-row tile (two panels) of a row source -- two box loads (lane 0) or 64 gather4 loads
+// (lane l: rows 4l .. 4l+3, both panels); 2 * kPB bytes complete on `bar` either way
+__device__ __forceinline__ void tma_stage_rows(uint8_t* buf, const CUtensorMap* map, const int32_t* __restrict__ idx,
+                                               long long row0, long long M, uint64_t* bar, int lane) {
+  const uint32_t dst = smem_u32(buf);
+  if (idx == nullptr) {
+    if (lane == 0) {
+      tma_load_2d(dst, map, 0, static_cast<int>(row0), bar);
+      tma_load_2d(dst + kPB, map, 64, static_cast<int>(row0), bar);
+    }
+  } else {
+    int r[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long grow = row0 + 4 * lane + j;
+      r[j] = grow < M ? __ldg(idx + grow) : kOobRow;
+    }
+    tma_gather4(dst + 4 * lane * 128, map, 0, r[0], r[1], r[2], r[3], bar);
+    tma_gather4(dst + kPB + 4 * lane * 128, map, 64, r[0], r[1], r[2], r[3], bar);
+  }
+}
 
 // Four 32 KB tile buffers rotate roles from tile to tile so that the next tile's rows stream in while the current
 // tile is still in its backward half: role r of tile `it` lives in buffer (r - it) mod 4, i.e. the next tile's A
@@ -114,7 +144,7 @@ __device__ __forceinline__ bool bf_pos_lo(uint32_t w) { return static_cast<int32
 __device__ __forceinline__ bool bf_pos_hi(uint32_t w) { return static_cast<int32_t>(w & 0xFFFF0000u) > 0; }
 
 template <int KP>
-__global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_constant__ Params p) {
   using L = Smem<KP>;
   using PT = Part<KP>;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -150,7 +180,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     sPar[3 * kH + i] = has_ln ? p.gamma[i] : 1.f;
   }
   if (tid == 0) {
-    for (int b = 0; b < B_NUM; ++b) mbar_init(&bars[b], b < B_MMA1 ? 4 : (b < B_E1 ? 1 : kEpiWarps));
+    // B_A / B_A2: one arrive.expect_tx of the loader (TMA) or the four reducer warps (KP == 1: plain stores)
+    mbar_init(&bars[B_A], KP == 2 ? 1 : 4);
+    mbar_init(&bars[B_A2], KP == 2 ? 1 : 4);
+    // B_GO / B_G: the four reducer warps (cp.async row gathers) + the loader (TMA part / result tile has left)
+    mbar_init(&bars[B_GO], 5);
+    mbar_init(&bars[B_G], 5);
+    for (int b = B_MMA1; b < B_ST; ++b) mbar_init(&bars[b], b < B_E1 ? 1 : (b < B_CS ? kEpiWarps : 4));
+    mbar_init(&bars[B_ST], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -164,8 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
   bool timed_out = false;
-  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == 1 || warp == 5);
-  long long* tm = reinterpret_cast<long long*>(smem + L::kTiming) + (warp == 0 ? 0 : (warp == 1 ? 16 : 32));
+  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kLoaderWarp || warp == 5);
+  long long* tm = reinterpret_cast<long long*>(smem + L::kTiming) + (warp == 0 ? 0 : (warp == kLoaderWarp ? 16 : 32));
   if (tm_on) {
     for (int i = 0; i < 16; ++i) tm[i] = 0;
   }
@@ -274,7 +311,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       }
     }
   } else if (warp <= 4) {
-    // =========================== movers ===========================
+    // =========================== reducers ===========================
+    // bias / beta gradients = column sums of the gradient tiles, read from shared memory while the main chain runs;
+    // with raw small-width inputs (KP == 1) or a narrow incoming gradient they also stage those by plain stores
     const int mt = tid - 32;
 #define MGN_W(b, ph)                                                      \
   {                                                                       \
@@ -289,29 +328,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
   __syncwarp();               \
   if (lane == 0) mbar_arrive(&bars[b]);
 #define MGN_MOVER_SYNC() asm volatile("bar.sync 1, 128;" ::: "memory")
-    const int rsub_m = mt >> 4;
-    const bool go2_shares_g2 = has_go2 && p.go2.idx == p.g2.idx && p.go2.idx != nullptr;
-    int32_t r_g1[16], r_g2[16], r_tmp[16];
-    // running column sums (fixed columns per thread) for the bias / beta gradients
+    // running column sums (fixed columns per thread)
     float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
           cs_beta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    // prologue: tile 0 (A, then the additive rows; published separately so GEMM1 never waits for the gathers)
-    if (n_my > 0) {
+    const int rsub_m = mt >> 4;
+    const bool go2_shares_g2 = has_go2 && p.go2.idx == p.g2.idx && p.go2.idx != nullptr;
+    const bool go1_gathered = !p.go_small && p.go1.idx != nullptr;
+    int32_t r_g1[16], r_g2[16], r_tmp[16];
+    if (n_my > 0) {  // prologue: tile 0
       const long long row00 = static_cast<long long>(blockIdx.x) * kRows;
+      if (KP == 1) {
+        stage_small(MGN_BUF(R_A, 0), p.small_x, p.small_in, p.small_is_f32, row00, p.M, mt);
+        MGN_PUBLISH(B_A);
+      }
       fetch_row_ids(has_g ? p.g1.idx : nullptr, row00, p.M, rsub_m, r_g1);
       fetch_row_ids(has_g2 ? p.g2.idx : (has_go2 ? p.go2.idx : nullptr), row00, p.M, rsub_m, r_g2);
-      if (KP == 2) {
-        fetch_row_ids(p.a.idx, row00, p.M, rsub_m, r_tmp);
-        stage_rows_async(MGN_BUF(R_A, 0), p.a, r_tmp, row00, p.M, mt);
-      } else {
-        stage_small(MGN_BUF(R_A, 0), p.small_x, p.small_in, p.small_is_f32, row00, p.M, mt);
-      }
-      cp_async_commit();
       if (has_g) stage_rows_async(MGN_BUF(R_X, 0), p.g1, r_g1, row00, p.M, mt);
       if (has_g2) stage_rows_async(MGN_BUF(R_H2, 0), p.g2, r_g2, row00, p.M, mt);
       cp_async_commit();
-      cp_async_wait<1>();
-      MGN_PUBLISH(B_A);
       cp_async_wait<0>();
       MGN_PUBLISH(B_G);
     }
@@ -325,13 +359,12 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
       uint8_t* bH1 = MGN_BUF(R_H1, it);
       uint8_t* bH2 = MGN_BUF(R_H2, it);
       if (more && has_g) fetch_row_ids(p.g1.idx, row0n, p.M, rsub_m, r_g1);  // used at the end of this tile
-      MGN_T(0);
-      // incoming gradient, once the layer-1 epilogue has consumed the additive rows (and GEMM1 the A rows)
       MGN_W(B_E1 + 0, par);
-      MGN_T(1);
-      if (!p.go_small) {  // go1 -> X, go2 -> A; summed in E3
-        fetch_row_ids(p.go1.idx, row0, p.M, rsub_m, r_tmp);
-        stage_rows_async(bX, p.go1, r_tmp, row0, p.M, mt);
+      if (!p.go_small) {  // gathered parts of the incoming gradient (go1 by rows -> X, go2 -> A); summed in E3
+        if (go1_gathered) {
+          fetch_row_ids(p.go1.idx, row0, p.M, rsub_m, r_tmp);
+          stage_rows_async(bX, p.go1, r_tmp, row0, p.M, mt);
+        }
         if (has_go2) {
           if (!go2_shares_g2) fetch_row_ids(p.go2.idx, row0, p.M, rsub_m, r_g2);
           stage_rows_async(bA, p.go2, r_g2, row0, p.M, mt);
@@ -340,7 +373,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         if (more && (has_g2 || go2_shares_g2))
           fetch_row_ids(has_g2 ? p.g2.idx : p.go2.idx, row0n, p.M, rsub_m, r_g2);  // used at the end of this tile
         cp_async_wait<0>();
-      } else {
+        MGN_PUBLISH(B_GO);
+      } else {  // narrow incoming gradient (decoder): zero-padded to 128 columns -> X
         const int chunk = mt & 15, rsub = mt >> 4;
         for (int i = 0; i < 16; ++i) {
           const int row = i * 8 + rsub;
@@ -358,72 +392,46 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
           v4.w = pack_bf16x2(f[6], f[7]);
           *reinterpret_cast<uint4*>(bX + (chunk >> 3) * kPB + sw128_offset(row, chunk & 7)) = v4;
         }
+        MGN_PUBLISH(B_GO);
       }
-      MGN_PUBLISH(B_GO);
-      MGN_T(2);
-      // after E3: X = g_out (summed), A = g_y.  Bias / beta gradients, then re-stage A once the layer-3 MMAs have
-      // consumed g_y
+      // after E3: X = g_out (summed), A = g_y
       MGN_W(B_E1 + 2, par);
-      MGN_T(3);
       colsum_tile(bX, mt, cs_beta);
       colsum_tile(bA, mt, cs_b3);
-      MGN_T(4);
-      MGN_W(B_MMA1 + 3, par);
-      MGN_T(5);
-      if (KP == 2) {
-        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_tmp);
-        stage_rows_async(bA, p.a, r_tmp, row0, p.M, mt);
-        cp_async_commit();
-        cp_async_wait<0>();
-      } else {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 0]);
+      if (KP == 1) {  // re-stage the layer-1 input once the layer-3 MMAs have consumed g_y
+        MGN_W(B_MMA1 + 3, par);
+        MGN_MOVER_SYNC();
         stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
+        MGN_PUBLISH(B_A2);
       }
-      MGN_PUBLISH(B_A2);
-      MGN_T(6);
       MGN_W(B_E1 + 3, par);
-      MGN_T(7);
       colsum_tile(bH2, mt, cs_b2);
-      MGN_T(8);
-      // the layer-2 MMAs have consumed g_z2: the next tile's A rows stream into this tile's H2 buffer
-      MGN_W(B_MMA1 + 4, par);
-      if (more) {
-        if (KP == 2) {
-          fetch_row_ids(p.a.idx, row0n, p.M, rsub_m, r_tmp);
-          stage_rows_async(bH2, p.a, r_tmp, row0n, p.M, mt);
-        } else {
-          stage_small(bH2, p.small_x, p.small_in, p.small_is_f32, row0n, p.M, mt);
-        }
-        cp_async_commit();
-      }
-      MGN_T(9);
-      MGN_W(B_E1 + 4, par);
-      MGN_T(10);
-      if (more) {  // the next tile's A rows have had a whole epilogue phase to land: publish them before anything else
-        cp_async_wait<0>();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
+      if (KP == 1 && more) {  // next tile's input into this tile's H2 buffer (free after the layer-2 MMAs)
+        MGN_W(B_MMA1 + 4, par);
+        MGN_MOVER_SYNC();
+        stage_small(bH2, p.small_x, p.small_in, p.small_is_f32, row0n, p.M, mt);
         MGN_PUBLISH(B_A);
       }
+      MGN_W(B_E1 + 4, par);
       colsum_tile(bH1, mt, cs_b1);
-      if (p.g_z1) store_rows(bH1, p.g_z1, p.g_z1_ld, row0, p.M, mt);
-      MGN_T(11);
-      // the layer-1 MMAs have consumed A and g_z1: the next tile's additive rows stream into those buffers
-      MGN_W(B_MMA1 + 6, par);
-      if (more) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
+      if (more) {  // next tile's additive rows -> this tile's A and H1 buffers (free after the layer-1 MMAs)
+        MGN_W(B_MMA1 + 6, par);
+        MGN_W(B_ST, par);
         if (has_g) stage_rows_async(bA, p.g1, r_g1, row0n, p.M, mt);
         if (has_g2) stage_rows_async(bH1, p.g2, r_g2, row0n, p.M, mt);
         cp_async_commit();
-      }
-      MGN_T(12);
-      MGN_W(B_E1 + 5, par);
-      MGN_T(13);
-      if (need_ga) store_rows(bX, p.g_a, kH, row0, p.M, mt);
-      if (more) {
         cp_async_wait<0>();
-        MGN_PUBLISH(B_G);  // also orders this warp's reads of X (g_A store) before the next tile's E1 writes h1 there
+        MGN_PUBLISH(B_G);
       }
-      MGN_T(14);
     }
 #undef MGN_W
-    asm volatile("bar.sync 10, 384;" ::: "memory");  // movers + epilogue: nobody reads a tile buffer any more
+    asm volatile("bar.sync 10, 384;" ::: "memory");  // reducers + epilogue: nobody reads a tile buffer any more
     {
       const int chunk = mt & 15, rsub = mt >> 4;
 #pragma unroll
@@ -434,6 +442,97 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
         scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
       }
     }
+  } else if (warp == kLoaderWarp) {
+    // =========================== loader (TMA) ===========================
+    // every bulk tensor load / gather / store of the CTA.  A tile's rows are requested as early as their buffer is
+    // free: the next tile's A right after this tile's layer-2 MMAs, its additive rows after the layer-1 MMAs.
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+    const bool go1_tma = !p.go_small && p.go1.idx == nullptr;
+    if (n_my > 0) {  // prologue: tile 0
+      const long long row00 = static_cast<long long>(blockIdx.x) * kRows;
+      if (lane == 0) {
+        if (KP == 2) mbar_arrive_expect_tx(&bars[B_A], 2 * kPB);
+        mbar_arrive(&bars[B_G]);  // (no earlier result tile to wait for)
+      }
+      __syncwarp();
+      if (KP == 2) tma_stage_rows(MGN_BUF(R_A, 0), &p.m_a, nullptr, row00, p.M, &bars[B_A], lane);
+    }
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      const bool more = it + 1 < n_my;
+      const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+      const long long row0n = row0 + static_cast<long long>(gridDim.x) * kRows;  // next tile of this CTA
+      uint8_t* bA = MGN_BUF(R_A, it);
+      uint8_t* bX = MGN_BUF(R_X, it);
+      uint8_t* bH1 = MGN_BUF(R_H1, it);
+      uint8_t* bH2 = MGN_BUF(R_H2, it);
+      MGN_T(0);
+      // dense incoming gradient once E1 has consumed the additive rows: go1 -> X
+      MGN_W(B_E1 + 0, par);
+      MGN_T(1);
+      if (lane == 0) {
+        if (go1_tma) mbar_arrive_expect_tx(&bars[B_GO], 2 * kPB);
+        else mbar_arrive(&bars[B_GO]);
+      }
+      __syncwarp();
+      if (go1_tma) tma_stage_rows(bX, &p.m_go1, nullptr, row0, p.M, &bars[B_GO], lane);
+      MGN_T(2);
+      if (KP == 2) {
+        // layer-1 input again (for its weight gradient) once the layer-3 MMAs and the column sums are done with g_y
+        MGN_W(B_MMA1 + 3, par);
+        MGN_W(B_CS + 0, par);
+        MGN_T(3);
+        if (lane == 0) mbar_arrive_expect_tx(&bars[B_A2], 2 * kPB);
+        __syncwarp();
+        tma_stage_rows(bA, &p.m_a, nullptr, row0, p.M, &bars[B_A2], lane);
+        MGN_T(4);
+        if (more) {  // next tile's layer-1 input -> this tile's H2 buffer
+          MGN_W(B_MMA1 + 4, par);
+          MGN_W(B_CS + 1, par);
+          MGN_T(5);
+          if (lane == 0) mbar_arrive_expect_tx(&bars[B_A], 2 * kPB);
+          __syncwarp();
+          tma_stage_rows(bH2, &p.m_a, nullptr, row0n, p.M, &bars[B_A], lane);
+          MGN_T(6);
+        }
+      }
+      // g_z1 tile (H1) -> global
+      MGN_W(B_E1 + 4, par);
+      MGN_T(7);
+      if (lane == 0) {
+        if (p.g_z1 != nullptr) {
+          tma_store_2d(&p.m_gz1, smem_u32(bH1), 0, static_cast<int>(row0));
+          tma_store_2d(&p.m_gz1, smem_u32(bH1) + kPB, 64, static_cast<int>(row0));
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        mbar_arrive(&bars[B_ST]);
+      }
+      __syncwarp();
+      MGN_T(8);
+      MGN_W(B_E1 + 5, par);
+      MGN_T(9);
+      if (lane == 0) {
+        if (need_ga) {  // g_A tile (X) -> global
+          tma_store_2d(&p.m_ga, smem_u32(bX), 0, static_cast<int>(row0));
+          tma_store_2d(&p.m_ga, smem_u32(bX) + kPB, 64, static_cast<int>(row0));
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        if (more) mbar_arrive(&bars[B_G]);  // X is the next tile's H1: its E1 may write there now
+      }
+      __syncwarp();
+      MGN_T(10);
+    }
+#undef MGN_W
+    if (lane == 0) tma_store_wait_all();
   } else {
     // =========================== epilogue (8 warps) ===========================
     // two warps per TMEM lane quarter: warp (q, ch) owns tile rows [32q, 32q+32) (thread = row = TMEM lane)
@@ -691,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
     }
   }
   if (tm_on) {
-    const int role = warp == 0 ? 0 : (warp == 1 ? 1 : 2);
+    const int role = warp == 0 ? 0 : (warp == kLoaderWarp ? 1 : 2);
     for (int i = 0; i < 16; ++i) p.timing[role * 32 + i] = tm[i];
   }
 
@@ -702,7 +801,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const Params p
 
   // ---------------- write this CTA's partial gradients ----------------
   float* part = p.partials + static_cast<long long>(blockIdx.x) * p.part_floats;
-  if (warp >= 5) {
+  if (warp >= 5 && warp < kLoaderWarp) {
     const int q = warp & 3;
     const int ch = (warp - 5) >> 2;
     const int row = q * 32 + lane;  // TMEM lane = output-feature row of the weight gradient
@@ -827,6 +926,21 @@ extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const vo
   const int grid = bwd_grid(M);
   int rc;
   int n1;
+  {  // tensor maps of every table the loader warp touches
+    auto mk = [&](CUtensorMap* m, const bwd::RowSrc& s) -> int {
+      if (s.tab == nullptr) return 0;
+      return tma_make_rows_map(m, s.tab + s.col0, s.idx ? bwd::kOobRow : M, s.ld, s.idx ? 1 : 128);
+    };
+    int e = 0;
+    if (small_in <= 0) e |= mk(&p.m_a, p.a);
+    e |= mk(&p.m_g1, p.g1);
+    e |= mk(&p.m_g2, p.g2);
+    if (!p.go_small) e |= mk(&p.m_go1, p.go1);
+    e |= mk(&p.m_go2, p.go2);
+    if (g_a) e |= tma_make_rows_map(&p.m_ga, g_a, M, bwd::kH, 128);
+    if (g_z1) e |= tma_make_rows_map(&p.m_gz1, g_z1, M, p.g_z1_ld, 128);
+    if (e != 0) return MGN_EINVAL;
+  }
   if (small_in > 0) {
     MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && g_a == nullptr && ld_w1 >= small_in);
     p.k1_true = small_in;
