@@ -145,18 +145,22 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
       float acc[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = 0.f;
-      int32_t j = b + g;
-      // 4 rows in flight per group
-      for (; j + 3 * R < e; j += 4 * R) {
+      // up to 4 rows in flight per lane group, also for short segments (mesh in-degrees are ~6: a predicated batch
+      // keeps every row of the segment in flight at once instead of one dependent load per iteration)
+      for (int32_t j = b + g; j < e; j += 4 * R) {
         uint4 v[4];
+        bool on[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int64_t row = eids ? __ldg(eids + j + u * R) : (j + u * R);
-          if (active) v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+          on[u] = active && (j + u * R < e);
+          if (on[u]) {
+            const int64_t row = eids ? __ldg(eids + j + u * R) : (j + u * R);
+            v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+          }
         }
-        if (active) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < 4; ++u) {
+          if (on[u]) {
             Vec16<T> t;
             t.raw = v[u];
             float f[V];
@@ -164,17 +168,6 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
 #pragma unroll
             for (int k = 0; k < V; ++k) acc[k] += f[k];
           }
-        }
-      }
-      for (; j < e; j += R) {
-        const int64_t row = eids ? __ldg(eids + j) : j;
-        if (active) {
-          Vec16<T> t;
-          t.raw = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
-          float f[V];
-          t.unpack(f);
-#pragma unroll
-          for (int k = 0; k < V; ++k) acc[k] += f[k];
         }
       }
 #pragma unroll

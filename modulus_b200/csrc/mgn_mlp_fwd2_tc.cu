@@ -304,9 +304,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       break;                                                              \
     }                                                                     \
   }
-#define MGN_EPI_SYNC()                               \
-  tc_fence_before_sync();                            \
-  asm volatile("bar.sync 2, 256;" ::: "memory");     \
+// the two warps that share tile rows (same TMEM lane quarter) synchronise on their own named barrier
+#define MGN_ROW_SYNC()                                            \
+  tc_fence_before_sync();                                         \
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");       \
   tc_fence_after_sync()
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
@@ -319,29 +320,36 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       tc_fence_after_sync();
       if (!p.single) {
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
-        float f[16], f2[16];
-        if (has_g1) row_load16(bG1, row, c0 + g * 16, f);
-        if (has_g2) row_load16(bG2, row, c0 + g * 16, f2);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = c0 + 32 * hh;
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t ga[16], gb[16];
+        if (has_g1) row_load32p(bG1, row, cc, ga);
+        if (has_g2) row_load32p(bG2, row, cc, gb);
         tmem_ld_wait();
-        uint32_t pk[8];
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float z0 = __uint_as_float(v[2 * j]) + b1[g * 16 + 2 * j];
-          float z1 = __uint_as_float(v[2 * j + 1]) + b1[g * 16 + 2 * j + 1];
+        for (int u = 0; u < 8; ++u) {  // 4 columns per step: one 16-byte parameter load instead of four scalar ones
+          const float4 bb = reinterpret_cast<const float4*>(b1 + 32 * hh)[u];
+          float z0 = __uint_as_float(v[4 * u]) + bb.x, z1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+          float z2 = __uint_as_float(v[4 * u + 2]) + bb.z, z3 = __uint_as_float(v[4 * u + 3]) + bb.w;
           if (has_g1) {
-            z0 += f[2 * j];
-            z1 += f[2 * j + 1];
+            z0 += bf_lo(ga[2 * u]);
+            z1 += bf_hi(ga[2 * u]);
+            z2 += bf_lo(ga[2 * u + 1]);
+            z3 += bf_hi(ga[2 * u + 1]);
           }
           if (has_g2) {
-            z0 += f2[2 * j];
-            z1 += f2[2 * j + 1];
+            z0 += bf_lo(gb[2 * u]);
+            z1 += bf_hi(gb[2 * u]);
+            z2 += bf_lo(gb[2 * u + 1]);
+            z3 += bf_hi(gb[2 * u + 1]);
           }
-          pk[j] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+          pk[2 * u] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+          pk[2 * u + 1] = pack_bf16x2(fmaxf(z2, 0.f), fmaxf(z3, 0.f));
         }
-        tmem_st8(t_h + g * 8, pk);
+        tmem_st16(t_h + 16 * hh, pk);
       }
       tmem_st_wait();
       tc_fence_before_sync();
@@ -353,16 +361,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       MGN_T(2);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
         tmem_ld_wait();
-        uint32_t pk[8];
+        uint32_t pk[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          pk[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[g * 16 + 2 * j], 0.f),
-                              fmaxf(__uint_as_float(v[2 * j + 1]) + b2[g * 16 + 2 * j + 1], 0.f));
-        tmem_st8(t_h + g * 8, pk);
+        for (int u = 0; u < 8; ++u) {
+          const float4 bb = reinterpret_cast<const float4*>(b2 + 32 * hh)[u];
+          pk[2 * u] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * u]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * u + 1]) + bb.y, 0.f));
+          pk[2 * u + 1] =
+              pack_bf16x2(fmaxf(__uint_as_float(v[4 * u + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * u + 3]) + bb.w, 0.f));
+        }
+        tmem_st16(t_h + 16 * hh, pk);
       }
       tmem_st_wait();
       tc_fence_before_sync();
@@ -376,65 +387,79 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       tc_fence_after_sync();
       float mu = 0.f, rstd = 1.f;
       if (has_ln) {
-        float s = 0.f;
+        // one pass over the accumulator for both row sums (fp32), exchanged between the two column halves of a row
+        // through spare TMEM columns; only the two warps that share the rows synchronise
+        float s = 0.f, ss = 0.f;
 #pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + g * 16, v);
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) s += __uint_as_float(v[j]) + b3[g * 16 + j];
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
+            const float y0 = __uint_as_float(v[4 * u]) + bb.x, y1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+            const float y2 = __uint_as_float(v[4 * u + 2]) + bb.z, y3 = __uint_as_float(v[4 * u + 3]) + bb.w;
+            s += (y0 + y1) + (y2 + y3);
+            ss = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, ss))));
+          }
         }
-        // exchange the partial row sums of the two column halves through spare TMEM columns
-        tmem_st2(t_x + ch * 2, __float_as_uint(s), 0u);
+        MGN_T(6);
+        tmem_st2(t_x + ch * 2, __float_as_uint(s), __float_as_uint(ss));
         tmem_st_wait();
-        MGN_EPI_SYNC();
+        MGN_ROW_SYNC();
         uint32_t o0, o1;
         tmem_ld2(t_x + (ch ^ 1) * 2, o0, o1);
         tmem_ld_wait();
+        MGN_ROW_SYNC();  // the partner has read this tile's sums before the next tile overwrites them
         mu = (s + __uint_as_float(o0)) * (1.f / kH);
-        float qv = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          uint32_t v[16];
-          tmem_ld16(t_acc + g * 16, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float d = __uint_as_float(v[j]) + b3[g * 16 + j] - mu;
-            qv = fmaf(d, d, qv);
-          }
-        }
-        MGN_EPI_SYNC();  // partner has read the first exchange
-        tmem_st2(t_x + ch * 2, __float_as_uint(qv), 0u);
-        tmem_st_wait();
-        MGN_EPI_SYNC();
-        tmem_ld2(t_x + (ch ^ 1) * 2, o0, o1);
-        tmem_ld_wait();
-        rstd = rsqrtf((qv + __uint_as_float(o0)) * (1.f / kH) + p.eps);
+        const float var = fmaxf((ss + __uint_as_float(o1)) * (1.f / kH) - mu * mu, 0.f);
+        rstd = rsqrtf(var + p.eps);
+        MGN_T(7);
       }
       const uint8_t* rbuf = p.res_is_a ? bAcur : bG2;
       const bool has_res = p.res.tab != nullptr || p.res_is_a;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
-        uint32_t v[16];
-        tmem_ld16(t_acc + g * 16, v);
-        float r[16];
-        if (has_res) row_load16(rbuf, row, c0 + g * 16, r);
+      for (int hh = 0; hh < 2; ++hh) {
+        const int cc = c0 + 32 * hh;
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t r[16];
+        if (has_res) row_load32p(rbuf, row, cc, r);
         tmem_ld_wait();
-        float y[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float x = __uint_as_float(v[j]) + b3[g * 16 + j];
-          y[j] = has_ln ? ((x - mu) * rstd * gam[g * 16 + j] + bet[g * 16 + j]) : x;
-          if (has_res) y[j] += r[j];
-        }
         if (!direct_out) {
-          row_store16(bAcur, row, c0 + g * 16, y);
+          uint32_t o[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
+            float y[4] = {__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
+                          __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w};
+            if (has_ln) {
+              const float4 gg = reinterpret_cast<const float4*>(gam + 32 * hh)[u];
+              const float4 be = reinterpret_cast<const float4*>(bet + 32 * hh)[u];
+              y[0] = (y[0] - mu) * rstd * gg.x + be.x;
+              y[1] = (y[1] - mu) * rstd * gg.y + be.y;
+              y[2] = (y[2] - mu) * rstd * gg.z + be.z;
+              y[3] = (y[3] - mu) * rstd * gg.w + be.w;
+            }
+            if (has_res) {
+              y[0] += bf_lo(r[2 * u]);
+              y[1] += bf_hi(r[2 * u]);
+              y[2] += bf_lo(r[2 * u + 1]);
+              y[3] += bf_hi(r[2 * u + 1]);
+            }
+            o[2 * u] = pack_bf16x2(y[0], y[1]);
+            o[2 * u + 1] = pack_bf16x2(y[2], y[3]);
+          }
+          row_store32p(bAcur, row, cc, o);
         } else if (grow < p.M) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (c0 + g * 16 + j < p.n_out) p.out[grow * p.ld_out + c0 + g * 16 + j] = __float2bfloat16_rn(y[j]);
+          for (int j = 0; j < 32; ++j) {
+            float y = __uint_as_float(v[j]) + b3[32 * hh + j];
+            if (has_ln) y = (y - mu) * rstd * gam[32 * hh + j] + bet[32 * hh + j];
+            if (has_res) y += (j & 1) ? bf_hi(r[j >> 1]) : bf_lo(r[j >> 1]);
+            if (cc + j < p.n_out) p.out[grow * p.ld_out + cc + j] = __float2bfloat16_rn(y);
+          }
         }
       }
       tc_fence_before_sync();

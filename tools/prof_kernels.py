@@ -90,4 +90,4 @@ t = tbuf.cpu().view(3, 32)
 print("FWD2 kernel, CTA 0, cycles per tile")
 print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // per_cta for v in t[0, :5].tolist()], "total", int(t[0].sum()) // per_cta)
 print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // per_cta for v in t[1, :5].tolist()], "total", int(t[1].sum()) // per_cta)
-print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 :", [int(v) // per_cta for v in t[2, :6].tolist()], "total", int(t[2].sum()) // per_cta)
+print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 pass2 | E3 stats | E3 exchange :", [int(v) // per_cta for v in t[2, :8].tolist()], "total", int(t[2].sum()) // per_cta)
