@@ -235,6 +235,11 @@ int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_t ld1, cons
  * pipeline (cp.async staging, coalesced stores).  Wider products are issued per 128-column block. */
 int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,
                      const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
+/* out[M, 128 nb] (row stride ld_out) = x[M, 128 kb] (row stride ld_x) W[128 nb, 128 kb]^T (+ residual[M,128], nb == 1),
+ * kb * nb <= 3: TMA-staged persistent tcgen05 pipeline, one pass over x and one over out (the projection table
+ * P = nfeat Wp^T with kb = 1, nb = 3 and the node-feature gradient g_nfeat + T Wp with kb = 3, nb = 1). */
+int mgn_node_gemm_tc(const void* x, int64_t ld_x, int kb, int64_t M, const float* w, int64_t ld_w, int nb,
+                     const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
 size_t mgn_wgrad_tc_workspace_bytes(int64_t M, int n_blocks);
 int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const void* x, int64_t ld_x, int64_t M,
                  float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, int* status,

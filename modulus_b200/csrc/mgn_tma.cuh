@@ -32,13 +32,14 @@ static inline TmaEncodeTiledFn tma_encoder() {
   return fn;
 }
 
-// Tensor map over columns [0, 128) of a bf16 table starting at `base` (16-byte aligned) with `rows` rows and a row
+// Tensor map over columns [0, cols) of a bf16 table starting at `base` (16-byte aligned) with `rows` rows and a row
 // stride of `ld` elements (multiple of 8): box = {64 columns, box_rows}.  Returns 0 or a negative error.
-static inline int tma_make_rows_map(CUtensorMap* m, const void* base, long long rows, long long ld, int box_rows) {
+static inline int tma_make_rows_map(CUtensorMap* m, const void* base, long long rows, long long ld, int box_rows,
+                                    int cols = 128) {
   TmaEncodeTiledFn enc = tma_encoder();
   if (enc == nullptr) return -100;
   if (rows <= 0) rows = 1;
-  const cuuint64_t gdim[2] = {128, static_cast<cuuint64_t>(rows)};
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * 2};
   const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t estr[2] = {1, 1};

@@ -39,7 +39,19 @@ def agg():
 def csr():
     return ops.segment_sum(efeat, 0, 128, plan.csr_offsets, plan.csr_eids, N)
 
-for name, fn in (("fwd_g edge", fwd), ("fwd2 edge", fwd2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr)):
+nfeat = r(N, 128).bfloat16(); T3 = r(N, 384).bfloat16(); wp = r(384, 128) / 11; wpt = wp.t().contiguous()
+
+def lin_p():
+    return ops.linear_tc(nfeat, wp)
+
+def lin_t():
+    return ops.linear_tc(T3, wpt, residual=nfeat)
+
+def wgrad():
+    return ops.wgrad_tc(T3, nfeat)
+
+for name, fn in (("fwd2 edge", fwd2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr),
+                 ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -68,19 +80,6 @@ names = {0: "MMA  : wA+E6prev | g1 | wE1 | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 |
 for r in range(3):
     print(names[r])
     print("   cycles/tile:", [int(v) // per_cta for v in t[r, :16].tolist()], " total/tile:", int(t[r].sum()) // per_cta)
-
-tbuf.zero_()
-_lib.call("mgn_debug_set_fwd_timing", tbuf.data_ptr())
-fwd(); torch.cuda.synchronize()
-_lib.call("mgn_debug_set_fwd_timing", None)
-t = tbuf.cpu().view(3, 32)
-print("FWD kernel, CTA 0, cycles per tile")
-print(" MMA   : wait acc_free | wait full (sum) | issue GEMM1 | wait h_ready L2 | wait h_ready L3 | issue L2/L3")
-print("   ", [int(v) // per_cta for v in t[0, :6].tolist()], "total", int(t[0].sum()) // per_cta)
-print(" LOADER: wait empty (sum) | issue+publish (sum)")
-print("   ", [int(v) // per_cta for v in t[1, :2].tolist()], "total", int(t[1].sum()) // per_cta)
-print(" EPI(one of two groups; per its tile): wait L1 | wait L2 | epi L1 | epi L2 | wait out | (gap) | LN stats | store")
-print("   ", [int(v) // max(per_cta // 2, 1) for v in t[2, :8].tolist()], "total", int(t[2].sum()) // max(per_cta // 2, 1))
 
 tbuf.zero_()
 _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
