@@ -195,6 +195,95 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
   }
 }
 
+// Same sum, same order, more bytes in flight: when one lane group covers a whole row (chunks == G) a warp takes S
+// consecutive segments at a time and issues the first U rows per lane group of ALL of them before consuming any
+// (mesh in-degrees are ~6: with G = 16 that is the whole segment), i.e. S*U 16-byte loads in flight per lane
+// instead of one dependent load per short segment.  Longer segments finish in the tail loop.
+template <typename T, int G, int S, int U>
+__global__ void __launch_bounds__(256)
+segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, const int32_t* __restrict__ offsets,
+                         const int32_t* __restrict__ eids, int64_t n_seg, T* __restrict__ out, int64_t ld_out,
+                         int64_t out_col0, int mean, int accumulate) {
+  constexpr int V = Num<T>::kVec;
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / G, c = lane % G;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const T* col = in + in_col0 + static_cast<int64_t>(c) * V;
+  for (int64_t s0 = warp * S; s0 < n_seg; s0 += nwarps * S) {
+    int32_t b[S], e[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const bool valid = s0 + i < n_seg;
+      b[i] = valid ? __ldg(offsets + s0 + i) : 0;
+      e[i] = valid ? __ldg(offsets + s0 + i + 1) : 0;
+    }
+    int64_t rows[S][U];
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t j = b[i] + g + u * R;
+        rows[i][u] = (j < e[i]) ? (eids ? static_cast<int64_t>(__ldg(eids + j)) : static_cast<int64_t>(j)) : -1;
+      }
+    uint4 v[S][U];
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rows[i][u] >= 0) v[i][u] = ldg16(col + rows[i][u] * ld_in);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (rows[i][u] >= 0) {
+          Vec16<T> t;
+          t.raw = v[i][u];
+          float f[V];
+          t.unpack(f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] += f[k];
+        }
+      }
+      for (int32_t j = b[i] + g + U * R; j < e[i]; j += R) {  // long segments (uniform per warp)
+        const int64_t row = eids ? __ldg(eids + j) : j;
+        Vec16<T> t;
+        t.raw = ldg16(col + row * ld_in);
+        float f[V];
+        t.unpack(f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += f[k];
+      }
+#pragma unroll
+      for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
+      }
+      if (g == 0 && s0 + i < n_seg) {
+        const float scale = mean ? 1.f / static_cast<float>(max(e[i] - b[i], 1)) : 1.f;
+        T* o = out + (s0 + i) * ld_out + out_col0 + static_cast<int64_t>(c) * V;
+        Vec16<T> t;
+        if (accumulate) {
+          t.raw = *reinterpret_cast<const uint4*>(o);
+          float f[V];
+          t.unpack(f);
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] = f[k] + acc[k] * scale;
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) acc[k] *= scale;
+        }
+        t.pack(acc);
+        *reinterpret_cast<uint4*>(o) = t.raw;
+      }
+    }
+  }
+}
+
 template <typename T>
 __global__ void segment_sum_scalar_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int D,
                                           const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids,
@@ -327,6 +416,11 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
 #define MGN_SEG(G)                                                                                     \
   segment_sum_vec_kernel<T, G><<<grid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
                                                      o_, ld_out, out_col0, mean, accumulate)
+    if (chunks == 16) {
+      segment_sum_batch_kernel<T, 16, 4, 3><<<grid_for((n_seg + 3) / 4 * 32), 256, 0, MGN_ST(st)>>>(
+          i_, ld_in, in_col0, offsets, eids, n_seg, o_, ld_out, out_col0, mean, accumulate);
+      return mgn_launch_status();
+    }
     if (chunks <= 4) MGN_SEG(4);
     else if (chunks <= 8) MGN_SEG(8);
     else if (chunks <= 16) MGN_SEG(16);
