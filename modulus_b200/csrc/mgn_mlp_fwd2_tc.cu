@@ -24,12 +24,14 @@
 #include "mgn_common.cuh"
 #include "mgn_tc.cuh"
 #include "mgn_tile.cuh"
+#include "mgn_tma.cuh"
 
 namespace mgn {
 namespace fwd2 {
 
 using namespace tile;
-constexpr int kThreads = 416;
+constexpr int kLoaderWarp = 13;  // TMA: dense A tiles in, result tiles out
+constexpr int kThreads = 32 * (kLoaderWarp + 1);
 constexpr int kH = 128;
 
 struct Params {
@@ -51,9 +53,13 @@ struct Params {
   long long ld_out;
   int* status;
   long long* timing;
+  int tma_a, tma_out;  // dense A tiles arrive / result tiles leave through the loader warp (tensor maps below)
+  alignas(64) CUtensorMap m_a, m_out;
 };
 
-enum { B_IN = 0, B_M1 = 1, B_M2 = 2, B_M3 = 3, B_H1 = 4, B_H2 = 5, B_OUT = 6, B_NUM = 7 };
+// B_IN: next tile staged (four mover warps: gathered / small rows; loader: dense A tile by TMA);
+// B_STD: the result tile of a tile has left its A buffer
+enum { B_IN = 0, B_M1 = 1, B_M2 = 2, B_M3 = 3, B_H1 = 4, B_H2 = 5, B_OUT = 6, B_STD = 7, B_NUM = 8 };
 
 template <int KP>
 struct Smem {
@@ -78,7 +84,7 @@ struct Smem {
   }
 
 template <int KP>
-__global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_constant__ Params p) {
   using L = Smem<KP>;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -116,7 +122,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
     sPar[4 * kH + i] = (has_ln && p.beta) ? p.beta[i] : 0.f;
   }
   if (tid == 0) {
-    mbar_init(&bars[B_IN], 4);
+    mbar_init(&bars[B_IN], 5);
+    mbar_init(&bars[B_STD], 1);
     mbar_init(&bars[B_M1], 1);
     mbar_init(&bars[B_M2], 1);
     mbar_init(&bars[B_M3], 1);
@@ -125,13 +132,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
     mbar_init(&bars[B_OUT], 8);
     mbar_fence_init();
   }
-  if (warp == 0) tmem_alloc(tmem_slot, 256);
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
   fence_proxy_async_smem();
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tAcc = tmem, tH = tmem + 128, tX = tmem + 192;
+  // two accumulators (tile parity): the next tile's first GEMM runs while this tile's last epilogue drains the other one
+  const uint32_t tAcc0 = tmem, tH = tmem + 256, tX = tmem + 320;
 
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
@@ -157,15 +165,18 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
     timed_out = true;            \
     break;                       \
   }
-        MGN_W(B_IN, par);
-        if (it > 0) MGN_W(B_OUT, par ^ 1);  // previous tile's epilogue has drained the accumulator
-        MGN_T(0);
-        tc_fence_after_sync();
+        const uint32_t tAcc = tAcc0 + par * 128;
+        if (p.single || it == 0) {  // (otherwise this tile's first GEMM was issued during the previous tile)
+          MGN_W(B_IN, par);
+          if (it > 0) MGN_W(B_OUT, par ^ 1);  // single-GEMM mode: the tile two back has drained this accumulator
+          MGN_T(0);
+          tc_fence_after_sync();
 #pragma unroll
-        for (int k = 0; k < KP * 4; ++k)
-          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3), idesc,
-                  k != 0);
-        umma_commit(&bars[B_M1]);
+          for (int k = 0; k < KP * 4; ++k)
+            umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3), idesc,
+                    k != 0);
+          umma_commit(&bars[B_M1]);
+        }
         MGN_T(1);
         if (p.single) continue;
         MGN_W(B_H1, par);
@@ -183,6 +194,19 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
           umma_ts(tAcc, tH + k * 8, umma_desc_kmajor(aW3 + (k >> 2) * kPB, k & 3), idesc, k != 0);
         umma_commit(&bars[B_M3]);
         MGN_T(4);
+        if (it + 1 < n_my) {
+          // next tile's first GEMM into the other accumulator (drained by E3 of the tile before this one, which every
+          // epilogue warp finished before it signalled B_H2 of this tile); it overlaps this tile's E3
+          MGN_W(B_IN, par ^ 1);
+          tc_fence_after_sync();
+          const uint32_t aAn = aA0 + ((it + 1) & 1) * 2 * kPB;
+          const uint32_t tAccN = tAcc0 + (par ^ 1) * 128;
+#pragma unroll
+          for (int k = 0; k < KP * 4; ++k)
+            umma_ss(tAccN, umma_desc_kmajor(aAn + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3), idesc,
+                    k != 0);
+          umma_commit(&bars[B_M1]);
+        }
 #undef MGN_W
       }
     }
@@ -207,8 +231,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
     // prologue: tile 0
     if (n_my > 0) {
       if (KP == 2) {
-        fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_a);
-        stage_rows_async(bA0, p.a, r_a, row0, p.M, mt);
+        if (!p.tma_a) {
+          fetch_row_ids(p.a.idx, row0, p.M, rsub_m, r_a);
+          stage_rows_async(bA0, p.a, r_a, row0, p.M, mt);
+        }
       } else {
         stage_small(bA0, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
       }
@@ -222,7 +248,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       }
       cp_async_commit();
       if (n_my > 1) {  // row ids of tile 1
-        if (KP == 2) fetch_row_ids(p.a.idx, row0 + stride, p.M, rsub_m, r_a);
+        if (KP == 2 && !p.tma_a) fetch_row_ids(p.a.idx, row0 + stride, p.M, rsub_m, r_a);
         if (has_g1) fetch_row_ids(p.g1.idx, row0 + stride, p.M, rsub_m, r_g1);
         if (use_g2buf) fetch_row_ids(g2src.idx, row0 + stride, p.M, rsub_m, r_g2);
       }
@@ -238,7 +264,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       uint8_t* bAcur = bA0 + (it & 1) * 2 * kPB;
       uint8_t* bAnext = bA0 + ((it + 1) & 1) * 2 * kPB;
       // next tile's A rows stream into the other A buffer right away (its previous output was stored last iteration)
-      if (more) {
+      if (more && !p.tma_a) {
+        if (p.tma_out && it > 0) MGN_W(B_STD, par ^ 1);  // the loader's store of tile it - 1 has left that buffer
         if (KP == 2) stage_rows_async(bAnext, p.a, r_a, row1, p.M, mt);
         else stage_small(bAnext, p.small_x, p.small_in, p.small_is_f32, row1, p.M, mt);
       }
@@ -269,9 +296,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_IN]);
       }
-      if (!direct_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
+      if (!direct_out && !p.tma_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
       if (more && it + 2 < n_my) {  // row ids two tiles ahead of the running one
-        if (KP == 2) fetch_row_ids(p.a.idx, row1 + stride, p.M, rsub_m, r_a);
+        if (KP == 2 && !p.tma_a) fetch_row_ids(p.a.idx, row1 + stride, p.M, rsub_m, r_a);
         if (has_g1) fetch_row_ids(p.g1.idx, row1 + stride, p.M, rsub_m, r_g1);
         if (use_g2buf) fetch_row_ids(g2src.idx, row1 + stride, p.M, rsub_m, r_g2);
       }
@@ -281,6 +308,42 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
       row0 = row1;
     }
 #undef MGN_W
+  } else if (warp == kLoaderWarp) {
+    // =========================== loader (TMA) ===========================
+    if (lane == 0) {
+      const long long stride = static_cast<long long>(gridDim.x) * kRows;
+      long long row0 = static_cast<long long>(blockIdx.x) * kRows;
+      auto load_a = [&](uint8_t* buf, long long r0) {
+        if (p.tma_a) {
+          mbar_arrive_expect_tx(&bars[B_IN], 2 * kPB);
+          tma_load_2d(smem_u32(buf), &p.m_a, 0, static_cast<int>(r0), &bars[B_IN]);
+          tma_load_2d(smem_u32(buf) + kPB, &p.m_a, 64, static_cast<int>(r0), &bars[B_IN]);
+        } else {
+          mbar_arrive(&bars[B_IN]);
+        }
+      };
+      if (n_my > 0) load_a(bA0, row0);
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = it & 1;
+        uint8_t* bAcur = bA0 + (it & 1) * 2 * kPB;
+        uint8_t* bAnext = bA0 + ((it + 1) & 1) * 2 * kPB;
+        if (it + 1 < n_my) {
+          // (this tile's B_IN phase must be complete before an arrival may count for the next tile's)
+          if (!wait_clk(&bars[B_IN], par)) { timed_out = true; break; }
+          load_a(bAnext, row0 + stride);  // that buffer's previous result tile left it during the last iteration
+        }
+        if (!wait_clk(&bars[B_OUT], par)) { timed_out = true; break; }
+        if (p.tma_out) {
+          tma_store_2d(&p.m_out, smem_u32(bAcur), 0, static_cast<int>(row0));
+          tma_store_2d(&p.m_out, smem_u32(bAcur) + kPB, 64, static_cast<int>(row0));
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+        mbar_arrive(&bars[B_STD]);
+        row0 += stride;
+      }
+      tma_store_wait_all();
+    }
   } else {
     // =========================== epilogue (8 warps) ===========================
     const int q = warp & 3;
@@ -288,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
     const int row = q * 32 + lane;
     const int c0 = ch * 64;
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t t_acc = tAcc + lane_off + c0;
+    const uint32_t t_acc0 = tAcc0 + lane_off + c0;
     const uint32_t t_h = tH + lane_off + ch * 32;
     const uint32_t t_x = tX + lane_off;
     const float* b1 = sPar + c0;
@@ -311,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
   tc_fence_after_sync()
     for (int it = 0; it < n_my; ++it) {
       const uint32_t par = it & 1;
+      const uint32_t t_acc = t_acc0 + par * 128;
       uint8_t* bAcur = bA0 + (it & 1) * 2 * kPB;
       const long long grow = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows + row;
       // ---- E1: h1 = relu(acc + b1 + G1 + G2) -> TMEM (packed bf16)
@@ -462,6 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
           }
         }
       }
+      fence_proxy_async_smem();  // the result tile leaves through the async proxy (TMA store)
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_OUT]);
@@ -476,7 +541,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const Params 
   if (timed_out && p.status != nullptr) atomicOr(p.status, 1);
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 static long long* g_timing = nullptr;
@@ -493,6 +558,10 @@ static int launch(Params& p, cudaStream_t st) {
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
   p.timing = g_timing;
+  p.tma_a = KP == 2 && p.a.idx == nullptr;
+  p.tma_out = p.n_out == kH;
+  if (p.tma_a && tma_make_rows_map(&p.m_a, p.a.tab + p.a.col0, p.M, p.a.ld, 128) != 0) return MGN_EINVAL;
+  if (p.tma_out && tma_make_rows_map(&p.m_out, p.out, p.M, p.ld_out, 128) != 0) return MGN_EINVAL;
   mlp3_fwd2_tc_kernel<KP><<<grid, kThreads, L::kTotal, MGN_ST(st)>>>(p);
   return mgn_launch_status();
 }
