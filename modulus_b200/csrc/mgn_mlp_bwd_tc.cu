@@ -82,8 +82,9 @@ enum { kStatusTimeout = 1, kStatusSmem = 2 };
 // B_GO: incoming gradient rows staged; B_A2: layer-1 input rows staged again for the weight gradient;
 // B_MMA1 + k: k-th group of MMAs of the tile has completed; B_E1 + k: k-th epilogue phase has completed.
 // B_CS + k: the reducer warps have finished the k-th column-sum pass (its buffers may be overwritten).
-// B_ST: the g_z1 result tile has left the H1 buffer.
-enum { B_A = 0, B_G = 1, B_GO = 2, B_A2 = 3, B_MMA1 = 4, B_E1 = 11, B_CS = 17, B_ST = 20, B_NUM = 21 };
+// B_ST: the g_z1 result tile has left the H1 buffer.  B_W3 / B_W2: the weight-gradient MMAs of layer 3 / 2 have
+// completed (B_MMA1 + 3 / + 4 fire as soon as the data-gradient MMAs issued before them have).
+enum { B_A = 0, B_G = 1, B_GO = 2, B_A2 = 3, B_MMA1 = 4, B_E1 = 11, B_CS = 17, B_ST = 20, B_W3 = 21, B_W2 = 22, B_NUM = 23 };
 
 // loader warp: stage one 128-row tile (two panels) of a row source -- two box loads (lane 0) or 64 gather4 loads
 // (lane l: rows 4l .. 4l+3, both panels); 2 * kPB bytes complete on `bar` either way
@@ -107,10 +108,10 @@ __device__ __forceinline__ void tma_stage_rows(uint8_t* buf, const CUtensorMap* 
   }
 }
 
-// Four 32 KB tile buffers rotate roles from tile to tile so that the next tile's rows stream in while the current
-// tile is still in its backward half: role r of tile `it` lives in buffer (r - it) mod 4, i.e. the next tile's A
-// takes over this tile's H2 buffer (free after the layer-2 MMAs), its G1 this tile's A buffer and its G2 this
-// tile's H1 buffer (both free after the layer-1 MMAs).
+// Four 32 KB tile buffers.  Buffer 0 always holds the layer-1 input (A -> go2 rows -> g_y -> A again -> next tile's
+// A); the other three rotate roles from tile to tile so that the next tile's gathered rows stream in while this tile
+// is still in its backward half: the next tile's G1 takes over this tile's H2 buffer (free after the layer-2 MMAs),
+// its G2 this tile's H1 buffer (free after the layer-1 MMAs) and its H1 this tile's X buffer (once g_A has left).
 enum { R_A = 0, R_X = 1, R_H1 = 2, R_H2 = 3 };
 
 template <int KP>
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
   float* sPar = reinterpret_cast<float*>(smem + L::kPar);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L::kTmemSlot);
-#define MGN_BUF(role, it) (buf0 + ((((role) - (it)) & 3) * (2 * kPB)))
+#define MGN_BUF(role, it) (buf0 + ((role) == R_A ? 0 : 1 + (((role) - 1 + 2 * ((it) % 3)) % 3)) * (2 * kPB))
 
   const bool has_ln = p.gamma != nullptr;
   const bool has_g = p.g1.tab != nullptr;
@@ -188,6 +189,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
     mbar_init(&bars[B_G], 5);
     for (int b = B_MMA1; b < B_ST; ++b) mbar_init(&bars[b], b < B_E1 ? 1 : (b < B_CS ? kEpiWarps : 4));
     mbar_init(&bars[B_ST], 1);
+    mbar_init(&bars[B_W3], 1);
+    mbar_init(&bars[B_W2], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
 
   // per-CTA reduction scratch (bias / beta column sums of the movers, gamma sums of the epilogue): the H2 buffer
   // of this CTA's last tile, which nobody touches after that tile's layer-2 MMAs
-  float* scratch = reinterpret_cast<float*>(MGN_BUF(R_H2, n_my - 1));
+  float* scratch = reinterpret_cast<float*>(MGN_BUF(R_H2, n_my > 0 ? n_my - 1 : 0));
 
   if (warp == 0) {
     // =========================== MMA issuer ===========================
@@ -224,9 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       const uint32_t id_nn1 = umma_idesc_bf16(128, N1, 0, 1);
       for (int it = 0; it < n_my; ++it) {
         const uint32_t par = it & 1;
-        const uint32_t aA = a0 + ((R_A - it) & 3) * (2 * kPB);
-        const uint32_t aH1 = a0 + ((R_H1 - it) & 3) * (2 * kPB);
-        const uint32_t aH2 = a0 + ((R_H2 - it) & 3) * (2 * kPB);
+        const uint32_t aA = a0;
+        const uint32_t aH1 = smem_u32(MGN_BUF(R_H1, it));
+        const uint32_t aH2 = smem_u32(MGN_BUF(R_H2, it));
 #define MGN_W(b, ph)                         \
   if (!wait_clk(&bars[b], ph)) {             \
     timed_out = true;                        \
@@ -270,10 +273,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA1 + 3]);  // E4 may read the accumulator while the weight-gradient MMAs run
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
-        umma_commit(&bars[B_MMA1 + 3]);
+        umma_commit(&bars[B_W3]);
         MGN_T(7);
         // ---- layer 2: gW2 += g_z2^T h1 ; acc = g_z2 W2        (g_z2 in the H2 buffer)
         MGN_W(B_E1 + 3, par);
@@ -282,10 +286,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA1 + 4]);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
-        umma_commit(&bars[B_MMA1 + 4]);
+        umma_commit(&bars[B_W2]);
         MGN_T(9);
         // ---- layer 1: acc = g_z1 W1 (epilogue may start on it at once) ; gW1 += g_z1^T A
         //      (g_z1 in the H1 buffer, A re-staged in the A buffer)
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 0]);
       if (KP == 1) {  // re-stage the layer-1 input once the layer-3 MMAs have consumed g_y
-        MGN_W(B_MMA1 + 3, par);
+        MGN_W(B_W3, par);
         MGN_MOVER_SYNC();
         stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0, p.M, mt);
         MGN_PUBLISH(B_A2);
@@ -410,20 +415,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       colsum_tile(bH2, mt, cs_b2);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
-      if (KP == 1 && more) {  // next tile's input into this tile's H2 buffer (free after the layer-2 MMAs)
-        MGN_W(B_MMA1 + 4, par);
-        MGN_MOVER_SYNC();
-        stage_small(bH2, p.small_x, p.small_in, p.small_is_f32, row0n, p.M, mt);
-        MGN_PUBLISH(B_A);
+      if (more && has_g) {  // next tile's G1 rows -> this tile's H2 buffer (free after the layer-2 MMAs)
+        MGN_W(B_W2, par);
+        stage_rows_async(bH2, p.g1, r_g1, row0n, p.M, mt);
+        cp_async_commit();
       }
       MGN_W(B_E1 + 4, par);
       colsum_tile(bH1, mt, cs_b1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
-      if (more) {  // next tile's additive rows -> this tile's A and H1 buffers (free after the layer-1 MMAs)
+      if (more) {  // next tile's G2 rows -> this tile's H1 buffer (free after the layer-1 MMAs and the g_z1 store)
         MGN_W(B_MMA1 + 6, par);
+        if (KP == 1) {  // ... and its raw input -> the A buffer
+          MGN_MOVER_SYNC();
+          stage_small(bA, p.small_x, p.small_in, p.small_is_f32, row0n, p.M, mt);
+          MGN_PUBLISH(B_A);
+        }
         MGN_W(B_ST, par);
-        if (has_g) stage_rows_async(bA, p.g1, r_g1, row0n, p.M, mt);
         if (has_g2) stage_rows_async(bH1, p.g2, r_g2, row0n, p.M, mt);
         cp_async_commit();
         cp_async_wait<0>();
@@ -472,7 +480,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       uint8_t* bA = MGN_BUF(R_A, it);
       uint8_t* bX = MGN_BUF(R_X, it);
       uint8_t* bH1 = MGN_BUF(R_H1, it);
-      uint8_t* bH2 = MGN_BUF(R_H2, it);
       MGN_T(0);
       // dense incoming gradient once E1 has consumed the additive rows: go1 -> X
       MGN_W(B_E1 + 0, par);
@@ -486,22 +493,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       MGN_T(2);
       if (KP == 2) {
         // layer-1 input again (for its weight gradient) once the layer-3 MMAs and the column sums are done with g_y
-        MGN_W(B_MMA1 + 3, par);
+        MGN_W(B_W3, par);
         MGN_W(B_CS + 0, par);
         MGN_T(3);
         if (lane == 0) mbar_arrive_expect_tx(&bars[B_A2], 2 * kPB);
         __syncwarp();
         tma_stage_rows(bA, &p.m_a, nullptr, row0, p.M, &bars[B_A2], lane);
         MGN_T(4);
-        if (more) {  // next tile's layer-1 input -> this tile's H2 buffer
-          MGN_W(B_MMA1 + 4, par);
-          MGN_W(B_CS + 1, par);
-          MGN_T(5);
-          if (lane == 0) mbar_arrive_expect_tx(&bars[B_A], 2 * kPB);
-          __syncwarp();
-          tma_stage_rows(bH2, &p.m_a, nullptr, row0n, p.M, &bars[B_A], lane);
-          MGN_T(6);
-        }
       }
       // g_z1 tile (H1) -> global
       MGN_W(B_E1 + 4, par);
@@ -516,6 +514,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
         mbar_arrive(&bars[B_ST]);
       }
       __syncwarp();
+      MGN_T(5);
+      if (KP == 2 && more) {  // next tile's layer-1 input -> the A buffer, as soon as the layer-1 MMAs are done with it
+        MGN_W(B_MMA1 + 6, par);
+        MGN_T(6);
+        if (lane == 0) mbar_arrive_expect_tx(&bars[B_A], 2 * kPB);
+        __syncwarp();
+        tma_stage_rows(bA, &p.m_a, nullptr, row0n, p.M, &bars[B_A], lane);
+      }
       MGN_T(8);
       MGN_W(B_E1 + 5, par);
       MGN_T(9);
@@ -726,18 +732,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       MGN_W(B_MMA1 + 3, par);
       MGN_T(7);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + 32 * hh, v);
-        uint32_t h[16];
-        row_load32p(bH2, row, c0 + 32 * hh, h);
-        tmem_ld_wait();
+      {
+        // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+        uint32_t hq[2][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          h[j] = pack_bf16x2(bf_pos_lo(h[j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                             bf_pos_hi(h[j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
-        row_store32p(bH2, row, c0 + 32 * hh, h);
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          row_load32p(bH2, row, c0 + 32 * hh, hq[hh]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        }
+        MGN_W(B_W3, par);
+        row_store32p(bH2, row, c0, hq[0]);
+        row_store32p(bH2, row, c0 + 32, hq[1]);
       }
       MGN_EPI_DONE(B_E1 + 3);
       MGN_T(8);
@@ -745,18 +756,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       MGN_W(B_MMA1 + 4, par);
       MGN_T(9);
       tc_fence_after_sync();
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        uint32_t v[32];
-        tmem_ld32(t_acc + 32 * hh, v);
-        uint32_t h[16];
-        row_load32p(bH1, row, c0 + 32 * hh, h);
-        tmem_ld_wait();
+      {
+        // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+        uint32_t hq[2][16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          h[j] = pack_bf16x2(bf_pos_lo(h[j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                             bf_pos_hi(h[j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
-        row_store32p(bH1, row, c0 + 32 * hh, h);
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          row_load32p(bH1, row, c0 + 32 * hh, hq[hh]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        }
+        MGN_W(B_W2, par);
+        row_store32p(bH1, row, c0, hq[0]);
+        row_store32p(bH1, row, c0 + 32, hq[1]);
       }
       MGN_EPI_DONE(B_E1 + 4);
       MGN_T(10);

@@ -74,6 +74,12 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst_smem, const CUtensorMap
       "r"(r0), "r"(r1), "r"(r2), "r"(r3)
       : "memory");
 }
+// global -> L2 only: the box will be requested by a later tma_load_2d (hides the HBM round trip)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int col, int row) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(map)),
+               "r"(col), "r"(row)
+               : "memory");
+}
 // shared -> global, one {64 x box_rows} box at (col, row), clipped at the table bounds (bulk async-group)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src_smem, int col, int row) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(

@@ -75,7 +75,7 @@ t = tbuf.cpu().view(3, 32)
 n_tiles = (E + 127) // 128
 per_cta = -(-n_tiles // 148)
 names = {0: "MMA  : wA+E6prev | g1 | wE1 | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 | wE5 | dgrad1+wA2 | wgrad1",
-         1: "LOADER: top | wE1 | issue go1 | wMMA4+CS0 | issue A2 | wMMA5+CS1 | issue A' | wE5 | st gz1 | wE6 | st gA",
+         1: "LOADER: top | wE1 | issue go1 | wW3+CS0 | issue A2 | wE5+st gz1 | wMMA7 | - | issue A' | wE6 | st gA",
          2: "EPI  : wMMA1+G | E1 | wMMA2 | E2 | wMMA3 | wGO | E3 | wMMA4 | E4 | wMMA5 | E5 | wMMA6 | E6"}
 for r in range(3):
     print(names[r])
