@@ -5,8 +5,10 @@
 
 One "step" = zero_grad -> forward -> MSE loss -> backward of a 15-layer, hidden-128 MeshGraphNet
 (examples/cfd/vortex_shedding_mgn/train.py:151-166 of the reference; optimizer excluded)
-on a synthetic mesh.  N=1 default workload is BASELINE.json configs[1] (2-D triangle mesh, 100k
-nodes / ~600k edges, bf16).  With N>1 ranks (torchrun) the mesh grows N-fold and is partitioned
+on a synthetic mesh.  N=1 default workload is c3 = BASELINE.json configs[2] (3-D surface mesh, 1M nodes /
+~6M edges, bf16): the configuration north_star's target is quoted on, and the per-GPU share of the 8M-node
+configs[3] at 8 GPUs; c2 (configs[1], 100k nodes) and c1 remain selectable.  With N>1 ranks (torchrun) the mesh
+grows N-fold and is partitioned
 with DistributedGraph (weak scaling, halo exchange = NCCL all-to-all); value = global edges / max
 over ranks of the device time.
 
@@ -44,6 +46,17 @@ WORKLOADS = {
     "c2": ("triangle_grid_mesh", (316, 317), 6, 3, 3, "bf16"),   # 100k nodes / ~600k edges
     "c3": ("torus_surface_mesh", (1000, 1000), 11, 4, 4, "bf16"),  # 1M nodes / 6M edges
 }
+
+
+def load_traffic(kernel, workload):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r01_ncu_traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        return json.load(open(p)).get(workload, {}).get(kernel)
+    except Exception:
+        return None
 
 
 def load_peaks():
@@ -309,6 +322,7 @@ def run_b200(args, rank, world, local_rank):
                 ach = amount / (avg_ms * 1e-3) / 1e12
                 roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tc_sust"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tc_sust"], "traffic": None}
+            roof["traffic"] = load_traffic(top, args.workload) if world == 1 else None
             roof["avg_launch_ms"] = avg_ms
             roof["share_of_step"] = shares[top]["ms"] / max(sum(v["ms"] for v in shares.values()), 1e-9)
             roof["peak_source"] = peaks["src"]
@@ -349,7 +363,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
 
