@@ -222,6 +222,19 @@ int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x
                     float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
                     size_t workspace_bytes, int* status, mgn_stream_t stream);
 
+/* MeshEdgeBlock.forward + the "sum" aggregation of the following MeshNodeBlock in one pass (mesh_edge_block.py:88-96,
+ * utils.py:337-378): efeat_out[e] = efeat[e] + LN(MLP(efeat[e] W1a^T + P_src[src[e]] + P_dst[dst[e]])) for CSC-ordered
+ * edges, and agg[v] = sum of efeat_out over the incoming edges of v, taken from the result tiles while they are still
+ * in shared memory (fixed summation order; nodes without incoming edges get zeros). */
+size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t n_edges);
+int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const int32_t* src_idx, int64_t p_src_ld,
+                          int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
+                          int64_t p_dst_col0, int64_t n_edges, const float* w1, int64_t ld_w1, const float* b1,
+                          const float* w2, const float* b2, const float* w3, const float* b3,
+                          const float* gamma, const float* beta, float eps, void* efeat_out,
+                          const int32_t* csc_offsets, int64_t n_dst, void* agg, int64_t ld_agg,
+                          void* workspace, size_t workspace_bytes, int* status, mgn_stream_t stream);
+
 /* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):
  *   mgn_linear_tc : out[M,128] (row stride ld_out) = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual[M,128])
  *                   x_k are [M,128] column blocks with row stride ld_k; W is [128, 128*n_tab] with row stride ld_w

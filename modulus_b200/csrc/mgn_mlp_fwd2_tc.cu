@@ -54,12 +54,24 @@ struct Params {
   int* status;
   long long* timing;
   int tma_a, tma_out;  // dense A tiles arrive / result tiles leave through the loader warp (tensor maps below)
+  // fused aggregate_and_concat sum (models/gnn_layers/utils.py:337-378): the output rows are CSC-ordered edges, so a
+  // destination's rows are contiguous; the mover warps sum each segment from the result tile in shared memory.
+  // Segments wholly inside a tile go straight to agg; a tile's first and last segment go to fp32 records that
+  // agg_fixup_kernel combines in tile order (deterministic)
+  const int32_t* seg_off;  // [n_seg + 1] CSC offsets (nullptr: no aggregation)
+  const int32_t* seg_id;   // [M] destination of every row, ascending
+  long long n_seg;
+  bf16* agg;               // [n_seg, 128], row stride ld_agg
+  long long ld_agg;
+  float* agg_part;         // [2 * n_tiles][128]
+  int32_t* agg_part_v;     // [2 * n_tiles] destination id of each record, -1: empty
   alignas(64) CUtensorMap m_a, m_out;
 };
 
 // B_IN: next tile staged (four mover warps: gathered / small rows; loader: dense A tile by TMA);
 // B_STD: the result tile of a tile has left its A buffer
-enum { B_IN = 0, B_M1 = 1, B_M2 = 2, B_M3 = 3, B_H1 = 4, B_H2 = 5, B_OUT = 6, B_STD = 7, B_NUM = 8 };
+// B_AGG: the mover warps have finished reading a result tile for the fused aggregation
+enum { B_IN = 0, B_M1 = 1, B_M2 = 2, B_M3 = 3, B_H1 = 4, B_H2 = 5, B_OUT = 6, B_STD = 7, B_AGG = 8, B_NUM = 9 };
 
 template <int KP>
 struct Smem {
@@ -71,7 +83,7 @@ struct Smem {
   static constexpr int kG2 = kG1 + 2 * kPB;
   static constexpr int kPar = kG2 + 2 * kPB;  // b1, b2, b3, gamma, beta
   static constexpr int kBars = kPar + 5 * kH * 4;
-  static constexpr int kTmemSlot = kBars + 8 * 8;
+  static constexpr int kTmemSlot = kBars + 10 * 8;
   static constexpr int kTiming = kTmemSlot + 16;  // 3 roles x 8 x int64
   static constexpr int kTotal = kTiming + 3 * 8 * 8;
 };
@@ -124,6 +136,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
   if (tid == 0) {
     mbar_init(&bars[B_IN], 5);
     mbar_init(&bars[B_STD], 1);
+    mbar_init(&bars[B_AGG], 4);
     mbar_init(&bars[B_M1], 1);
     mbar_init(&bars[B_M2], 1);
     mbar_init(&bars[B_M3], 1);
@@ -297,6 +310,43 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         if (lane == 0) mbar_arrive(&bars[B_IN]);
       }
       if (!direct_out && !p.tma_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
+      if (p.seg_off != nullptr) {  // segmented sum of the result tile by destination
+        const long long rem = p.M - row0;
+        const int nrows = rem < kRows ? static_cast<int>(rem) : kRows;
+        const int v_first = __ldg(p.seg_id + row0), v_last = __ldg(p.seg_id + row0 + nrows - 1);
+        const int chunk = mt & 15, sl = mt >> 4;
+        const long long tile = row0 / kRows;
+        const uint8_t* col = bAcur + (chunk >> 3) * kPB;
+        for (int v = v_first + sl; v <= v_last; v += 8) {
+          const long long ob = __ldg(p.seg_off + v), oe = __ldg(p.seg_off + v + 1);
+          const int b = static_cast<int>((ob > row0 ? ob : row0) - row0);
+          const int e = static_cast<int>((oe < row0 + nrows ? oe : row0 + nrows) - row0);
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          for (int r = b; r < e; ++r) {
+            const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));
+            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[2 * k] += bf_lo(w[k]);
+              acc[2 * k + 1] += bf_hi(w[k]);
+            }
+          }
+          if (v == v_first || v == v_last) {
+            const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);
+            float4* d = reinterpret_cast<float4*>(p.agg_part + rec * kH + chunk * 8);
+            d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+            if (chunk == 0) p.agg_part_v[rec] = v;
+          } else {
+            *reinterpret_cast<uint4*>(p.agg + static_cast<long long>(v) * p.ld_agg + chunk * 8) =
+                make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                           pack_bf16x2(acc[6], acc[7]));
+          }
+        }
+        if (v_first == v_last && mt == 0) p.agg_part_v[tile * 2 + 1] = -1;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_AGG]);
+      }
       if (more && it + 2 < n_my) {  // row ids two tiles ahead of the running one
         if (KP == 2 && !p.tma_a) fetch_row_ids(p.a.idx, row1 + stride, p.M, rsub_m, r_a);
         if (has_g1) fetch_row_ids(p.g1.idx, row1 + stride, p.M, rsub_m, r_g1);
@@ -330,6 +380,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         if (it + 1 < n_my) {
           // (this tile's B_IN phase must be complete before an arrival may count for the next tile's)
           if (!wait_clk(&bars[B_IN], par)) { timed_out = true; break; }
+          if (p.seg_off != nullptr && it > 0 && !wait_clk(&bars[B_AGG], par ^ 1)) { timed_out = true; break; }
           load_a(bAnext, row0 + stride);  // that buffer's previous result tile left it during the last iteration
         }
         if (!wait_clk(&bars[B_OUT], par)) { timed_out = true; break; }
@@ -544,6 +595,46 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+// Combine the per-tile boundary records of the fused aggregation (see Params::seg_off): one warp per record; the
+// first record of a run of equal destination ids sums the run in record (= tile) order, writes the row, and
+// zero-fills the destination rows that fall between two tiles (nodes without incoming edges).
+__global__ void __launch_bounds__(256) agg_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_v,
+                                                        long long n_rec, bf16* __restrict__ agg, long long ld_agg,
+                                                        long long n_seg) {
+  const long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rec) return;
+  const int v = part_v[r];
+  if (v < 0) return;
+  long long q = r - 1;
+  while (q >= 0 && part_v[q] < 0) --q;
+  const int vp = q >= 0 ? part_v[q] : -1;
+  if (vp == v) return;  // not the head of its run
+  const uint2 zero = make_uint2(0u, 0u);
+  // (only a tile's FIRST record can have unwritten rows before it: everything between a tile's first and last segment
+  //  was written by the main kernel, empty segments included)
+  if ((r & 1) == 0)
+    for (long long g = static_cast<long long>(vp) + 1; g < v; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
+  float4 acc = reinterpret_cast<const float4*>(part + r * kH)[lane];
+  long long k = r + 1;
+  for (; k < n_rec; ++k) {
+    const int vk = part_v[k];
+    if (vk == v) {
+      const float4 t = reinterpret_cast<const float4*>(part + k * kH)[lane];
+      acc.x += t.x;
+      acc.y += t.y;
+      acc.z += t.z;
+      acc.w += t.w;
+    } else if (vk >= 0) {
+      break;
+    }
+  }
+  *reinterpret_cast<uint2*>(agg + static_cast<long long>(v) * ld_agg + lane * 4) =
+      make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  if (k >= n_rec)  // last run: trailing nodes without incoming edges
+    for (long long g = static_cast<long long>(v) + 1; g < n_seg; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
+}
+
 static long long* g_timing = nullptr;
 
 template <int KP>
@@ -576,13 +667,28 @@ extern "C" int mgn_debug_set_fwd2_timing(void* dev_buf) {
   return MGN_OK;
 }
 
-extern "C" int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+extern "C" size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t M) {
+  if (M <= 0) return 0;
+  const size_t n_tiles = static_cast<size_t>((M + tile::kRows - 1) / tile::kRows);
+  return 2 * n_tiles * (fwd2::kH * sizeof(float) + sizeof(int32_t));
+}
+
+struct AggArgs {
+  const int32_t* seg_off = nullptr;
+  int64_t n_seg = 0;
+  void* agg = nullptr;
+  int64_t ld_agg = 0;
+  void* workspace = nullptr;
+  size_t workspace_bytes = 0;
+};
+
+static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
                                 int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
                                 int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
                                 int64_t g2_col0, const void* res_tab, int res_is_a, int64_t M, const float* w1,
                                 int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
                                 const float* b3, const float* gamma, const float* beta, int n_out, float eps, void* out,
-                                int64_t ld_out, int* status, mgn_stream_t stream) {
+                                int64_t ld_out, int* status, mgn_stream_t stream, const AggArgs& ag) {
   MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= fwd2::kH && ld_out >= n_out);
   MGN_CHECK_ARG(gamma == nullptr || n_out == fwd2::kH);
   if (M == 0) return MGN_OK;
@@ -613,14 +719,66 @@ extern "C" int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const v
   p.ld_out = ld_out;
   p.status = status;
   cudaStream_t st = as_stream(stream);
+  const long long n_tiles = (M + tile::kRows - 1) / tile::kRows;
+  if (ag.seg_off != nullptr) {  // fused aggregation: rows are CSC-ordered edges, g2_idx is their destination
+    MGN_CHECK_ARG(g2_idx != nullptr && ag.agg != nullptr && ag.n_seg > 0 && ag.ld_agg >= fwd2::kH && ag.ld_agg % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(ag.agg) & 15) == 0 && n_out == fwd2::kH && ag.workspace != nullptr);
+    if (ag.workspace_bytes < mgn_mlp3_fwd2_agg_workspace_bytes(M)) return MGN_EWORKSPACE;
+    p.seg_off = ag.seg_off;
+    p.seg_id = g2_idx;
+    p.n_seg = ag.n_seg;
+    p.agg = static_cast<bf16*>(ag.agg);
+    p.ld_agg = ag.ld_agg;
+    p.agg_part = static_cast<float*>(ag.workspace);
+    p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * n_tiles * fwd2::kH);
+  }
+  int rc;
   if (small_in > 0) {
     MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && ld_w1 >= small_in && g1_tab == nullptr);
     p.k1_true = small_in;
-    return fwd2::launch<1>(p, st);
+    rc = fwd2::launch<1>(p, st);
+  } else {
+    MGN_CHECK_ARG(a_tab != nullptr && ld_w1 >= fwd2::kH && (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0);
+    p.k1_true = fwd2::kH;
+    rc = fwd2::launch<2>(p, st);
   }
-  MGN_CHECK_ARG(a_tab != nullptr && ld_w1 >= fwd2::kH && (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0);
-  p.k1_true = fwd2::kH;
-  return fwd2::launch<2>(p, st);
+  if (rc != MGN_OK || ag.seg_off == nullptr) return rc;
+  const long long n_rec = 2 * n_tiles;
+  fwd2::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
+      p.agg_part, p.agg_part_v, n_rec, p.agg, p.ld_agg, p.n_seg);
+  return mgn_launch_status();
+}
+
+extern "C" int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+                                int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
+                                int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
+                                int64_t g2_col0, const void* res_tab, int res_is_a, int64_t M, const float* w1,
+                                int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                                const float* b3, const float* gamma, const float* beta, int n_out, float eps, void* out,
+                                int64_t ld_out, int* status, mgn_stream_t stream) {
+  return fwd2_run(a_tab, a_idx, small_x, small_in, small_is_f32, g1_tab, g1_idx, g1_ld, g1_col0, g2_tab, g2_idx, g2_ld, g2_col0,
+                  res_tab, res_is_a, M, w1, ld_w1, b1, w2, b2, w3, b3, gamma, beta, n_out, eps, out, ld_out, status, stream,
+                  AggArgs{});
+}
+
+extern "C" int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const int32_t* src_idx, int64_t p_src_ld,
+                                     int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
+                                     int64_t p_dst_col0, int64_t n_edges, const float* w1, int64_t ld_w1, const float* b1,
+                                     const float* w2, const float* b2, const float* w3, const float* b3,
+                                     const float* gamma, const float* beta, float eps, void* efeat_out,
+                                     const int32_t* csc_offsets, int64_t n_dst, void* agg, int64_t ld_agg,
+                                     void* workspace, size_t workspace_bytes, int* status, mgn_stream_t stream) {
+  MGN_CHECK_ARG(efeat && p_src && src_idx && p_dst && dst_idx && csc_offsets && agg && efeat_out);
+  AggArgs ag;
+  ag.seg_off = csc_offsets;
+  ag.n_seg = n_dst;
+  ag.agg = agg;
+  ag.ld_agg = ld_agg;
+  ag.workspace = workspace;
+  ag.workspace_bytes = workspace_bytes;
+  return fwd2_run(efeat, nullptr, nullptr, 0, 0, p_src, src_idx, p_src_ld, p_src_col0, p_dst, dst_idx, p_dst_ld, p_dst_col0,
+                  nullptr, 1, n_edges, w1, ld_w1, b1, w2, b2, w3, b3, gamma, beta, fwd2::kH, eps, efeat_out, fwd2::kH, status,
+                  stream, ag);
 }
 
 // out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); W [128, >=128] fp32

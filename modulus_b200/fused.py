@@ -152,9 +152,10 @@ class FusedProcessorFn(torch.autograd.Function):
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
             P = _node_linear(nfeat, wp)  # [N, 3H]
-            if halo is None:
-                efeat_new = ops.mlp3_fwd2_tc(efeat, None, None, P, src, 0, P, dst, H, E, ew[0][:, :H], ew[1], ew[2],
-                                             ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps, res_is_a=True)
+            agg = None
+            if halo is None:  # edge update and destination sums in one pass over the edge rows
+                efeat_new, agg = ops.edge_block_fwd_tc(efeat, P, src, dst, plan.csc_offsets, N, ew[0][:, :H], ew[1],
+                                                       ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps)
             else:
                 efeat_new = torch.empty_like(efeat)
                 work, Ps, keep = halo.start_fwd(P)  # all-to-all of the source projections, in flight
@@ -171,7 +172,8 @@ class FusedProcessorFn(torch.autograd.Function):
                 run(0, halo.e0, Ps, src[:halo.e0])
                 run(halo.e1, E, Ps, src[halo.e1:])
                 del keep
-            agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
+            if agg is None:
+                agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
             nfeat_new = ops.mlp3_fwd2_tc(agg, None, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
                                          nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
             saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else [])

@@ -496,6 +496,23 @@ def mlp3_fwd2_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional
     return out
 
 
+def edge_block_fwd_tc(efeat: Tensor, P: Tensor, src: Tensor, dst: Tensor, csc_offsets: Tensor, n_dst: int,
+                      w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta, eps: float = 1e-5):
+    """MeshEdgeBlock forward fused with the sum aggregation of the next MeshNodeBlock
+    (include/mgn_b200.h: mgn_edge_block_fwd_tc).  P [N, >=2H]: source projections in columns [0,H), destination
+    projections in [H,2H).  Returns (efeat_new [E,H], agg [n_dst,H]) bf16."""
+    E = efeat.shape[0]
+    dev = efeat.device
+    out = torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    agg = torch.empty((n_dst, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    nbytes = _lib.load().mgn_mlp3_fwd2_agg_workspace_bytes(E)
+    ws = _ws(nbytes, dev)
+    call("mgn_edge_block_fwd_tc", _p(efeat), _p(P), _p(src), P.stride(0), 0, _p(P), _p(dst), P.stride(0), TC_HIDDEN, E,
+         _p(w1a), w1a.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), eps, _p(out),
+         _p(csc_offsets), n_dst, _p(agg), agg.stride(0), _p(ws), nbytes, _p(tc_status(dev)), _stream())
+    return out, agg
+
+
 def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
                 g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
                 g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int,

@@ -310,3 +310,47 @@ def test_mlp3_fwd2_tc_encoder_and_decoder_forms(M):
     ops.tc_check(DEV)
     assert out.shape == (M, 3)
     assert rel_err(out.float(), ref) < 1.5e-2
+
+
+@pytest.mark.parametrize("case", ["mesh", "hubs_and_isolated", "single_tile", "one_segment"])
+def test_edge_block_fwd_with_fused_aggregation(case):
+    """mgn_edge_block_fwd_tc: same edge rows as the plain fused forward, and agg == segmented sum of those rows by
+    destination (incl. segments that straddle tiles, a hub longer than a tile, and nodes without incoming edges)."""
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(11)
+    if case == "mesh":
+        N = 5000
+        deg = torch.randint(4, 9, (N,), generator=g)
+    elif case == "hubs_and_isolated":
+        N = 3000
+        deg = torch.randint(0, 7, (N,), generator=g)
+        deg[0] = 0; deg[1] = 0; deg[17] = 300; deg[18] = 0; deg[19] = 0; deg[1500] = 129; deg[-1] = 0; deg[-2] = 0
+    elif case == "single_tile":
+        N = 40
+        deg = torch.randint(0, 4, (N,), generator=g)
+        deg[3] = 5
+    else:
+        N = 7
+        deg = torch.zeros(N, dtype=torch.long)
+        deg[4] = 1000
+    offsets = torch.zeros(N + 1, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(deg, 0).int()
+    E = int(offsets[-1])
+    dst = torch.repeat_interleave(torch.arange(N), deg).int()
+    src = torch.randint(0, N, (E,), generator=g).int()
+    p = make_params(384, seed=5)
+    d = dev_params(p)
+    A = bf(torch.randn(E, 128, generator=g)).to(DEV).bfloat16()
+    P = bf(torch.randn(N, 384, generator=g) * 0.5).to(DEV).bfloat16()
+    srcd, dstd, offd = src.to(DEV), dst.to(DEV), offsets.to(DEV)
+    args = (d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"])
+    ref_rows = ops.mlp3_fwd2_tc(A, None, None, P, srcd, 0, P, dstd, 128, E, *args, res_is_a=True)
+    out, agg = ops.edge_block_fwd_tc(A, P, srcd, dstd, offd, N, *args)
+    out2, agg2 = ops.edge_block_fwd_tc(A, P, srcd, dstd, offd, N, *args)
+    ops.tc_check(DEV)
+    assert torch.equal(out, ref_rows)
+    ref_agg = torch.zeros(N, 128, dtype=torch.float64, device=DEV).index_add_(0, dstd.long(), out.double())
+    assert rel_err(agg.float(), ref_agg) < 1e-2  # bf16 rounding of the stored sums
+    assert float(agg[deg.to(DEV) == 0].abs().max() if bool((deg == 0).any()) else 0.0) == 0.0
+    assert torch.equal(agg, agg2) and torch.equal(out, out2)
