@@ -1,0 +1,107 @@
+// mgn_agg.cuh — destination sums fused into the edge kernels (aggregate_and_concat "sum" of the reference,
+// models/gnn_layers/utils.py:337-378, and its transpose in backward).
+//
+// Edge rows are in CSC order, so the rows of one destination are contiguous.  While a 128-row result tile is still in
+// shared memory four warps sum each destination segment of the tile (fp32, rows in ascending order).  Segments that
+// lie wholly inside the tile -- empty ones included -- are written straight to the [n_dst, 128] table; the tile's
+// first and last segment may continue in a neighbouring tile, so they go to fp32 records (two per tile) that
+// agg_fixup_kernel combines in tile order: no atomics, bit-reproducible.
+#pragma once
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+#include "mgn_tile.cuh"
+
+namespace mgn {
+namespace agg {
+
+using namespace tile;
+constexpr int kH = 128;
+
+static inline size_t workspace_bytes(int64_t M) {
+  if (M <= 0) return 0;
+  const size_t n_tiles = static_cast<size_t>((M + kRows - 1) / kRows);
+  return 2 * n_tiles * (kH * sizeof(float) + sizeof(int32_t));
+}
+
+// 128 threads (mt = 0..127): thread = (16-byte column chunk, segment lane); buf = result tile (two swizzled panels)
+__device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, long long M,
+                                                 const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_id,
+                                                 bf16* __restrict__ out, long long ld_out, float* __restrict__ part,
+                                                 int32_t* __restrict__ part_v, int mt) {
+  const long long rem = M - row0;
+  const int nrows = rem < kRows ? static_cast<int>(rem) : kRows;
+  const int v_first = __ldg(seg_id + row0), v_last = __ldg(seg_id + row0 + nrows - 1);
+  const int chunk = mt & 15, sl = mt >> 4;
+  const long long tile = row0 / kRows;
+  const uint8_t* col = buf + (chunk >> 3) * kPB;
+  for (int v = v_first + sl; v <= v_last; v += 8) {
+    const long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
+    const int b = static_cast<int>((ob > row0 ? ob : row0) - row0);
+    const int e = static_cast<int>((oe < row0 + nrows ? oe : row0 + nrows) - row0);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = b; r < e; ++r) {
+      const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * k] += bf_lo(w[k]);
+        acc[2 * k + 1] += bf_hi(w[k]);
+      }
+    }
+    if (v == v_first || v == v_last) {
+      const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);
+      float4* d = reinterpret_cast<float4*>(part + rec * kH + chunk * 8);
+      d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      if (chunk == 0) part_v[rec] = v;
+    } else {
+      *reinterpret_cast<uint4*>(out + static_cast<long long>(v) * ld_out + chunk * 8) =
+          make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                     pack_bf16x2(acc[6], acc[7]));
+    }
+  }
+  if (v_first == v_last && mt == 0) part_v[tile * 2 + 1] = -1;
+}
+
+// Combine the per-tile boundary records of the fused aggregation (see Params::seg_off): one warp per record; the
+// first record of a run of equal destination ids sums the run in record (= tile) order, writes the row, and
+// zero-fills the destination rows that fall between two tiles (nodes without incoming edges).
+static __global__ void __launch_bounds__(256) agg_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_v,
+                                                        long long n_rec, bf16* __restrict__ agg, long long ld_agg,
+                                                        long long n_seg) {
+  const long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= n_rec) return;
+  const int v = part_v[r];
+  if (v < 0) return;
+  long long q = r - 1;
+  while (q >= 0 && part_v[q] < 0) --q;
+  const int vp = q >= 0 ? part_v[q] : -1;
+  if (vp == v) return;  // not the head of its run
+  const uint2 zero = make_uint2(0u, 0u);
+  // (only a tile's FIRST record can have unwritten rows before it: everything between a tile's first and last segment
+  //  was written by the main kernel, empty segments included)
+  if ((r & 1) == 0)
+    for (long long g = static_cast<long long>(vp) + 1; g < v; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
+  float4 acc = reinterpret_cast<const float4*>(part + r * kH)[lane];
+  long long k = r + 1;
+  for (; k < n_rec; ++k) {
+    const int vk = part_v[k];
+    if (vk == v) {
+      const float4 t = reinterpret_cast<const float4*>(part + k * kH)[lane];
+      acc.x += t.x;
+      acc.y += t.y;
+      acc.z += t.z;
+      acc.w += t.w;
+    } else if (vk >= 0) {
+      break;
+    }
+  }
+  *reinterpret_cast<uint2*>(agg + static_cast<long long>(v) * ld_agg + lane * 4) =
+      make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
+  if (k >= n_rec)  // last run: trailing nodes without incoming edges
+    for (long long g = static_cast<long long>(v) + 1; g < n_seg; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
+}
+
+}  // namespace agg
+}  // namespace mgn

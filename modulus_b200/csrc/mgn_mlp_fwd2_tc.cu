@@ -25,6 +25,7 @@
 #include "mgn_tc.cuh"
 #include "mgn_tile.cuh"
 #include "mgn_tma.cuh"
+#include "mgn_agg.cuh"
 
 namespace mgn {
 namespace fwd2 {
@@ -311,39 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       }
       if (!direct_out && !p.tma_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
       if (p.seg_off != nullptr) {  // segmented sum of the result tile by destination
-        const long long rem = p.M - row0;
-        const int nrows = rem < kRows ? static_cast<int>(rem) : kRows;
-        const int v_first = __ldg(p.seg_id + row0), v_last = __ldg(p.seg_id + row0 + nrows - 1);
-        const int chunk = mt & 15, sl = mt >> 4;
-        const long long tile = row0 / kRows;
-        const uint8_t* col = bAcur + (chunk >> 3) * kPB;
-        for (int v = v_first + sl; v <= v_last; v += 8) {
-          const long long ob = __ldg(p.seg_off + v), oe = __ldg(p.seg_off + v + 1);
-          const int b = static_cast<int>((ob > row0 ? ob : row0) - row0);
-          const int e = static_cast<int>((oe < row0 + nrows ? oe : row0 + nrows) - row0);
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          for (int r = b; r < e; ++r) {
-            const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));
-            const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              acc[2 * k] += bf_lo(w[k]);
-              acc[2 * k + 1] += bf_hi(w[k]);
-            }
-          }
-          if (v == v_first || v == v_last) {
-            const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);
-            float4* d = reinterpret_cast<float4*>(p.agg_part + rec * kH + chunk * 8);
-            d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-            d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            if (chunk == 0) p.agg_part_v[rec] = v;
-          } else {
-            *reinterpret_cast<uint4*>(p.agg + static_cast<long long>(v) * p.ld_agg + chunk * 8) =
-                make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                           pack_bf16x2(acc[6], acc[7]));
-          }
-        }
-        if (v_first == v_last && mt == 0) p.agg_part_v[tile * 2 + 1] = -1;
+        agg::tile_segment_sum(bAcur, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AGG]);
       }
@@ -595,46 +564,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-// Combine the per-tile boundary records of the fused aggregation (see Params::seg_off): one warp per record; the
-// first record of a run of equal destination ids sums the run in record (= tile) order, writes the row, and
-// zero-fills the destination rows that fall between two tiles (nodes without incoming edges).
-__global__ void __launch_bounds__(256) agg_fixup_kernel(const float* __restrict__ part, const int32_t* __restrict__ part_v,
-                                                        long long n_rec, bf16* __restrict__ agg, long long ld_agg,
-                                                        long long n_seg) {
-  const long long r = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (r >= n_rec) return;
-  const int v = part_v[r];
-  if (v < 0) return;
-  long long q = r - 1;
-  while (q >= 0 && part_v[q] < 0) --q;
-  const int vp = q >= 0 ? part_v[q] : -1;
-  if (vp == v) return;  // not the head of its run
-  const uint2 zero = make_uint2(0u, 0u);
-  // (only a tile's FIRST record can have unwritten rows before it: everything between a tile's first and last segment
-  //  was written by the main kernel, empty segments included)
-  if ((r & 1) == 0)
-    for (long long g = static_cast<long long>(vp) + 1; g < v; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
-  float4 acc = reinterpret_cast<const float4*>(part + r * kH)[lane];
-  long long k = r + 1;
-  for (; k < n_rec; ++k) {
-    const int vk = part_v[k];
-    if (vk == v) {
-      const float4 t = reinterpret_cast<const float4*>(part + k * kH)[lane];
-      acc.x += t.x;
-      acc.y += t.y;
-      acc.z += t.z;
-      acc.w += t.w;
-    } else if (vk >= 0) {
-      break;
-    }
-  }
-  *reinterpret_cast<uint2*>(agg + static_cast<long long>(v) * ld_agg + lane * 4) =
-      make_uint2(pack_bf16x2(acc.x, acc.y), pack_bf16x2(acc.z, acc.w));
-  if (k >= n_rec)  // last run: trailing nodes without incoming edges
-    for (long long g = static_cast<long long>(v) + 1; g < n_seg; ++g) *reinterpret_cast<uint2*>(agg + g * ld_agg + lane * 4) = zero;
-}
-
 static long long* g_timing = nullptr;
 
 template <int KP>
@@ -667,11 +596,7 @@ extern "C" int mgn_debug_set_fwd2_timing(void* dev_buf) {
   return MGN_OK;
 }
 
-extern "C" size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t M) {
-  if (M <= 0) return 0;
-  const size_t n_tiles = static_cast<size_t>((M + tile::kRows - 1) / tile::kRows);
-  return 2 * n_tiles * (fwd2::kH * sizeof(float) + sizeof(int32_t));
-}
+extern "C" size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t M) { return agg::workspace_bytes(M); }
 
 struct AggArgs {
   const int32_t* seg_off = nullptr;
@@ -744,7 +669,7 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
   }
   if (rc != MGN_OK || ag.seg_off == nullptr) return rc;
   const long long n_rec = 2 * n_tiles;
-  fwd2::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
+  agg::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
       p.agg_part, p.agg_part_v, n_rec, p.agg, p.ld_agg, p.n_seg);
   return mgn_launch_status();
 }
