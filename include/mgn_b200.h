@@ -235,6 +235,21 @@ int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const int32_t* s
                           const int32_t* csc_offsets, int64_t n_dst, void* agg, int64_t ld_agg,
                           void* workspace, size_t workspace_bytes, int* status, mgn_stream_t stream);
 
+/* The same over one of several consecutive row ranges of the edge table (partitioned graphs run the interior range while
+ * the halo exchange is in flight): pointers / indices are those of the range, row_base its CSC position, total_tiles the
+ * sum of ceil(rows/128) over all ranges, rec_base that sum over the ranges before this one; the workspace
+ * (2 * total_tiles * 516 bytes) is shared and mgn_agg_fixup completes agg once every range has run. */
+int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, const int32_t* src_idx, int64_t p_src_ld,
+                               int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
+                               int64_t p_dst_col0, int64_t n_rows, const float* w1, int64_t ld_w1,
+                               const float* b1, const float* w2, const float* b2, const float* w3,
+                               const float* b3, const float* gamma, const float* beta, float eps,
+                               void* efeat_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
+                               int64_t ld_agg, void* workspace, size_t workspace_bytes, int64_t row_base,
+                               int64_t total_tiles, int64_t rec_base, int* status, mgn_stream_t stream);
+int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,
+                  mgn_stream_t stream);
+
 /* mgn_mlp3_bwd_tc for the edge block + the destination sums of its g_z1 rows (the transposed dst-side gather of
  * concat_efeat, utils.py:94-148): gz1_agg[v] = sum of g_z1 over the incoming edges of v, fused like the forward one. */
 int mgn_mlp3_bwd_agg_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,

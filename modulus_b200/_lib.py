@@ -131,7 +131,7 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
             return "tensor", 8.0 * 128 * 128 * M
         k1 = small_in if small_in > 0 else 128
         return "tensor", 2.0 * M * (k1 * 128 + 2 * 128 * 128)
-    if name == "mgn_edge_block_fwd_tc":
+    if name in ("mgn_edge_block_fwd_tc", "mgn_edge_block_fwd_part_tc"):
         return "tensor", 10.0 * 128 * 128 * a[9]
     if name == "mgn_node_gemm_tc":
         kb, M, nb, res = a[2], a[3], a[6], a[7]

@@ -24,20 +24,25 @@ static inline size_t workspace_bytes(int64_t M) {
 }
 
 // 128 threads (mt = 0..127): thread = (16-byte column chunk, segment lane); buf = result tile (two swizzled panels)
+// row0 / M / seg_id are relative to the rows this launch covers; row_base = position of its row 0 in the CSC order
+// (seg_off holds global positions), rec_base = index of its first tile's records (several launches over consecutive
+// row ranges share one record array in row order and one fix-up)
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, long long M,
                                                  const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_id,
                                                  bf16* __restrict__ out, long long ld_out, float* __restrict__ part,
-                                                 int32_t* __restrict__ part_v, int mt) {
+                                                 int32_t* __restrict__ part_v, int mt, long long row_base = 0,
+                                                 long long rec_base = 0) {
   const long long rem = M - row0;
   const int nrows = rem < kRows ? static_cast<int>(rem) : kRows;
   const int v_first = __ldg(seg_id + row0), v_last = __ldg(seg_id + row0 + nrows - 1);
   const int chunk = mt & 15, sl = mt >> 4;
-  const long long tile = row0 / kRows;
+  const long long tile = rec_base + row0 / kRows;
   const uint8_t* col = buf + (chunk >> 3) * kPB;
+  const long long g0 = row_base + row0;  // global position of the tile's first row
   for (int v = v_first + sl; v <= v_last; v += 8) {
     const long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
-    const int b = static_cast<int>((ob > row0 ? ob : row0) - row0);
-    const int e = static_cast<int>((oe < row0 + nrows ? oe : row0 + nrows) - row0);
+    const int b = static_cast<int>((ob > g0 ? ob : g0) - g0);
+    const int e = static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int r = b; r < e; ++r) {
       const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));

@@ -66,6 +66,8 @@ struct Params {
   long long ld_agg;
   float* agg_part;         // [2 * n_tiles][128]
   int32_t* agg_part_v;     // [2 * n_tiles] destination id of each record, -1: empty
+  long long agg_row_base;  // CSC position of this launch's row 0
+  long long agg_rec_base;  // record index (in tiles) of this launch's first tile
   alignas(64) CUtensorMap m_a, m_out;
 };
 
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       }
       if (!direct_out && !p.tma_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
       if (p.seg_off != nullptr) {  // segmented sum of the result tile by destination
-        agg::tile_segment_sum(bAcur, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
+        agg::tile_segment_sum(bAcur, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt,
+                              p.agg_row_base, p.agg_rec_base);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AGG]);
       }
@@ -605,6 +608,12 @@ struct AggArgs {
   int64_t ld_agg = 0;
   void* workspace = nullptr;
   size_t workspace_bytes = 0;
+  // several launches over consecutive row ranges of one edge table: position of this launch's row 0, total rows of
+  // the table (sizes the shared record array), index of this launch's first tile record, run the fix-up after it
+  int64_t row_base = 0;
+  int64_t total_tiles = 0;
+  int64_t rec_base = 0;
+  int fixup = 1;
 };
 
 static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
@@ -648,14 +657,19 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
   if (ag.seg_off != nullptr) {  // fused aggregation: rows are CSC-ordered edges, g2_idx is their destination
     MGN_CHECK_ARG(g2_idx != nullptr && ag.agg != nullptr && ag.n_seg > 0 && ag.ld_agg >= fwd2::kH && ag.ld_agg % 8 == 0 &&
                   (reinterpret_cast<uintptr_t>(ag.agg) & 15) == 0 && n_out == fwd2::kH && ag.workspace != nullptr);
-    if (ag.workspace_bytes < mgn_mlp3_fwd2_agg_workspace_bytes(M)) return MGN_EWORKSPACE;
+    const long long tot_tiles = ag.total_tiles > 0 ? ag.total_tiles : n_tiles;
+    MGN_CHECK_ARG(ag.rec_base >= 0 && ag.rec_base + n_tiles <= tot_tiles && ag.row_base >= 0);
+    if (ag.workspace_bytes < static_cast<size_t>(2 * tot_tiles) * (fwd2::kH * sizeof(float) + sizeof(int32_t)))
+      return MGN_EWORKSPACE;
     p.seg_off = ag.seg_off;
     p.seg_id = g2_idx;
     p.n_seg = ag.n_seg;
     p.agg = static_cast<bf16*>(ag.agg);
     p.ld_agg = ag.ld_agg;
     p.agg_part = static_cast<float*>(ag.workspace);
-    p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * n_tiles * fwd2::kH);
+    p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * tot_tiles * fwd2::kH);
+    p.agg_row_base = ag.row_base;
+    p.agg_rec_base = ag.rec_base;
   }
   int rc;
   if (small_in > 0) {
@@ -667,8 +681,8 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
     p.k1_true = fwd2::kH;
     rc = fwd2::launch<2>(p, st);
   }
-  if (rc != MGN_OK || ag.seg_off == nullptr) return rc;
-  const long long n_rec = 2 * n_tiles;
+  if (rc != MGN_OK || ag.seg_off == nullptr || !ag.fixup) return rc;
+  const long long n_rec = 2 * (ag.total_tiles > 0 ? ag.total_tiles : n_tiles);
   agg::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
       p.agg_part, p.agg_part_v, n_rec, p.agg, p.ld_agg, p.n_seg);
   return mgn_launch_status();
@@ -704,6 +718,47 @@ extern "C" int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const
   return fwd2_run(efeat, nullptr, nullptr, 0, 0, p_src, src_idx, p_src_ld, p_src_col0, p_dst, dst_idx, p_dst_ld, p_dst_col0,
                   nullptr, 1, n_edges, w1, ld_w1, b1, w2, b2, w3, b3, gamma, beta, fwd2::kH, eps, efeat_out, fwd2::kH, status,
                   stream, ag);
+}
+
+// One of several launches over consecutive row ranges [row_base, row_base + n_rows) of one CSC-ordered edge table
+// (the partitioned path runs the interior edges while the halo exchange is in flight, then the boundary runs):
+// pointers / indices are those of the range, total_tiles = sum over the launches of ceil(rows / 128), rec_base = that sum
+// over the ranges before this one.  mgn_agg_fixup finishes the destination sums once every range has run.
+extern "C" int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, const int32_t* src_idx, int64_t p_src_ld,
+                                          int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
+                                          int64_t p_dst_col0, int64_t n_rows, const float* w1, int64_t ld_w1,
+                                          const float* b1, const float* w2, const float* b2, const float* w3,
+                                          const float* b3, const float* gamma, const float* beta, float eps,
+                                          void* efeat_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
+                                          int64_t ld_agg, void* workspace, size_t workspace_bytes, int64_t row_base,
+                                          int64_t total_tiles, int64_t rec_base, int* status, mgn_stream_t stream) {
+  if (n_rows == 0) return MGN_OK;
+  MGN_CHECK_ARG(efeat && p_src && src_idx && p_dst && dst_idx && csc_offsets && agg && efeat_out && total_tiles > 0);
+  AggArgs ag;
+  ag.seg_off = csc_offsets;
+  ag.n_seg = n_dst;
+  ag.agg = agg;
+  ag.ld_agg = ld_agg;
+  ag.workspace = workspace;
+  ag.workspace_bytes = workspace_bytes;
+  ag.row_base = row_base;
+  ag.total_tiles = total_tiles;
+  ag.rec_base = rec_base;
+  ag.fixup = 0;
+  return fwd2_run(efeat, nullptr, nullptr, 0, 0, p_src, src_idx, p_src_ld, p_src_col0, p_dst, dst_idx, p_dst_ld, p_dst_col0,
+                  nullptr, 1, n_rows, w1, ld_w1, b1, w2, b2, w3, b3, gamma, beta, fwd2::kH, eps, efeat_out, fwd2::kH, status,
+                  stream, ag);
+}
+
+extern "C" int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,
+                             mgn_stream_t stream) {
+  MGN_CHECK_ARG(workspace && agg && total_tiles > 0 && n_dst > 0 && ld_agg >= fwd2::kH);
+  float* part = static_cast<float*>(workspace);
+  int32_t* part_v = reinterpret_cast<int32_t*>(part + 2 * total_tiles * fwd2::kH);
+  const long long n_rec = 2 * total_tiles;
+  agg::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(as_stream(stream))>>>(
+      part, part_v, n_rec, static_cast<bf16*>(agg), ld_agg, n_dst);
+  return mgn_launch_status();
 }
 
 // out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); W [128, >=128] fp32

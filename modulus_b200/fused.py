@@ -159,19 +159,26 @@ class FusedProcessorFn(torch.autograd.Function):
                                                        ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps)
             else:
                 efeat_new = torch.empty_like(efeat)
+                agg = torch.empty((N, H), dtype=BF16, device=efeat.device)
                 work, Ps, keep = halo.start_fwd(P)  # all-to-all of the source projections, in flight
+                # three launches over consecutive row ranges share one aggregation record array (row order)
+                ranges = [(0, halo.e0), (halo.e0, halo.e1), (halo.e1, E)]
+                tiles = [-(-(hi - lo) // 128) for lo, hi in ranges]
+                ws = ops.agg_workspace(sum(tiles), efeat.device)
 
-                def run(lo, hi, g1, g1_idx):
+                def run(k, g1, g1_idx):
+                    lo, hi = ranges[k]
                     if hi > lo:
-                        ops.mlp3_fwd2_tc(efeat[lo:hi], None, None, g1, g1_idx, 0, P, dst[lo:hi], H, hi - lo,
-                                         ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps,
-                                         res_is_a=True, out=efeat_new[lo:hi])
+                        ops.edge_block_fwd_part_tc(efeat[lo:hi], g1, g1_idx, P, dst[lo:hi], plan.csc_offsets, N,
+                                                   ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps,
+                                                   efeat_new[lo:hi], agg, ws, lo, sum(tiles), sum(tiles[:k]))
 
-                run(halo.e0, halo.e1, P, halo.src_own)  # interior edges overlap the exchange
+                run(1, P, halo.src_own)  # interior edges overlap the exchange
                 if work is not None:
                     work.wait()
-                run(0, halo.e0, Ps, src[:halo.e0])
-                run(halo.e1, E, Ps, src[halo.e1:])
+                run(0, Ps, src[:halo.e0])
+                run(2, Ps, src[halo.e1:])
+                ops.agg_fixup(ws, sum(tiles), agg, N)
                 del keep
             if agg is None:
                 agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)

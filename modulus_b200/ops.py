@@ -513,6 +513,26 @@ def edge_block_fwd_tc(efeat: Tensor, P: Tensor, src: Tensor, dst: Tensor, csc_of
     return out, agg
 
 
+def agg_workspace(total_tiles: int, dev) -> Tensor:
+    """Record array shared by the launches of one partitioned edge forward (2 records of 128 fp32 + id per tile)."""
+    return _ws(2 * int(total_tiles) * (TC_HIDDEN * 4 + 4), dev)
+
+
+def edge_block_fwd_part_tc(efeat: Tensor, g1: Tensor, g1_idx: Tensor, P: Tensor, dst: Tensor, csc_offsets: Tensor,
+                           n_dst: int, w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta, eps: float, out: Tensor,
+                           agg: Tensor, ws: Tensor, row_base: int, total_tiles: int, rec_base: int) -> None:
+    """One row range of a partitioned edge forward with fused aggregation (mgn_edge_block_fwd_part_tc): source
+    projections from `g1` (local table or exchanged rows) via g1_idx, destination projections from P[:, H:2H]."""
+    call("mgn_edge_block_fwd_part_tc", _p(efeat), _p(g1), _p(g1_idx), g1.stride(0), 0, _p(P), _p(dst), P.stride(0),
+         TC_HIDDEN, efeat.shape[0], _p(w1a), w1a.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta),
+         eps, _p(out), _p(csc_offsets), n_dst, _p(agg), agg.stride(0), _p(ws), ws.numel(), row_base, total_tiles, rec_base,
+         _p(tc_status(efeat.device)), _stream())
+
+
+def agg_fixup(ws: Tensor, total_tiles: int, agg: Tensor, n_dst: int) -> None:
+    call("mgn_agg_fixup", _p(ws), total_tiles, _p(agg), agg.stride(0), n_dst, _stream())
+
+
 def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
                 g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
                 g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int,

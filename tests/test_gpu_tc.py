@@ -396,3 +396,45 @@ def test_mlp3_bwd_tc_fused_destination_sum(N, lo, hi):
     assert bool((T[:, :128] == 7).all()) and bool((T[:, 256:] == 7).all())  # neighbouring columns untouched
     if bool((deg == 0).any()):
         assert float(T[:, 128:256][deg.to(DEV) == 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cuts", [(0, 700), (300, 301), (129, 4000), (0, 0)])
+def test_edge_block_fwd_in_row_ranges_matches_single_launch(cuts):
+    """mgn_edge_block_fwd_part_tc over three consecutive row ranges + mgn_agg_fixup == one mgn_edge_block_fwd_tc launch
+    (the partitioned path runs the interior range first, then the boundary ranges)."""
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(21)
+    N = 1500
+    deg = torch.randint(0, 8, (N,), generator=g)
+    deg[40] = 260
+    offsets = torch.zeros(N + 1, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(deg, 0).int()
+    E = int(offsets[-1])
+    dst = torch.repeat_interleave(torch.arange(N), deg).int().to(DEV)
+    src = torch.randint(0, N, (E,), generator=g).int().to(DEV)
+    offd = offsets.to(DEV)
+    d = dev_params(make_params(384, seed=2))
+    A = torch.randn(E, 128, generator=g).to(DEV).bfloat16()
+    P = (torch.randn(N, 384, generator=g) * 0.5).to(DEV).bfloat16()
+    args = (d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"])
+    out1, agg1 = ops.edge_block_fwd_tc(A, P, src, dst, offd, N, *args)
+    e0, e1 = cuts[0], (cuts[1] if cuts[1] > 0 else E)
+    ranges = [(0, e0), (e0, e1), (e1, E)]
+    tiles = [-(-(hi - lo) // 128) for lo, hi in ranges]
+    ws = ops.agg_workspace(sum(tiles), DEV)
+    out3 = torch.empty_like(out1)
+    agg3 = torch.full((N, 128), 3.0, dtype=torch.bfloat16, device=DEV)
+    for k in (1, 0, 2):
+        lo, hi = ranges[k]
+        if hi > lo:
+            ops.edge_block_fwd_part_tc(A[lo:hi], P, src[lo:hi], P, dst[lo:hi], offd, N, *args, 1e-5, out3[lo:hi], agg3, ws,
+                                       lo, sum(tiles), sum(tiles[:k]))
+    ops.agg_fixup(ws, sum(tiles), agg3, N)
+    ops.tc_check(DEV)
+    assert torch.equal(out1, out3)
+    # summation order differs only where a range boundary splits a segment differently from the 128-row tiling
+    assert rel_err(agg3.float(), agg1.float()) < 1e-2
+    ref = torch.zeros(N, 128, dtype=torch.float64, device=DEV).index_add_(0, dst.long(), out1.double())
+    assert rel_err(agg3.float(), ref) < 1e-2
+    assert float(agg3[deg.to(DEV) == 0].abs().max()) == 0.0

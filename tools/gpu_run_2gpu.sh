@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-nvidia-smi -L > gpurun_out/smi2.txt
+timeout 600 python -m pytest tests/test_gpu_tc.py -m gpu -x -q -k "row_ranges or fused_aggregation" > gpurun_out/pytest_gpu_agg.log 2>&1; tail -4 gpurun_out/pytest_gpu_agg.log
 timeout 900 python -m pytest tests/test_gpu_dist.py -m gpu -x -q > gpurun_out/pytest_gpu_dist.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_dist.log
 tail -5 gpurun_out/pytest_gpu_dist.log
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_c3_2gpu.json 2> gpurun_out/bench_c3_2gpu.err; tail -c 1500 gpurun_out/bench_c3_2gpu.json; tail -5 gpurun_out/bench_c3_2gpu.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_c3_2gpu.json 2> gpurun_out/bench_c3_2gpu.err; tail -c 700 gpurun_out/bench_c3_2gpu.json; grep -E "Error|error" gpurun_out/bench_c3_2gpu.err | head -5
