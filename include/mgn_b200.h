@@ -103,6 +103,14 @@ int mgn_segment_sum(int dtype, const void* in, int64_t ld_in, int64_t in_col0, i
                     const int32_t* offsets, const int32_t* eids, int64_t n_segments, void* out,
                     int64_t ld_out, int64_t out_col0, int mean, int accumulate,
                     mgn_stream_t stream);
+/* mgn_segment_sum with hub handling for skewed-degree graphs: segments longer than 512 rows are split into 2048-row
+ * chunks, each summed by a whole CTA into an fp32 partial, partials combined in chunk order (bit-reproducible).
+ * n_rows = rows of `in` covered by the offsets; workspace >= mgn_segment_sum_workspace_bytes(n_rows, D). */
+size_t mgn_segment_sum_workspace_bytes(int64_t n_rows, int64_t D);
+int mgn_segment_sum_balanced(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                             const int32_t* offsets, const int32_t* eids, int64_t n_segments, void* out,
+                             int64_t ld_out, int64_t out_col0, int mean, int accumulate, int64_t n_rows,
+                             void* workspace, size_t workspace_bytes, mgn_stream_t stream);
 
 /* Row gather into a column slice (backward of the segmented sum, halo packing):
  *   out[r, out_col0 : out_col0+D] = scale_r * in[ idx ? idx[r] : r , in_col0 : in_col0+D ]

@@ -153,7 +153,7 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
     if name == "mgn_linear_bwd_weight":
         M, N, K = a[4], a[5], a[6]
         return "tensor", 2.0 * M * K * N
-    if name == "mgn_segment_sum":
+    if name in ("mgn_segment_sum", "mgn_segment_sum_balanced"):
         b, D, n_seg = _DT_BYTES[a[0]], a[4], a[7]
         return "hbm", None if PROFILE.n_edges is None else (PROFILE.n_edges + n_seg) * D * b + 4.0 * n_seg
     if name == "mgn_gather_rows":

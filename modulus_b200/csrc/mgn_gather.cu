@@ -119,6 +119,111 @@ __global__ void sum_efeat_scalar_kernel(const T* __restrict__ efeat, const T* __
 }
 
 // ---------------------------------------------------------------------------------------
+// Long segments (hub nodes of skewed-degree graphs).  A warp that meets a segment longer than kLongSeg rows does not
+// walk it: it appends ceil(len / kLongChunk) chunk entries to a worklist (one atomicAdd reserves a contiguous run, so
+// the order of the chunks inside a segment is fixed); segment_long_partial_kernel sums each chunk with a whole CTA
+// into an fp32 partial row, segment_long_combine_kernel adds the partials of a segment in chunk order.  Which run of
+// the worklist a segment lands in depends on timing, its value does not: results stay bit-reproducible.
+// ---------------------------------------------------------------------------------------
+constexpr int kLongSeg = 512;
+constexpr int kLongChunk = 2048;
+struct LongEntry {
+  int32_t seg, chunk, n_chunks, pad;
+};
+struct LongList {
+  int32_t* counter;    // [4] (counter, capacity overflow flag)
+  LongEntry* entries;  // [capacity]
+  int32_t capacity;
+};
+
+__device__ __forceinline__ void push_long_segment(const LongList& ll, int64_t s, int32_t len) {
+  const int32_t n = (len + kLongChunk - 1) / kLongChunk;
+  const int32_t base = atomicAdd(ll.counter, n);
+  if (base + n > ll.capacity) {
+    atomicExch(ll.counter + 1, 1);
+    return;
+  }
+  for (int32_t k = 0; k < n; ++k) ll.entries[base + k] = LongEntry{static_cast<int32_t>(s), k, n, 0};
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks,
+                            const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids, LongList ll,
+                            float* __restrict__ partials, int64_t D) {
+  constexpr int V = Num<T>::kVec;
+  const int n_entries = min(*ll.counter, ll.capacity);
+  __shared__ float red[8][32 * V];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int en = blockIdx.x; en < n_entries; en += gridDim.x) {
+    const LongEntry le = ll.entries[en];
+    const int32_t b = __ldg(offsets + le.seg) + le.chunk * kLongChunk;
+    const int32_t e = min(__ldg(offsets + le.seg + 1), b + kLongChunk);
+    for (int cb = 0; cb < chunks; cb += 32) {  // 32 column chunks (16 bytes each) per pass, one row per warp per load
+      const int c = cb + lane;
+      const bool active = c < chunks;
+      float acc[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      for (int32_t j = b + warp; j < e; j += 32) {  // 4 rows in flight per warp
+        uint4 v[4];
+        bool on[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          on[u] = active && (j + 8 * u < e);
+          if (on[u]) {
+            const int64_t row = eids ? __ldg(eids + j + 8 * u) : (j + 8 * u);
+            v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (on[u]) {
+            Vec16<T> t;
+            t.raw = v[u];
+            float f[V];
+            t.unpack(f);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += f[k];
+          }
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) red[warp][lane * V + k] = acc[k];
+      __syncthreads();
+      for (int i = threadIdx.x; i < 32 * V; i += blockDim.x) {
+        const int col = cb * V + i;
+        if (col < D) {
+          float sum = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) sum += red[w][i];
+          partials[static_cast<int64_t>(en) * D + col] = sum;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+segment_long_combine_kernel(LongList ll, const float* __restrict__ partials, int64_t D, const int32_t* __restrict__ offsets,
+                            T* __restrict__ out, int64_t ld_out, int64_t out_col0, int mean, int accumulate) {
+  const int n_entries = min(*ll.counter, ll.capacity);
+  for (int en = blockIdx.x; en < n_entries; en += gridDim.x) {
+    const LongEntry le = ll.entries[en];
+    if (le.chunk != 0) continue;
+    const float scale = mean ? 1.f / static_cast<float>(max(offsets[le.seg + 1] - offsets[le.seg], 1)) : 1.f;
+    for (int col = threadIdx.x; col < D; col += blockDim.x) {
+      float sum = 0.f;
+      for (int k = 0; k < le.n_chunks; ++k) sum += partials[static_cast<int64_t>(en + k) * D + col];
+      T* o = out + static_cast<int64_t>(le.seg) * ld_out + out_col0 + col;
+      const float prev = accumulate ? Num<T>::to_f(*o) : 0.f;
+      *o = Num<T>::from_f(prev + sum * scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Segmented sum.  One warp per segment; the warp is split into 32/G row groups of G lanes
 // (G = lanes needed for one row's 16-byte chunks), each group sums every (32/G)-th row in
 // fp32, then the groups are combined with a fixed xor-shuffle tree: no atomics, run-to-run
@@ -129,7 +234,7 @@ template <typename T, int G>
 __global__ void __launch_bounds__(256)
 segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks,
                        const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids, int64_t n_seg,
-                       T* __restrict__ out, int64_t ld_out, int64_t out_col0, int mean, int accumulate) {
+                       T* __restrict__ out, int64_t ld_out, int64_t out_col0, int mean, int accumulate, LongList ll) {
   constexpr int V = Num<T>::kVec;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -138,6 +243,10 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t s = warp; s < n_seg; s += nwarps) {
     const int32_t b = __ldg(offsets + s), e = __ldg(offsets + s + 1);
+    if (ll.counter != nullptr && e - b > kLongSeg) {  // hub: handed to the long-segment kernels
+      if (lane == 0) push_long_segment(ll, s, e - b);
+      continue;
+    }
     const float scale = mean ? 1.f / static_cast<float>(max(e - b, 1)) : 1.f;
     for (int cb = 0; cb < chunks; cb += G) {
       const int c = cb + l;
@@ -203,7 +312,7 @@ template <typename T, int G, int S, int U>
 __global__ void __launch_bounds__(256)
 segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, const int32_t* __restrict__ offsets,
                          const int32_t* __restrict__ eids, int64_t n_seg, T* __restrict__ out, int64_t ld_out,
-                         int64_t out_col0, int mean, int accumulate) {
+                         int64_t out_col0, int mean, int accumulate, LongList ll) {
   constexpr int V = Num<T>::kVec;
   constexpr int R = 32 / G;
   const int lane = threadIdx.x & 31;
@@ -213,11 +322,17 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
   const T* col = in + in_col0 + static_cast<int64_t>(c) * V;
   for (int64_t s0 = warp * S; s0 < n_seg; s0 += nwarps * S) {
     int32_t b[S], e[S];
+    bool is_long[S];
 #pragma unroll
     for (int i = 0; i < S; ++i) {
       const bool valid = s0 + i < n_seg;
       b[i] = valid ? __ldg(offsets + s0 + i) : 0;
       e[i] = valid ? __ldg(offsets + s0 + i + 1) : 0;
+      is_long[i] = ll.counter != nullptr && e[i] - b[i] > kLongSeg;
+      if (is_long[i]) {  // hub: handed to the long-segment kernels, nothing to do (and nothing written) here
+        if (lane == 0) push_long_segment(ll, s0 + i, e[i] - b[i]);
+        e[i] = b[i];
+      }
     }
     int64_t rows[S][U];
 #pragma unroll
@@ -263,7 +378,7 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
       }
-      if (g == 0 && s0 + i < n_seg) {
+      if (g == 0 && s0 + i < n_seg && !is_long[i]) {
         const float scale = mean ? 1.f / static_cast<float>(max(e[i] - b[i], 1)) : 1.f;
         T* o = out + (s0 + i) * ld_out + out_col0 + static_cast<int64_t>(c) * V;
         Vec16<T> t;
@@ -400,10 +515,12 @@ static int sum_efeat_fwd_t(const void* efeat, const void* sfeat, const void* dfe
   return mgn_launch_status();
 }
 
+static size_t long_capacity(int64_t n_rows) { return static_cast<size_t>(n_rows / kLongChunk + n_rows / kLongSeg + 16); }
+
 template <typename T>
 static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t D, const int32_t* offsets,
                          const int32_t* eids, int64_t n_seg, void* out, int64_t ld_out, int64_t out_col0, int mean,
-                         int accumulate, cudaStream_t st) {
+                         int accumulate, cudaStream_t st, int64_t n_rows = 0, void* workspace = nullptr) {
   constexpr int V = Num<T>::kVec;
   if (n_seg == 0 || D == 0) return MGN_OK;
   const bool vec = D % V == 0 && ld_in % V == 0 && in_col0 % V == 0 && ld_out % V == 0 && out_col0 % V == 0 &&
@@ -413,19 +530,34 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
   if (vec) {
     const int chunks = static_cast<int>(D / V);
     const int grid = grid_for(n_seg * 32);
+    LongList ll{nullptr, nullptr, 0};
+    float* partials = nullptr;
+    if (workspace != nullptr) {  // balanced variant: hubs go through the worklist
+      const size_t cap = long_capacity(n_rows);
+      ll.counter = static_cast<int32_t*>(workspace);
+      ll.entries = reinterpret_cast<LongEntry*>(static_cast<char*>(workspace) + 16);
+      ll.capacity = static_cast<int32_t>(cap);
+      partials = reinterpret_cast<float*>(static_cast<char*>(workspace) + 16 + cap * sizeof(LongEntry));
+      cudaError_t ce = cudaMemsetAsync(ll.counter, 0, 16, st);
+      if (ce != cudaSuccess) return static_cast<int>(ce);
+    }
 #define MGN_SEG(G)                                                                                     \
   segment_sum_vec_kernel<T, G><<<grid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
-                                                     o_, ld_out, out_col0, mean, accumulate)
-    if (chunks == 16) {
+                                                     o_, ld_out, out_col0, mean, accumulate, ll)
+    if (chunks == 16)
       segment_sum_batch_kernel<T, 16, 4, 3><<<grid_for((n_seg + 3) / 4 * 32), 256, 0, MGN_ST(st)>>>(
-          i_, ld_in, in_col0, offsets, eids, n_seg, o_, ld_out, out_col0, mean, accumulate);
-      return mgn_launch_status();
-    }
-    if (chunks <= 4) MGN_SEG(4);
+          i_, ld_in, in_col0, offsets, eids, n_seg, o_, ld_out, out_col0, mean, accumulate, ll);
+    else if (chunks <= 4) MGN_SEG(4);
     else if (chunks <= 8) MGN_SEG(8);
     else if (chunks <= 16) MGN_SEG(16);
     else MGN_SEG(32);
 #undef MGN_SEG
+    int rc = mgn_launch_status();
+    if (rc != MGN_OK || ll.counter == nullptr) return rc;
+    const int lgrid = ll.capacity < 4 * num_sms() ? ll.capacity : 4 * num_sms();
+    segment_long_partial_kernel<T><<<lgrid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, ll, partials, D);
+    segment_long_combine_kernel<T><<<lgrid, 256, 0, MGN_ST(st)>>>(ll, partials, D, offsets, o_, ld_out, out_col0, mean,
+                                                             accumulate);
   } else {
     segment_sum_scalar_kernel<T><<<grid_for(n_seg * D), 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, static_cast<int>(D),
                                                                       offsets, eids, n_seg, o_, ld_out, out_col0,
@@ -497,6 +629,31 @@ extern "C" int mgn_segment_sum(int dtype, const void* in, int64_t ld_in, int64_t
   if (dtype == MGN_BF16)
     return segment_sum_t<bf16>(in, ld_in, in_col0, D, offsets, eids, n_segments, out, ld_out, out_col0, mean,
                                accumulate, as_stream(stream));
+  return MGN_EINVAL;
+}
+
+/* mgn_segment_sum with hub handling: segments longer than 512 rows are split into 2048-row chunks summed by whole
+ * CTAs and combined in chunk order (skewed-degree graphs; same results run to run).  n_rows = rows of `in` that the
+ * offsets cover (sizes the worklist), workspace >= mgn_segment_sum_workspace_bytes(n_rows, D). */
+extern "C" size_t mgn_segment_sum_workspace_bytes(int64_t n_rows, int64_t D) {
+  if (n_rows <= 0) return 16;
+  return 16 + long_capacity(n_rows) * (sizeof(LongEntry) + static_cast<size_t>(D) * sizeof(float));
+}
+
+extern "C" int mgn_segment_sum_balanced(int dtype, const void* in, int64_t ld_in, int64_t in_col0, int64_t D,
+                                        const int32_t* offsets, const int32_t* eids, int64_t n_segments, void* out,
+                                        int64_t ld_out, int64_t out_col0, int mean, int accumulate, int64_t n_rows,
+                                        void* workspace, size_t workspace_bytes, mgn_stream_t stream) {
+  MGN_CHECK_ARG(n_segments >= 0 && D >= 0 && ld_in >= 0 && ld_out >= 0 && in_col0 >= 0 && out_col0 >= 0 && n_rows >= 0);
+  if (n_segments == 0) return MGN_OK;
+  MGN_CHECK_ARG(offsets && out && workspace);
+  if (workspace_bytes < mgn_segment_sum_workspace_bytes(n_rows, D)) return MGN_EWORKSPACE;
+  if (dtype == MGN_F32)
+    return segment_sum_t<float>(in, ld_in, in_col0, D, offsets, eids, n_segments, out, ld_out, out_col0, mean,
+                                accumulate, as_stream(stream), n_rows, workspace);
+  if (dtype == MGN_BF16)
+    return segment_sum_t<bf16>(in, ld_in, in_col0, D, offsets, eids, n_segments, out, ld_out, out_col0, mean,
+                               accumulate, as_stream(stream), n_rows, workspace);
   return MGN_EINVAL;
 }
 

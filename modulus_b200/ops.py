@@ -128,12 +128,39 @@ class GraphPlan:
 # ----------------------------------------------------------------------------------------
 # raw wrappers
 # ----------------------------------------------------------------------------------------
+LONG_SEGMENT = 512  # rows; csrc/mgn_gather.cu: kLongSeg
+_max_seg_cache: dict = {}
+
+
+def _has_long_segments(offsets: Tensor) -> bool:
+    """Whether an offsets array holds a segment longer than LONG_SEGMENT rows (hub nodes).  One host read-back per
+    offsets tensor (graph plans are built once); a stale entry only costs speed, both kernels are exact."""
+    key = (offsets.data_ptr(), offsets.numel())
+    hit = _max_seg_cache.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return True
+        hit = bool(offsets.numel() > 1 and int((offsets[1:] - offsets[:-1]).max()) > LONG_SEGMENT)
+        if len(_max_seg_cache) > 256:
+            _max_seg_cache.clear()
+        _max_seg_cache[key] = hit
+    return hit
+
+
 def segment_sum(inp: Tensor, in_col0: int, D: int, offsets: Tensor, eids: Optional[Tensor], n_seg: int,
                 out: Optional[Tensor] = None, out_col0: int = 0, mean: bool = False,
                 accumulate: bool = False) -> Tensor:
     if out is None:
         out = torch.empty((n_seg, D), dtype=inp.dtype, device=inp.device)
-    call("mgn_segment_sum", _dt(inp), _p(inp), inp.stride(0) if inp.dim() == 2 else D, in_col0, D,
+    ld_in = inp.stride(0) if inp.dim() == 2 else D
+    if _has_long_segments(offsets):  # skewed degrees: hubs are split across CTAs (mgn_segment_sum_balanced)
+        n_rows = inp.shape[0]
+        nbytes = _lib.load().mgn_segment_sum_workspace_bytes(n_rows, D)
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=inp.device)
+        call("mgn_segment_sum_balanced", _dt(inp), _p(inp), ld_in, in_col0, D, _p(offsets), _p(eids), n_seg, _p(out),
+             out.stride(0), out_col0, int(mean), int(accumulate), n_rows, _p(ws), nbytes, _stream())
+        return out
+    call("mgn_segment_sum", _dt(inp), _p(inp), ld_in, in_col0, D,
          _p(offsets), _p(eids), n_seg, _p(out), out.stride(0), out_col0, int(mean), int(accumulate), _stream())
     return out
 

@@ -263,3 +263,27 @@ def test_checkpoint_segments_give_same_result():
     o1, _, a1, b1 = _run_model(m1, g, graph)
     o2, _, a2, b2 = _run_model(m2, g, graph)
     assert torch.equal(o1, o2) and torch.equal(a1, a2) and torch.equal(b1, b2)
+
+
+@pytest.mark.parametrize("dtype,D", [(torch.float32, 128), (torch.bfloat16, 128), (torch.bfloat16, 512), (torch.float32, 40)])
+def test_segment_sum_with_hub_segments(dtype, D):
+    """Skewed degrees (BASELINE configs[4]): segments far longer than a warp's share go through the chunked worklist
+    (mgn_segment_sum_balanced); same values as a float64 index_add, mean and accumulate included, run to run identical."""
+    from modulus_b200 import ops
+    from modulus_b200.mesh import power_law_graph_csc
+
+    off, idx = power_law_graph_csc(3000, 60000, alpha=1.2, seed=1)
+    plan = _plan_from_csc(off, idx, 3000, 3000)
+    deg = (plan.csc_offsets[1:] - plan.csc_offsets[:-1]).long()
+    assert int(deg.max()) > 4 * ops.LONG_SEGMENT and ops._has_long_segments(plan.csc_offsets)
+    x = torch.randn(idx.numel(), D, device=DEV).to(dtype)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for offsets, eids, key in ((plan.csc_offsets, None, plan.dst), (plan.csr_offsets, plan.csr_eids, plan.src)):
+        ref = torch.zeros(3000, D, dtype=torch.float64, device=DEV).index_add_(0, key.long(), x.double())
+        out = ops.segment_sum(x, 0, D, offsets, eids, 3000)
+        assert rel_err(out.float(), ref) < tol
+        assert torch.equal(out, ops.segment_sum(x, 0, D, offsets, eids, 3000))
+        d = (offsets[1:] - offsets[:-1]).clamp_min(1).double()[:, None]
+        base = torch.ones(3000, D, device=DEV, dtype=dtype)
+        out_m = ops.segment_sum(x, 0, D, offsets, eids, 3000, out=base.clone(), mean=True, accumulate=True)
+        assert rel_err(out_m.float(), 1.0 + ref / d) < tol
