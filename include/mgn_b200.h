@@ -298,6 +298,9 @@ int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const void* x, int64
 /* Debug hook (not part of the drop-in surface): dev_buf = 96 x int64 that CTA 0 of subsequent
  * mgn_mlp3_bwd_tc launches fills with per-role, per-phase cycle counts; NULL disables. */
 int mgn_debug_set_bwd_timing(void* dev_buf);
+/* A/B hook: 0 routes mgn_edge_block_fwd*_tc to the second-generation (one tile in flight) kernel, 1 (default) to the
+ * two-tiles-in-flight kernel. */
+int mgn_debug_set_edge_fwd3(int on);
 int mgn_debug_set_fwd_timing(void* dev_buf);
 
 #ifdef __cplusplus

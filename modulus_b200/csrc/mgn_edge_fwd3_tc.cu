@@ -1,0 +1,495 @@
+// mgn_edge_fwd3_tc.cu — MeshEdgeBlock forward (+ destination sums), third generation: two tiles in flight.
+//
+//     z1[e]  = efeat[e] W1a^T + P_src[src[e]] + P_dst[dst[e]] + b1 ; h1 = relu(z1) ; h2 = relu(h1 W2^T + b2)
+//     out[e] = efeat[e] + LayerNorm(h2 W3^T + b3)                 agg[v] = sum of out[e] over the in-edges of v
+//
+// (physicsnemo/models/gnn_layers/mesh_edge_block.py:88-96 with the first Linear split per input block, and the "sum"
+// aggregation of utils.py:337-378; see modulus_b200/fused.py.)
+//
+// The second-generation kernel runs one 128-row tile at a time through GEMM1 -> E1 -> GEMM2 -> E2 -> GEMM3 -> E3: the
+// tensor core idles during the epilogue passes and the epilogue warps during the GEMMs (profiles/r01_phase_cycles_*).
+// Here every epilogue pass of one tile overlaps a GEMM of its neighbour; the epilogue warps run back to back
+//
+//        ... | E2(k)  E1(k+1)  E3(k) | E2(k+1)  E1(k+2)  E3(k+1) | ...
+//   MMA: ...   M2(k)->      M1(k+2)     M3(k)->      M2(k+1)-> ...          (each GEMM has a whole pass to finish)
+//
+// which needs three A tiles (this one's residual/output, the next one's, the one after streaming in), three TMEM
+// accumulators and two hidden-activation slots.  The third A buffer comes from not staging the destination
+// projections at all: edges are CSC-ordered, so the 32 rows of a warp share ~6 destination rows, and each epilogue
+// thread reads its 128 bytes of P_dst straight from global memory a full pass before it needs them.
+//
+// Warp roles (448 threads): warp 0 = MMA issuer + TMEM owner; warps 1-4 = movers (cp.async gather of the source
+// projections, destination sums of the result tile, mgn_agg.cuh); warps 5-12 = epilogue (two warps per TMEM lane
+// quarter, 64 columns each); warp 13 = loader (TMA: efeat tiles in, result tiles out).
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+#include "mgn_tile.cuh"
+#include "mgn_tma.cuh"
+#include "mgn_agg.cuh"
+#include "mgn_edge_fwd3.h"
+
+namespace mgn {
+namespace fwd3 {
+
+using namespace tile;
+constexpr int kH = 128;
+constexpr int kLoaderWarp = 13;
+constexpr int kThreads = 32 * (kLoaderWarp + 1);
+
+struct Params {
+  Args a;
+  long long* timing;
+  alignas(64) CUtensorMap m_a, m_out;
+};
+
+struct Smem {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = 2 * kPB;
+  static constexpr int kW3 = 4 * kPB;
+  static constexpr int kA = 6 * kPB;    // 3 tiles x 2 panels
+  static constexpr int kG1 = 12 * kPB;  // 2 panels
+  static constexpr int kPar = 14 * kPB;  // b1, b2, b3, gamma, beta
+  static constexpr int kBars = kPar + 5 * kH * 4;
+  static constexpr int kTmemSlot = kBars + 24 * 8;
+  static constexpr int kTotal = kTmemSlot + 16;
+};
+
+// B_A[3]: A tile of slot s landed (loader, tx).  B_G: source projections of the next tile staged (4 mover warps).
+// B_M1[3] / B_M2 / B_M3: GEMM k of a tile complete.  B_H1 / B_H2 / B_OUT[3]: epilogue pass complete (8 warps).
+// B_AGG[3]: movers have finished summing the result tile in slot s.  (Barriers that a waiter may trail by more than
+// one completion are kept per slot: a parity wait cannot tell two completions from none.)
+enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_NUM = 17 };
+
+__global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const Args& a = p.a;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0 && a.status) atomicOr(a.status, 2);
+    return;
+  }
+  uint8_t* sW1 = smem + Smem::kW1;
+  uint8_t* sW2 = smem + Smem::kW2;
+  uint8_t* sW3 = smem + Smem::kW3;
+  uint8_t* bA0 = smem + Smem::kA;
+  uint8_t* bG1 = smem + Smem::kG1;
+  float* sPar = reinterpret_cast<float*>(smem + Smem::kPar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::kTmemSlot);
+
+  stage_weight_ld(sW1, a.w1, a.ld_w1, kH, kH, 2, tid, kThreads);
+  stage_weight_ld(sW2, a.w2, kH, kH, kH, 2, tid, kThreads);
+  stage_weight_ld(sW3, a.w3, kH, kH, kH, 2, tid, kThreads);
+  for (int i = tid; i < kH; i += kThreads) {
+    sPar[i] = a.b1 ? a.b1[i] : 0.f;
+    sPar[kH + i] = a.b2 ? a.b2[i] : 0.f;
+    sPar[2 * kH + i] = a.b3 ? a.b3[i] : 0.f;
+    sPar[3 * kH + i] = a.gamma[i];
+    sPar[4 * kH + i] = a.beta ? a.beta[i] : 0.f;
+  }
+  if (tid == 0) {
+    for (int b = 0; b < B_NUM; ++b) {
+      int cnt = 1;
+      if (b == B_G || (b >= B_AGG && b < B_AGG + 3)) cnt = 4;
+      if (b == B_H1 || b == B_H2 || (b >= B_OUT && b < B_OUT + 3)) cnt = 8;
+      mbar_init(&bars[b], cnt);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  // TMEM: three accumulators (tile % 3), two hidden-activation slots of 64 packed columns (tile % 2)
+  const long long n_tiles = (a.M + kRows - 1) / kRows;
+  const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  const long long stride = static_cast<long long>(gridDim.x) * kRows;
+  const long long row_first = static_cast<long long>(blockIdx.x) * kRows;
+  bool timed_out = false;
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t aA0 = smem_u32(bA0), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+      const uint32_t idesc = umma_idesc_bf16(128, 128, 0, 0);
+#define MGN_W(b, ph)             \
+  if (!wait_clk(&bars[b], ph)) { \
+    timed_out = true;            \
+    break;                       \
+  }
+      auto gemm1 = [&](int j) {  // acc[j % 3] = A(j) W1a^T
+        const uint32_t aA = aA0 + (j % 3) * 2 * kPB, tAcc = tmem + (j % 3) * 128;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW1 + (k >> 2) * kPB, k & 3), idesc, k != 0);
+        umma_commit(&bars[B_M1 + j % 3]);
+      };
+      do {
+        // prologue: first GEMMs of tiles 0 and 1
+        for (int j = 0; j < 2 && j < n_my; ++j) {
+          if (!wait_clk(&bars[B_A + j], 0)) { timed_out = true; break; }
+          tc_fence_after_sync();
+          gemm1(j);
+        }
+        if (timed_out) break;
+        auto gemm2 = [&](int j) {  // acc[j % 3] = h1(j) W2^T, h1 in TMEM
+          const uint32_t tAcc = tmem + (j % 3) * 128, tHj = tmem + 384 + (j & 1) * 64;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) umma_ts(tAcc, tHj + q * 8, umma_desc_kmajor(aW2 + (q >> 2) * kPB, q & 3), idesc, q != 0);
+          umma_commit(&bars[B_M2]);
+        };
+        if (n_my > 0) {
+          if (!wait_clk(&bars[B_H1], 0)) { timed_out = true; break; }
+          tc_fence_after_sync();
+          gemm2(0);
+        }
+        // period k, in the order the epilogue releases things: E2(k) -> M3(k); E1(k+1) -> M2(k+1); E3(k-1) has drained an
+        // accumulator and A(k+2) has landed (well into the period: its slot held tile k-1's result) -> M1(k+2)
+        const bool tmm = p.timing != nullptr && blockIdx.x == 0;
+        long long tq[6] = {0, 0, 0, 0, 0, 0};
+        long long tl = clock64();
+#define MGN_TM(i)                    \
+  if (tmm) {                         \
+    const long long t_ = clock64();  \
+    tq[i] += t_ - tl;                \
+    tl = t_;                         \
+  }
+        for (int k = 0; k < n_my; ++k) {
+          const uint32_t par = k & 1;
+          const uint32_t tAcc = tmem + (k % 3) * 128, tHk = tmem + 384 + (k & 1) * 64;
+          MGN_W(B_H2, par);  // E2(k) done: h2 in TMEM
+          MGN_TM(0);
+          tc_fence_after_sync();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) umma_ts(tAcc, tHk + q * 8, umma_desc_kmajor(aW3 + (q >> 2) * kPB, q & 3), idesc, q != 0);
+          umma_commit(&bars[B_M3]);
+          MGN_TM(1);
+          if (k + 1 < n_my) {
+            MGN_W(B_H1, par ^ 1);  // E1(k+1) done: h1 in TMEM
+            MGN_TM(2);
+            tc_fence_after_sync();
+            gemm2(k + 1);
+            MGN_TM(3);
+          }
+          if (k + 2 < n_my) {
+            if (k >= 1) MGN_W(B_OUT + (k - 1) % 3, ((k - 1) / 3) & 1);
+            MGN_W(B_A + (k + 2) % 3, ((k + 2) / 3) & 1);
+            MGN_TM(4);
+            tc_fence_after_sync();
+            gemm1(k + 2);
+            MGN_TM(5);
+          }
+        }
+        if (tmm)
+          for (int i = 0; i < 6; ++i) p.timing[8 + i] = tq[i];
+      } while (false);
+#undef MGN_W
+    }
+  } else if (warp <= 4) {
+    // =========================== movers ===========================
+    const int mt = tid - 32;
+    const int rsub_m = mt >> 4;
+    const RowSrc g1{a.g1_tab, a.g1_idx, a.g1_ld, a.g1_col0};
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_PUBLISH_G()          \
+  cp_async_commit();             \
+  cp_async_wait<0>();            \
+  __syncwarp();                  \
+  if (lane == 0) mbar_arrive(&bars[B_G]);
+    int32_t r_g1[16];
+    do {
+      if (n_my > 0) {  // G1(0), then G1(1) as soon as E1(0) has consumed G1(0)
+        fetch_row_ids(g1.idx, row_first, a.M, rsub_m, r_g1);
+        stage_rows_async(bG1, g1, r_g1, row_first, a.M, mt);
+        if (n_my > 1) fetch_row_ids(g1.idx, row_first + stride, a.M, rsub_m, r_g1);
+        MGN_PUBLISH_G();
+      }
+      if (n_my > 1) {
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], 0))) { timed_out = true; break; }
+        stage_rows_async(bG1, g1, r_g1, row_first + stride, a.M, mt);
+        if (n_my > 2) fetch_row_ids(g1.idx, row_first + 2 * stride, a.M, rsub_m, r_g1);
+        MGN_PUBLISH_G();
+      }
+      for (int k = 0; k < n_my; ++k) {
+        const long long row0 = row_first + k * stride;
+        if (k + 2 < n_my) {  // period k: E1(k+1) has consumed G1(k+1) -> stage G1(k+2) while E3(k) runs
+          MGN_W(B_H1, (k + 1) & 1);
+          stage_rows_async(bG1, g1, r_g1, row0 + 2 * stride, a.M, mt);
+          if (k + 3 < n_my) fetch_row_ids(g1.idx, row0 + 3 * stride, a.M, rsub_m, r_g1);
+          MGN_PUBLISH_G();
+        }
+        // result tile k: destination sums from shared memory
+        MGN_W(B_OUT + k % 3, (k / 3) & 1);
+        if (a.seg_off != nullptr)
+          agg::tile_segment_sum(bA0 + (k % 3) * 2 * kPB, row0, a.M, a.seg_off, a.g2_idx, a.agg, a.ld_agg, a.agg_part,
+                                a.agg_part_v, mt, a.agg_row_base, a.agg_rec_base);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_AGG + k % 3]);
+      }
+    } while (false);
+#undef MGN_W
+  } else if (warp == kLoaderWarp) {
+    // =========================== loader (TMA) ===========================
+    if (lane == 0) {
+      auto load_a = [&](int j) {
+        const uint32_t dst = smem_u32(bA0) + (j % 3) * 2 * kPB;
+        const int r0 = static_cast<int>(row_first + j * stride);
+        mbar_arrive_expect_tx(&bars[B_A + j % 3], 2 * kPB);
+        tma_load_2d(dst, &p.m_a, 0, r0, &bars[B_A + j % 3]);
+        tma_load_2d(dst + kPB, &p.m_a, 64, r0, &bars[B_A + j % 3]);
+      };
+      for (int j = 0; j < 3 && j < n_my; ++j) load_a(j);
+      for (int k = 0; k < n_my; ++k) {
+        const uint32_t src = smem_u32(bA0) + (k % 3) * 2 * kPB;
+        const int r0 = static_cast<int>(row_first + k * stride);
+        if (!wait_clk(&bars[B_OUT + k % 3], (k / 3) & 1)) { timed_out = true; break; }
+        tma_store_2d(&p.m_out, src, 0, r0);
+        tma_store_2d(&p.m_out, src + kPB, 64, r0);
+        tma_store_commit();
+        if (k + 3 < n_my) {  // slot free once the store and the movers' sums have read it
+          tma_store_wait_read();
+          if (!wait_clk(&bars[B_AGG + k % 3], (k / 3) & 1)) { timed_out = true; break; }
+          load_a(k + 3);
+        }
+      }
+      tma_store_wait_all();
+    }
+  } else {
+    // =========================== epilogue (8 warps) ===========================
+    const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = ch * 64;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const float* b1 = sPar + c0;
+    const float* b2 = sPar + kH + c0;
+    const float* b3 = sPar + 2 * kH + c0;
+    const float* gam = sPar + 3 * kH + c0;
+    const float* bet = sPar + 4 * kH + c0;
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_ROW_SYNC()                                            \
+  tc_fence_before_sync();                                         \
+  asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");       \
+  tc_fence_after_sync()
+    // destination-projection row of this thread for a tile, and its 64 columns (8 x 16 bytes) straight from global
+    auto g2_row = [&](int j) -> int32_t {
+      const long long gr = row_first + j * stride + row;
+      return __ldg(a.g2_idx + (gr < a.M ? gr : a.M - 1));
+    };
+    uint4 gq[8];
+    auto g2_fetch = [&](int32_t r) {
+      const uint4* src = reinterpret_cast<const uint4*>(a.g2_tab + static_cast<long long>(r) * a.g2_ld + a.g2_col0 + c0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) gq[u] = __ldg(src + u);
+    };
+    // E1(j): h1 = relu(acc + b1 + G1 + G2) -> TMEM (packed bf16)
+    auto e1 = [&](int j) {
+      const uint32_t t_acc = tmem + (j % 3) * 128 + lane_off + c0;
+      const uint32_t t_h = tmem + 384 + (j & 1) * 64 + lane_off + ch * 32;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        uint32_t ga[16];
+        row_load32p(bG1, row, c0 + 32 * hh, ga);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float4 bb = reinterpret_cast<const float4*>(b1 + 32 * hh)[u];
+          const uint4 gd = gq[4 * hh + (u >> 1)];
+          const uint32_t d0 = (u & 1) ? gd.z : gd.x, d1 = (u & 1) ? gd.w : gd.y;
+          float z0 = __uint_as_float(v[4 * u]) + bb.x, z1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+          float z2 = __uint_as_float(v[4 * u + 2]) + bb.z, z3 = __uint_as_float(v[4 * u + 3]) + bb.w;
+          z0 += bf_lo(ga[2 * u]);
+          z1 += bf_hi(ga[2 * u]);
+          z2 += bf_lo(ga[2 * u + 1]);
+          z3 += bf_hi(ga[2 * u + 1]);
+          z0 += bf_lo(d0);
+          z1 += bf_hi(d0);
+          z2 += bf_lo(d1);
+          z3 += bf_hi(d1);
+          pk[2 * u] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+          pk[2 * u + 1] = pack_bf16x2(fmaxf(z2, 0.f), fmaxf(z3, 0.f));
+        }
+        tmem_st16(t_h + 16 * hh, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_H1]);
+    };
+    const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && warp == 5 && lane == 0;
+    long long tm[6] = {0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define MGN_T(i)                      \
+  if (tm_on) {                        \
+    const long long t_ = clock64();   \
+    tm[i] += t_ - tlast;              \
+    tlast = t_;                       \
+  }
+    do {
+      int32_t g2r = 0;
+      if (n_my > 0) {
+        g2_fetch(g2_row(0));
+        if (n_my > 1) g2r = g2_row(1);
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_M1], 0) && wait_clk(&bars[B_G], 0))) { timed_out = true; break; }
+        tc_fence_after_sync();
+        e1(0);
+      }
+      for (int k = 0; k < n_my; ++k) {
+        const uint32_t par = k & 1;
+        const uint32_t t_acc = tmem + (k % 3) * 128 + lane_off + c0;
+        const uint32_t t_h = tmem + 384 + (k & 1) * 64 + lane_off + ch * 32;
+        const uint32_t t_x = tmem + 384 + (k & 1) * 64 + lane_off;  // LayerNorm exchange: dead h2 columns of this tile
+        uint8_t* bAcur = bA0 + (k % 3) * 2 * kPB;
+        // the next tile's destination projections, in flight across E2(k)
+        if (k + 1 < n_my) {
+          g2_fetch(g2r);
+          if (k + 2 < n_my) g2r = g2_row(k + 2);
+        }
+        // ---- E2(k): h2 = relu(acc + b2) -> TMEM
+        MGN_T(5);
+        MGN_W(B_M2, par);
+        MGN_T(0);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = reinterpret_cast<const float4*>(b2 + 32 * hh)[u];
+            pk[2 * u] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * u]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * u + 1]) + bb.y, 0.f));
+            pk[2 * u + 1] =
+                pack_bf16x2(fmaxf(__uint_as_float(v[4 * u + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * u + 3]) + bb.w, 0.f));
+          }
+          tmem_st16(t_h + 16 * hh, pk);
+        }
+        tmem_st_wait();
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_H2]);
+        MGN_T(1);
+        // ---- E1(k+1)
+        if (k + 1 < n_my) {
+          MGN_W(B_M1 + (k + 1) % 3, ((k + 1) / 3) & 1);
+          MGN_W(B_G, (k + 1) & 1);
+          MGN_T(2);
+          tc_fence_after_sync();
+          e1(k + 1);
+          MGN_T(3);
+        }
+        // ---- E3(k): y = acc + b3 ; LayerNorm ; + residual ; -> result tile in place over the A tile
+        MGN_W(B_M3, par);
+        MGN_T(4);
+        tc_fence_after_sync();
+        float s = 0.f, ss = 0.f;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
+            const float y0 = __uint_as_float(v[4 * u]) + bb.x, y1 = __uint_as_float(v[4 * u + 1]) + bb.y;
+            const float y2 = __uint_as_float(v[4 * u + 2]) + bb.z, y3 = __uint_as_float(v[4 * u + 3]) + bb.w;
+            s += (y0 + y1) + (y2 + y3);
+            ss = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, ss))));
+          }
+        }
+        tmem_st2(t_x + ch * 2, __float_as_uint(s), __float_as_uint(ss));
+        tmem_st_wait();
+        MGN_ROW_SYNC();
+        uint32_t o0, o1;
+        tmem_ld2(t_x + (ch ^ 1) * 2, o0, o1);
+        tmem_ld_wait();
+        MGN_ROW_SYNC();  // the partner has read these columns before E1 of tile k + 2 stores h1 over them
+        const float mu = (s + __uint_as_float(o0)) * (1.f / kH);
+        const float var = fmaxf((ss + __uint_as_float(o1)) * (1.f / kH) - mu * mu, 0.f);
+        const float rstd = rsqrtf(var + a.eps);
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t r[16];
+          row_load32p(bAcur, row, cc, r);
+          tmem_ld_wait();
+          uint32_t o[16];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
+            const float4 gg = reinterpret_cast<const float4*>(gam + 32 * hh)[u];
+            const float4 be = reinterpret_cast<const float4*>(bet + 32 * hh)[u];
+            float y[4] = {__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
+                          __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w};
+            y[0] = (y[0] - mu) * rstd * gg.x + be.x + bf_lo(r[2 * u]);
+            y[1] = (y[1] - mu) * rstd * gg.y + be.y + bf_hi(r[2 * u]);
+            y[2] = (y[2] - mu) * rstd * gg.z + be.z + bf_lo(r[2 * u + 1]);
+            y[3] = (y[3] - mu) * rstd * gg.w + be.w + bf_hi(r[2 * u + 1]);
+            o[2 * u] = pack_bf16x2(y[0], y[1]);
+            o[2 * u + 1] = pack_bf16x2(y[2], y[3]);
+          }
+          row_store32p(bAcur, row, cc, o);
+        }
+        fence_proxy_async_smem();  // the result tile leaves through the async proxy (TMA store)
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_OUT + k % 3]);
+      }
+    } while (false);
+    MGN_T(5);
+    if (tm_on)
+      for (int i = 0; i < 6; ++i) p.timing[i] = tm[i];
+#undef MGN_W
+  }
+  if (timed_out && a.status != nullptr) atomicOr(a.status, 1);
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace fwd3
+
+static long long* g_fwd3_timing = nullptr;
+void edge_fwd3_set_timing(long long* buf) { g_fwd3_timing = buf; }
+
+int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
+  fwd3::Params p{};
+  p.a = args;
+  p.timing = g_fwd3_timing;
+  if (tma_make_rows_map(&p.m_a, args.a, args.M, 128, 128) != 0) return MGN_EINVAL;
+  if (tma_make_rows_map(&p.m_out, args.out, args.M, 128, 128) != 0) return MGN_EINVAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  const long long n_tiles = (args.M + tile::kRows - 1) / tile::kRows;
+  const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+  fwd3::edge_fwd3_kernel<<<grid, fwd3::kThreads, fwd3::Smem::kTotal, MGN_ST(st)>>>(p);
+  return mgn_launch_status();
+}
+
+}  // namespace mgn

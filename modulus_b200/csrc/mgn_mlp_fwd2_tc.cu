@@ -26,6 +26,7 @@
 #include "mgn_tile.cuh"
 #include "mgn_tma.cuh"
 #include "mgn_agg.cuh"
+#include "mgn_edge_fwd3.h"
 
 namespace mgn {
 namespace fwd2 {
@@ -595,11 +596,19 @@ static int launch(Params& p, cudaStream_t st) {
 using namespace mgn;
 
 extern "C" int mgn_debug_set_fwd2_timing(void* dev_buf) {
+  edge_fwd3_set_timing(static_cast<long long*>(dev_buf));  // (the edge-block kernel fills the first 6 slots)
   fwd2::g_timing = static_cast<long long*>(dev_buf);
   return MGN_OK;
 }
 
 extern "C" size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t M) { return agg::workspace_bytes(M); }
+
+static int g_use_fwd3 = 1;
+/* debug / A-B hook: 0 routes mgn_edge_block_fwd*_tc back to the second-generation kernel */
+extern "C" int mgn_debug_set_edge_fwd3(int on) {
+  g_use_fwd3 = on;
+  return MGN_OK;
+}
 
 struct AggArgs {
   const int32_t* seg_off = nullptr;
@@ -672,7 +681,38 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
     p.agg_rec_base = ag.rec_base;
   }
   int rc;
-  if (small_in > 0) {
+  // the edge block proper (gathered source / destination projections, LayerNorm, residual = input, destination sums)
+  // runs on the two-tiles-in-flight kernel (mgn_edge_fwd3_tc.cu)
+  const bool edge3 = g_use_fwd3 && ag.seg_off != nullptr && small_in <= 0 && a_tab != nullptr && a_idx == nullptr &&
+                     g1_tab != nullptr && g1_idx != nullptr && g2_tab != nullptr && g2_idx != nullptr && res_is_a &&
+                     gamma != nullptr && n_out == fwd2::kH && ld_out == fwd2::kH && ld_w1 >= fwd2::kH &&
+                     (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0;
+  if (edge3) {
+    fwd3::Args x{};
+    x.a = static_cast<const bf16*>(a_tab);
+    x.M = M;
+    x.g1_tab = static_cast<const bf16*>(g1_tab);
+    x.g1_idx = g1_idx;
+    x.g1_ld = g1_ld;
+    x.g1_col0 = g1_col0;
+    x.g2_tab = static_cast<const bf16*>(g2_tab);
+    x.g2_idx = g2_idx;
+    x.g2_ld = g2_ld;
+    x.g2_col0 = g2_col0;
+    x.w1 = w1; x.b1 = b1; x.w2 = w2; x.b2 = b2; x.w3 = w3; x.b3 = b3; x.gamma = gamma; x.beta = beta;
+    x.ld_w1 = ld_w1;
+    x.eps = eps;
+    x.out = static_cast<bf16*>(out);
+    x.seg_off = p.seg_off;
+    x.agg = p.agg;
+    x.ld_agg = p.ld_agg;
+    x.agg_part = p.agg_part;
+    x.agg_part_v = p.agg_part_v;
+    x.agg_row_base = p.agg_row_base;
+    x.agg_rec_base = p.agg_rec_base;
+    x.status = status;
+    rc = edge_fwd3_launch(x, st);
+  } else if (small_in > 0) {
     MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && ld_w1 >= small_in && g1_tab == nullptr);
     p.k1_true = small_in;
     rc = fwd2::launch<1>(p, st);

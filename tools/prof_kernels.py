@@ -28,6 +28,17 @@ def fwd2():
     return ops.mlp3_fwd2_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3,
                             gamma, beta, res_is_a=True)
 
+def eblk():
+    return ops.edge_block_fwd_tc(efeat, P, plan.src, plan.dst, plan.csc_offsets, N, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta)
+
+def eblk2():
+    from modulus_b200 import _lib as L
+    L.call("mgn_debug_set_edge_fwd3", 0)
+    try:
+        return eblk()
+    finally:
+        L.call("mgn_debug_set_edge_fwd3", 1)
+
 def bwd():
     return ops.mlp3_bwd_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, g_e, g_agg, plan.dst, E,
                            w1[:, :128], b1, w2, b2, w3, b3, gamma, 128, 1e-5, True, True, True,
@@ -50,7 +61,7 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
-for name, fn in (("fwd2 edge", fwd2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr),
+for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
@@ -90,3 +101,13 @@ print("FWD2 kernel, CTA 0, cycles per tile")
 print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // per_cta for v in t[0, :5].tolist()], "total", int(t[0].sum()) // per_cta)
 print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // per_cta for v in t[1, :5].tolist()], "total", int(t[1].sum()) // per_cta)
 print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 pass2 | E3 stats | E3 exchange :", [int(v) // per_cta for v in t[2, :8].tolist()], "total", int(t[2].sum()) // per_cta)
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
+eblk(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd2_timing", None)
+t = tbuf.cpu()
+print("FWD3 edge-block kernel, CTA 0, epilogue cycles per tile: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :",
+      [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
+print("FWD3 MMA thread: wait E2 | issue M3 | wait E1' | issue M2' | wait E3prev+A'' | issue M1'' :",
+      [int(v) // per_cta for v in t[8:14].tolist()], "total", int(t[8:14].sum()) // per_cta)
