@@ -258,20 +258,6 @@ int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, const int32
 int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,
                   mgn_stream_t stream);
 
-/* mgn_mlp3_bwd_tc for the edge block + the destination sums of its g_z1 rows (the transposed dst-side gather of
- * concat_efeat, utils.py:94-148): gz1_agg[v] = sum of g_z1 over the incoming edges of v, fused like the forward one. */
-int mgn_mlp3_bwd_agg_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
-                        int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
-                        int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
-                        int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
-                        const int32_t* go2_idx, int64_t M,
-                        const float* w1, int64_t ld_w1, const float* b1, const float* w2, const float* b2,
-                        const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
-                        int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
-                        float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
-                        size_t workspace_bytes, int* status, const int32_t* csc_offsets, int64_t n_dst, void* gz1_agg,
-                        int64_t ld_agg, void* agg_workspace, size_t agg_workspace_bytes, mgn_stream_t stream);
-
 /* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):
  *   mgn_linear_tc : out[M,128] (row stride ld_out) = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual[M,128])
  *                   x_k are [M,128] column blocks with row stride ld_k; W is [128, 128*n_tab] with row stride ld_w

@@ -115,7 +115,7 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
     if name == "mgn_mlp3_fwd_tc_g":
         M, g2 = a[10], a[6]
         return "tensor", (10.0 if g2 else 8.0) * 128 * 128 * M  # useful flops of the concat formulation
-    if name in ("mgn_mlp3_bwd_tc", "mgn_mlp3_bwd_agg_tc"):
+    if name == "mgn_mlp3_bwd_tc":
         small_in, g1, g2, M = a[3], a[5], a[9], a[17]
         if g2:
             return "tensor", 20.0 * 128 * 128 * M  # edge block: dgrad + wgrad = 2 x forward

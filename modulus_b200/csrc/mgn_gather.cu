@@ -309,7 +309,7 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
 // (mesh in-degrees are ~6: with G = 16 that is the whole segment), i.e. S*U 16-byte loads in flight per lane
 // instead of one dependent load per short segment.  Longer segments finish in the tail loop.
 template <typename T, int G, int S, int U>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)  // two blocks per SM: the bytes in flight are what this kernel lives on
 segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, const int32_t* __restrict__ offsets,
                          const int32_t* __restrict__ eids, int64_t n_seg, T* __restrict__ out, int64_t ld_out,
                          int64_t out_col0, int mean, int accumulate, LongList ll) {

@@ -30,7 +30,6 @@
 #include "mgn_reduce.cuh"
 #include "mgn_tile.cuh"
 #include "mgn_tma.cuh"
-#include "mgn_agg.cuh"
 
 namespace mgn {
 
@@ -64,14 +63,6 @@ struct Params {
   long long part_floats;
   int* status;
   long long* timing;    // debug: [3 roles][32] cycle counters of CTA 0 (nullable)
-  // fused destination sum of the g_z1 rows (mgn_agg.cuh): CSC offsets, destination of every row (ascending), output
-  // table [n_seg,128] (row stride ld_agg), boundary records.  seg_off == nullptr: off
-  const int32_t* seg_off;
-  const int32_t* seg_id;
-  bf16* agg;
-  long long ld_agg;
-  float* agg_part;
-  int32_t* agg_part_v;
   // tensor maps (mgn_tma.cuh): a row source without idx uses a {64 x 128} box map, one with idx a {64 x 1} gather map
   // whose row extent is kOobRow, so that the index kOobRow (rows past M) reads as zeros
   alignas(64) CUtensorMap m_a, m_g1, m_g2, m_go1, m_go2, m_ga, m_gz1;
@@ -433,8 +424,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       colsum_tile(bH1, mt, cs_b1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
-      if (p.seg_off != nullptr)  // destination sums of the g_z1 tile
-        agg::tile_segment_sum(bH1, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
       if (more) {  // next tile's G2 rows -> this tile's H1 buffer (free after the layer-1 MMAs and the g_z1 store)
         MGN_W(B_MMA1 + 6, par);
         if (KP == 1) {  // ... and its raw input -> the A buffer
@@ -443,7 +432,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
           MGN_PUBLISH(B_A);
         }
         MGN_W(B_ST, par);
-        if (p.seg_off != nullptr) MGN_MOVER_SYNC();  // every reducer warp has finished summing the g_z1 tile
         if (has_g2) stage_rows_async(bH1, p.g2, r_g2, row0n, p.M, mt);
         cp_async_commit();
         cp_async_wait<0>();
@@ -909,16 +897,7 @@ extern "C" size_t mgn_mlp3_bwd_tc_workspace_bytes(int64_t M) {
   return static_cast<size_t>(bwd_grid(M)) * bwd::Part<2>::kTotal * sizeof(float);
 }
 
-struct BwdAgg {
-  const int32_t* seg_off = nullptr;
-  int64_t n_seg = 0;
-  void* agg = nullptr;
-  int64_t ld_agg = 0;
-  void* workspace = nullptr;
-  size_t workspace_bytes = 0;
-};
-
-static int bwd_run(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
+extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
                                int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
                                int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
                                int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
@@ -927,7 +906,7 @@ static int bwd_run(const void* a_tab, const int32_t* a_idx, const void* small_x,
                                const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
                                int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
                                float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
-                               size_t workspace_bytes, int* status, mgn_stream_t stream, const BwdAgg& ag) {
+                               size_t workspace_bytes, int* status, mgn_stream_t stream) {
   MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && n_out >= 1 && n_out <= bwd::kH && go1 != nullptr);
   MGN_CHECK_ARG(gamma == nullptr || n_out == bwd::kH);
   if (M == 0) return MGN_OK;  // caller zero-fills gradients of an empty batch
@@ -978,18 +957,6 @@ static int bwd_run(const void* a_tab, const int32_t* a_idx, const void* small_x,
     if (g_z1) e |= tma_make_rows_map(&p.m_gz1, g_z1, M, p.g_z1_ld, 128);
     if (e != 0) return MGN_EINVAL;
   }
-  if (ag.seg_off != nullptr) {  // rows are CSC-ordered edges, g2_idx is their destination
-    MGN_CHECK_ARG(g2_idx != nullptr && ag.agg != nullptr && ag.n_seg > 0 && ag.ld_agg >= bwd::kH && ag.ld_agg % 8 == 0 &&
-                  (reinterpret_cast<uintptr_t>(ag.agg) & 15) == 0 && ag.workspace != nullptr && small_in <= 0);
-    if (ag.workspace_bytes < agg::workspace_bytes(M)) return MGN_EWORKSPACE;
-    const long long n_tiles_ = (M + bwd::kRows - 1) / bwd::kRows;
-    p.seg_off = ag.seg_off;
-    p.seg_id = g2_idx;
-    p.agg = static_cast<bf16*>(ag.agg);
-    p.ld_agg = ag.ld_agg;
-    p.agg_part = static_cast<float*>(ag.workspace);
-    p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * n_tiles_ * bwd::kH);
-  }
   if (small_in > 0) {
     MGN_CHECK_ARG(small_x != nullptr && small_in <= 64 && g_a == nullptr && ld_w1 >= small_in);
     p.k1_true = small_in;
@@ -1020,50 +987,5 @@ static int bwd_run(const void* a_tab, const int32_t* a_idx, const void* small_x,
   rp.seg[ns++] = ReduceSeg{g_beta, bwd::kH, 1, bwd::kH, oB1 + 4 * bwd::kH, bwd::kH};
   rp.n_seg = ns;
   reduce_cta_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
-  rc = mgn_launch_status();
-  if (rc != MGN_OK || ag.seg_off == nullptr) return rc;
-  const long long n_rec = 2 * ((M + bwd::kRows - 1) / bwd::kRows);
-  agg::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
-      p.agg_part, p.agg_part_v, n_rec, p.agg, p.ld_agg, ag.n_seg);
   return mgn_launch_status();
-}
-
-extern "C" int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
-                               int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
-                               int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
-                               int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
-                               const int32_t* go2_idx, int64_t M,
-                               const float* w1, int64_t ld_w1, const float* b1, const float* w2, const float* b2,
-                               const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
-                               int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
-                               float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
-                               size_t workspace_bytes, int* status, mgn_stream_t stream) {
-  return bwd_run(a_tab, a_idx, small_x, small_in, small_is_f32, g1_tab, g1_idx, g1_ld, g1_col0, g2_tab, g2_idx, g2_ld, g2_col0,
-                 go1, go1_idx, go2, go2_idx, M, w1, ld_w1, b1, w2, b2, w3, b3, gamma, n_out, eps, g_a, add_gout, g_z1, g_z1_ld,
-                 g_w1, ld_gw1, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta, workspace, workspace_bytes, status, stream, BwdAgg{});
-}
-
-/* same + destination sums of the g_z1 rows into gz1_agg[n_dst,128] (row stride ld_agg) */
-extern "C" int mgn_mlp3_bwd_agg_tc(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
-                               int small_is_f32, const void* g1_tab, const int32_t* g1_idx, int64_t g1_ld,
-                               int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx, int64_t g2_ld,
-                               int64_t g2_col0, const void* go1, const int32_t* go1_idx, const void* go2,
-                               const int32_t* go2_idx, int64_t M,
-                               const float* w1, int64_t ld_w1, const float* b1, const float* w2, const float* b2,
-                               const float* w3, const float* b3, const float* gamma, int n_out, float eps, void* g_a,
-                               int add_gout, void* g_z1, int64_t g_z1_ld, float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2,
-                               float* g_b2, float* g_w3, float* g_b3, float* g_gamma, float* g_beta, void* workspace,
-                               size_t workspace_bytes, int* status, const int32_t* csc_offsets, int64_t n_dst, void* gz1_agg, int64_t ld_agg,
-                               void* agg_workspace, size_t agg_workspace_bytes, mgn_stream_t stream) {
-  BwdAgg ag;
-  ag.seg_off = csc_offsets;
-  ag.n_seg = n_dst;
-  ag.agg = gz1_agg;
-  ag.ld_agg = ld_agg;
-  ag.workspace = agg_workspace;
-  ag.workspace_bytes = agg_workspace_bytes;
-  MGN_CHECK_ARG(csc_offsets != nullptr);
-  return bwd_run(a_tab, a_idx, small_x, small_in, small_is_f32, g1_tab, g1_idx, g1_ld, g1_col0, g2_tab, g2_idx, g2_ld, g2_col0,
-                 go1, go1_idx, go2, go2_idx, M, w1, ld_w1, b1, w2, b2, w3, b3, gamma, n_out, eps, g_a, add_gout, g_z1, g_z1_ld,
-                 g_w1, ld_gw1, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta, workspace, workspace_bytes, status, stream, ag);
 }

@@ -37,7 +37,6 @@ from .ops import GraphPlan, TC_HIDDEN, _p, _stream
 
 Tensor = torch.Tensor
 ENABLED = True  # tests flip this to compare against the generic (unfused) kernels
-FUSE_BWD_DST_SUM = False  # see FusedProcessorFn.backward
 H = TC_HIDDEN
 BF16 = torch.bfloat16
 
@@ -205,10 +204,9 @@ class FusedProcessorFn(torch.autograd.Function):
         g_e: Optional[Tensor] = None
         grads: List[Optional[Tensor]] = [None] * len(params)
         f32 = dict(dtype=torch.float32, device=dev)
-        # The edge backward kernel can also emit the destination sums of g_z1 (mgn_mlp3_bwd_agg_tc), but its reducer
-        # warps are already the busiest role there: measured at c3 the fused pass costs +1.1 ms per layer against
-        # 0.38 ms for the stand-alone CSC sum, so the backward keeps the separate kernel (forward fuses: movers idle).
-        fuse_dst_sum = halo is None and FUSE_BWD_DST_SUM
+        # (Fusing the destination sums of g_z1 into the edge backward kernel was built and measured: its reducer warps
+        #  are already the busiest role and the kernel is at its register limit -- +1.1 ms per layer fused against
+        #  0.38 ms for the stand-alone CSC sum, and +7 % on the kernel even with the option off.  Forward fuses them.)
         for l in range(L - 1, -1, -1):
             efeat, nfeat, agg, P = saved[ns * l: ns * l + 4]
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
@@ -230,13 +228,11 @@ class FusedProcessorFn(torch.autograd.Function):
             g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, g1, src, 0, P, dst, H, go1, go2, go2_idx, E,
                                          ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
                                          True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6], ge[7],
-                                         go1_idx=go1_idx, agg_offsets=plan.csc_offsets if fuse_dst_sum else None,
-                                         agg_out=T[:, H:2 * H] if fuse_dst_sum else None)
+                                         go1_idx=go1_idx)
             # ---- per-node reductions of the gathered-row gradient, then the node-level GEMMs
             if halo is None:
                 ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
-                if not fuse_dst_sum:
-                    ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
             else:
                 # gradient of every referenced source row (incl. halo rows) goes back to its owner while the
                 # destination-side sum runs; owners accumulate in a fixed order

@@ -567,12 +567,9 @@ def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[
                 w1: Tensor, b1, w2, b2, w3, b3, gamma, n_out: int, eps: float,
                 want_ga: bool, add_gout: bool, want_gz1: bool,
                 g_w1: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta,
-                go1_idx: Optional[Tensor] = None, g_z1_out: Optional[Tensor] = None,
-                agg_offsets: Optional[Tensor] = None, agg_out: Optional[Tensor] = None):
+                go1_idx: Optional[Tensor] = None, g_z1_out: Optional[Tensor] = None):
     """Fused backward (include/mgn_b200.h: mgn_mlp3_bwd_tc).  Gradient tensors are caller-allocated fp32
-    (g_w1 may be a column-block view); returns (g_a, g_z1) bf16 [M,128] or None.  With agg_offsets (CSC offsets of
-    the CSC-ordered edge rows, g2_idx = destinations) the destination sums of g_z1 are written to agg_out
-    [n_dst, 128] in the same pass (mgn_mlp3_bwd_agg_tc)."""
+    (g_w1 may be a column-block view); returns (g_a, g_z1) bf16 [M,128] or None."""
     dev = go1.device
     g_a = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if want_ga else None
     g_z1 = g_z1_out
@@ -589,13 +586,7 @@ def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[
               _p(gamma), n_out, eps, _p(g_a), int(add_gout), _p(g_z1), 0 if g_z1 is None else g_z1.stride(0), _p(g_w1),
               g_w1.stride(0), _p(g_b1), _p(g_w2), _p(g_b2), _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes,
               _p(tc_status(dev)))
-    if agg_offsets is None:
-        call("mgn_mlp3_bwd_tc", *common, _stream())
-    else:
-        abytes = _lib.load().mgn_mlp3_fwd2_agg_workspace_bytes(M)
-        aws = _ws(abytes, dev)
-        call("mgn_mlp3_bwd_agg_tc", *common, _p(agg_offsets), agg_out.shape[0], _p(agg_out), agg_out.stride(0), _p(aws),
-             abytes, _stream())
+    call("mgn_mlp3_bwd_tc", *common, _stream())
     return g_a, g_z1
 
 

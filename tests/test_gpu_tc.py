@@ -356,48 +356,6 @@ def test_edge_block_fwd_with_fused_aggregation(case):
     assert torch.equal(agg, agg2) and torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("N,lo,hi", [(4000, 3, 9), (900, 0, 5)])
-def test_mlp3_bwd_tc_fused_destination_sum(N, lo, hi):
-    """mgn_mlp3_bwd_agg_tc: the destination sums written by the edge backward kernel equal the segmented sum of the
-    g_z1 rows it stores (bf16 rounding of the sums aside), and everything else is unchanged."""
-    from modulus_b200 import ops
-
-    g = torch.Generator().manual_seed(N)
-    deg = torch.randint(lo, hi, (N,), generator=g)
-    deg[N // 2] = 200
-    offsets = torch.zeros(N + 1, dtype=torch.int32)
-    offsets[1:] = torch.cumsum(deg, 0).int()
-    E = int(offsets[-1])
-    dst = torch.repeat_interleave(torch.arange(N), deg).int().to(DEV)
-    src = torch.randint(0, N, (E,), generator=g).int().to(DEV)
-    offd = offsets.to(DEV)
-    d = dev_params(make_params(384, seed=9))
-    r = lambda *s: torch.randn(*s, generator=g)
-    A, P = r(E, 128).to(DEV).bfloat16(), (r(N, 384) * 0.5).to(DEV).bfloat16()
-    g_e, g_agg = r(E, 128).to(DEV).bfloat16(), r(N, 128).to(DEV).bfloat16()
-
-    def run(with_agg):
-        gw1 = torch.empty(128, 384, device=DEV)
-        gs = [torch.empty(128, 128, device=DEV), torch.empty(128, 128, device=DEV)] + [torch.empty(128, device=DEV) for _ in range(5)]
-        T = torch.full((N, 384), 7.0, dtype=torch.bfloat16, device=DEV)
-        ga, gz1 = ops.mlp3_bwd_tc(A, None, None, P, src, 0, P, dst, 128, g_e, g_agg, dst, E, d["w1"][:, :128], d["b1"],
-                                  d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], 128, 1e-5, True, True, True,
-                                  gw1[:, :128], gs[2], gs[0], gs[3], gs[1], gs[4], gs[5], gs[6],
-                                  agg_offsets=offd if with_agg else None, agg_out=T[:, 128:256] if with_agg else None)
-        return ga, gz1, gw1[:, :128].clone(), gs, T
-
-    ga0, gz0, gw0, gs0, _ = run(False)
-    ga1, gz1, gw1, gs1, T = run(True)
-    ops.tc_check(DEV)
-    assert torch.equal(ga0, ga1) and torch.equal(gz0, gz1) and torch.equal(gw0, gw1)
-    assert all(torch.equal(a, b) for a, b in zip(gs0, gs1))
-    ref = torch.zeros(N, 128, dtype=torch.float64, device=DEV).index_add_(0, dst.long(), gz1.double())
-    assert rel_err(T[:, 128:256].float(), ref) < 1e-2
-    assert bool((T[:, :128] == 7).all()) and bool((T[:, 256:] == 7).all())  # neighbouring columns untouched
-    if bool((deg == 0).any()):
-        assert float(T[:, 128:256][deg.to(DEV) == 0].abs().max()) == 0.0
-
-
 @pytest.mark.parametrize("cuts", [(0, 700), (300, 301), (129, 4000), (0, 0)])
 def test_edge_block_fwd_in_row_ranges_matches_single_launch(cuts):
     """mgn_edge_block_fwd_part_tc over three consecutive row ranges + mgn_agg_fixup == one mgn_edge_block_fwd_tc launch
