@@ -312,7 +312,7 @@ def test_mlp3_fwd2_tc_encoder_and_decoder_forms(M):
     assert rel_err(out.float(), ref) < 1.5e-2
 
 
-@pytest.mark.parametrize("case", ["mesh", "hubs_and_isolated", "single_tile", "one_segment"])
+@pytest.mark.parametrize("case", ["mesh", "many_tiles_per_cta", "hubs_and_isolated", "single_tile", "one_segment"])
 def test_edge_block_fwd_with_fused_aggregation(case):
     """mgn_edge_block_fwd_tc: same edge rows as the plain fused forward, and agg == segmented sum of those rows by
     destination (incl. segments that straddle tiles, a hub longer than a tile, and nodes without incoming edges)."""
@@ -321,6 +321,9 @@ def test_edge_block_fwd_with_fused_aggregation(case):
     g = torch.Generator().manual_seed(11)
     if case == "mesh":
         N = 5000
+        deg = torch.randint(4, 9, (N,), generator=g)
+    elif case == "many_tiles_per_cta":  # ~7 tiles per CTA: the steady state of the two-tiles-in-flight pipeline
+        N = 22000                       # (A-slot, accumulator and barrier-phase reuse), not just its prologue
         deg = torch.randint(4, 9, (N,), generator=g)
     elif case == "hubs_and_isolated":
         N = 3000
