@@ -1,3 +1,4 @@
+# N-GPU weak-scaling bench: gpurun --gpus N -- "bash tools/gpu_bench_ngpu.sh N"
 set -x
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l > gpurun_out/smi8.txt

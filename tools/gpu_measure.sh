@@ -1,3 +1,4 @@
+# Single-GPU measurement set of a round: gpurun --timeout 2400 -- "bash tools/gpu_measure.sh"; then python tools/summarize_ncu.py rNN
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt; nproc >> gpurun_out/smi.txt
