@@ -233,13 +233,14 @@ int mgn_mlp3_bwd_tc(const void* a_tab, const int32_t* a_idx, const void* small_x
 /* MeshEdgeBlock.forward + the "sum" aggregation of the following MeshNodeBlock in one pass (mesh_edge_block.py:88-96,
  * utils.py:337-378): efeat_out[e] = efeat[e] + LN(MLP(efeat[e] W1a^T + P_src[src[e]] + P_dst[dst[e]])) for CSC-ordered
  * edges, and agg[v] = sum of efeat_out over the incoming edges of v, taken from the result tiles while they are still
- * in shared memory (fixed summation order; nodes without incoming edges get zeros). */
+ * in shared memory (fixed summation order; nodes without incoming edges get zeros).  h1_out (nullable, [n_edges,128]
+ * bf16) receives the first hidden activation relu(z1) for mgn_edge_block_bwd_tc. */
 size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t n_edges);
 int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const int32_t* src_idx, int64_t p_src_ld,
                           int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
                           int64_t p_dst_col0, int64_t n_edges, const float* w1, int64_t ld_w1, const float* b1,
                           const float* w2, const float* b2, const float* w3, const float* b3,
-                          const float* gamma, const float* beta, float eps, void* efeat_out,
+                          const float* gamma, const float* beta, float eps, void* efeat_out, void* h1_out,
                           const int32_t* csc_offsets, int64_t n_dst, void* agg, int64_t ld_agg,
                           void* workspace, size_t workspace_bytes, int* status, mgn_stream_t stream);
 
@@ -252,11 +253,26 @@ int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, const int32
                                int64_t p_dst_col0, int64_t n_rows, const float* w1, int64_t ld_w1,
                                const float* b1, const float* w2, const float* b2, const float* w3,
                                const float* b3, const float* gamma, const float* beta, float eps,
-                               void* efeat_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
+                               void* efeat_out, void* h1_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
                                int64_t ld_agg, void* workspace, size_t workspace_bytes, int64_t row_base,
                                int64_t total_tiles, int64_t rec_base, int* status, mgn_stream_t stream);
 int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,
                   mgn_stream_t stream);
+
+/* MeshEdgeBlock backward from the first hidden activation h1 = relu(z1) that mgn_edge_block_fwd_tc stored (no gather
+ * of the projection rows, no GEMM1 recompute): go1 (dense, or gathered by go1_idx) + go2[go2_idx] = gradient of the
+ * block output; writes g_efeat [n_edges,128], g_z1 [n_edges,128] (row stride g_z1_ld; its CSC / CSR sums are the
+ * gradients of the destination / source projection rows) and the fp32 parameter gradients of W1[:, :128] (row stride
+ * ld_gw1), b1, W2, b2, W3, b3, gamma, beta (deterministic per-CTA partials + ordered reduction). */
+size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges);
+int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, const int32_t* go1_idx,
+                          const void* go2, const int32_t* go2_idx, int64_t n_edges, const float* w1,
+                          int64_t ld_w1, const float* w2, const float* b2, const float* w3, const float* b3,
+                          const float* gamma, float eps, void* g_efeat, void* g_z1, int64_t g_z1_ld,
+                          float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
+                          float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
+                          int* status, mgn_stream_t stream);
+int mgn_debug_set_edge_bwd2_timing(void* dev_buf);
 
 /* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):
  *   mgn_linear_tc : out[M,128] (row stride ld_out) = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual[M,128])

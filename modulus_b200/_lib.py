@@ -115,6 +115,8 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
     if name == "mgn_mlp3_fwd_tc_g":
         M, g2 = a[10], a[6]
         return "tensor", (10.0 if g2 else 8.0) * 128 * 128 * M  # useful flops of the concat formulation
+    if name == "mgn_edge_block_bwd_tc":
+        return "tensor", 20.0 * 128 * 128 * a[6]  # useful flops of the reference formulation (dgrad + wgrad = 2 x forward)
     if name == "mgn_mlp3_bwd_tc":
         small_in, g1, g2, M = a[3], a[5], a[9], a[17]
         if g2:

@@ -1,0 +1,741 @@
+// mgn_edge_bwd2_tc.cu — MeshEdgeBlock backward with the first hidden activation kept from the forward pass.
+//
+// The generic fused backward (mgn_mlp_bwd_tc.cu) recomputes the whole forward chain per tile: for the edge block that
+// is the gather of both projection rows, GEMM1 and the widest epilogue pass, and the gathers are what the tile
+// boundary waits for.  The third-generation forward (mgn_edge_fwd3_tc.cu) leaves h1 = relu(z1) in global memory
+// (+ E*H*2 bytes each way, far below what the HBM has to spare at this kernel's pace), so here a tile starts from a
+// TMA load of h1:
+//
+//   recompute       h2 = relu(h1 W2^T + b2) ; y = h2 W3^T + b3
+//   LayerNorm bwd   g_out = go1 (+ go2 rows) ; g_y = rstd (ghat - mean(ghat) - xhat mean(ghat xhat)), ghat = g_out gamma
+//   layer 3         gW3 += g_y^T h2 ; g_z2 = (g_y W3) * (h2 > 0)
+//   layer 2         gW2 += g_z2^T h1 ; g_z1 = (g_z2 W2) * (h1 > 0)
+//   layer 1         gW1a += g_z1^T efeat ; g_efeat = g_z1 W1a + g_out        (g_z1 also leaves: its CSC / CSR sums are
+//                                                                              the gradient of the projection rows)
+//
+// = the backward of physicsnemo/models/gnn_layers/mesh_edge_block.py:88-96 (autograd over cuBLAS / ATen there).
+// No gathered operand except the go2 rows, no b1, no source / destination tables.  Four 32 KB tile buffers: buffer 0
+// = go2 rows -> g_y -> efeat tile; the other three rotate (H1' = H2, H2' = X, X' = H1) so that the next tile's h1
+// streams in right after the layer-2 MMAs and its incoming-gradient rows right after the layer-1 MMAs.
+// Roles as in the generic kernel: warp 0 MMA issuer, warps 1-4 reducers (go2 gather, column sums), warps 5-12
+// epilogue, warp 13 loader (TMA).
+#include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+#include "mgn_reduce.cuh"
+#include "mgn_tile.cuh"
+#include "mgn_tma.cuh"
+
+namespace mgn {
+namespace bwd2 {
+
+using namespace tile;
+constexpr int kEpiWarps = 8;
+constexpr int kLoaderWarp = 5 + kEpiWarps;
+constexpr int kThreads = 32 * (kLoaderWarp + 1);
+constexpr int kH = 128;
+constexpr int kOobRow = 1 << 30;
+
+struct Params {
+  const bf16* h1;       // [M,128]
+  RowSrc go1, go2;      // incoming gradient rows, summed (go2 optional, gathered)
+  long long M;
+  const float *w1, *w2, *b2, *w3, *b3, *gamma;
+  long long ld_w1;
+  float eps;
+  float* partials;      // [gridDim.x][Part::kTotal]
+  long long part_floats;
+  int* status;
+  long long* timing;
+  alignas(64) CUtensorMap m_a, m_h1, m_go1, m_ga, m_gz1;
+};
+
+struct Part {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = kH * kH;
+  static constexpr int kW3 = kW2 + kH * kH;
+  static constexpr int kB1 = kW3 + kH * kH;
+  static constexpr int kB2 = kB1 + kH;
+  static constexpr int kB3 = kB2 + kH;
+  static constexpr int kGamma = kB3 + kH;
+  static constexpr int kBeta = kGamma + kH;
+  static constexpr int kTotal = kBeta + kH;
+};
+
+struct Smem {
+  static constexpr int kW1 = 0;
+  static constexpr int kW2 = 2 * kPB;
+  static constexpr int kW3 = 4 * kPB;
+  static constexpr int kBuf = 6 * kPB;        // 4 tile buffers x 2 panels
+  static constexpr int kPar = kBuf + 8 * kPB;  // b2, b3, gamma
+  static constexpr int kBars = kPar + 4 * kH * 4;
+  static constexpr int kTmemSlot = kBars + 24 * 8;
+  static constexpr int kTiming = kTmemSlot + 16;
+  static constexpr int kTotal = kTiming + 3 * 16 * 8;
+};
+
+// B_H1L: h1 tile landed (loader, tx).  B_GO: incoming-gradient rows staged (4 reducer warps + loader).  B_A2: efeat
+// tile staged for the layer-1 weight gradient (loader, tx).  B_MMA + k: GEMM2, GEMM3, dgrad3, dgrad2, dgrad1, wgrad1
+// complete; B_W3 / B_W2: weight-gradient MMAs of layer 3 / 2 complete.  B_E + k: E2, E3, E4, E5, E6 complete.
+// B_CS + k: column sums after E3 / E4 / E5 done.  B_ST / B_XF: the g_z1 / g_A result tile has left its buffer.
+enum { B_H1L = 0, B_GO = 1, B_A2 = 2, B_MMA = 3, B_W3 = 9, B_W2 = 10, B_E = 11, B_CS = 16, B_ST = 19, B_XF = 20, B_NUM = 21 };
+enum { R_A = -1, R_X = 0, R_H1 = 1, R_H2 = 2 };
+
+__device__ __forceinline__ bool bf_pos_lo(uint32_t w) { return static_cast<int32_t>(w << 16) > 0; }
+__device__ __forceinline__ bool bf_pos_hi(uint32_t w) { return static_cast<int32_t>(w & 0xFFFF0000u) > 0; }
+
+__device__ __forceinline__ void tma_tile(uint8_t* buf, const CUtensorMap* map, long long row0, uint64_t* bar) {
+  const uint32_t dst = smem_u32(buf);
+  tma_load_2d(dst, map, 0, static_cast<int>(row0), bar);
+  tma_load_2d(dst + kPB, map, 64, static_cast<int>(row0), bar);
+}
+
+__global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_constant__ Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if ((smem_u32(smem) & 1023u) != 0) {
+    if (tid == 0 && p.status) atomicOr(p.status, 2);
+    return;
+  }
+  uint8_t* sW1 = smem + Smem::kW1;
+  uint8_t* sW2 = smem + Smem::kW2;
+  uint8_t* sW3 = smem + Smem::kW3;
+  uint8_t* buf0 = smem + Smem::kBuf;
+  float* sPar = reinterpret_cast<float*>(smem + Smem::kPar);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kBars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::kTmemSlot);
+// buffer 0 = A; X / H1 / H2 of tile `it` = buffer 1 + (role + it) % 3
+#define MGN_BUF(role, it) (buf0 + ((role) < 0 ? 0 : 1 + (((role) + (it)) % 3)) * (2 * kPB))
+  const bool has_go2 = p.go2.tab != nullptr;
+  constexpr bool has_ln = true;
+  constexpr bool need_ga = true;
+  (void)has_ln;
+  (void)need_ga;
+
+  stage_weight_ld(sW1, p.w1, p.ld_w1, kH, kH, 2, tid, kThreads);
+  stage_weight_ld(sW2, p.w2, kH, kH, kH, 2, tid, kThreads);
+  stage_weight_ld(sW3, p.w3, kH, kH, kH, 2, tid, kThreads);
+  for (int i = tid; i < kH; i += kThreads) {
+    sPar[kH + i] = p.b2 ? p.b2[i] : 0.f;
+    sPar[2 * kH + i] = p.b3 ? p.b3[i] : 0.f;
+    sPar[3 * kH + i] = p.gamma[i];
+  }
+  if (tid == 0) {
+    mbar_init(&bars[B_H1L], 1);
+    mbar_init(&bars[B_GO], 5);
+    mbar_init(&bars[B_A2], 1);
+    for (int b = B_MMA; b < B_E; ++b) mbar_init(&bars[b], 1);
+    for (int b = B_E; b < B_CS; ++b) mbar_init(&bars[b], kEpiWarps);
+    for (int b = B_CS; b < B_ST; ++b) mbar_init(&bars[b], 4);
+    mbar_init(&bars[B_ST], 1);
+    mbar_init(&bars[B_XF], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tAcc = tmem, tW1 = tmem + 128, tW2 = tmem + 256, tW3 = tmem + 384;
+
+  const long long n_tiles = (p.M + kRows - 1) / kRows;
+  const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
+  bool timed_out = false;
+  const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == kLoaderWarp || warp == 5);
+  long long* tm = reinterpret_cast<long long*>(smem + Smem::kTiming) + (warp == 0 ? 0 : (warp == kLoaderWarp ? 16 : 32));
+  if (tm_on)
+    for (int i = 0; i < 16; ++i) tm[i] = 0;
+  long long tlast = clock64();
+#define MGN_T(i)                      \
+  if (tm_on) {                        \
+    const long long t_ = clock64();   \
+    tm[i] += t_ - tlast;              \
+    tlast = t_;                       \
+  }
+  float* scratch = reinterpret_cast<float*>(MGN_BUF(R_H2, n_my > 0 ? n_my - 1 : 0));
+
+  if (warp == 0) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t aA = smem_u32(buf0);
+      const uint32_t aW1 = smem_u32(sW1), aW2 = smem_u32(sW2), aW3 = smem_u32(sW3);
+      const uint32_t id_nt = umma_idesc_bf16(128, 128, 0, 0);   // D = A(K-major) * B(K-major)^T
+      const uint32_t id_tn = umma_idesc_bf16(128, 128, 1, 1);   // D = A(MN)^T * B(MN)          (wgrad)
+      const uint32_t id_nn = umma_idesc_bf16(128, 128, 0, 1);   // D = A(K-major) * B(MN)       (dgrad)
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = it & 1;
+        const uint32_t aH1 = smem_u32(MGN_BUF(R_H1, it));
+        const uint32_t aH2 = smem_u32(MGN_BUF(R_H2, it));
+#define MGN_W(b, ph)                         \
+  if (!wait_clk(&bars[b], ph)) {             \
+    timed_out = true;                        \
+    break;                                   \
+  }
+        // ---- GEMM2: acc = h1 W2^T   (h1 streamed in during the previous tile)
+        MGN_W(B_H1L, par);
+        if (it > 0) MGN_W(B_E + 4, par ^ 1);  // the previous tile's last epilogue has drained the accumulator
+        MGN_T(0);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH1 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW2 + (k >> 2) * kPB, k & 3), id_nt, k != 0);
+        umma_commit(&bars[B_MMA + 0]);
+        MGN_T(1);
+        // ---- GEMM3: acc = h2 W3^T
+        MGN_W(B_E + 0, par);
+        MGN_T(2);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_kmajor(aW3 + (k >> 2) * kPB, k & 3), id_nt, k != 0);
+        umma_commit(&bars[B_MMA + 1]);
+        MGN_T(3);
+        // ---- layer 3: acc = g_y W3 ; gW3 += g_y^T h2          (g_y in the A buffer)
+        MGN_W(B_E + 1, par);
+        MGN_T(4);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA + 2]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
+        umma_commit(&bars[B_W3]);
+        MGN_T(5);
+        // ---- layer 2: acc = g_z2 W2 ; gW2 += g_z2^T h1        (g_z2 in the H2 buffer)
+        MGN_W(B_E + 2, par);
+        MGN_T(6);
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA + 3]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
+        umma_commit(&bars[B_W2]);
+        MGN_T(7);
+        // ---- layer 1: acc = g_z1 W1a (epilogue may start on it at once) ; gW1a += g_z1^T efeat
+        MGN_W(B_E + 3, par);
+        MGN_T(8);
+        MGN_W(B_A2, par);  // (also orders every reducer's column sums of X before E6 rewrites X)
+        tc_fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          umma_ss(tAcc, umma_desc_kmajor(aH1 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW1, k, kPB), id_nn, k != 0);
+        umma_commit(&bars[B_MMA + 4]);
+        MGN_T(9);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          umma_ss(tW1, umma_desc_mnmajor(aH1, j, kPB), umma_desc_mnmajor(aA, j, kPB), id_tn, (it | j) != 0);
+        umma_commit(&bars[B_MMA + 5]);
+        MGN_T(10);
+#undef MGN_W
+      }
+    }
+  } else if (warp <= 4) {
+    // =========================== reducers ===========================
+    const int mt = tid - 32;
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_PUBLISH(b)        \
+  fence_proxy_async_smem();   \
+  __syncwarp();               \
+  if (lane == 0) mbar_arrive(&bars[b]);
+    float cs_b1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cs_b3[8] = {0, 0, 0, 0, 0, 0, 0, 0},
+          cs_beta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int rsub_m = mt >> 4;
+    const bool go1_gathered = p.go1.idx != nullptr;
+    int32_t r_go[16];
+    // gathered parts of a tile's incoming gradient: go1 by rows -> X, go2 rows -> A
+    auto stage_go = [&](long long r0, uint8_t* bXn, uint8_t* bAn) {
+      if (go1_gathered) {
+        fetch_row_ids(p.go1.idx, r0, p.M, rsub_m, r_go);
+        stage_rows_async(bXn, p.go1, r_go, r0, p.M, mt);
+      }
+      if (has_go2) {
+        if (!(go1_gathered && p.go2.idx == p.go1.idx)) fetch_row_ids(p.go2.idx, r0, p.M, rsub_m, r_go);
+        stage_rows_async(bAn, p.go2, r_go, r0, p.M, mt);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    };
+    if (n_my > 0) {
+      stage_go(static_cast<long long>(blockIdx.x) * kRows, MGN_BUF(R_X, 0), MGN_BUF(R_A, 0));
+      MGN_PUBLISH(B_GO);
+    }
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      const bool more = it + 1 < n_my;
+      const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+      const long long row0n = row0 + static_cast<long long>(gridDim.x) * kRows;
+      uint8_t* bA = MGN_BUF(R_A, it);
+      uint8_t* bX = MGN_BUF(R_X, it);
+      uint8_t* bH1 = MGN_BUF(R_H1, it);
+      uint8_t* bH2 = MGN_BUF(R_H2, it);
+      // after E3: X = g_out (summed), A = g_y
+      MGN_W(B_E + 1, par);
+      colsum_tile(bX, mt, cs_beta);
+      colsum_tile(bA, mt, cs_b3);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 0]);
+      MGN_W(B_E + 2, par);
+      colsum_tile(bH2, mt, cs_b2);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
+      MGN_W(B_E + 3, par);
+      colsum_tile(bH1, mt, cs_b1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
+      if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X' = H1 once g_z1 has left
+        MGN_W(B_MMA + 5, par);
+        if (go1_gathered) MGN_W(B_ST, par);
+        stage_go(row0n, bH1, bA);
+        MGN_PUBLISH(B_GO);
+      }
+    }
+#undef MGN_W
+    asm volatile("bar.sync 10, 384;" ::: "memory");  // reducers + epilogue: nobody reads a tile buffer any more
+    {
+      const int chunk = mt & 15, rsub = mt >> 4;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        scratch[(0 * 8 + rsub) * kH + chunk * 8 + j] = cs_b1[j];
+        scratch[(1 * 8 + rsub) * kH + chunk * 8 + j] = cs_b2[j];
+        scratch[(2 * 8 + rsub) * kH + chunk * 8 + j] = cs_b3[j];
+        scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
+      }
+    }
+  } else if (warp == kLoaderWarp) {
+    // =========================== loader (TMA) ===========================
+    if (lane == 0) {
+      const bool go1_tma = p.go1.idx == nullptr;
+#define MGN_W(b, ph)             \
+  if (!wait_clk(&bars[b], ph)) { \
+    timed_out = true;            \
+    break;                       \
+  }
+      if (n_my > 0) {
+        const long long row00 = static_cast<long long>(blockIdx.x) * kRows;
+        mbar_arrive_expect_tx(&bars[B_H1L], 2 * kPB);
+        tma_tile(MGN_BUF(R_H1, 0), &p.m_h1, row00, &bars[B_H1L]);
+        if (go1_tma) {
+          mbar_arrive_expect_tx(&bars[B_GO], 2 * kPB);
+          tma_tile(MGN_BUF(R_X, 0), &p.m_go1, row00, &bars[B_GO]);
+        } else {
+          mbar_arrive(&bars[B_GO]);
+        }
+      }
+      for (int it = 0; it < n_my; ++it) {
+        const uint32_t par = it & 1;
+        const bool more = it + 1 < n_my;
+        const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+        const long long row0n = row0 + static_cast<long long>(gridDim.x) * kRows;
+        uint8_t* bA = MGN_BUF(R_A, it);
+        uint8_t* bX = MGN_BUF(R_X, it);
+        uint8_t* bH1 = MGN_BUF(R_H1, it);
+        uint8_t* bH2 = MGN_BUF(R_H2, it);
+        MGN_T(0);
+        // efeat tile for the layer-1 weight gradient, once the layer-3 MMAs and the column sums are done with g_y
+        MGN_W(B_W3, par);
+        MGN_W(B_CS + 0, par);
+        MGN_T(1);
+        mbar_arrive_expect_tx(&bars[B_A2], 2 * kPB);
+        tma_tile(bA, &p.m_a, row0, &bars[B_A2]);
+        if (more) {  // next tile's h1 -> this tile's H2 buffer (free after the layer-2 MMAs and its column sums)
+          MGN_W(B_W2, par);
+          MGN_W(B_CS + 1, par);
+          MGN_T(2);
+          mbar_arrive_expect_tx(&bars[B_H1L], 2 * kPB);
+          tma_tile(bH2, &p.m_h1, row0n, &bars[B_H1L]);
+        }
+        // g_z1 tile (H1) -> global
+        MGN_W(B_E + 3, par);
+        MGN_T(3);
+        tma_store_2d(&p.m_gz1, smem_u32(bH1), 0, static_cast<int>(row0));
+        tma_store_2d(&p.m_gz1, smem_u32(bH1) + kPB, 64, static_cast<int>(row0));
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&bars[B_ST]);
+        MGN_T(4);
+        if (more) {  // next tile's dense incoming gradient -> X' = this tile's H1 buffer
+          MGN_W(B_MMA + 5, par);
+          MGN_W(B_CS + 2, par);
+          MGN_T(5);
+          if (go1_tma) {
+            mbar_arrive_expect_tx(&bars[B_GO], 2 * kPB);
+            tma_tile(bH1, &p.m_go1, row0n, &bars[B_GO]);
+          } else {
+            mbar_arrive(&bars[B_GO]);
+          }
+        }
+        // g_A tile (X) -> global; X is the next tile's H2: its E2 may write there once the store has read it
+        MGN_W(B_E + 4, par);
+        MGN_T(6);
+        tma_store_2d(&p.m_ga, smem_u32(bX), 0, static_cast<int>(row0));
+        tma_store_2d(&p.m_ga, smem_u32(bX) + kPB, 64, static_cast<int>(row0));
+        tma_store_commit();
+        tma_store_wait_read();
+        mbar_arrive(&bars[B_XF]);
+        MGN_T(7);
+      }
+#undef MGN_W
+      tma_store_wait_all();
+    }
+  } else {
+    // =========================== epilogue (8 warps) ===========================
+    const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
+    const int row = q * 32 + lane;
+    const int c0 = ch * 64;
+    const uint32_t t_acc = tAcc + (static_cast<uint32_t>(q * 32) << 16) + c0;
+    const float* b2 = sPar + kH + c0;
+    const float* b3 = sPar + 2 * kH + c0;
+    const float* gam = sPar + 3 * kH + c0;
+    const uint32_t xch_own = ch * kPB + sw128_offset(row, 0);
+    const uint32_t xch_other = (ch ^ 1) * kPB + sw128_offset(row, 0);
+    float gg[4] = {0.f, 0.f, 0.f, 0.f};
+#define MGN_W(b, ph)                                                      \
+  {                                                                       \
+    const bool ok_ = __all_sync(0xffffffffu, wait_clk(&bars[b], ph));     \
+    if (!ok_) {                                                           \
+      timed_out = true;                                                   \
+      break;                                                              \
+    }                                                                     \
+  }
+#define MGN_EPI_DONE(b)       \
+  fence_proxy_async_smem();   \
+  tc_fence_before_sync();     \
+  __syncwarp();               \
+  if (lane == 0) mbar_arrive(&bars[b]);
+#define MGN_ROW_SYNC() asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory")
+    for (int it = 0; it < n_my; ++it) {
+      const uint32_t par = it & 1;
+      uint8_t* bA = MGN_BUF(R_A, it);
+      uint8_t* bX = MGN_BUF(R_X, it);
+      uint8_t* bH1 = MGN_BUF(R_H1, it);
+      uint8_t* bH2 = MGN_BUF(R_H2, it);
+      // ---- E2: h2 = relu(acc + b2) -> H2   (H2 is the previous tile's X: its g_A tile must have left)
+      MGN_W(B_MMA + 0, par);
+      if (it > 0) MGN_W(B_XF, par ^ 1);
+      MGN_T(0);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        tmem_ld32(t_acc + 32 * hh, v);
+        tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[32 * hh + 2 * j], 0.f),
+                             fmaxf(__uint_as_float(v[2 * j + 1]) + b2[32 * hh + 2 * j + 1], 0.f));
+        row_store32p(bH2, row, c0 + 32 * hh, o);
+      }
+      MGN_EPI_DONE(B_E + 0);
+      MGN_T(1);
+      // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> X ; g_y -> A
+      MGN_W(B_MMA + 1, par);
+      MGN_T(2);
+      MGN_W(B_GO, par);
+      MGN_T(3);
+      tc_fence_after_sync();
+      {
+        float s_y = 0.f, s_yy = 0.f, s_g = 0.f, s_gy = 0.f;
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          row_load32p(bX, row, cc, go);
+          if (has_go2) {
+            uint32_t g2[16];
+            row_load32p(bA, row, cc, g2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
+            row_store32p(bX, row, cc, go);
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]) + b3[32 * hh + j];
+            const float gh = ((j & 1) ? bf_hi(go[j >> 1]) : bf_lo(go[j >> 1])) * gam[32 * hh + j];
+            s_y += y;
+            s_yy = fmaf(y, y, s_yy);
+            s_g += gh;
+            s_gy = fmaf(gh, y, s_gy);
+          }
+        }
+        *reinterpret_cast<float4*>(bA + xch_own) = make_float4(s_y, s_yy, s_g, s_gy);
+        MGN_ROW_SYNC();
+        {
+          const float4 t = *reinterpret_cast<const float4*>(bA + xch_other);
+          s_y += t.x;
+          s_yy += t.y;
+          s_g += t.z;
+          s_gy += t.w;
+        }
+        MGN_ROW_SYNC();  // both halves have read the exchange before g_y overwrites the A buffer
+        const float mu = s_y * (1.f / kH);
+        const float var = fmaxf(s_yy * (1.f / kH) - mu * mu, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        const float m1 = s_g * (1.f / kH);
+        const float m2 = (s_gy - mu * s_g) * rstd * (1.f / kH);  // mean(ghat * xhat)
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          const int cc = c0 + 32 * hh;
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          row_load32p(bX, row, cc, go);
+          tmem_ld_wait();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float t[16];
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = 16 * h + 2 * j;  // column within this 32-column half
+              const float g0 = bf_lo(go[c >> 1]), g1v = bf_hi(go[c >> 1]);
+              const float x0 = (__uint_as_float(v[c]) + b3[32 * hh + c] - mu) * rstd;
+              const float x1 = (__uint_as_float(v[c + 1]) + b3[32 * hh + c + 1] - mu) * rstd;
+              const float y0 = rstd * (g0 * gam[32 * hh + c] - m1 - x0 * m2);
+              const float y1 = rstd * (g1v * gam[32 * hh + c + 1] - m1 - x1 * m2);
+              o[j] = pack_bf16x2(y0, y1);
+              t[2 * j] = g0 * x0;  // gamma-gradient contribution of this row
+              t[2 * j + 1] = g1v * x1;
+            }
+            uint8_t* base = bA + ch * kPB;
+            const int c8 = 4 * hh + 2 * h;
+            *reinterpret_cast<uint4*>(base + sw128_offset(row, c8)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + 1)) = make_uint4(o[4], o[5], o[6], o[7]);
+            const float cs = warp_colsum16(t, lane);
+            if (hh == 0) gg[h] += cs;
+            else gg[2 + h] += cs;
+          }
+        }
+      }
+      MGN_EPI_DONE(B_E + 1);
+      MGN_T(4);
+      // ---- E4: g_z2 = acc * (h2 > 0), in place in H2
+      MGN_W(B_MMA + 2, par);
+      tc_fence_after_sync();
+      {
+        // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+        uint32_t hq[2][16];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          row_load32p(bH2, row, c0 + 32 * hh, hq[hh]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        }
+        MGN_W(B_W3, par);
+        row_store32p(bH2, row, c0, hq[0]);
+        row_store32p(bH2, row, c0 + 32, hq[1]);
+      }
+      MGN_EPI_DONE(B_E + 2);
+      MGN_T(5);
+      // ---- E5: g_z1 = acc * (h1 > 0), in place in H1
+      MGN_W(B_MMA + 3, par);
+      tc_fence_after_sync();
+      {
+        // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+        uint32_t hq[2][16];
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          row_load32p(bH1, row, c0 + 32 * hh, hq[hh]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
+                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+        }
+        MGN_W(B_W2, par);
+        row_store32p(bH1, row, c0, hq[0]);
+        row_store32p(bH1, row, c0 + 32, hq[1]);
+      }
+      MGN_EPI_DONE(B_E + 3);
+      MGN_T(6);
+      // ---- E6: g_A = acc (+ g_out), in place in X (runs while the layer-1 weight-gradient MMAs execute)
+      MGN_W(B_MMA + 4, par);
+      tc_fence_after_sync();
+      {
+#pragma unroll 1
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t v[32];
+          tmem_ld32(t_acc + 32 * hh, v);
+          uint32_t go[16];
+          row_load32p(bX, row, c0 + 32 * hh, go);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bf_lo(go[j]),
+                                __uint_as_float(v[2 * j + 1]) + bf_hi(go[j]));
+          row_store32p(bX, row, c0 + 32 * hh, go);
+        }
+      }
+      MGN_EPI_DONE(B_E + 4);
+      MGN_T(7);
+    }
+#undef MGN_W
+    asm volatile("bar.sync 10, 384;" ::: "memory");  // reducers + epilogue: nobody reads a tile buffer any more
+    if (lane < 16) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) scratch[4 * 8 * kH + q * kH + c0 + g * 16 + lane] = gg[g];
+    }
+  }
+  if (tm_on) {
+    const int role = warp == 0 ? 0 : (warp == kLoaderWarp ? 1 : 2);
+    for (int i = 0; i < 16; ++i) p.timing[role * 32 + i] = tm[i];
+  }
+  if (timed_out && p.status != nullptr) atomicOr(p.status, 1);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+
+  // ---------------- write this CTA's partial gradients ----------------
+  float* part = p.partials + static_cast<long long>(blockIdx.x) * p.part_floats;
+  if (warp >= 5 && warp < kLoaderWarp) {
+    const int q = warp & 3;
+    const int ch = (warp - 5) >> 2;
+    const int row = q * 32 + lane;  // TMEM lane = output-feature row of the weight gradient
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+#pragma unroll 1
+    for (int w = 0; w < 3; ++w) {
+      const uint32_t t = (w == 0 ? tW1 : (w == 1 ? tW2 : tW3)) + lane_off;
+      const int ncol = kH;
+      float* dst = part + (w == 0 ? Part::kW1 : (w == 1 ? Part::kW2 : Part::kW3)) + row * ncol;
+#pragma unroll 1
+      for (int g = ch * (ncol / 64); g < (ch + 1) * (ncol / 64); ++g) {  // this warp's half of the columns
+        uint32_t v[32];
+        tmem_ld32(t + g * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          reinterpret_cast<float4*>(dst + g * 32)[u] =
+              make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                          __uint_as_float(v[4 * u + 3]));
+      }
+    }
+  }
+  if (tid < kH) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] += scratch[(k * 8 + r) * kH + tid];
+    }
+    float sg = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) sg += scratch[4 * 8 * kH + w * kH + tid];
+    part[Part::kB1 + tid] = s[0];
+    part[Part::kB2 + tid] = s[1];
+    part[Part::kB3 + tid] = s[2];
+    part[Part::kBeta + tid] = s[3];
+    part[Part::kGamma + tid] = sg;
+  }
+  tc_fence_before_sync();
+  __syncthreads();  // every tcgen05.ld of the dump above has completed
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+
+}  // namespace bwd2
+}  // namespace mgn
+
+using namespace mgn;
+
+static int bwd2_grid(int64_t M) {
+  const long long n_tiles = (M + bwd2::kRows - 1) / bwd2::kRows;
+  return static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
+}
+
+static long long* g_bwd2_timing = nullptr;
+extern "C" int mgn_debug_set_edge_bwd2_timing(void* dev_buf) {
+  g_bwd2_timing = static_cast<long long*>(dev_buf);
+  return MGN_OK;
+}
+
+extern "C" size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges) {
+  if (n_edges <= 0) return 0;
+  return static_cast<size_t>(bwd2_grid(n_edges)) * bwd2::Part::kTotal * sizeof(float);
+}
+
+extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, const int32_t* go1_idx,
+                                     const void* go2, const int32_t* go2_idx, int64_t n_edges, const float* w1,
+                                     int64_t ld_w1, const float* w2, const float* b2, const float* w3, const float* b3,
+                                     const float* gamma, float eps, void* g_efeat, void* g_z1, int64_t g_z1_ld,
+                                     float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
+                                     float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
+                                     int* status, mgn_stream_t stream) {
+  const int64_t M = n_edges;
+  MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && gamma && ld_w1 >= bwd2::kH);
+  if (M == 0) return MGN_OK;
+  MGN_CHECK_ARG(efeat && h1 && go1 && g_efeat && g_z1 && workspace);
+  MGN_CHECK_ARG(g_z1_ld >= bwd2::kH && g_z1_ld % 8 == 0);
+  for (const void* q : {efeat, h1, go1, go2, static_cast<const void*>(g_efeat), static_cast<const void*>(g_z1)})
+    MGN_CHECK_ARG((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+  if (workspace_bytes < mgn_edge_block_bwd_tc_workspace_bytes(M)) return MGN_EWORKSPACE;
+  bwd2::Params p{};
+  p.h1 = static_cast<const bf16*>(h1);
+  p.go1 = tile::RowSrc{static_cast<const bf16*>(go1), go1_idx, bwd2::kH, 0};
+  p.go2 = tile::RowSrc{static_cast<const bf16*>(go2), go2_idx, bwd2::kH, 0};
+  MGN_CHECK_ARG(go2 == nullptr || go2_idx != nullptr);
+  p.M = M;
+  p.w1 = w1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3; p.gamma = gamma;
+  p.ld_w1 = ld_w1;
+  p.eps = eps;
+  p.partials = static_cast<float*>(workspace);
+  p.part_floats = bwd2::Part::kTotal;
+  p.status = status;
+  p.timing = g_bwd2_timing;
+  int e = tma_make_rows_map(&p.m_a, efeat, M, bwd2::kH, 128);
+  e |= tma_make_rows_map(&p.m_h1, h1, M, bwd2::kH, 128);
+  if (go1_idx == nullptr) e |= tma_make_rows_map(&p.m_go1, go1, M, bwd2::kH, 128);
+  e |= tma_make_rows_map(&p.m_ga, g_efeat, M, bwd2::kH, 128);
+  e |= tma_make_rows_map(&p.m_gz1, g_z1, M, g_z1_ld, 128);
+  if (e != 0) return MGN_EINVAL;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+    configured = true;
+  }
+  cudaStream_t st = as_stream(stream);
+  const int grid = bwd2_grid(M);
+  bwd2::edge_bwd2_kernel<<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  int rc = mgn_launch_status();
+  if (rc != MGN_OK) return rc;
+  ReduceParams rp{};
+  rp.partials = p.partials;
+  rp.stride = p.part_floats;
+  rp.n_parts = grid;
+  using PT = bwd2::Part;
+  int ns = 0;
+  rp.seg[ns++] = ReduceSeg{g_w1, ld_gw1, bwd2::kH, bwd2::kH, PT::kW1, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_w2, bwd2::kH, bwd2::kH, bwd2::kH, PT::kW2, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_w3, bwd2::kH, bwd2::kH, bwd2::kH, PT::kW3, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_b1, bwd2::kH, 1, bwd2::kH, PT::kB1, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_b2, bwd2::kH, 1, bwd2::kH, PT::kB2, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_b3, bwd2::kH, 1, bwd2::kH, PT::kB3, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_gamma, bwd2::kH, 1, bwd2::kH, PT::kGamma, bwd2::kH};
+  rp.seg[ns++] = ReduceSeg{g_beta, bwd2::kH, 1, bwd2::kH, PT::kBeta, bwd2::kH};
+  rp.n_seg = ns;
+  reduce_cta_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
+  return mgn_launch_status();
+}

@@ -18,6 +18,7 @@ struct Args {
   long long ld_w1;
   float eps;
   bf16* out;  // [M,128]
+  bf16* h1_out;  // [M,128] first hidden activation relu(z1), kept for the backward pass (nullptr: not stored)
   // fused destination sums (mgn_agg.cuh); seg_off == nullptr: off
   const int32_t* seg_off;
   bf16* agg;

@@ -623,6 +623,7 @@ struct AggArgs {
   int64_t total_tiles = 0;
   int64_t rec_base = 0;
   int fixup = 1;
+  void* h1_out = nullptr;  // edge form on the third-generation kernel: keep relu(z1) for the backward pass
 };
 
 static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x, int small_in,
@@ -687,7 +688,9 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
                      g1_tab != nullptr && g1_idx != nullptr && g2_tab != nullptr && g2_idx != nullptr && res_is_a &&
                      gamma != nullptr && n_out == fwd2::kH && ld_out == fwd2::kH && ld_w1 >= fwd2::kH &&
                      (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0;
+  if (!edge3 && ag.h1_out != nullptr) return MGN_EINVAL;  // only the third-generation edge kernel stores h1
   if (edge3) {
+    MGN_CHECK_ARG(ag.h1_out == nullptr || (reinterpret_cast<uintptr_t>(ag.h1_out) & 15) == 0);
     fwd3::Args x{};
     x.a = static_cast<const bf16*>(a_tab);
     x.M = M;
@@ -703,6 +706,7 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
     x.ld_w1 = ld_w1;
     x.eps = eps;
     x.out = static_cast<bf16*>(out);
+    x.h1_out = static_cast<bf16*>(ag.h1_out);
     x.seg_off = p.seg_off;
     x.agg = p.agg;
     x.ld_agg = p.ld_agg;
@@ -744,11 +748,12 @@ extern "C" int mgn_edge_block_fwd_tc(const void* efeat, const void* p_src, const
                                      int64_t p_src_col0, const void* p_dst, const int32_t* dst_idx, int64_t p_dst_ld,
                                      int64_t p_dst_col0, int64_t n_edges, const float* w1, int64_t ld_w1, const float* b1,
                                      const float* w2, const float* b2, const float* w3, const float* b3,
-                                     const float* gamma, const float* beta, float eps, void* efeat_out,
+                                     const float* gamma, const float* beta, float eps, void* efeat_out, void* h1_out,
                                      const int32_t* csc_offsets, int64_t n_dst, void* agg, int64_t ld_agg,
                                      void* workspace, size_t workspace_bytes, int* status, mgn_stream_t stream) {
   MGN_CHECK_ARG(efeat && p_src && src_idx && p_dst && dst_idx && csc_offsets && agg && efeat_out);
   AggArgs ag;
+  ag.h1_out = h1_out;
   ag.seg_off = csc_offsets;
   ag.n_seg = n_dst;
   ag.agg = agg;
@@ -769,12 +774,13 @@ extern "C" int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, 
                                           int64_t p_dst_col0, int64_t n_rows, const float* w1, int64_t ld_w1,
                                           const float* b1, const float* w2, const float* b2, const float* w3,
                                           const float* b3, const float* gamma, const float* beta, float eps,
-                                          void* efeat_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
+                                          void* efeat_out, void* h1_out, const int32_t* csc_offsets, int64_t n_dst, void* agg,
                                           int64_t ld_agg, void* workspace, size_t workspace_bytes, int64_t row_base,
                                           int64_t total_tiles, int64_t rec_base, int* status, mgn_stream_t stream) {
   if (n_rows == 0) return MGN_OK;
   MGN_CHECK_ARG(efeat && p_src && src_idx && p_dst && dst_idx && csc_offsets && agg && efeat_out && total_tiles > 0);
   AggArgs ag;
+  ag.h1_out = h1_out;
   ag.seg_off = csc_offsets;
   ag.n_seg = n_dst;
   ag.agg = agg;

@@ -37,6 +37,7 @@ from .ops import GraphPlan, TC_HIDDEN, _p, _stream
 
 Tensor = torch.Tensor
 ENABLED = True  # tests flip this to compare against the generic (unfused) kernels
+KEEP_H1 = True  # the edge forward stores relu(z1); the edge backward starts from it instead of recomputing GEMM1
 H = TC_HIDDEN
 BF16 = torch.bfloat16
 
@@ -153,9 +154,11 @@ class FusedProcessorFn(torch.autograd.Function):
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
             P = _node_linear(nfeat, wp)  # [N, 3H]
             agg = None
+            # relu(z1) of the edge MLP, kept for the backward pass (mgn_edge_block_bwd_tc starts from it)
+            h1 = torch.empty((E, H), dtype=BF16, device=efeat.device) if KEEP_H1 else None
             if halo is None:  # edge update and destination sums in one pass over the edge rows
                 efeat_new, agg = ops.edge_block_fwd_tc(efeat, P, src, dst, plan.csc_offsets, N, ew[0][:, :H], ew[1],
-                                                       ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps)
+                                                       ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps=eps, h1_out=h1)
             else:
                 efeat_new = torch.empty_like(efeat)
                 agg = torch.empty((N, H), dtype=BF16, device=efeat.device)
@@ -170,7 +173,8 @@ class FusedProcessorFn(torch.autograd.Function):
                     if hi > lo:
                         ops.edge_block_fwd_part_tc(efeat[lo:hi], g1, g1_idx, P, dst[lo:hi], plan.csc_offsets, N,
                                                    ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], ew[7], eps,
-                                                   efeat_new[lo:hi], agg, ws, lo, sum(tiles), sum(tiles[:k]))
+                                                   efeat_new[lo:hi], agg, ws, lo, sum(tiles), sum(tiles[:k]),
+                                                   h1_out=None if h1 is None else h1[lo:hi])
 
                 run(1, P, halo.src_own)  # interior edges overlap the exchange
                 if work is not None:
@@ -183,9 +187,9 @@ class FusedProcessorFn(torch.autograd.Function):
                 agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
             nfeat_new = ops.mlp3_fwd2_tc(agg, None, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
                                          nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
-            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else [])
+            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else []) + ([h1] if h1 is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
-        ctx.plan, ctx.L, ctx.eps, ctx.halo = plan, L, eps, halo
+        ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1 = plan, L, eps, halo, KEEP_H1
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
         return nfeat
@@ -194,7 +198,7 @@ class FusedProcessorFn(torch.autograd.Function):
     def backward(ctx, g_n: Tensor):
         plan: GraphPlan = ctx.plan
         L, eps, halo = ctx.L, ctx.eps, ctx.halo
-        ns = 4 if halo is None else 5
+        ns = (4 if halo is None else 5) + (1 if ctx.keep_h1 else 0)
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         saved = ctx.saved_tensors[:ctx.n_saved]
@@ -225,10 +229,16 @@ class FusedProcessorFn(torch.autograd.Function):
             else:
                 go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
             g1 = P if halo is None else saved[ns * l + 4]  # source projections: local table or exchanged rows
-            g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, g1, src, 0, P, dst, H, go1, go2, go2_idx, E,
-                                         ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
-                                         True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6], ge[7],
-                                         go1_idx=go1_idx)
+            if ctx.keep_h1:
+                h1 = saved[ns * l + ns - 1]
+                g_e, g_z1e = ops.edge_block_bwd_tc(efeat, h1, go1, go1_idx, go2, go2_idx, ew[0][:, :H], ew[2], ew[3], ew[4],
+                                                   ew[5], ew[6], eps, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5],
+                                                   ge[6], ge[7])
+            else:
+                g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, g1, src, 0, P, dst, H, go1, go2, go2_idx, E,
+                                             ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
+                                             True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6],
+                                             ge[7], go1_idx=go1_idx)
             # ---- per-node reductions of the gathered-row gradient, then the node-level GEMMs
             if halo is None:
                 ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)

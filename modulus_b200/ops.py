@@ -524,7 +524,7 @@ def mlp3_fwd2_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional
 
 
 def edge_block_fwd_tc(efeat: Tensor, P: Tensor, src: Tensor, dst: Tensor, csc_offsets: Tensor, n_dst: int,
-                      w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta, eps: float = 1e-5):
+                      w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta, eps: float = 1e-5, h1_out: Optional[Tensor] = None):
     """MeshEdgeBlock forward fused with the sum aggregation of the next MeshNodeBlock
     (include/mgn_b200.h: mgn_edge_block_fwd_tc).  P [N, >=2H]: source projections in columns [0,H), destination
     projections in [H,2H).  Returns (efeat_new [E,H], agg [n_dst,H]) bf16."""
@@ -535,7 +535,7 @@ def edge_block_fwd_tc(efeat: Tensor, P: Tensor, src: Tensor, dst: Tensor, csc_of
     nbytes = _lib.load().mgn_mlp3_fwd2_agg_workspace_bytes(E)
     ws = _ws(nbytes, dev)
     call("mgn_edge_block_fwd_tc", _p(efeat), _p(P), _p(src), P.stride(0), 0, _p(P), _p(dst), P.stride(0), TC_HIDDEN, E,
-         _p(w1a), w1a.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), eps, _p(out),
+         _p(w1a), w1a.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), eps, _p(out), _p(h1_out),
          _p(csc_offsets), n_dst, _p(agg), agg.stride(0), _p(ws), nbytes, _p(tc_status(dev)), _stream())
     return out, agg
 
@@ -547,17 +547,37 @@ def agg_workspace(total_tiles: int, dev) -> Tensor:
 
 def edge_block_fwd_part_tc(efeat: Tensor, g1: Tensor, g1_idx: Tensor, P: Tensor, dst: Tensor, csc_offsets: Tensor,
                            n_dst: int, w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta, eps: float, out: Tensor,
-                           agg: Tensor, ws: Tensor, row_base: int, total_tiles: int, rec_base: int) -> None:
+                           agg: Tensor, ws: Tensor, row_base: int, total_tiles: int, rec_base: int,
+                           h1_out: Optional[Tensor] = None) -> None:
     """One row range of a partitioned edge forward with fused aggregation (mgn_edge_block_fwd_part_tc): source
     projections from `g1` (local table or exchanged rows) via g1_idx, destination projections from P[:, H:2H]."""
     call("mgn_edge_block_fwd_part_tc", _p(efeat), _p(g1), _p(g1_idx), g1.stride(0), 0, _p(P), _p(dst), P.stride(0),
          TC_HIDDEN, efeat.shape[0], _p(w1a), w1a.stride(0), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta),
-         eps, _p(out), _p(csc_offsets), n_dst, _p(agg), agg.stride(0), _p(ws), ws.numel(), row_base, total_tiles, rec_base,
+         eps, _p(out), _p(h1_out), _p(csc_offsets), n_dst, _p(agg), agg.stride(0), _p(ws), ws.numel(), row_base, total_tiles,
+         rec_base,
          _p(tc_status(efeat.device)), _stream())
 
 
 def agg_fixup(ws: Tensor, total_tiles: int, agg: Tensor, n_dst: int) -> None:
     call("mgn_agg_fixup", _p(ws), total_tiles, _p(agg), agg.stride(0), n_dst, _stream())
+
+
+def edge_block_bwd_tc(efeat: Tensor, h1: Tensor, go1: Tensor, go1_idx: Optional[Tensor], go2: Optional[Tensor],
+                      go2_idx: Optional[Tensor], w1a: Tensor, w2, b2, w3, b3, gamma, eps: float,
+                      g_w1a: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta):
+    """MeshEdgeBlock backward from the stored h1 (include/mgn_b200.h: mgn_edge_block_bwd_tc).  Returns
+    (g_efeat, g_z1) bf16 [E,128]; parameter gradients go to the caller-allocated fp32 tensors."""
+    E = efeat.shape[0]
+    dev = efeat.device
+    g_e = torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    g_z1 = torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    nbytes = _lib.load().mgn_edge_block_bwd_tc_workspace_bytes(E)
+    ws = _ws(nbytes, dev)
+    call("mgn_edge_block_bwd_tc", _p(efeat), _p(h1), _p(go1), _p(go1_idx), _p(go2), _p(go2_idx), E, _p(w1a), w1a.stride(0),
+         _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), eps, _p(g_e), _p(g_z1), g_z1.stride(0), _p(g_w1a), g_w1a.stride(0),
+         _p(g_b1), _p(g_w2), _p(g_b2), _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes, _p(tc_status(dev)),
+         _stream())
+    return g_e, g_z1
 
 
 def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],

@@ -399,3 +399,53 @@ def test_edge_block_fwd_in_row_ranges_matches_single_launch(cuts):
     ref = torch.zeros(N, 128, dtype=torch.float64, device=DEV).index_add_(0, dst.long(), out1.double())
     assert rel_err(agg3.float(), ref) < 1e-2
     assert float(agg3[deg.to(DEV) == 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,first_layer", [(6000, False), (22000, False), (900, True), (1, False)])
+def test_edge_block_bwd_from_stored_h1_matches_recompute(N, first_layer):
+    """mgn_edge_block_bwd_tc (starts from the h1 the forward stored) == mgn_mlp3_bwd_tc edge form (recomputes it):
+    same g_efeat / g_z1 rows, same parameter gradients; incl. the first backward layer's gathered go1."""
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(N + 3)
+    deg = torch.randint(1 if N == 1 else 3, 9, (N,), generator=g)
+    offsets = torch.zeros(N + 1, dtype=torch.int32)
+    offsets[1:] = torch.cumsum(deg, 0).int()
+    E = int(offsets[-1])
+    dst = torch.repeat_interleave(torch.arange(N), deg).int().to(DEV)
+    src = torch.randint(0, N, (E,), generator=g).int().to(DEV)
+    d = dev_params(make_params(384, seed=13))
+    r = lambda *s: torch.randn(*s, generator=g)
+    A, P = r(E, 128).to(DEV).bfloat16(), (r(N, 384) * 0.5).to(DEV).bfloat16()
+    g_e, g_agg = r(E, 128).to(DEV).bfloat16(), r(N, 128).to(DEV).bfloat16()
+    h1 = torch.empty(E, 128, dtype=torch.bfloat16, device=DEV)
+    ops.edge_block_fwd_tc(A, P, src, dst, offsets.to(DEV), N, d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"],
+                          d["gamma"], d["beta"], h1_out=h1)
+    z1 = A.float() @ d["w1"][:, :128].bfloat16().float().T + P[src.long(), :128].float() + P[dst.long(), 128:256].float() + d["b1"]
+    assert rel_err(h1.float(), torch.relu(z1)) < 1.5e-2
+    if first_layer:
+        go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
+    else:
+        go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
+
+    def grads():
+        gw1 = torch.zeros(128, 384, device=DEV)
+        return gw1, [torch.empty(128, device=DEV), torch.empty(128, 128, device=DEV), torch.empty(128, device=DEV),
+                     torch.empty(128, 128, device=DEV), torch.empty(128, device=DEV), torch.empty(128, device=DEV),
+                     torch.empty(128, device=DEV)]
+
+    gw1a, ga = grads()
+    ref_ge, ref_gz1 = ops.mlp3_bwd_tc(A, None, None, P, src, 0, P, dst, 128, go1, go2, go2_idx, E, d["w1"][:, :128], d["b1"],
+                                      d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], 128, 1e-5, True, True, True,
+                                      gw1a[:, :128], *ga, go1_idx=go1_idx)
+    gw1b, gb = grads()
+    out_ge, out_gz1 = ops.edge_block_bwd_tc(A, h1, go1, go1_idx, go2, go2_idx, d["w1"][:, :128], d["w2"], d["b2"], d["w3"],
+                                            d["b3"], d["gamma"], 1e-5, gw1b[:, :128], *gb)
+    out_ge2, out_gz12 = ops.edge_block_bwd_tc(A, h1, go1, go1_idx, go2, go2_idx, d["w1"][:, :128], d["w2"], d["b2"], d["w3"],
+                                              d["b3"], d["gamma"], 1e-5, gw1b[:, :128], *gb)
+    ops.tc_check(DEV)
+    assert torch.equal(out_ge, ref_ge) and torch.equal(out_gz1, ref_gz1)
+    assert torch.equal(out_ge, out_ge2) and torch.equal(out_gz1, out_gz12)
+    assert rel_err(gw1b[:, :128], gw1a[:, :128]) < 1e-5
+    for x, y in zip(gb, ga):
+        assert rel_err(x, y) < 1e-5

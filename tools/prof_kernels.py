@@ -44,6 +44,16 @@ def bwd():
                            w1[:, :128], b1, w2, b2, w3, b3, gamma, 128, 1e-5, True, True, True,
                            gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4])
 
+h1s = torch.empty(E, 128, dtype=torch.bfloat16, device=DEV)
+ops.edge_block_fwd_tc(efeat, P, plan.src, plan.dst, plan.csc_offsets, N, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta, h1_out=h1s)
+
+def eblk_h1():
+    return ops.edge_block_fwd_tc(efeat, P, plan.src, plan.dst, plan.csc_offsets, N, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta, h1_out=h1s)
+
+def bwd2():
+    return ops.edge_block_bwd_tc(efeat, h1s, g_e, None, g_agg, plan.dst, w1[:, :128], w2, b2, w3, b3, gamma, 1e-5,
+                                 gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4])
+
 def agg():
     return ops.segment_sum(efeat, 0, 128, plan.csc_offsets, None, N)
 
@@ -61,7 +71,7 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
-for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("bwd edge", bwd), ("segsum csc", agg), ("segsum csr", csr),
+for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
@@ -111,3 +121,21 @@ print("FWD3 edge-block kernel, CTA 0, epilogue cycles per tile: wait M2 | E2 | w
       [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
 print("FWD3 MMA thread: wait E2 | issue M3 | wait E1' | issue M2' | wait E3prev+A'' | issue M1'' :",
       [int(v) // per_cta for v in t[8:14].tolist()], "total", int(t[8:14].sum()) // per_cta)
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_edge_bwd2_timing", tbuf.data_ptr())
+bwd2(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_edge_bwd2_timing", None)
+t = tbuf.cpu().view(3, 32)
+print("BWD2 (from h1) kernel, CTA 0, cycles per tile")
+print(" MMA   : wH1+E6prev | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 | wE5 | dgrad1 | wgrad1 :", [int(v) // per_cta for v in t[0, :11].tolist()], "total", int(t[0].sum()) // per_cta)
+print(" LOADER: top | wW3+CS0 | wW2+CS1 | wE5 | st gz1 | wMMA7+CS2 | wE6 | st gA :", [int(v) // per_cta for v in t[1, :8].tolist()], "total", int(t[1].sum()) // per_cta)
+print(" EPI   : wMMA2+XF | E2 | wMMA3 | wGO | E3 | E4 | E5 | E6 :", [int(v) // per_cta for v in t[2, :8].tolist()], "total", int(t[2].sum()) // per_cta)
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
+eblk_h1(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd2_timing", None)
+t = tbuf.cpu()
+print("FWD3 + h1 store, epilogue: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :", [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
+print("FWD3 + h1 store, MMA thread: wait E2 | issue M3 | wait E1' | issue M2' | wait E3prev+A'' | issue M1'' :", [int(v) // per_cta for v in t[8:14].tolist()])
