@@ -39,7 +39,7 @@ constexpr int kThreads = 32 * (kLoaderWarp + 1);
 struct Params {
   Args a;
   long long* timing;
-  alignas(64) CUtensorMap m_a, m_out, m_h1;
+  alignas(64) CUtensorMap m_a, m_out;
 };
 
 struct Smem {
@@ -58,8 +58,7 @@ struct Smem {
 // B_M1[3] / B_M2 / B_M3: GEMM k of a tile complete.  B_H1 / B_H2 / B_OUT[3]: epilogue pass complete (8 warps).
 // B_AGG[3]: movers have finished summing the result tile in slot s.  (Barriers that a waiter may trail by more than
 // one completion are kept per slot: a parity wait cannot tell two completions from none.)
-// B_G1F: the h1 tile (written over the consumed G1 rows for the backward pass) has left the G1 buffer (loader).
-enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_G1F = 17, B_NUM = 18 };
+enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_NUM = 17 };
 
 __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -214,20 +213,28 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
         if (n_my > 1) fetch_row_ids(g1.idx, row_first + stride, a.M, rsub_m, r_g1);
         MGN_PUBLISH_G();
       }
-      const int b_free = a.h1_out != nullptr ? B_G1F : B_H1;  // G1 buffer consumed (and, if stored, h1 has left it)
-      if (n_my > 1) {
-        if (!__all_sync(0xffffffffu, wait_clk(&bars[b_free], 0))) { timed_out = true; break; }
-        stage_rows_async(bG1, g1, r_g1, row_first + stride, a.M, mt);
-        if (n_my > 2) fetch_row_ids(g1.idx, row_first + 2 * stride, a.M, rsub_m, r_g1);
-        MGN_PUBLISH_G();
+      // E1(j) has consumed G1(j) and (if kept for the backward pass) left h1(j) in the same buffer: the movers write
+      // it out with the row mapping of the gather that follows, so each thread overwrites only what it has read
+      if (n_my > 1 || (n_my > 0 && a.h1_out != nullptr)) {
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], 0))) { timed_out = true; break; }
+        if (a.h1_out != nullptr) store_rows(bG1, a.h1_out, kH, row_first, a.M, mt);
+        if (n_my > 1) {
+          stage_rows_async(bG1, g1, r_g1, row_first + stride, a.M, mt);
+          if (n_my > 2) fetch_row_ids(g1.idx, row_first + 2 * stride, a.M, rsub_m, r_g1);
+          MGN_PUBLISH_G();
+        }
       }
       for (int k = 0; k < n_my; ++k) {
         const long long row0 = row_first + k * stride;
-        if (k + 2 < n_my) {  // period k: E1(k+1) has consumed G1(k+1) -> stage G1(k+2) while E3(k) runs
-          MGN_W(b_free, (k + 1) & 1);
-          stage_rows_async(bG1, g1, r_g1, row0 + 2 * stride, a.M, mt);
-          if (k + 3 < n_my) fetch_row_ids(g1.idx, row0 + 3 * stride, a.M, rsub_m, r_g1);
-          MGN_PUBLISH_G();
+        if (k + 2 < n_my || (k + 1 < n_my && a.h1_out != nullptr)) {
+          // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
+          MGN_W(B_H1, (k + 1) & 1);
+          if (a.h1_out != nullptr) store_rows(bG1, a.h1_out, kH, row0 + stride, a.M, mt);
+          if (k + 2 < n_my) {
+            stage_rows_async(bG1, g1, r_g1, row0 + 2 * stride, a.M, mt);
+            if (k + 3 < n_my) fetch_row_ids(g1.idx, row0 + 3 * stride, a.M, rsub_m, r_g1);
+            MGN_PUBLISH_G();
+          }
         }
         // result tile k: destination sums from shared memory
         MGN_W(B_OUT + k % 3, (k / 3) & 1);
@@ -250,21 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
         tma_load_2d(dst + kPB, &p.m_a, 64, r0, &bars[B_A + j % 3]);
       };
       for (int j = 0; j < 3 && j < n_my; ++j) load_a(j);
-      auto store_h1 = [&](int j) -> bool {  // E1(j) left relu(z1) of tile j in the G1 buffer
-        if (!wait_clk(&bars[B_H1], j & 1)) return false;
-        const int r0 = static_cast<int>(row_first + j * stride);
-        tma_store_2d(&p.m_h1, smem_u32(bG1), 0, r0);
-        tma_store_2d(&p.m_h1, smem_u32(bG1) + kPB, 64, r0);
-        tma_store_commit();
-        tma_store_wait_read();
-        mbar_arrive(&bars[B_G1F]);
-        return true;
-      };
-      if (a.h1_out != nullptr && n_my > 0 && !store_h1(0)) timed_out = true;
       for (int k = 0; k < n_my && !timed_out; ++k) {
         const uint32_t src = smem_u32(bA0) + (k % 3) * 2 * kPB;
         const int r0 = static_cast<int>(row_first + k * stride);
-        if (a.h1_out != nullptr && k + 1 < n_my && !store_h1(k + 1)) { timed_out = true; break; }
         if (!wait_clk(&bars[B_OUT + k % 3], (k / 3) & 1)) { timed_out = true; break; }
         tma_store_2d(&p.m_out, src, 0, r0);
         tma_store_2d(&p.m_out, src + kPB, 64, r0);
@@ -314,6 +309,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
     };
     // E1(j): h1 = relu(acc + b1 + G1 + G2) -> TMEM (packed bf16)
     auto e1 = [&](int j) {
+      // (pin the prefetched destination-projection words here: without it the compiler hoists their unpacking above
+      //  the preceding pass, which then stalls on the global loads it was meant to cover)
+#pragma unroll
+      for (int u = 0; u < 8; ++u) asm volatile("" : "+r"(gq[u].x), "+r"(gq[u].y), "+r"(gq[u].z), "+r"(gq[u].w));
       const uint32_t t_acc = tmem + (j % 3) * 128 + lane_off + c0;
       const uint32_t t_h = tmem + 384 + (j & 1) * 64 + lane_off + ch * 32;
 #pragma unroll
@@ -346,7 +345,6 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
         if (a.h1_out != nullptr) row_store32p(bG1, row, c0 + 32 * hh, pk);  // over this thread's own consumed G1 span
       }
       tmem_st_wait();
-      if (a.h1_out != nullptr) fence_proxy_async_smem();  // the h1 tile leaves through the async proxy (TMA store)
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_H1]);
@@ -496,7 +494,6 @@ int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   p.timing = g_fwd3_timing;
   if (tma_make_rows_map(&p.m_a, args.a, args.M, 128, 128) != 0) return MGN_EINVAL;
   if (tma_make_rows_map(&p.m_out, args.out, args.M, 128, 128) != 0) return MGN_EINVAL;
-  if (args.h1_out != nullptr && tma_make_rows_map(&p.m_h1, args.h1_out, args.M, 128, 128) != 0) return MGN_EINVAL;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
