@@ -15,8 +15,9 @@
 //
 // = the backward of physicsnemo/models/gnn_layers/mesh_edge_block.py:88-96 (autograd over cuBLAS / ATen there).
 // No gathered operand except the go2 rows, no b1, no source / destination tables.  Four 32 KB tile buffers: buffer 0
-// = go2 rows -> g_y -> efeat tile; the other three rotate (H1' = H2, H2' = X, X' = H1) so that the next tile's h1
-// streams in right after the layer-2 MMAs and its incoming-gradient rows right after the layer-1 MMAs.
+// = go2 rows -> g_y -> efeat tile; buffer 1 = X (go1 -> g_out -> g_efeat); H1 and H2 swap the other two from tile to
+// tile, so that the next tile's h1 streams in right after the layer-2 MMAs; its incoming-gradient rows follow the
+// layer-1 MMAs (go2) and the g_efeat store (go1).
 // Roles as in the generic kernel: warp 0 MMA issuer, warps 1-4 reducers (go2 gather, column sums), warps 5-12
 // epilogue, warp 13 loader (TMA).
 #include "mgn_common.cuh"
@@ -33,7 +34,6 @@ constexpr int kEpiWarps = 8;
 constexpr int kLoaderWarp = 5 + kEpiWarps;
 constexpr int kThreads = 32 * (kLoaderWarp + 1);
 constexpr int kH = 128;
-constexpr int kOobRow = 1 << 30;
 
 struct Params {
   const bf16* h1;       // [M,128]
@@ -103,8 +103,9 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
   float* sPar = reinterpret_cast<float*>(smem + Smem::kPar);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::kBars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + Smem::kTmemSlot);
-// buffer 0 = A; X / H1 / H2 of tile `it` = buffer 1 + (role + it) % 3
-#define MGN_BUF(role, it) (buf0 + ((role) < 0 ? 0 : 1 + (((role) + (it)) % 3)) * (2 * kPB))
+// buffer 0 = A, buffer 1 = X; H1 / H2 swap buffers 2 and 3 from tile to tile (the next tile's h1 streams into this
+// tile's H2 buffer)
+#define MGN_BUF(role, it) (buf0 + ((role) < 0 ? 0 : ((role) == R_X ? 1 : ((role) == R_H1 ? 2 + ((it) & 1) : 3 - ((it) & 1)))) * (2 * kPB))
   const bool has_go2 = p.go2.tab != nullptr;
   constexpr bool has_ln = true;
   constexpr bool need_ga = true;
@@ -294,10 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
       colsum_tile(bH1, mt, cs_b1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
-      if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X' = H1 once g_z1 has left
+      if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X once g_efeat has left
         MGN_W(B_MMA + 5, par);
-        if (go1_gathered) MGN_W(B_ST, par);
-        stage_go(row0n, bH1, bA);
+        if (go1_gathered) MGN_W(B_XF, par);
+        stage_go(row0n, bX, bA);
         MGN_PUBLISH(B_GO);
       }
     }
@@ -365,18 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
         tma_store_wait_read();
         mbar_arrive(&bars[B_ST]);
         MGN_T(4);
-        if (more) {  // next tile's dense incoming gradient -> X' = this tile's H1 buffer
-          MGN_W(B_MMA + 5, par);
-          MGN_W(B_CS + 2, par);
-          MGN_T(5);
-          if (go1_tma) {
-            mbar_arrive_expect_tx(&bars[B_GO], 2 * kPB);
-            tma_tile(bH1, &p.m_go1, row0n, &bars[B_GO]);
-          } else {
-            mbar_arrive(&bars[B_GO]);
-          }
-        }
-        // g_A tile (X) -> global; X is the next tile's H2: its E2 may write there once the store has read it
+        // g_efeat tile (X) -> global, then the next tile's dense incoming gradient into the same buffer
         MGN_W(B_E + 4, par);
         MGN_T(6);
         tma_store_2d(&p.m_ga, smem_u32(bX), 0, static_cast<int>(row0));
@@ -384,6 +374,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
         tma_store_commit();
         tma_store_wait_read();
         mbar_arrive(&bars[B_XF]);
+        if (more) {
+          if (go1_tma) {
+            mbar_arrive_expect_tx(&bars[B_GO], 2 * kPB);
+            tma_tile(bX, &p.m_go1, row0n, &bars[B_GO]);
+          } else {
+            mbar_arrive(&bars[B_GO]);
+          }
+        }
         MGN_T(7);
       }
 #undef MGN_W
@@ -422,9 +420,14 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
       uint8_t* bX = MGN_BUF(R_X, it);
       uint8_t* bH1 = MGN_BUF(R_H1, it);
       uint8_t* bH2 = MGN_BUF(R_H2, it);
-      // ---- E2: h2 = relu(acc + b2) -> H2   (H2 is the previous tile's X: its g_A tile must have left)
+      // ---- E2: h2 = relu(acc + b2) -> H2   (H2 is the previous tile's H1: its layer-1 MMAs, its g_z1 store and its
+      //      column sums must be done with it)
       MGN_W(B_MMA + 0, par);
-      if (it > 0) MGN_W(B_XF, par ^ 1);
+      if (it > 0) {
+        MGN_W(B_MMA + 5, par ^ 1);
+        MGN_W(B_ST, par ^ 1);
+        MGN_W(B_CS + 2, par ^ 1);
+      }
       MGN_T(0);
       tc_fence_after_sync();
 #pragma unroll 1
