@@ -258,17 +258,27 @@ int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, const int32
                                int64_t total_tiles, int64_t rec_base, int* status, mgn_stream_t stream);
 int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,
                   mgn_stream_t stream);
+/* MeshNodeBlock.forward (mesh_node_block.py:82-92) with the first Linear split per input block:
+ *   nfeat_out[v] = nfeat[v] + LN(MLP(agg[v] W1a^T + P_node[v] + b1)),  P_node = columns [p_col0, p_col0+128) of p_tab;
+ * h1_out (nullable, [n_nodes,128] bf16) receives relu(z1) for mgn_edge_block_bwd_tc with add_gout = 0. */
+int mgn_node_block_fwd_tc(const void* agg, const void* p_tab, int64_t p_ld, int64_t p_col0, const void* nfeat,
+                          int64_t n_nodes, const float* w1, int64_t ld_w1, const float* b1, const float* w2,
+                          const float* b2, const float* w3, const float* b3, const float* gamma,
+                          const float* beta, float eps, void* nfeat_out, void* h1_out, int* status,
+                          mgn_stream_t stream);
 
 /* MeshEdgeBlock backward from the first hidden activation h1 = relu(z1) that mgn_edge_block_fwd_tc stored (no gather
  * of the projection rows, no GEMM1 recompute): go1 (dense, or gathered by go1_idx) + go2[go2_idx] = gradient of the
  * block output; writes g_efeat [n_edges,128], g_z1 [n_edges,128] (row stride g_z1_ld; its CSC / CSR sums are the
  * gradients of the destination / source projection rows) and the fp32 parameter gradients of W1[:, :128] (row stride
- * ld_gw1), b1, W2, b2, W3, b3, gamma, beta (deterministic per-CTA partials + ordered reduction). */
+ * ld_gw1), b1, W2, b2, W3, b3, gamma, beta (deterministic per-CTA partials + ordered reduction).  add_gout = 1: the
+ * block's residual runs over the layer-1 input rows (edge block: g_efeat = g_z1 W1a + g_out); 0 for the node block,
+ * whose layer-1 input is the aggregate (efeat := agg, h1 from mgn_node_block_fwd_tc, g_efeat := g_agg). */
 size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges);
 int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, const int32_t* go1_idx,
                           const void* go2, const int32_t* go2_idx, int64_t n_edges, const float* w1,
                           int64_t ld_w1, const float* w2, const float* b2, const float* w3, const float* b3,
-                          const float* gamma, float eps, void* g_efeat, void* g_z1, int64_t g_z1_ld,
+                          const float* gamma, float eps, int add_gout, void* g_efeat, void* g_z1, int64_t g_z1_ld,
                           float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
                           float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
                           int* status, mgn_stream_t stream);

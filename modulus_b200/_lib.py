@@ -135,6 +135,8 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
         return "tensor", 2.0 * M * (k1 * 128 + 2 * 128 * 128)
     if name in ("mgn_edge_block_fwd_tc", "mgn_edge_block_fwd_part_tc"):
         return "tensor", 10.0 * 128 * 128 * a[9]
+    if name == "mgn_node_block_fwd_tc":
+        return "tensor", 8.0 * 128 * 128 * a[5]
     if name == "mgn_node_gemm_tc":
         kb, M, nb, res = a[2], a[3], a[6], a[7]
         return "hbm", 2.0 * M * 128 * (kb + nb + (1 if res else 0))  # one pass over x, (residual,) out

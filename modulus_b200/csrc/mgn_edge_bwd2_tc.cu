@@ -89,6 +89,9 @@ __device__ __forceinline__ void tma_tile(uint8_t* buf, const CUtensorMap* map, l
   tma_load_2d(dst + kPB, map, 64, static_cast<int>(row0), bar);
 }
 
+// kAddGout: the block's residual runs over the layer-1 input rows (edge block: g_a = g_z1 W1a + g_out); false for the
+// node block.  Compile-time: a run-time flag in the last epilogue pass costs the edge instance 9 % through spills.
+template <bool kAddGout>
 __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -583,12 +586,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
           uint32_t v[32];
           tmem_ld32(t_acc + 32 * hh, v);
           uint32_t go[16];
-          row_load32p(bX, row, c0 + 32 * hh, go);
+          if (kAddGout) row_load32p(bX, row, c0 + 32 * hh, go);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + bf_lo(go[j]),
-                                __uint_as_float(v[2 * j + 1]) + bf_hi(go[j]));
+            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + (kAddGout ? bf_lo(go[j]) : 0.f),
+                                __uint_as_float(v[2 * j + 1]) + (kAddGout ? bf_hi(go[j]) : 0.f));
           row_store32p(bX, row, c0 + 32 * hh, go);
         }
       }
@@ -682,7 +685,7 @@ extern "C" size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges) {
 extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, const int32_t* go1_idx,
                                      const void* go2, const int32_t* go2_idx, int64_t n_edges, const float* w1,
                                      int64_t ld_w1, const float* w2, const float* b2, const float* w3, const float* b3,
-                                     const float* gamma, float eps, void* g_efeat, void* g_z1, int64_t g_z1_ld,
+                                     const float* gamma, float eps, int add_gout, void* g_efeat, void* g_z1, int64_t g_z1_ld,
                                      float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
                                      float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
                                      int* status, mgn_stream_t stream) {
@@ -715,13 +718,16 @@ extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const vo
   if (e != 0) return MGN_EINVAL;
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+    cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
     if (ce != cudaSuccess) return static_cast<int>(ce);
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
   const int grid = bwd2_grid(M);
-  bwd2::edge_bwd2_kernel<<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  if (add_gout) bwd2::edge_bwd2_kernel<true><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  else bwd2::edge_bwd2_kernel<false><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
   int rc = mgn_launch_status();
   if (rc != MGN_OK) return rc;
   ReduceParams rp{};

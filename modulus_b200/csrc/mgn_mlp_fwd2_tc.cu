@@ -53,6 +53,7 @@ struct Params {
   float eps;
   bf16* out;
   long long ld_out;
+  bf16* h1_out;  // [M,128] relu(z1), kept for mgn_edge_block_bwd_tc (nullptr: not stored)
   int* status;
   long long* timing;
   int tma_a, tma_out;  // dense A tiles arrive / result tiles leave through the loader warp (tensor maps below)
@@ -290,6 +291,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       // the additive-row buffers are free once the layer-1 epilogue has consumed them
       if (!p.single) MGN_W(B_H1, par);
       MGN_T(1);
+      // h1 of this tile (left in the G1 buffer by E1) -> global, with the row mapping of the gather that follows
+      if (p.h1_out != nullptr) store_rows(bG1, p.h1_out, kH, row0, p.M, mt);
       if (more && has_g1) stage_rows_async(bG1, p.g1, r_g1, row1, p.M, mt);
       if (more && use_g2buf && !res_g2) stage_rows_async(bG2, g2src, r_g2, row1, p.M, mt);
       // (single-GEMM mode has no layer-1 epilogue to order against: publishing early could run two barrier phases
@@ -438,6 +441,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
           pk[2 * u + 1] = pack_bf16x2(fmaxf(z2, 0.f), fmaxf(z3, 0.f));
         }
         tmem_st16(t_h + 16 * hh, pk);
+        if (p.h1_out != nullptr) row_store32p(bG1, row, cc, pk);  // over this thread's own consumed G1 span
       }
       tmem_st_wait();
       tc_fence_before_sync();
@@ -688,7 +692,10 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
                      g1_tab != nullptr && g1_idx != nullptr && g2_tab != nullptr && g2_idx != nullptr && res_is_a &&
                      gamma != nullptr && n_out == fwd2::kH && ld_out == fwd2::kH && ld_w1 >= fwd2::kH &&
                      (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0;
-  if (!edge3 && ag.h1_out != nullptr) return MGN_EINVAL;  // only the third-generation edge kernel stores h1
+  if (!edge3 && ag.h1_out != nullptr) {  // second-generation kernel: multi-GEMM forms with a 128-wide hidden layer
+    MGN_CHECK_ARG((reinterpret_cast<uintptr_t>(ag.h1_out) & 15) == 0);
+    p.h1_out = static_cast<bf16*>(ag.h1_out);
+  }
   if (edge3) {
     MGN_CHECK_ARG(ag.h1_out == nullptr || (reinterpret_cast<uintptr_t>(ag.h1_out) & 15) == 0);
     fwd3::Args x{};
@@ -794,6 +801,21 @@ extern "C" int mgn_edge_block_fwd_part_tc(const void* efeat, const void* p_src, 
   return fwd2_run(efeat, nullptr, nullptr, 0, 0, p_src, src_idx, p_src_ld, p_src_col0, p_dst, dst_idx, p_dst_ld, p_dst_col0,
                   nullptr, 1, n_rows, w1, ld_w1, b1, w2, b2, w3, b3, gamma, beta, fwd2::kH, eps, efeat_out, fwd2::kH, status,
                   stream, ag);
+}
+
+/* MeshNodeBlock.forward (mesh_node_block.py:82-92) with the first Linear split per input block:
+ *   nfeat_out[v] = nfeat[v] + LN(MLP(agg[v] W1a^T + P_node[v] + b1)),  P_node = columns [p_col0, p_col0+128) of p_tab;
+ * h1_out (nullable) receives relu(z1) for mgn_edge_block_bwd_tc (add_gout = 0). */
+extern "C" int mgn_node_block_fwd_tc(const void* agg, const void* p_tab, int64_t p_ld, int64_t p_col0, const void* nfeat,
+                                     int64_t n_nodes, const float* w1, int64_t ld_w1, const float* b1, const float* w2,
+                                     const float* b2, const float* w3, const float* b3, const float* gamma,
+                                     const float* beta, float eps, void* nfeat_out, void* h1_out, int* status,
+                                     mgn_stream_t stream) {
+  MGN_CHECK_ARG(agg && p_tab && nfeat && nfeat_out);
+  AggArgs ag;
+  ag.h1_out = h1_out;
+  return fwd2_run(agg, nullptr, nullptr, 0, 0, p_tab, nullptr, p_ld, p_col0, nullptr, nullptr, 0, 0, nfeat, 0, n_nodes, w1,
+                  ld_w1, b1, w2, b2, w3, b3, gamma, beta, fwd2::kH, eps, nfeat_out, fwd2::kH, status, stream, ag);
 }
 
 extern "C" int mgn_agg_fixup(void* workspace, int64_t total_tiles, void* agg, int64_t ld_agg, int64_t n_dst,

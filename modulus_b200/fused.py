@@ -185,9 +185,10 @@ class FusedProcessorFn(torch.autograd.Function):
                 del keep
             if agg is None:
                 agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
-            nfeat_new = ops.mlp3_fwd2_tc(agg, None, None, P, None, 2 * H, None, None, 0, N, nw[0][:, :H], nw[1], nw[2],
-                                         nw[3], nw[4], nw[5], nw[6], nw[7], eps=eps, residual=nfeat)
-            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else []) + ([h1] if h1 is not None else [])
+            h1n = torch.empty((N, H), dtype=BF16, device=nfeat.device) if KEEP_H1 else None
+            nfeat_new = ops.node_block_fwd_tc(agg, P, 2 * H, nfeat, nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6],
+                                              nw[7], eps=eps, h1_out=h1n)
+            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else []) + ([h1, h1n] if h1 is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
         ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1 = plan, L, eps, halo, KEEP_H1
         ctx.save_for_backward(*saved, *params)
@@ -198,7 +199,7 @@ class FusedProcessorFn(torch.autograd.Function):
     def backward(ctx, g_n: Tensor):
         plan: GraphPlan = ctx.plan
         L, eps, halo = ctx.L, ctx.eps, ctx.halo
-        ns = (4 if halo is None else 5) + (1 if ctx.keep_h1 else 0)
+        ns = (4 if halo is None else 5) + (2 if ctx.keep_h1 else 0)
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         saved = ctx.saved_tensors[:ctx.n_saved]
@@ -219,10 +220,15 @@ class FusedProcessorFn(torch.autograd.Function):
             gn = [gnw1] + [torch.empty_like(t, dtype=torch.float32) for t in nw[1:]]
             T = torch.empty((N, 3 * H), dtype=BF16, device=dev)
             # ---- node block: g_agg = dL/d agg, g_z1 (node) -> T[:, 2H:3H]
-            g_agg, _ = ops.mlp3_bwd_tc(agg, None, None, P, None, 2 * H, None, None, 0, g_n, None, None, N,
-                                       nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6], H, eps,
-                                       True, False, True, gnw1[:, :H], gn[1], gn[2], gn[3], gn[4], gn[5], gn[6], gn[7],
-                                       g_z1_out=T[:, 2 * H:])
+            if ctx.keep_h1:  # from the stored h1 of the node MLP (no residual over its layer-1 input: add_gout = 0)
+                g_agg, _ = ops.edge_block_bwd_tc(agg, saved[ns * l + ns - 1], g_n, None, None, None, nw[0][:, :H], nw[2],
+                                                 nw[3], nw[4], nw[5], nw[6], eps, gnw1[:, :H], gn[1], gn[2], gn[3], gn[4],
+                                                 gn[5], gn[6], gn[7], add_gout=False, g_z1_out=T[:, 2 * H:])
+            else:
+                g_agg, _ = ops.mlp3_bwd_tc(agg, None, None, P, None, 2 * H, None, None, 0, g_n, None, None, N,
+                                           nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6], H, eps,
+                                           True, False, True, gnw1[:, :H], gn[1], gn[2], gn[3], gn[4], gn[5], gn[6],
+                                           gn[7], g_z1_out=T[:, 2 * H:])
             # ---- edge block: g_out = g_e + g_agg[dst]
             if g_e is None:
                 go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
@@ -230,7 +236,7 @@ class FusedProcessorFn(torch.autograd.Function):
                 go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
             g1 = P if halo is None else saved[ns * l + 4]  # source projections: local table or exchanged rows
             if ctx.keep_h1:
-                h1 = saved[ns * l + ns - 1]
+                h1 = saved[ns * l + ns - 2]
                 g_e, g_z1e = ops.edge_block_bwd_tc(efeat, h1, go1, go1_idx, go2, go2_idx, ew[0][:, :H], ew[2], ew[3], ew[4],
                                                    ew[5], ew[6], eps, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5],
                                                    ge[6], ge[7])

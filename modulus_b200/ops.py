@@ -540,6 +540,16 @@ def edge_block_fwd_tc(efeat: Tensor, P: Tensor, src: Tensor, dst: Tensor, csc_of
     return out, agg
 
 
+def node_block_fwd_tc(agg: Tensor, P: Tensor, p_col0: int, nfeat: Tensor, w1a: Tensor, b1, w2, b2, w3, b3, gamma, beta,
+                      eps: float = 1e-5, h1_out: Optional[Tensor] = None) -> Tensor:
+    """MeshNodeBlock forward (include/mgn_b200.h: mgn_node_block_fwd_tc); optionally keeps relu(z1) for the backward."""
+    N = agg.shape[0]
+    out = torch.empty((N, TC_HIDDEN), dtype=torch.bfloat16, device=agg.device)
+    call("mgn_node_block_fwd_tc", _p(agg), _p(P), P.stride(0), p_col0, _p(nfeat), N, _p(w1a), w1a.stride(0), _p(b1), _p(w2),
+         _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), eps, _p(out), _p(h1_out), _p(tc_status(agg.device)), _stream())
+    return out
+
+
 def agg_workspace(total_tiles: int, dev) -> Tensor:
     """Record array shared by the launches of one partitioned edge forward (2 records of 128 fp32 + id per tile)."""
     return _ws(2 * int(total_tiles) * (TC_HIDDEN * 4 + 4), dev)
@@ -564,17 +574,19 @@ def agg_fixup(ws: Tensor, total_tiles: int, agg: Tensor, n_dst: int) -> None:
 
 def edge_block_bwd_tc(efeat: Tensor, h1: Tensor, go1: Tensor, go1_idx: Optional[Tensor], go2: Optional[Tensor],
                       go2_idx: Optional[Tensor], w1a: Tensor, w2, b2, w3, b3, gamma, eps: float,
-                      g_w1a: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta):
+                      g_w1a: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta, add_gout: bool = True,
+                      g_z1_out: Optional[Tensor] = None):
     """MeshEdgeBlock backward from the stored h1 (include/mgn_b200.h: mgn_edge_block_bwd_tc).  Returns
     (g_efeat, g_z1) bf16 [E,128]; parameter gradients go to the caller-allocated fp32 tensors."""
     E = efeat.shape[0]
     dev = efeat.device
     g_e = torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
-    g_z1 = torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
+    g_z1 = g_z1_out if g_z1_out is not None else torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
     nbytes = _lib.load().mgn_edge_block_bwd_tc_workspace_bytes(E)
     ws = _ws(nbytes, dev)
     call("mgn_edge_block_bwd_tc", _p(efeat), _p(h1), _p(go1), _p(go1_idx), _p(go2), _p(go2_idx), E, _p(w1a), w1a.stride(0),
-         _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), eps, _p(g_e), _p(g_z1), g_z1.stride(0), _p(g_w1a), g_w1a.stride(0),
+         _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), eps, int(add_gout), _p(g_e), _p(g_z1), g_z1.stride(0), _p(g_w1a),
+         g_w1a.stride(0),
          _p(g_b1), _p(g_w2), _p(g_b2), _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes, _p(tc_status(dev)),
          _stream())
     return g_e, g_z1

@@ -449,3 +449,46 @@ def test_edge_block_bwd_from_stored_h1_matches_recompute(N, first_layer):
     assert rel_err(gw1b[:, :128], gw1a[:, :128]) < 1e-5
     for x, y in zip(gb, ga):
         assert rel_err(x, y) < 1e-5
+
+
+@pytest.mark.parametrize("N", [300, 40000])
+def test_node_block_fwd_keeps_h1_and_bwd_from_it_matches_recompute(N):
+    """mgn_node_block_fwd_tc == mgn_mlp3_fwd2_tc node form (+ h1), and mgn_edge_block_bwd_tc(add_gout=0) from that h1 ==
+    mgn_mlp3_bwd_tc node form (g_agg, g_z1 written into a [N,384] column block, parameter gradients)."""
+    from modulus_b200 import ops
+
+    g = torch.Generator().manual_seed(N)
+    r = lambda *s: torch.randn(*s, generator=g)
+    d = dev_params(make_params(256, seed=17))
+    agg, nfe = r(N, 128).to(DEV).bfloat16(), r(N, 128).to(DEV).bfloat16()
+    P = (r(N, 384) * 0.5).to(DEV).bfloat16()
+    g_n = r(N, 128).to(DEV).bfloat16()
+    args = (d["w1"][:, :128], d["b1"], d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], d["beta"])
+    ref = ops.mlp3_fwd2_tc(agg, None, None, P, None, 256, None, None, 0, N, *args, residual=nfe)
+    h1 = torch.empty(N, 128, dtype=torch.bfloat16, device=DEV)
+    out = ops.node_block_fwd_tc(agg, P, 256, nfe, *args, h1_out=h1)
+    ops.tc_check(DEV)
+    assert torch.equal(out, ref)
+    z1 = agg.float() @ d["w1"][:, :128].bfloat16().float().T + P[:, 256:].float() + d["b1"]
+    assert rel_err(h1.float(), torch.relu(z1)) < 1.5e-2
+
+    def grads():
+        return torch.zeros(128, 256, device=DEV), [torch.empty(128, device=DEV), torch.empty(128, 128, device=DEV),
+                                                   torch.empty(128, device=DEV), torch.empty(128, 128, device=DEV),
+                                                   torch.empty(128, device=DEV), torch.empty(128, device=DEV),
+                                                   torch.empty(128, device=DEV)]
+
+    gw_a, ga = grads()
+    Ta = torch.full((N, 384), 2.0, dtype=torch.bfloat16, device=DEV)
+    ref_gagg, _ = ops.mlp3_bwd_tc(agg, None, None, P, None, 256, None, None, 0, g_n, None, None, N, d["w1"][:, :128], d["b1"],
+                                  d["w2"], d["b2"], d["w3"], d["b3"], d["gamma"], 128, 1e-5, True, False, True,
+                                  gw_a[:, :128], *ga, g_z1_out=Ta[:, 256:])
+    gw_b, gb = grads()
+    Tb = torch.full((N, 384), 2.0, dtype=torch.bfloat16, device=DEV)
+    out_gagg, _ = ops.edge_block_bwd_tc(agg, h1, g_n, None, None, None, d["w1"][:, :128], d["w2"], d["b2"], d["w3"], d["b3"],
+                                        d["gamma"], 1e-5, gw_b[:, :128], *gb, add_gout=False, g_z1_out=Tb[:, 256:])
+    ops.tc_check(DEV)
+    assert torch.equal(out_gagg, ref_gagg) and torch.equal(Ta, Tb)
+    assert rel_err(gw_b[:, :128], gw_a[:, :128]) < 1e-5
+    for x, y in zip(gb, ga):
+        assert rel_err(x, y) < 1e-5
