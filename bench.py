@@ -323,6 +323,8 @@ def run_b200(args, rank, world, local_rank):
                 roof = {"kernel": top, "bound": "tensor", "achieved": ach, "peak": peaks["tc_sust"], "unit": "TFLOP/s",
                         "frac": ach / peaks["tc_sust"], "traffic": None}
             roof["traffic"] = load_traffic(top, args.workload) if world == 1 else None
+            if roof["traffic"] is not None:
+                roof["traffic_launch"] = "one edge-form launch (E rows) under ncu --set full; avg_launch_ms averages edge and node launches"
             roof["avg_launch_ms"] = avg_ms
             roof["share_of_step"] = shares[top]["ms"] / max(sum(v["ms"] for v in shares.values()), 1e-9)
             roof["peak_source"] = peaks["src"]

@@ -11,7 +11,7 @@ timeout 600 python bench.py --workload c2 --no-cpu > gpurun_out/bench_c2.json 2>
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -c 800 gpurun_out/bench_ref.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_c3.csv python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log
-for k in mlp3_bwd_tc_kernel edge_fwd3_kernel mlp3_fwd2_tc_kernel segment_sum_batch_kernel node_gemm_tc_kernel; do
+for k in edge_bwd2_kernel edge_fwd3_kernel mlp3_bwd_tc_kernel mlp3_fwd2_tc_kernel segment_sum_batch_kernel node_gemm_tc_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/r01_full_$k python tools/prof_kernels.py 1000 1000 1 > gpurun_out/ncu_$k.log 2>&1
 done
 ls -la gpurun_out | head -30

@@ -48,7 +48,7 @@ if __name__ == "__main__":
     if os.path.exists(ll):
         launch_list(ll, f"ncu launch list, `bench.py --steps 1 --warmup 3 --no-cpu` (c3, {tag})", os.path.join(PROF, f"{tag}_launches_c3.md"))
     traffic = {"c3": {}}
-    entry = {"mlp3_bwd_tc_kernel": "mgn_mlp3_bwd_tc", "edge_fwd3_kernel": "mgn_edge_block_fwd_tc", "mlp3_fwd2_tc_kernel": "mgn_mlp3_fwd2_tc", "segment_sum_batch_kernel": "mgn_segment_sum",
+    entry = {"edge_bwd2_kernel": "mgn_edge_block_bwd_tc", "mlp3_bwd_tc_kernel": "mgn_mlp3_bwd_tc", "edge_fwd3_kernel": "mgn_edge_block_fwd_tc", "mlp3_fwd2_tc_kernel": "mgn_mlp3_fwd2_tc", "segment_sum_batch_kernel": "mgn_segment_sum",
              "node_gemm_tc_kernel": "mgn_node_gemm_tc"}
     with open(os.path.join(PROF, f"{tag}_ncu_full_summary.md"), "w") as f:
         f.write(f"# ncu --set full --clock-control none, one launch each at the c3 size (tools/prof_kernels.py 1000 1000 1), {tag}\n\n")
