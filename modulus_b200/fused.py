@@ -100,6 +100,22 @@ class HaloContext:
         if e1 > e0:
             self.src_own = own_rows[src[e0:e1] - own_off].to(torch.int32).contiguous()
         self.halo_rows = self.n_src_local - own_cnt
+        # ---- remote-only exchange (used when the backward does not need the exchanged rows again, KEEP_H1): the
+        # rank's own rows never travel.  Sources are re-indexed into an extended table [partition rows ; halo rows]:
+        # own source k -> its partition row, halo source -> n_part + its slot in the received (rank-ordered) rows.
+        xp = self.xplan
+        so, sc = int(sum(xp.send_splits[:rank])), int(xp.send_splits[rank])
+        self.send_idx_remote = torch.cat([xp.send_idx[:so], xp.send_idx[so + sc:]]).contiguous()
+        self.send_splits_r = [0 if r == rank else int(v) for r, v in enumerate(xp.send_splits)]
+        self.recv_splits_r = [0 if r == rank else int(v) for r, v in enumerate(xp.recv_splits)]
+        slot = torch.where(src < own_off, src, src - own_cnt)
+        own_of_src = own_rows[(src - own_off).clamp(0, max(own_cnt - 1, 0))] if own_cnt > 0 else torch.zeros_like(src)
+        self.src_ext = torch.where(owned, own_of_src, self.n_part + slot).to(torch.int32).contiguous()
+        self.csrx_offsets, self.csrx_eids = ops._group_by_key(self.src_ext, self.n_part + self.halo_rows)
+        # received halo gradients touch only the few partition rows this rank sends out: group them by those rows
+        self.sent_rows, inv = torch.unique(self.send_idx_remote.long(), return_inverse=True)
+        self.acc_remote = ops._group_by_key(inv.to(torch.int32).contiguous(), int(self.sent_rows.numel()))
+        self.remote_only = du._backend_has_alltoall(self.group)
 
     # forward: pack -> all-to-all (async) ; returns (work, recv buffer [n_src_local, H], packed keep-alive)
     def start_fwd(self, P: Tensor):
@@ -129,6 +145,33 @@ class HaloContext:
             return work, recv
         return None, du.all_to_all_rows(g_rows, xp.recv_splits, xp.send_splits, group=self.group)
 
+    # remote-only variants: only halo rows are packed / sent / accumulated
+    def start_fwd_remote(self, P: Tensor):
+        import torch.distributed as dist
+
+        n = int(self.send_idx_remote.numel())
+        packed = ops.gather_rows(P, 0, H, self.send_idx_remote, n) if n > 0 else P.new_empty((0, H))
+        recv = P.new_empty((self.halo_rows, H))
+        work = dist.all_to_all_single(recv, packed, list(self.recv_splits_r), list(self.send_splits_r), group=self.group,
+                                      async_op=True)
+        return work, recv, packed
+
+    def start_bwd_remote(self, g_halo: Tensor):
+        import torch.distributed as dist
+
+        recv = g_halo.new_empty((int(self.send_idx_remote.numel()), H))
+        work = dist.all_to_all_single(recv, g_halo, list(self.send_splits_r), list(self.recv_splits_r), group=self.group,
+                                      async_op=True)
+        return work, recv
+
+    def finish_bwd_remote(self, work, recv: Tensor, out: Tensor, out_col0: int):
+        work.wait()
+        if recv.shape[0] > 0:  # fixed-order sums per sent row, then one add per (unique) row
+            offsets, ids = self.acc_remote
+            part = ops.segment_sum(recv, 0, H, offsets, ids, int(self.sent_rows.numel()))
+            cols = out[:, out_col0:out_col0 + H]
+            cols[self.sent_rows] = (cols[self.sent_rows].float() + part.float()).to(out.dtype)
+
     def finish_bwd(self, work, recv: Tensor, out: Tensor, out_col0: int):
         if work is not None:
             work.wait()
@@ -139,6 +182,11 @@ class HaloContext:
 # ----------------------------------------------------------------------------------------
 # processor
 # ----------------------------------------------------------------------------------------
+def Ps_saved(halo, remote_only: bool) -> bool:
+    """Whether the exchanged source-projection table of a layer is kept for the backward pass."""
+    return halo is not None and not remote_only
+
+
 class FusedProcessorFn(torch.autograd.Function):
     """args: nfeat [N,H] bf16, efeat [E,H] bf16, plan, L, then 16 parameters per layer:
     edge (w1 [H,3H], b1, w2, b2, w3, b3, gamma, beta), node (w1 [H,2H], b1, w2, b2, w3, b3, gamma, beta)."""
@@ -152,7 +200,12 @@ class FusedProcessorFn(torch.autograd.Function):
         for l in range(L):
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
-            P = _node_linear(nfeat, wp)  # [N, 3H]
+            remote_only = halo is not None and halo.remote_only and KEEP_H1
+            if remote_only:  # P with room for the halo rows of its source-projection columns behind the partition rows
+                P_ext = torch.empty((N + halo.halo_rows, 3 * H), dtype=BF16, device=nfeat.device)
+                P = _node_linear(nfeat, wp, out=P_ext[:N])
+            else:
+                P = _node_linear(nfeat, wp)  # [N, 3H]
             agg = None
             # relu(z1) of the edge MLP, kept for the backward pass (mgn_edge_block_bwd_tc starts from it)
             h1 = torch.empty((E, H), dtype=BF16, device=efeat.device) if KEEP_H1 else None
@@ -162,7 +215,11 @@ class FusedProcessorFn(torch.autograd.Function):
             else:
                 efeat_new = torch.empty_like(efeat)
                 agg = torch.empty((N, H), dtype=BF16, device=efeat.device)
-                work, Ps, keep = halo.start_fwd(P)  # all-to-all of the source projections, in flight
+                if remote_only:
+                    work, recv_r, keep = halo.start_fwd_remote(P)  # halo rows only; own rows never travel
+                    Ps = None
+                else:
+                    work, Ps, keep = halo.start_fwd(P)  # all-to-all of the source projections, in flight
                 # three launches over consecutive row ranges share one aggregation record array (row order)
                 ranges = [(0, halo.e0), (halo.e0, halo.e1), (halo.e1, E)]
                 tiles = [-(-(hi - lo) // 128) for lo, hi in ranges]
@@ -176,11 +233,19 @@ class FusedProcessorFn(torch.autograd.Function):
                                                    efeat_new[lo:hi], agg, ws, lo, sum(tiles), sum(tiles[:k]),
                                                    h1_out=None if h1 is None else h1[lo:hi])
 
-                run(1, P, halo.src_own)  # interior edges overlap the exchange
-                if work is not None:
+                if remote_only:
+                    run(1, P_ext, halo.src_ext[halo.e0:halo.e1])  # interior edges (own sources) overlap the exchange
                     work.wait()
-                run(0, Ps, src[:halo.e0])
-                run(2, Ps, src[halo.e1:])
+                    if halo.halo_rows > 0:
+                        P_ext[N:, :H].copy_(recv_r)
+                    run(0, P_ext, halo.src_ext[:halo.e0])
+                    run(2, P_ext, halo.src_ext[halo.e1:])
+                else:
+                    run(1, P, halo.src_own)  # interior edges overlap the exchange
+                    if work is not None:
+                        work.wait()
+                    run(0, Ps, src[:halo.e0])
+                    run(2, Ps, src[halo.e1:])
                 ops.agg_fixup(ws, sum(tiles), agg, N)
                 del keep
             if agg is None:
@@ -188,9 +253,10 @@ class FusedProcessorFn(torch.autograd.Function):
             h1n = torch.empty((N, H), dtype=BF16, device=nfeat.device) if KEEP_H1 else None
             nfeat_new = ops.node_block_fwd_tc(agg, P, 2 * H, nfeat, nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6],
                                               nw[7], eps=eps, h1_out=h1n)
-            saved += [efeat, nfeat, agg, P] + ([Ps] if halo is not None else []) + ([h1, h1n] if h1 is not None else [])
+            saved += [efeat, nfeat, agg, P] + ([Ps] if Ps_saved(halo, remote_only) else []) + ([h1, h1n] if h1 is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
         ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1 = plan, L, eps, halo, KEEP_H1
+        ctx.remote_only = halo is not None and halo.remote_only and KEEP_H1
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
         return nfeat
@@ -199,7 +265,7 @@ class FusedProcessorFn(torch.autograd.Function):
     def backward(ctx, g_n: Tensor):
         plan: GraphPlan = ctx.plan
         L, eps, halo = ctx.L, ctx.eps, ctx.halo
-        ns = (4 if halo is None else 5) + (2 if ctx.keep_h1 else 0)
+        ns = (5 if Ps_saved(halo, ctx.remote_only) else 4) + (2 if ctx.keep_h1 else 0)
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         saved = ctx.saved_tensors[:ctx.n_saved]
@@ -234,7 +300,7 @@ class FusedProcessorFn(torch.autograd.Function):
                 go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
             else:
                 go1, go1_idx, go2, go2_idx = g_e, None, g_agg, dst
-            g1 = P if halo is None else saved[ns * l + 4]  # source projections: local table or exchanged rows
+            g1 = saved[ns * l + 4] if Ps_saved(halo, ctx.remote_only) else P  # exchanged rows / local table
             if ctx.keep_h1:
                 h1 = saved[ns * l + ns - 2]
                 g_e, g_z1e = ops.edge_block_bwd_tc(efeat, h1, go1, go1_idx, go2, go2_idx, ew[0][:, :H], ew[2], ew[3], ew[4],
@@ -249,6 +315,14 @@ class FusedProcessorFn(torch.autograd.Function):
             if halo is None:
                 ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
                 ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+            elif ctx.remote_only:
+                # own sources accumulate straight into their partition rows; only the halo rows' gradients travel
+                ops.segment_sum(g_z1e, 0, H, halo.csrx_offsets[:N + 1], halo.csrx_eids, N, out=T, out_col0=0)
+                g_halo = (ops.segment_sum(g_z1e, 0, H, halo.csrx_offsets[N:], halo.csrx_eids, halo.halo_rows)
+                          if halo.halo_rows > 0 else g_z1e.new_empty((0, H)))
+                work, recv = halo.start_bwd_remote(g_halo)
+                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+                halo.finish_bwd_remote(work, recv, T, 0)
             else:
                 # gradient of every referenced source row (incl. halo rows) goes back to its owner while the
                 # destination-side sum runs; owners accumulate in a fixed order
