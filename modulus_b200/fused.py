@@ -58,6 +58,27 @@ def _node_wgrad(g: Tensor, x: Tensor) -> Tensor:
 # ----------------------------------------------------------------------------------------
 # halo exchange of the source-row projections (partitioned graphs)
 # ----------------------------------------------------------------------------------------
+def remote_only_index(src: Tensor, own_off: int, own_cnt: int, own_rows: Tensor, n_part: int, send_idx: Tensor,
+                      send_splits: Sequence[int], rank: int):
+    """Pure index maps of the remote-only halo exchange (see HaloContext).
+
+    src        [E]  local source id of every edge, in the rank-ordered local source space of the reference
+                    (distributed_graph.py:336-368): [rows owned by rank 0 | rank 1 | ...]
+    own_rows   [own_cnt] partition row of the k-th own source (= scatter_indices[rank])
+    send_idx   peer-major partition rows this rank sends (cat of scatter_indices), send_splits its split sizes
+
+    Returns (src_ext [E]: own source -> its partition row, halo source -> n_part + slot among the received rows in
+    rank order; send_idx_remote: send_idx without the own block)."""
+    src = src.long()
+    owned = (src >= own_off) & (src < own_off + own_cnt)
+    slot = torch.where(src < own_off, src, src - own_cnt)
+    own_of_src = own_rows.long()[(src - own_off).clamp(0, max(own_cnt - 1, 0))] if own_cnt > 0 else torch.zeros_like(src)
+    src_ext = torch.where(owned, own_of_src, n_part + slot)
+    so, sc = int(sum(send_splits[:rank])), int(send_splits[rank])
+    send_idx_remote = torch.cat([send_idx[:so], send_idx[so + sc:]])
+    return src_ext, send_idx_remote
+
+
 class HaloContext:
     """Per-graph state of the fused path on a partitioned graph (reference: DistributedGraph
     .get_src_node_features_in_local_graph, distributed_graph.py:999-1011 -> indexed_all_to_all_v).
@@ -104,13 +125,12 @@ class HaloContext:
         # rank's own rows never travel.  Sources are re-indexed into an extended table [partition rows ; halo rows]:
         # own source k -> its partition row, halo source -> n_part + its slot in the received (rank-ordered) rows.
         xp = self.xplan
-        so, sc = int(sum(xp.send_splits[:rank])), int(xp.send_splits[rank])
-        self.send_idx_remote = torch.cat([xp.send_idx[:so], xp.send_idx[so + sc:]]).contiguous()
+        src_ext, send_idx_remote = remote_only_index(src, own_off, own_cnt, own_rows, self.n_part, xp.send_idx,
+                                                     xp.send_splits, rank)
+        self.send_idx_remote = send_idx_remote.contiguous()
         self.send_splits_r = [0 if r == rank else int(v) for r, v in enumerate(xp.send_splits)]
         self.recv_splits_r = [0 if r == rank else int(v) for r, v in enumerate(xp.recv_splits)]
-        slot = torch.where(src < own_off, src, src - own_cnt)
-        own_of_src = own_rows[(src - own_off).clamp(0, max(own_cnt - 1, 0))] if own_cnt > 0 else torch.zeros_like(src)
-        self.src_ext = torch.where(owned, own_of_src, self.n_part + slot).to(torch.int32).contiguous()
+        self.src_ext = src_ext.to(torch.int32).contiguous()
         self.csrx_offsets, self.csrx_eids = ops._group_by_key(self.src_ext, self.n_part + self.halo_rows)
         # received halo gradients touch only the few partition rows this rank sends out: group them by those rows
         self.sent_rows, inv = torch.unique(self.send_idx_remote.long(), return_inverse=True)

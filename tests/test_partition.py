@@ -201,3 +201,74 @@ def test_large_mesh_partition_is_fast_and_consistent():
     assert gp.num_local_src_nodes == sum(s[3] for s in gp.sizes)
     assert int(gp.local_indices.max()) == gp.num_local_src_nodes - 1
     assert int(gp.local_offsets[-1]) == gp.num_local_indices
+
+
+@pytest.mark.parametrize("P", [2, 3])
+def test_remote_only_halo_index_emulated_exchange(P):
+    """fused.remote_only_index: with only the halo rows exchanged, every rank's extended table [partition rows ; halo rows]
+    read through src_ext equals the reference halo exchange (get_src_node_features_in_local_graph,
+    distributed_graph.py:999-1011) read through the local source ids -- and the transposed accumulate gives every
+    owner the sum over all ranks' edges.  The all-to-all is emulated by indexing (partition functions are pure)."""
+    from modulus_b200.fused import remote_only_index
+    from modulus_b200.mesh import random_graph_csc
+
+    N = 60
+    off, idx = random_graph_csc(N, N, 1, 5, seed=P)
+    parts = [partition_graph_nodewise(off, idx, P, r, "cpu") for r in range(P)]
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(N, 4, generator=g, dtype=torch.float64)                    # global source features
+    ext, sends, srcs = [], [], []
+    for r, gp in enumerate(parts):
+        own_off = int(sum(gp.sizes[q][r] for q in range(r)))
+        own_cnt = int(gp.sizes[r][r])
+        n_part = int(gp.num_src_nodes_in_each_partition[r])
+        src = gp.local_indices.long()
+        send_idx = torch.cat([i.long() for i in gp.scatter_indices])
+        send_splits = [int(gp.sizes[r][q]) for q in range(P)]
+        src_ext, send_remote = remote_only_index(src, own_off, own_cnt, gp.scatter_indices[r], n_part, send_idx, send_splits, r)
+        ext.append((src_ext, n_part, own_off, own_cnt)); sends.append((send_remote, send_splits)); srcs.append(src)
+    part_feat = [feat[gp.map_partitioned_src_ids_to_global.long()] for gp in parts]   # rows each rank owns
+    # forward: rank r receives, in rank order, what every other rank packs for it
+    for r, gp in enumerate(parts):
+        recv = []
+        for q in range(P):
+            if q == r:
+                continue
+            send_remote, splits = sends[q]
+            before = sum(splits[:r]) - (splits[q] if q < r else 0)                # position of the block for r without q's own block
+            recv.append(part_feat[q][send_remote[before:before + splits[r]]])
+        src_ext, n_part, own_off, own_cnt = ext[r]
+        table = torch.cat([part_feat[r]] + recv) if recv else part_feat[r]
+        got = table[src_ext]
+        # reference semantics: local source id -> global id through the rank-ordered unique source list
+        uniq_global = torch.cat([parts[q].map_partitioned_src_ids_to_global.long()[parts[q].scatter_indices[r].long()]
+                                 for q in range(P)])
+        want = feat[uniq_global[srcs[r]]]
+        assert torch.equal(got, want), r
+    # backward: per-edge gradients summed per extended row; halo rows go back to their owners
+    g_edge = [torch.randn(int(s.numel()), 4, generator=g, dtype=torch.float64) for s in srcs]
+    total = torch.zeros(N, 4, dtype=torch.float64)
+    for r, gp in enumerate(parts):
+        uniq_global = torch.cat([parts[q].map_partitioned_src_ids_to_global.long()[parts[q].scatter_indices[r].long()]
+                                 for q in range(P)])
+        total.index_add_(0, uniq_global[srcs[r]], g_edge[r])
+    acc = [torch.zeros(int(e[1]), 4, dtype=torch.float64) for e in ext]
+    halo_grad = []
+    for r in range(P):
+        src_ext, n_part, own_off, own_cnt = ext[r]
+        n_halo = int(parts[r].num_local_src_nodes) - own_cnt
+        full = torch.zeros(n_part + n_halo, 4, dtype=torch.float64).index_add_(0, src_ext, g_edge[r])
+        acc[r] += full[:n_part]
+        halo_grad.append(full[n_part:])
+    for r in range(P):                                                               # rank r's halo rows, rank-ordered blocks
+        pos = 0
+        for q in range(P):
+            if q == r:
+                continue
+            cnt = int(parts[r].sizes[q][r])
+            send_remote, splits = sends[q]
+            before = sum(splits[:r]) - (splits[q] if q < r else 0)
+            acc[q].index_add_(0, send_remote[before:before + cnt], halo_grad[r][pos:pos + cnt])
+            pos += cnt
+    for r, gp in enumerate(parts):
+        assert torch.allclose(acc[r], total[gp.map_partitioned_src_ids_to_global.long()], atol=1e-12), r
