@@ -273,7 +273,10 @@ int mgn_node_block_fwd_tc(const void* agg, const void* p_tab, int64_t p_ld, int6
  * gradients of the destination / source projection rows) and the fp32 parameter gradients of W1[:, :128] (row stride
  * ld_gw1), b1, W2, b2, W3, b3, gamma, beta (deterministic per-CTA partials + ordered reduction).  add_gout = 1: the
  * block's residual runs over the layer-1 input rows (edge block: g_efeat = g_z1 W1a + g_out); 0 for the node block,
- * whose layer-1 input is the aggregate (efeat := agg, h1 from mgn_node_block_fwd_tc, g_efeat := g_agg). */
+ * whose layer-1 input is the aggregate (efeat := agg, h1 from mgn_node_block_fwd_tc, g_efeat := g_agg).
+ * csc_offsets (nullable; edge block only): also write gz1_agg[v] = sum of g_z1 over the incoming edges of v (rows are
+ * CSC-ordered edges with destinations dst_idx; workspace mgn_mlp3_fwd2_agg_workspace_bytes(n_edges)) -- the gradient
+ * of the destination projection rows, taken from the g_z1 tiles while they are in shared memory. */
 size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges);
 int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, const int32_t* go1_idx,
                           const void* go2, const int32_t* go2_idx, int64_t n_edges, const float* w1,
@@ -281,7 +284,9 @@ int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, co
                           const float* gamma, float eps, int add_gout, void* g_efeat, void* g_z1, int64_t g_z1_ld,
                           float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
                           float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
-                          int* status, mgn_stream_t stream);
+                          const int32_t* csc_offsets, const int32_t* dst_idx, int64_t n_dst, void* gz1_agg,
+                          int64_t ld_agg, void* agg_workspace, size_t agg_workspace_bytes, int* status,
+                          mgn_stream_t stream);
 int mgn_debug_set_edge_bwd2_timing(void* dev_buf);
 
 /* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):

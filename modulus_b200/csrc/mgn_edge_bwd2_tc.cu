@@ -25,6 +25,7 @@
 #include "mgn_reduce.cuh"
 #include "mgn_tile.cuh"
 #include "mgn_tma.cuh"
+#include "mgn_agg.cuh"
 
 namespace mgn {
 namespace bwd2 {
@@ -42,6 +43,14 @@ struct Params {
   const float *w1, *w2, *b2, *w3, *b3, *gamma;
   long long ld_w1;
   float eps;
+  // fused destination sums of the g_z1 rows (mgn_agg.cuh; kAgg instances): CSC offsets, destination of every row
+  // (ascending), output table [n_dst,128] with row stride ld_agg, boundary records
+  const int32_t* seg_off;
+  const int32_t* seg_id;
+  bf16* agg;
+  long long ld_agg;
+  float* agg_part;
+  int32_t* agg_part_v;
   float* partials;      // [gridDim.x][Part::kTotal]
   long long part_floats;
   int* status;
@@ -91,7 +100,9 @@ __device__ __forceinline__ void tma_tile(uint8_t* buf, const CUtensorMap* map, l
 
 // kAddGout: the block's residual runs over the layer-1 input rows (edge block: g_a = g_z1 W1a + g_out); false for the
 // node block.  Compile-time: a run-time flag in the last epilogue pass costs the edge instance 9 % through spills.
-template <bool kAddGout>
+// kAgg: the reducer warps also sum the g_z1 tile by destination segment (they have the slack for it in this kernel:
+// no projection-row gathers).
+template <bool kAddGout, bool kAgg>
 __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -296,6 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
       if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
       MGN_W(B_E + 3, par);
       colsum_tile(bH1, mt, cs_b1);
+      if (kAgg) agg::tile_segment_sum(bH1, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
       if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X once g_efeat has left
@@ -688,7 +700,9 @@ extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const vo
                                      const float* gamma, float eps, int add_gout, void* g_efeat, void* g_z1, int64_t g_z1_ld,
                                      float* g_w1, int64_t ld_gw1, float* g_b1, float* g_w2, float* g_b2, float* g_w3,
                                      float* g_b3, float* g_gamma, float* g_beta, void* workspace, size_t workspace_bytes,
-                                     int* status, mgn_stream_t stream) {
+                                     const int32_t* csc_offsets, const int32_t* dst_idx, int64_t n_dst, void* gz1_agg,
+                                     int64_t ld_agg, void* agg_workspace, size_t agg_workspace_bytes, int* status,
+                                     mgn_stream_t stream) {
   const int64_t M = n_edges;
   MGN_CHECK_ARG(M >= 0 && w1 && w2 && w3 && gamma && ld_w1 >= bwd2::kH);
   if (M == 0) return MGN_OK;
@@ -716,18 +730,34 @@ extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const vo
   e |= tma_make_rows_map(&p.m_ga, g_efeat, M, bwd2::kH, 128);
   e |= tma_make_rows_map(&p.m_gz1, g_z1, M, g_z1_ld, 128);
   if (e != 0) return MGN_EINVAL;
+  const bool with_agg = csc_offsets != nullptr;
+  if (with_agg) {  // rows are CSC-ordered edges with destinations dst_idx
+    MGN_CHECK_ARG(add_gout && dst_idx && gz1_agg && n_dst > 0 && ld_agg >= bwd2::kH && ld_agg % 8 == 0 &&
+                  (reinterpret_cast<uintptr_t>(gz1_agg) & 15) == 0 && agg_workspace != nullptr);
+    if (agg_workspace_bytes < agg::workspace_bytes(M)) return MGN_EWORKSPACE;
+    const long long n_tiles_ = (M + bwd2::kRows - 1) / bwd2::kRows;
+    p.seg_off = csc_offsets;
+    p.seg_id = dst_idx;
+    p.agg = static_cast<bf16*>(gz1_agg);
+    p.ld_agg = ld_agg;
+    p.agg_part = static_cast<float*>(agg_workspace);
+    p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * n_tiles_ * bwd2::kH);
+  }
   static bool configured = false;
   if (!configured) {
-    cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+    cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
     if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+      ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
     if (ce != cudaSuccess) return static_cast<int>(ce);
     configured = true;
   }
   cudaStream_t st = as_stream(stream);
   const int grid = bwd2_grid(M);
-  if (add_gout) bwd2::edge_bwd2_kernel<true><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
-  else bwd2::edge_bwd2_kernel<false><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  if (with_agg) bwd2::edge_bwd2_kernel<true, true><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  else if (add_gout) bwd2::edge_bwd2_kernel<true, false><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
+  else bwd2::edge_bwd2_kernel<false, false><<<grid, bwd2::kThreads, bwd2::Smem::kTotal, MGN_ST(st)>>>(p);
   int rc = mgn_launch_status();
   if (rc != MGN_OK) return rc;
   ReduceParams rp{};
@@ -746,5 +776,10 @@ extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const vo
   rp.seg[ns++] = ReduceSeg{g_beta, bwd2::kH, 1, bwd2::kH, PT::kBeta, bwd2::kH};
   rp.n_seg = ns;
   reduce_cta_partials_kernel<<<dim3(64, ns), 256, 0, MGN_ST(st)>>>(rp);
+  rc = mgn_launch_status();
+  if (rc != MGN_OK || !with_agg) return rc;
+  const long long n_rec = 2 * ((M + bwd2::kRows - 1) / bwd2::kRows);
+  agg::agg_fixup_kernel<<<static_cast<unsigned>((n_rec * 32 + 255) / 256), 256, 0, MGN_ST(st)>>>(
+      p.agg_part, p.agg_part_v, n_rec, p.agg, p.ld_agg, n_dst);
   return mgn_launch_status();
 }

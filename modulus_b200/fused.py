@@ -37,6 +37,7 @@ from .ops import GraphPlan, TC_HIDDEN, _p, _stream
 
 Tensor = torch.Tensor
 ENABLED = True  # tests flip this to compare against the generic (unfused) kernels
+FUSE_BWD_DST_SUM = True  # the h1 backward kernel also emits the destination sums of g_z1 (its reducer warps have the slack)
 KEEP_H1 = True  # the edge forward stores relu(z1); the edge backward starts from it instead of recomputing GEMM1
 H = TC_HIDDEN
 BF16 = torch.bfloat16
@@ -323,25 +324,31 @@ class FusedProcessorFn(torch.autograd.Function):
             g1 = saved[ns * l + 4] if Ps_saved(halo, ctx.remote_only) else P  # exchanged rows / local table
             if ctx.keep_h1:
                 h1 = saved[ns * l + ns - 2]
+                fuse_dst = FUSE_BWD_DST_SUM  # destination sums T[:, H:2H] out of the same kernel
                 g_e, g_z1e = ops.edge_block_bwd_tc(efeat, h1, go1, go1_idx, go2, go2_idx, ew[0][:, :H], ew[2], ew[3], ew[4],
                                                    ew[5], ew[6], eps, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5],
-                                                   ge[6], ge[7])
+                                                   ge[6], ge[7], csc_offsets=plan.csc_offsets if fuse_dst else None,
+                                                   dst=dst if fuse_dst else None,
+                                                   dst_sum_out=T[:, H:2 * H] if fuse_dst else None)
             else:
                 g_e, g_z1e = ops.mlp3_bwd_tc(efeat, None, None, g1, src, 0, P, dst, H, go1, go2, go2_idx, E,
                                              ew[0][:, :H], ew[1], ew[2], ew[3], ew[4], ew[5], ew[6], H, eps,
                                              True, True, True, gew1[:, :H], ge[1], ge[2], ge[3], ge[4], ge[5], ge[6],
                                              ge[7], go1_idx=go1_idx)
             # ---- per-node reductions of the gathered-row gradient, then the node-level GEMMs
+            have_dst = ctx.keep_h1 and FUSE_BWD_DST_SUM
             if halo is None:
                 ops.segment_sum(g_z1e, 0, H, plan.csr_offsets, plan.csr_eids, plan.n_src, out=T, out_col0=0)
-                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+                if not have_dst:
+                    ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
             elif ctx.remote_only:
                 # own sources accumulate straight into their partition rows; only the halo rows' gradients travel
                 ops.segment_sum(g_z1e, 0, H, halo.csrx_offsets[:N + 1], halo.csrx_eids, N, out=T, out_col0=0)
                 g_halo = (ops.segment_sum(g_z1e, 0, H, halo.csrx_offsets[N:], halo.csrx_eids, halo.halo_rows)
                           if halo.halo_rows > 0 else g_z1e.new_empty((0, H)))
                 work, recv = halo.start_bwd_remote(g_halo)
-                ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
+                if not have_dst:
+                    ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
                 halo.finish_bwd_remote(work, recv, T, 0)
             else:
                 # gradient of every referenced source row (incl. halo rows) goes back to its owner while the

@@ -575,7 +575,8 @@ def agg_fixup(ws: Tensor, total_tiles: int, agg: Tensor, n_dst: int) -> None:
 def edge_block_bwd_tc(efeat: Tensor, h1: Tensor, go1: Tensor, go1_idx: Optional[Tensor], go2: Optional[Tensor],
                       go2_idx: Optional[Tensor], w1a: Tensor, w2, b2, w3, b3, gamma, eps: float,
                       g_w1a: Tensor, g_b1, g_w2, g_b2, g_w3, g_b3, g_gamma, g_beta, add_gout: bool = True,
-                      g_z1_out: Optional[Tensor] = None):
+                      g_z1_out: Optional[Tensor] = None, csc_offsets: Optional[Tensor] = None,
+                      dst: Optional[Tensor] = None, dst_sum_out: Optional[Tensor] = None):
     """MeshEdgeBlock backward from the stored h1 (include/mgn_b200.h: mgn_edge_block_bwd_tc).  Returns
     (g_efeat, g_z1) bf16 [E,128]; parameter gradients go to the caller-allocated fp32 tensors."""
     E = efeat.shape[0]
@@ -584,11 +585,14 @@ def edge_block_bwd_tc(efeat: Tensor, h1: Tensor, go1: Tensor, go1_idx: Optional[
     g_z1 = g_z1_out if g_z1_out is not None else torch.empty((E, TC_HIDDEN), dtype=torch.bfloat16, device=dev)
     nbytes = _lib.load().mgn_edge_block_bwd_tc_workspace_bytes(E)
     ws = _ws(nbytes, dev)
+    abytes = _lib.load().mgn_mlp3_fwd2_agg_workspace_bytes(E) if csc_offsets is not None else 0
+    aws = _ws(abytes, dev) if csc_offsets is not None else None
     call("mgn_edge_block_bwd_tc", _p(efeat), _p(h1), _p(go1), _p(go1_idx), _p(go2), _p(go2_idx), E, _p(w1a), w1a.stride(0),
          _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), eps, int(add_gout), _p(g_e), _p(g_z1), g_z1.stride(0), _p(g_w1a),
          g_w1a.stride(0),
-         _p(g_b1), _p(g_w2), _p(g_b2), _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes, _p(tc_status(dev)),
-         _stream())
+         _p(g_b1), _p(g_w2), _p(g_b2), _p(g_w3), _p(g_b3), _p(g_gamma), _p(g_beta), _p(ws), nbytes,
+         _p(csc_offsets), _p(dst), 0 if dst_sum_out is None else dst_sum_out.shape[0], _p(dst_sum_out),
+         0 if dst_sum_out is None else dst_sum_out.stride(0), _p(aws), abytes, _p(tc_status(dev)), _stream())
     return g_e, g_z1
 
 

@@ -449,6 +449,17 @@ def test_edge_block_bwd_from_stored_h1_matches_recompute(N, first_layer):
     assert rel_err(gw1b[:, :128], gw1a[:, :128]) < 1e-5
     for x, y in zip(gb, ga):
         assert rel_err(x, y) < 1e-5
+    # the same launch can emit the destination sums of g_z1 (gradient of the destination projection rows)
+    T = torch.full((N, 384), 4.0, dtype=torch.bfloat16, device=DEV)
+    gw1c, gc = grads()
+    ge3, gz3 = ops.edge_block_bwd_tc(A, h1, go1, go1_idx, go2, go2_idx, d["w1"][:, :128], d["w2"], d["b2"], d["w3"], d["b3"],
+                                     d["gamma"], 1e-5, gw1c[:, :128], *gc, csc_offsets=offsets.to(DEV), dst=dst,
+                                     dst_sum_out=T[:, 128:256])
+    ops.tc_check(DEV)
+    assert torch.equal(ge3, ref_ge) and torch.equal(gz3, ref_gz1)
+    want = torch.zeros(N, 128, dtype=torch.float64, device=DEV).index_add_(0, dst.long(), gz3.double())
+    assert rel_err(T[:, 128:256].float(), want) < 1e-2
+    assert bool((T[:, :128] == 4).all()) and bool((T[:, 256:] == 4).all())
 
 
 @pytest.mark.parametrize("N", [300, 40000])

@@ -54,6 +54,13 @@ def bwd2():
     return ops.edge_block_bwd_tc(efeat, h1s, g_e, None, g_agg, plan.dst, w1[:, :128], w2, b2, w3, b3, gamma, 1e-5,
                                  gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4])
 
+Tz = torch.empty(N, 384, dtype=torch.bfloat16, device=DEV)
+
+def bwd2_dst():
+    return ops.edge_block_bwd_tc(efeat, h1s, g_e, None, g_agg, plan.dst, w1[:, :128], w2, b2, w3, b3, gamma, 1e-5,
+                                 gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4], csc_offsets=plan.csc_offsets,
+                                 dst=plan.dst, dst_sum_out=Tz[:, 128:256])
+
 def agg():
     return ops.segment_sum(efeat, 0, 128, plan.csc_offsets, None, N)
 
@@ -71,7 +78,7 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
-for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("segsum csc", agg), ("segsum csr", csr),
+for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
