@@ -312,6 +312,32 @@ int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const void* x, int64
                  float* out, int64_t ld_out, void* workspace, size_t workspace_bytes, int* status,
                  mgn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The steps either side of the path.
+ * ---------------------------------------------------------------------------------------- */
+/* Multi-tensor Adam: one launch (plus a one-thread step-counter tick) updates all n tensors.
+ * Replaces: apex.optimizers.FusedAdam / torch.optim.Adam at examples/cfd/vortex_shedding_mgn/train.py:111-123,
+ *           and GradScaler.step's skip-on-inf (:161-163) through found_inf / inv_scale.
+ * params / grads / exp_avg / exp_avg_sq: DEVICE arrays of n fp32 device pointers (grads[i] may be NULL: tensor
+ * skipped); numel: DEVICE int64[n]; chunk c covers elements [chunk_start[c], chunk_start[c] + chunk_elems) of tensor
+ * chunk_tensor[c] (chunk_elems a multiple of 4).  step: DEVICE float counter, incremented by this call before the
+ * update (bias corrections 1 - beta^step in double); lr_dev / inv_scale / found_inf: optional DEVICE scalars
+ * (learning rate override, gradient multiplier 1/loss_scale, skip flag).  adamw != 0: decoupled weight decay,
+ * else L2 added to the gradient (torch.optim.Adam).  Update order and rounding follow torch's single-tensor Adam.
+ * No host synchronisation, CUDA-graph capturable. */
+int mgn_adam_multi_step(void* const* params, const void* const* grads, void* const* exp_avg,
+                        void* const* exp_avg_sq, const int64_t* numel, const int32_t* chunk_tensor,
+                        const int64_t* chunk_start, int64_t n_chunks, int64_t chunk_elems, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int adamw, float* step,
+                        const float* lr_dev, const float* inv_scale, const float* found_inf,
+                        mgn_stream_t stream);
+/* out[e, 0:dim] = pos[src[e]] - pos[dst[e]], out[e, dim] = its Euclidean norm, then (x - mu[k]) / sd[k] per column
+ * when mu / sd (fp32 [dim+1], optional) are given.  pos fp32 [n, dim], dim in {2, 3}; out fp32 [E, dim+1].
+ * Replaces: VortexSheddingDataset.add_edge_features + normalize_edge
+ *           (datapipes/gnn/vortex_shedding_dataset.py:324-349). */
+int mgn_edge_features(const float* pos, int dim, const int32_t* src, const int32_t* dst, int64_t n_edges,
+                      const float* mu, const float* sd, float* out, mgn_stream_t stream);
+
 /* Debug hook (not part of the drop-in surface): dev_buf = 96 x int64 that CTA 0 of subsequent
  * mgn_mlp3_bwd_tc launches fills with per-role, per-phase cycle counts; NULL disables. */
 int mgn_debug_set_bwd_timing(void* dev_buf);

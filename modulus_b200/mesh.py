@@ -110,3 +110,48 @@ def power_law_graph_csc(num_nodes: int, num_edges: int, alpha: float = 1.2, seed
     offsets[1:] = torch.cumsum(deg, 0)
     indices = torch.randint(0, num_nodes, (int(offsets[-1]),), generator=g, dtype=torch.int64)
     return offsets.to(device), indices.to(device)
+
+
+# ----------------------------------------------------------------------------------------------
+# graph construction from mesh cells + edge features on the device
+# ----------------------------------------------------------------------------------------------
+def graph_from_cells(cells: torch.Tensor, num_nodes: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Triangle (or any polygon) cells [C, k] -> bidirected, de-duplicated graph as a CSC
+    (offsets int64 [N+1], indices int64 [E], in-edges of a node sorted by source id).
+
+    Same edge SET as the reference's `cell_to_adj` + `dgl.to_bidirected`
+    (datapipes/gnn/vortex_shedding_dataset.py:307-322): edge (cells[i][j] -> cells[i][j+1 mod k]) for every
+    cell side, plus the reverse of each, duplicates removed.  Runs wherever `cells` lives; on CUDA the sort /
+    unique / scan are torch's device primitives, nothing touches the host."""
+    cells = cells.to(torch.int64)
+    a = cells.reshape(-1)
+    b = torch.roll(cells, shifts=-1, dims=1).reshape(-1)
+    src = torch.cat([a, b])
+    dst = torch.cat([b, a])
+    return _csc_from_pairs(src, dst, num_nodes, num_nodes)
+
+
+def edge_features(pos: torch.Tensor, src: torch.Tensor, dst: torch.Tensor, mu: torch.Tensor = None,
+                  std: torch.Tensor = None) -> torch.Tensor:
+    """[E, dim+1] fp32 = (pos[src] - pos[dst], its norm), normalised per column by (x - mu) / std when given:
+    `add_edge_features` + `normalize_edge` of the reference (vortex_shedding_dataset.py:324-349) as one CUDA
+    pass (mgn_edge_features).  `src` / `dst` are the int32 endpoint arrays of a GraphPlan.  CUDA only."""
+    from . import ops
+
+    ops.require_cuda(pos, src, dst, mu, std)
+    if pos.dim() != 2 or pos.shape[1] not in (2, 3):
+        raise ValueError(f"pos must be [N, 2] or [N, 3], got {tuple(pos.shape)}")
+    dim = pos.shape[1]
+    for t in (mu, std):
+        if t is not None and t.numel() != dim + 1:
+            raise AssertionError("Graph edge data must be same size as stats.")  # vortex_shedding_dataset.py:343-348
+    pos = pos.contiguous().float()
+    src = src.to(torch.int32).contiguous()
+    dst = dst.to(torch.int32).contiguous()
+    mu = None if mu is None else mu.reshape(-1).contiguous().float()
+    std = None if std is None else std.reshape(-1).contiguous().float()
+    out = torch.empty((src.numel(), dim + 1), dtype=torch.float32, device=pos.device)
+    ops.call("mgn_edge_features", pos.data_ptr(), dim, src.data_ptr(), dst.data_ptr(), src.numel(),
+             None if mu is None else mu.data_ptr(), None if std is None else std.data_ptr(), out.data_ptr(),
+             torch.cuda.current_stream().cuda_stream)
+    return out

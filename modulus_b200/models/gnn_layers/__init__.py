@@ -9,6 +9,8 @@ from .distributed_graph import (  # noqa: F401
 )
 from .graph import CuGraphCSC  # noqa: F401
 from .mesh_edge_block import MeshEdgeBlock  # noqa: F401
+from .mesh_graph_decoder import MeshGraphDecoder  # noqa: F401
+from .mesh_graph_encoder import MeshGraphEncoder  # noqa: F401
 from .mesh_graph_mlp import MeshGraphEdgeMLPConcat, MeshGraphEdgeMLPSum, MeshGraphMLP  # noqa: F401
 from .mesh_node_block import MeshNodeBlock  # noqa: F401
 from .utils import aggregate_and_concat, concat_efeat, sum_efeat  # noqa: F401

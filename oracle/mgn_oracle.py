@@ -242,3 +242,49 @@ def indexed_all_to_all_v_emulated(tensors: Sequence[Tensor], scatter_indices: Se
             assert parts[p].shape[0] == sizes[p][r]
         out.append(torch.cat(parts, dim=0))
     return out
+
+
+# ----------------------------------------------------------------------------------------
+# the steps either side of the path
+# ----------------------------------------------------------------------------------------
+def cells_to_bidirected_coo(cells: Tensor, num_nodes: int) -> Tuple[Tensor, Tensor]:
+    """`cell_to_adj` + `create_graph` (datapipes/gnn/vortex_shedding_dataset.py:307-322): one directed edge per
+    cell side (vertex j -> vertex j+1 mod 3), then `dgl.to_bidirected` (DGL v2.4, unpinned third party: adds
+    every reverse edge and removes duplicates; the coalesced result is ordered by (src, dst))."""
+    cells = cells.to(torch.int64)
+    src = cells[:, [0, 1, 2]].reshape(-1)
+    dst = cells[:, [1, 2, 0]].reshape(-1)
+    s = torch.cat([src, dst])
+    d = torch.cat([dst, src])
+    key = torch.unique(s * num_nodes + d)
+    return torch.div(key, num_nodes, rounding_mode="floor"), key % num_nodes
+
+
+def edge_features(pos: Tensor, src: Tensor, dst: Tensor, mu: Optional[Tensor] = None,
+                  std: Optional[Tensor] = None) -> Tensor:
+    """`add_edge_features` (:324-333): cat(pos[src] - pos[dst], ||.||) and `normalize_edge` (:342-349):
+    (x - mu) / std."""
+    disp = pos[src.long()] - pos[dst.long()]
+    x = torch.cat((disp, torch.linalg.norm(disp, dim=-1, keepdim=True)), dim=1)
+    if mu is not None:
+        x = (x - mu) / std
+    return x
+
+
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float = 1e-3, beta1: float = 0.9,
+              beta2: float = 0.999, eps: float = 1e-8, weight_decay: float = 0.0, adamw: bool = False) -> None:
+    """In-place Adam update, the arithmetic of torch.optim.Adam's single-tensor path (torch 2.x
+    optim/adam.py `_single_tensor_adam`, the optimizer of examples/cfd/vortex_shedding_mgn/train.py:122);
+    `step` is the 1-based count AFTER this update.  Pinned against torch.optim.Adam / AdamW in
+    tests/test_train_step.py."""
+    if weight_decay != 0.0:
+        if adamw:
+            p.mul_(1.0 - lr * weight_decay)
+        else:
+            g = g + weight_decay * p
+    m.lerp_(g, 1.0 - beta1)
+    v.mul_(beta2).addcmul_(g, g, value=1.0 - beta2)
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))

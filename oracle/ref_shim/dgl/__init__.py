@@ -143,3 +143,15 @@ def rand_graph(num_nodes, num_edges):
 
 
 backend = SimpleNamespace(name="pytorch")
+
+
+def to_bidirected(g, copy_ndata=False):
+    """DGL semantics (dgl.to_bidirected, v2.4: add_reverse_edges + to_simple): the union of every edge and its
+    reverse with duplicates removed; the result is coalesced, i.e. edges ordered by (src, dst)."""
+    n = g.num_nodes()
+    s = torch.cat([g._src, g._dst])
+    d = torch.cat([g._dst, g._src])
+    key = torch.unique(s * n + d)
+    out = DGLGraph(torch.div(key, n, rounding_mode="floor"), key % n)
+    out._num_src = out._num_dst = n
+    return out

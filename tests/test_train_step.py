@@ -1,0 +1,243 @@
+"""The steps either side of the message-passing path:
+  * mesh cells -> bidirected graph -> edge features -> normalisation
+    (reference: datapipes/gnn/vortex_shedding_dataset.py:307-349; golden tests/golden/ref_datapipe_graph.pt)
+  * FusedAdam, one multi-tensor launch (reference: examples/cfd/vortex_shedding_mgn/train.py:111-123 =
+    torch.optim.Adam / apex FusedAdam).
+CPU part pins the oracle; GPU part checks the CUDA path through the C ABI."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import mgn_oracle as O
+
+DEV = "cuda"
+
+
+# ------------------------------------------------------------------------------ oracle pins (CPU)
+@pytest.mark.parametrize("dim", [2, 3])
+def test_oracle_datapipe_matches_reference(dim):
+    g = load_golden("ref_datapipe_graph.pt")
+    c = g[f"dim{dim}"]
+    n = c["pos"].shape[0]
+    src, dst = O.cells_to_bidirected_coo(g["cells"], n)
+    assert torch.equal(src, c["src"].long()) and torch.equal(dst, c["dst"].long())  # integer work: bit exact
+    assert torch.equal(O.edge_features(c["pos"], src, dst), c["edge_features"])
+    assert torch.equal(O.edge_features(c["pos"], src, dst, c["mu"], c["std"]), c["edge_features_normalized"])
+
+
+def test_graph_from_cells_same_edge_set_as_reference():
+    """Product host function (pure index arithmetic, runs on CPU too): same edge set, CSC order."""
+    from modulus_b200.mesh import graph_from_cells
+
+    g = load_golden("ref_datapipe_graph.pt")
+    c = g["dim2"]
+    n = c["pos"].shape[0]
+    offsets, indices = graph_from_cells(g["cells"], n)
+    src, dst = O.coo_from_csc(offsets, indices)
+    ours = torch.unique(dst * n + src)
+    ref = torch.unique(c["dst"].long() * n + c["src"].long())
+    assert indices.numel() == c["src"].numel() and torch.equal(ours, ref)
+    # in-edges of a node are sorted by source id: CSC order == sort by (dst, src)
+    assert torch.equal(dst * n + src, ours)
+
+
+@pytest.mark.parametrize("wd,adamw", [(0.0, False), (0.01, False), (0.01, True)])
+def test_oracle_adam_matches_torch(wd, adamw):
+    torch.manual_seed(0)
+    p0 = torch.randn(257)
+    ref_p = p0.clone().requires_grad_(True)
+    opt = (torch.optim.AdamW if adamw else torch.optim.Adam)([ref_p], lr=3e-3, weight_decay=wd, foreach=False)
+    p, m, v = p0.clone(), torch.zeros(257), torch.zeros(257)
+    for step in range(1, 6):
+        g = torch.randn(257)
+        ref_p.grad = g.clone()
+        opt.step()
+        O.adam_step(p, g, m, v, step, lr=3e-3, weight_decay=wd, adamw=adamw)
+        assert torch.allclose(p, ref_p.detach(), rtol=1e-6, atol=1e-7)
+
+
+def test_fused_adam_argument_errors():
+    from modulus_b200.optim import FusedAdam
+
+    w = torch.nn.Parameter(torch.zeros(4))
+    with pytest.raises(RuntimeError):
+        FusedAdam([w], amsgrad=True)
+    with pytest.raises(ValueError):
+        FusedAdam([w], lr=-1.0)
+    with pytest.raises(ValueError):
+        FusedAdam([w], betas=(1.0, 0.9))
+    opt = FusedAdam([w])
+    w.grad = torch.ones(4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+
+
+# ------------------------------------------------------------------------------ CUDA path (GPU)
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim", [2, 3])
+def test_edge_features_kernel_matches_reference(dim):
+    from modulus_b200.mesh import edge_features, graph_from_cells
+    from modulus_b200.ops import GraphPlan
+
+    g = load_golden("ref_datapipe_graph.pt")
+    c = g[f"dim{dim}"]
+    n = c["pos"].shape[0]
+    # reference edge order
+    out = edge_features(c["pos"].to(DEV), c["src"].to(DEV), c["dst"].to(DEV))
+    assert torch.allclose(out.cpu(), c["edge_features"], rtol=1e-6, atol=1e-7)
+    outn = edge_features(c["pos"].to(DEV), c["src"].to(DEV), c["dst"].to(DEV), c["mu"].to(DEV), c["std"].to(DEV))
+    assert torch.allclose(outn.cpu(), c["edge_features_normalized"], rtol=1e-5, atol=1e-6)
+    # whole device pipeline: cells -> CSC -> plan -> features, against the oracle on the same edges
+    offsets, indices = graph_from_cells(g["cells"].to(DEV), n)
+    plan = GraphPlan.from_csc(offsets, indices, n, n)
+    out2 = edge_features(c["pos"].to(DEV), plan.src, plan.dst, c["mu"].to(DEV), c["std"].to(DEV))
+    ref2 = O.edge_features(c["pos"], plan.src.cpu(), plan.dst.cpu(), c["mu"], c["std"])
+    assert torch.allclose(out2.cpu(), ref2, rtol=1e-5, atol=1e-6)
+    with pytest.raises(AssertionError):
+        edge_features(c["pos"].to(DEV), plan.src, plan.dst, c["mu"][:2].to(DEV), c["std"].to(DEV))
+
+
+@pytest.mark.gpu
+def test_edge_features_large_roundtrip_property():
+    """1 M-node torus: features of edge (u->v) are minus those of (v->u) in the displacement columns and equal in
+    the norm column (size-independent property at the BASELINE size)."""
+    from modulus_b200.mesh import edge_features, torus_surface_mesh
+    from modulus_b200.ops import GraphPlan
+
+    mesh = torus_surface_mesh(1000, 1000, device=DEV)
+    n = mesh["num_nodes"]
+    plan = GraphPlan.from_csc(mesh["offsets"], mesh["indices"], n, n)
+    ef = edge_features(mesh["coords"], plan.src, plan.dst)
+    assert torch.allclose(ef, mesh["edge_features"], rtol=1e-5, atol=1e-6)
+    key = plan.dst.long() * n + plan.src.long()      # sorted (CSC order)
+    rkey = plan.src.long() * n + plan.dst.long()     # key of the reverse edge
+    pos = torch.searchsorted(key, rkey)
+    assert torch.equal(key[pos], rkey)
+    assert torch.equal(ef[pos, :3], -ef[:, :3]) and torch.equal(ef[pos, 3], ef[:, 3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wd,adamw", [(0.0, False), (0.01, False), (0.01, True)])
+def test_fused_adam_matches_torch_adam(wd, adamw):
+    from modulus_b200.optim import FusedAdam
+
+    torch.manual_seed(1)
+    shapes = [(128, 384), (128,), (3, 5), (1,), (4099,), (128, 128)]
+    ours = [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ours]
+    opt = FusedAdam(ours, lr=3e-3, weight_decay=wd, adam_w_mode=adamw)
+    ropt = (torch.optim.AdamW if adamw else torch.optim.Adam)(ref, lr=3e-3, weight_decay=wd, foreach=False)
+    for step in range(6):
+        for i, (p, r) in enumerate(zip(ours, ref)):
+            if step == 5 and i == 2:
+                p.grad, r.grad = None, None          # a parameter without a gradient is skipped (last step: torch
+                # would not advance this parameter's own step count, the fused counter is per group)
+                continue
+            gr = torch.randn(*r.shape)
+            r.grad = gr
+            p.grad = gr.to(DEV)                      # fresh tensor every step: the pointer table is refreshed
+        opt.step()
+        ropt.step()
+        for p, r in zip(ours, ref):
+            assert torch.allclose(p.detach().cpu(), r.detach(), rtol=2e-6, atol=2e-7), step
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert float(sd["state"][0]["step"]) == 6.0
+    assert torch.allclose(sd["state"][0]["exp_avg"].cpu(), ropt.state_dict()["state"][0]["exp_avg"], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_fused_adam_state_dict_roundtrip_with_torch_adam():
+    """A torch.optim.Adam checkpoint continues under FusedAdam with the same trajectory."""
+    from modulus_b200.optim import FusedAdam
+
+    torch.manual_seed(2)
+    w = torch.randn(300, device=DEV)
+    a = torch.nn.Parameter(w.clone())
+    b = torch.nn.Parameter(w.clone())
+    ta = torch.optim.Adam([a], lr=1e-2)
+    grads = [torch.randn(300, device=DEV) for _ in range(6)]
+    for g in grads[:3]:
+        a.grad = g.clone()
+        ta.step()
+    fb = FusedAdam([b], lr=1e-2)
+    b.data.copy_(a.data)
+    fb.load_state_dict(ta.state_dict())
+    for g in grads[3:]:
+        a.grad = g.clone()
+        ta.step()
+        b.grad = g.clone()
+        fb.step()
+    assert torch.allclose(a, b, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.gpu
+def test_fused_adam_skip_on_found_inf_and_inv_scale():
+    from modulus_b200.optim import FusedAdam
+
+    torch.manual_seed(3)
+    p = torch.nn.Parameter(torch.randn(1000, device=DEV))
+    r = torch.nn.Parameter(p.detach().clone())
+    opt, ropt = FusedAdam([p], lr=1e-2), torch.optim.Adam([r], lr=1e-2)
+    g = torch.randn(1000, device=DEV)
+    p.grad = g * 8.0
+    before = p.detach().clone()
+    opt.step(found_inf=torch.ones(1, device=DEV), inv_scale=torch.full((1,), 0.125, device=DEV))
+    assert torch.equal(p.detach(), before) and float(opt.state[p]["step"]) == 0.0
+    opt.step(found_inf=torch.zeros(1, device=DEV), inv_scale=torch.full((1,), 0.125, device=DEV))
+    r.grad = g
+    ropt.step()
+    assert torch.allclose(p, r, rtol=2e-6, atol=2e-7)
+
+
+@pytest.mark.gpu
+def test_training_step_with_fused_adam_in_a_cuda_graph():
+    """zero_grad -> forward -> loss -> backward -> FusedAdam.step captured as ONE CUDA graph (what the reference
+    does with StaticCaptureTraining, utils/capture.py:341) and replayed: same parameters as the eager loop."""
+    from modulus_b200.mesh import triangle_grid_mesh
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.optim import FusedAdam
+
+    mesh = triangle_grid_mesh(20, 21, device=DEV)
+    n = mesh["num_nodes"]
+    graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n, n)
+    torch.manual_seed(4)
+    nf, ef, tgt = torch.randn(n, 6, device=DEV), mesh["edge_features"], torch.randn(n, 3, device=DEV)
+
+    def make():
+        torch.manual_seed(5)
+        model = MeshGraphNet(6, 3, 3, processor_size=3).to(DEV)
+        return model, FusedAdam(model.parameters(), lr=1e-3)
+
+    def step(model, opt):
+        opt.zero_grad(set_to_none=False)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(nf, ef, graph)
+        loss = torch.nn.functional.mse_loss(out.float(), tgt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    eager, eopt = make()
+    for _ in range(5):
+        step(eager, eopt)
+
+    model, opt = make()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):                      # warm-up on a side stream: plans, workspaces, static gradients
+            step(model, opt)
+    torch.cuda.current_stream().wait_stream(s)
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        loss = step(model, opt)
+    for _ in range(3):                          # capture itself executes nothing: 2 warm-up + 3 replays = 5 steps
+        cg.replay()
+    torch.cuda.synchronize()
+    assert float(opt.state[next(model.parameters())]["step"]) == 5.0
+    assert torch.isfinite(loss).all()
+    for (k, a), b in zip(eager.named_parameters(), model.parameters()):
+        # bf16 forward/backward: replays follow the same kernels, so only atomics-free summation order could differ
+        assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), k
