@@ -47,7 +47,7 @@ class ScatterVAutograd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tensor, sizes, dim=0, src=0, group=None):
         out = scatter_v_wrapper(tensor, sizes, dim=dim, src=src, group=group)
-        ctx.tensor, ctx.sizes, ctx.dim, ctx.src, ctx.group = tensor, sizes, dim, src, group
+        ctx.sizes, ctx.dim, ctx.src, ctx.group = sizes, dim, src, group
         return out
 
     @staticmethod

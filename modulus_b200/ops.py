@@ -361,15 +361,34 @@ class MLPFn(torch.autograd.Function):
         else:
             out = y
         ctx.cfg = (act, n_linear, has_norm, need_pre, residual is not None)
-        ctx.params = (ws, bs, gamma)
-        ctx.acts = (inputs, pres, y, mean, rstd)
+        # everything the backward reads goes through save_for_backward: `y` IS the output when there is neither a
+        # LayerNorm nor a residual, and an output kept as a plain ctx attribute forms a reference cycle with its
+        # own grad_fn (the iteration's autograd graph -- AccumulateGrad nodes included -- would outlive the step)
+        saved: List[Tensor] = []
+
+        def keep(t: Optional[Tensor]) -> int:
+            if t is None:
+                return -1
+            saved.append(t)
+            return len(saved) - 1
+
+        ctx.slots = ([keep(t) for t in ws], [keep(t) for t in bs], keep(gamma), [keep(t) for t in inputs],
+                     [keep(t) for t in pres], keep(y), keep(mean), keep(rstd))
+        ctx.save_for_backward(*saved)
         return out
 
     @staticmethod
     def backward(ctx, g):
         act, n_linear, has_norm, need_pre, has_res = ctx.cfg
-        ws, bs, gamma = ctx.params
-        inputs, pres, y, mean, rstd = ctx.acts
+        saved = ctx.saved_tensors
+
+        def get(i: int) -> Optional[Tensor]:
+            return None if i < 0 else saved[i]
+
+        s_ws, s_bs, s_gamma, s_inputs, s_pres, s_y, s_mean, s_rstd = ctx.slots
+        ws, bs, gamma = [get(i) for i in s_ws], [get(i) for i in s_bs], get(s_gamma)
+        inputs, pres = [get(i) for i in s_inputs], [get(i) for i in s_pres]
+        y, mean, rstd = get(s_y), get(s_mean), get(s_rstd)
         g = _c(g)
         grads: List[Optional[Tensor]] = [None] * (2 * n_linear + (2 if has_norm else 0))
         g_res = g if (has_res and ctx.needs_input_grad[1]) else None

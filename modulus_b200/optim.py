@@ -46,6 +46,9 @@ class _Table:
         self.ring = [(torch.zeros((4, max(n, 1)), dtype=torch.int64).pin_memory(), torch.cuda.Event())
                      for _ in range(4)]
         self.ring_pos = 0
+        self.pending_rows = None  # pointer rows seen during a graph capture, uploaded by prepare_replay()
+        self.lr_dev = torch.zeros((), dtype=torch.float32, device=device)  # learning rate a captured step reads
+        self.lr_host: Optional[float] = None
         self.ptrs = torch.zeros((4, max(n, 1)), dtype=torch.int64, device=device)
         self.key: Optional[Tuple[int, ...]] = None
         self.state = state
@@ -62,8 +65,16 @@ class _Table:
         if key == self.key:
             return
         if torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("FusedAdam: tensor addresses changed during CUDA graph capture; keep gradients static "
-                               "(zero_grad(set_to_none=False)) and run one eager step before capturing")
+            # gradients freed before the capture are re-created inside the graph's memory pool, so their addresses
+            # are only known now.  Nothing is recorded for them: the captured kernel reads the device table at replay
+            # time, and prepare_replay() uploads these rows eagerly after the capture and before the first replay.
+            self.pending_rows = rows
+            self.key = key
+            return
+        self.upload(rows)
+        self.key = key
+
+    def upload(self, rows) -> None:
         host, event = self.ring[self.ring_pos % len(self.ring)]
         if self.ring_pos >= len(self.ring):
             event.synchronize()
@@ -71,7 +82,7 @@ class _Table:
         host.copy_(torch.tensor(rows, dtype=torch.int64))
         self.ptrs.copy_(host, non_blocking=True)
         event.record()
-        self.key = key
+        self.pending_rows = None
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -130,6 +141,22 @@ class FusedAdam(torch.optim.Optimizer):
         if hasattr(self, "_tables"):
             self._tables.clear()
 
+    def prepare_replay(self) -> None:
+        """Host-side bookkeeping around a captured step; call it before capturing and before every replay.  Mirrors
+        each group's host-side learning rate (what LR schedulers update) into the device scalar a captured step
+        reads -- one tiny fill per group and only when the value changed -- and uploads pointer rows that were first
+        seen during the capture (gradients re-created inside the graph's memory pool)."""
+        for gi, group in enumerate(self.param_groups):
+            tab = self._tables.get(gi)
+            if tab is None:
+                tab = self._init_group(gi, group)
+            lr = group["lr"]
+            if not isinstance(lr, Tensor) and tab.lr_host != float(lr):
+                tab.lr_dev.fill_(float(lr))
+                tab.lr_host = float(lr)
+            if tab.pending_rows is not None and not torch.cuda.is_current_stream_capturing():
+                tab.upload(tab.pending_rows)
+
     # ------------------------------------------------------------------ step
     @torch.no_grad()
     def step(self, closure=None, found_inf: Optional[Tensor] = None, inv_scale: Optional[Tensor] = None):
@@ -150,6 +177,12 @@ class FusedAdam(torch.optim.Optimizer):
             tab.refresh()
             lr = group["lr"]
             lr_dev = lr if isinstance(lr, Tensor) else None
+            if lr_dev is None and torch.cuda.is_current_stream_capturing():
+                # a by-value learning rate would be frozen into the graph: read it from the device instead;
+                # `prepare_replay()` (called by StaticCaptureTraining before each replay) follows the scheduler
+                if tab.lr_host != float(lr):
+                    raise RuntimeError("FusedAdam: call prepare_replay() before capturing a step")
+                lr_dev = tab.lr_dev
             b1, b2 = group["betas"]
             rc = lib.mgn_adam_multi_step(
                 tab.ptrs[0].data_ptr(), tab.ptrs[1].data_ptr(), tab.ptrs[2].data_ptr(), tab.ptrs[3].data_ptr(),

@@ -4,6 +4,8 @@
   * FusedAdam, one multi-tensor launch (reference: examples/cfd/vortex_shedding_mgn/train.py:111-123 =
     torch.optim.Adam / apex FusedAdam).
 CPU part pins the oracle; GPU part checks the CUDA path through the C ABI."""
+import copy
+
 import pytest
 import torch
 
@@ -162,7 +164,7 @@ def test_fused_adam_state_dict_roundtrip_with_torch_adam():
         ta.step()
     fb = FusedAdam([b], lr=1e-2)
     b.data.copy_(a.data)
-    fb.load_state_dict(ta.state_dict())
+    fb.load_state_dict(copy.deepcopy(ta.state_dict()))  # load_state_dict aliases same-device tensors
     for g in grads[3:]:
         a.grad = g.clone()
         ta.step()
@@ -192,8 +194,8 @@ def test_fused_adam_skip_on_found_inf_and_inv_scale():
 
 @pytest.mark.gpu
 def test_training_step_with_fused_adam_in_a_cuda_graph():
-    """zero_grad -> forward -> loss -> backward -> FusedAdam.step captured as ONE CUDA graph (what the reference
-    does with StaticCaptureTraining, utils/capture.py:341) and replayed: same parameters as the eager loop."""
+    """zero_grad -> forward -> loss -> backward -> FusedAdam.step captured by hand as ONE CUDA graph with static
+    gradients (zero_grad(set_to_none=False)) and replayed: same parameters as the eager loop."""
     from modulus_b200.mesh import triangle_grid_mesh
     from modulus_b200.models.gnn_layers import CuGraphCSC
     from modulus_b200.models.meshgraphnet import MeshGraphNet
@@ -230,6 +232,7 @@ def test_training_step_with_fused_adam_in_a_cuda_graph():
         for _ in range(2):                      # warm-up on a side stream: plans, workspaces, static gradients
             step(model, opt)
     torch.cuda.current_stream().wait_stream(s)
+    opt.prepare_replay()                        # learning rate -> device scalar the captured step reads
     cg = torch.cuda.CUDAGraph()
     with torch.cuda.graph(cg):
         loss = step(model, opt)
@@ -241,3 +244,146 @@ def test_training_step_with_fused_adam_in_a_cuda_graph():
     for (k, a), b in zip(eager.named_parameters(), model.parameters()):
         # bf16 forward/backward: replays follow the same kernels, so only atomics-free summation order could differ
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-5), k
+
+
+# ------------------------------------------------------------------------------ StaticCaptureTraining
+def test_static_capture_argument_errors():
+    from modulus_b200.capture import StaticCaptureTraining
+
+    lin = torch.nn.Linear(2, 2)
+    opt = torch.optim.Adam(lin.parameters())
+    with pytest.raises(ValueError):
+        StaticCaptureTraining(model=lin, optim=opt, compile=True)
+    with pytest.raises(ValueError):
+        StaticCaptureTraining(model=lin, optim=opt, amp_type=torch.float16)
+    with pytest.raises(ValueError):
+        StaticCaptureTraining(model=lin, optim=opt, amp_type=torch.float32)
+    with pytest.raises(ValueError):
+        StaticCaptureTraining(model="not a module", optim=opt)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        StaticCaptureTraining(model=lin, optim=opt)
+
+
+def _capture_case(n_layers=3):
+    from modulus_b200.mesh import triangle_grid_mesh
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+
+    mesh = triangle_grid_mesh(20, 21, device=DEV)
+    n = mesh["num_nodes"]
+    graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n, n)
+    g = torch.Generator().manual_seed(4)
+    data = [(torch.randn(n, 6, generator=g).to(DEV), torch.randn(n, 3, generator=g).to(DEV)) for _ in range(7)]
+    return graph, mesh["edge_features"], data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_amp,fused_opt", [(True, True), (False, True), (True, False)])
+def test_static_capture_training_matches_eager_loop(use_amp, fused_opt):
+    """The reference's training-step decorator (utils/capture.py:341): 2 eager warm-up calls, one recording call,
+    then replays, with a LambdaLR scheduler stepping between calls and new data copied into static inputs.  Same
+    parameters as the plain loop; with FusedAdam the optimizer step is inside the graph."""
+    from modulus_b200.capture import StaticCaptureTraining
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.optim import FusedAdam
+
+    graph, ef, data = _capture_case()
+
+    def make():
+        torch.manual_seed(5)
+        model = MeshGraphNet(6, 3, 3, processor_size=3).to(DEV)
+        opt = FusedAdam(model.parameters(), lr=1e-3) if fused_opt else torch.optim.Adam(model.parameters(), lr=1e-3)
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda e: 0.8 ** e)
+        return model, opt, sched
+
+    eager, eopt, esched = make()
+    for nf, tgt in data:
+        eopt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_amp):
+            loss_e = torch.nn.functional.mse_loss(eager(nf, ef, graph).float(), tgt)
+        loss_e.backward()
+        eopt.step()
+        esched.step()
+
+    model, opt, sched = make()
+    s_nf, s_tgt = torch.empty_like(data[0][0]), torch.empty_like(data[0][1])
+
+    @StaticCaptureTraining(model=model, optim=opt, use_amp=use_amp, cuda_graph_warmup=2)
+    def training_step(nf, tgt):
+        return torch.nn.functional.mse_loss(model(nf, ef, graph).float(), tgt)
+
+    for nf, tgt in data:
+        s_nf.copy_(nf)
+        s_tgt.copy_(tgt)
+        loss = training_step(s_nf, s_tgt)
+        sched.step()
+    torch.cuda.synchronize()
+    assert torch.allclose(loss, loss_e.detach(), rtol=1e-3, atol=1e-6)
+    tol = dict(rtol=2e-3, atol=2e-5) if use_amp else dict(rtol=1e-4, atol=1e-6)
+    for (k, a), b in zip(eager.named_parameters(), model.parameters()):
+        assert torch.allclose(a, b, **tol), k
+    if fused_opt:
+        assert float(opt.state[next(model.parameters())]["step"]) == float(len(data))
+
+
+@pytest.mark.gpu
+def test_static_capture_evaluate_no_grad():
+    """Inference caller of the same forward (examples/cfd/vortex_shedding_mgn/inference.py): replays follow the
+    static input."""
+    from modulus_b200.capture import StaticCaptureEvaluateNoGrad
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+
+    graph, ef, data = _capture_case()
+    torch.manual_seed(6)
+    model = MeshGraphNet(6, 3, 3, processor_size=3).to(DEV)
+    s_nf = torch.empty_like(data[0][0])
+
+    @StaticCaptureEvaluateNoGrad(model=model, cuda_graph_warmup=1)
+    def predict(nf):
+        return model(nf, ef, graph)
+
+    for nf, _ in data[:4]:
+        s_nf.copy_(nf)
+        out = predict(s_nf)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            ref = model(nf, ef, graph)
+        assert torch.equal(out, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_amp", [False, True])
+def test_capture_after_eager_steps_on_the_default_stream(use_amp):
+    """Eager steps on the default stream followed by a capture on a side stream: the autograd graph of an eager step
+    (and with it the AccumulateGrad nodes bound to the default stream) must be gone once its loss is dropped --
+    without waiting for the garbage collector -- or the recording fails with cudaErrorStreamCaptureImplicit."""
+    import gc
+
+    from modulus_b200.capture import StaticCaptureTraining
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.optim import FusedAdam
+
+    graph, ef, data = _capture_case()
+    torch.manual_seed(7)
+    model = MeshGraphNet(6, 3, 3, processor_size=2).to(DEV)
+    opt = FusedAdam(model.parameters(), lr=1e-3)
+    nf, tgt = data[0]
+    gc.collect()
+    gc.disable()
+    try:
+        for _ in range(2):
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=use_amp):
+                loss = torch.nn.functional.mse_loss(model(nf, ef, graph).float(), tgt)
+            loss.backward()
+            opt.step()
+        del loss
+
+        @StaticCaptureTraining(model=model, optim=opt, use_amp=use_amp, cuda_graph_warmup=1)
+        def training_step(nf, tgt):
+            return torch.nn.functional.mse_loss(model(nf, ef, graph).float(), tgt)
+
+        for _ in range(3):
+            out = training_step(nf, tgt)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+    finally:
+        gc.enable()

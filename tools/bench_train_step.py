@@ -3,7 +3,7 @@
   (a) optimizer step over the default MeshGraphNet's 263 parameter tensors (2.33 M parameters):
       torch.optim.Adam (foreach), torch.optim.Adam(fused=True) and modulus_b200.optim.FusedAdam (one launch)
   (b) c1 (1.9 k nodes, launch-bound) and c2 training step = zero_grad + forward + MSE + backward + FusedAdam.step,
-      eager vs captured as one CUDA graph
+      eager vs modulus_b200.capture.StaticCaptureTraining (one CUDA graph launch per step)
 
     python tools/bench_train_step.py [reps=20]      ->  markdown on stdout
 """
@@ -15,6 +15,7 @@ from modulus_b200.mesh import triangle_grid_mesh
 from modulus_b200.models.gnn_layers import CuGraphCSC
 from modulus_b200.models.meshgraphnet import MeshGraphNet
 from modulus_b200.optim import FusedAdam
+from modulus_b200.capture import StaticCaptureTraining
 
 DEV = "cuda:0"
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
@@ -64,7 +65,7 @@ for wname, (nx, ny), bf16 in (("c1", (42, 45), False), ("c2", (316, 317), True))
     nf, ef, tgt = torch.randn(n, 6, device=DEV), mesh["edge_features"], torch.randn(n, 3, device=DEV)
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad(set_to_none=True)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
             out = model(nf, ef, graph)
         loss = torch.nn.functional.mse_loss(out.float(), tgt)
@@ -73,16 +74,10 @@ for wname, (nx, ny), bf16 in (("c1", (42, 45), False), ("c2", (316, 317), True))
         return loss
 
     t_eager = timed(step)
-    try:
-        s = torch.cuda.Stream()
-        s.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(s):
-            step()
-        torch.cuda.current_stream().wait_stream(s)
-        cg = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(cg):
-            step()
-        t_graph = timed(cg.replay)
-        print(f"| {wname} | {n} | {E} | {'bf16' if bf16 else 'f32'} | {t_eager:.3f} | {t_graph:.3f} | {t_eager / t_graph:.2f}x |")
-    except Exception as ex:  # report, do not hide
-        print(f"| {wname} | {n} | {E} | {'bf16' if bf16 else 'f32'} | {t_eager:.3f} | capture failed: {type(ex).__name__}: {str(ex)[:120]} | |")
+
+    @StaticCaptureTraining(model=model, optim=opt, use_amp=bf16, cuda_graph_warmup=2)
+    def captured(nf, tgt):
+        return torch.nn.functional.mse_loss(model(nf, ef, graph).float(), tgt)
+
+    t_graph = timed(lambda: captured(nf, tgt))
+    print(f"| {wname} | {n} | {E} | {'bf16' if bf16 else 'f32'} | {t_eager:.3f} | {t_graph:.3f} | {t_eager / t_graph:.2f}x |")
