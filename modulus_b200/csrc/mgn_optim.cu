@@ -120,10 +120,14 @@ __global__ void edge_features_kernel(const float* __restrict__ pos, const int32_
   d[DIM] = sqrtf(ss);
 #pragma unroll
   for (int k = 0; k <= DIM; ++k) {
-    float x = d[k];
-    if (mu != nullptr) x -= mu[k];
-    if (sd != nullptr) x /= sd[k];
-    out[e * (DIM + 1) + k] = x;
+    if (mu != nullptr) d[k] -= mu[k];
+    if (sd != nullptr) d[k] /= sd[k];
+  }
+  if constexpr (DIM == 3) {  // a 3-D row is exactly 16 bytes: one 128-bit store per edge, fully coalesced
+    *reinterpret_cast<float4*>(out + e * 4) = make_float4(d[0], d[1], d[2], d[3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k <= DIM; ++k) out[e * (DIM + 1) + k] = d[k];
   }
 }
 
@@ -157,6 +161,7 @@ extern "C" int mgn_edge_features(const float* pos, int dim, const int32_t* src, 
   MGN_CHECK_ARG(n_edges >= 0 && (dim == 2 || dim == 3));
   if (n_edges == 0) return MGN_OK;
   MGN_CHECK_ARG(pos && src && dst && out);
+  if (dim == 3 && (reinterpret_cast<uintptr_t>(out) & 15) != 0) return MGN_EALIGN;
   cudaStream_t st = as_stream(stream);
   const unsigned grid = static_cast<unsigned>((n_edges + 255) / 256);
   if (dim == 2)

@@ -81,3 +81,38 @@ for wname, (nx, ny), bf16 in (("c1", (42, 45), False), ("c2", (316, 317), True))
 
     t_graph = timed(lambda: captured(nf, tgt))
     print(f"| {wname} | {n} | {E} | {'bf16' if bf16 else 'f32'} | {t_eager:.3f} | {t_graph:.3f} | {t_eager / t_graph:.2f}x |")
+
+print("\n## (c) step before the path at the c3 size: edge features of a 1 M-node / 6 M-edge surface mesh (fp32)\n")
+from modulus_b200.mesh import edge_features, graph_from_cells, torus_surface_mesh
+from modulus_b200.ops import GraphPlan
+import json
+peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+PEAK = json.load(open(peaks_path)).get("hbm_gbs", 6550.0) if os.path.exists(peaks_path) else 6550.0
+mesh = torus_surface_mesh(1000, 1000, device=DEV)
+n, E = mesh["num_nodes"], int(mesh["indices"].numel())
+plan = GraphPlan.from_csc(mesh["offsets"], mesh["indices"], n, n)
+pos = mesh["coords"]
+mu, sd = mesh["edge_features"].mean(0), mesh["edge_features"].std(0)
+
+
+def torch_expr():
+    d = pos[plan.src.long()] - pos[plan.dst.long()]
+    return (torch.cat((d, torch.linalg.norm(d, dim=-1, keepdim=True)), 1) - mu) / sd
+
+
+t_k = timed(lambda: edge_features(pos, plan.src, plan.dst, mu, sd))
+t_t = timed(torch_expr)
+alg = E * (2 * 4 + 4 * 4) + n * 12  # endpoint ids + output row per edge, coordinate table once
+print("| implementation | ms | algorithmic MB | GB/s | frac of HBM peak |")
+print("|---|---:|---:|---:|---:|")
+print(f"| mgn_edge_features (one launch) | {t_k:.4f} | {alg / 1e6:.1f} | {alg / t_k / 1e6:.0f} | {alg / t_k / 1e6 / PEAK:.2f} |")
+print(f"| torch expression (gather, sub, norm, cat, normalise) | {t_t:.4f} | {alg / 1e6:.1f} | {alg / t_t / 1e6:.0f} | {alg / t_t / 1e6 / PEAK:.2f} |")
+# cells -> graph (sort + unique + scan on the device)
+i = torch.arange(1000, device=DEV).view(-1, 1).expand(1000, 1000)
+j = torch.arange(1000, device=DEV).view(1, -1).expand(1000, 1000)
+a, b, c, d = (i * 1000 + j), (i * 1000 + (j + 1) % 1000), (((i + 1) % 1000) * 1000 + j), (((i + 1) % 1000) * 1000 + (j + 1) % 1000)
+cells = torch.cat([torch.stack([a, b, d], -1).reshape(-1, 3), torch.stack([a, d, c], -1).reshape(-1, 3)])
+t_g = timed(lambda: graph_from_cells(cells, n), n=5, warm=1)
+off, idx = graph_from_cells(cells, n)
+print(f"\ngraph_from_cells: {cells.shape[0]} triangles -> {idx.numel()} directed edges in {t_g:.2f} ms "
+      f"(same CSC as the generator: {bool(torch.equal(off, mesh['offsets']) and torch.equal(idx, mesh['indices']))})")
