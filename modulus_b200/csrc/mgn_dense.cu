@@ -35,20 +35,37 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sa_i, int64_t sa_r, const TB*
 
   const bool a_r_contig = (sa_r == 1);
   const bool b_j_contig = (sb_j == 1);
-  for (int64_t r0 = r_begin; r0 < r_end; r0 += GB_K) {
+  // register-staged double buffering: the global loads of step r0 + GB_K are issued before the FMAs of step r0, so
+  // their latency overlaps the arithmetic instead of being exposed once per step
+  float pa[4], pb[4];
+  auto gload = [&](int64_t r0) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = t + u * 256;
       int ii, rr;
       if (a_r_contig) { rr = idx % GB_K; ii = idx / GB_K; } else { ii = idx % GB_M; rr = idx / GB_M; }
       const int64_t gi = i0 + ii, gr = r0 + rr;
-      As[rr][ii] = (gi < I && gr < r_end) ? Num<TA>::to_f(A[gi * sa_i + gr * sa_r]) : 0.f;
+      pa[u] = (gi < I && gr < r_end) ? Num<TA>::to_f(A[gi * sa_i + gr * sa_r]) : 0.f;
       int jj, rb;
       if (b_j_contig) { jj = idx % GB_N; rb = idx / GB_N; } else { rb = idx % GB_K; jj = idx / GB_K; }
       const int64_t gj = j0 + jj, grb = r0 + rb;
-      Bs[rb][jj] = (gj < J && grb < r_end) ? Num<TB>::to_f(B[grb * sb_r + gj * sb_j]) : 0.f;
+      pb[u] = (gj < J && grb < r_end) ? Num<TB>::to_f(B[grb * sb_r + gj * sb_j]) : 0.f;
+    }
+  };
+  if (r_begin < r_end) gload(r_begin);
+  for (int64_t r0 = r_begin; r0 < r_end; r0 += GB_K) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + u * 256;
+      int ii, rr;
+      if (a_r_contig) { rr = idx % GB_K; ii = idx / GB_K; } else { ii = idx % GB_M; rr = idx / GB_M; }
+      As[rr][ii] = pa[u];
+      int jj, rb;
+      if (b_j_contig) { jj = idx % GB_N; rb = idx / GB_N; } else { rb = idx % GB_K; jj = idx / GB_K; }
+      Bs[rb][jj] = pb[u];
     }
     __syncthreads();
+    if (r0 + GB_K < r_end) gload(r0 + GB_K);
 #pragma unroll
     for (int k = 0; k < GB_K; ++k) {
       float a[4], b[4];
@@ -93,17 +110,29 @@ linear_fwd_kernel(const T* __restrict__ X, int64_t ldx, const float* __restrict_
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-  for (int64_t r0 = 0; r0 < K; r0 += GB_K) {
+  float pa[4], pb[4];  // next step's operands, loaded while this step's FMAs run
+  auto gload = [&](int64_t r0) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int idx = t + u * 256;
       const int rr = idx % GB_K, ii = idx / GB_K;
       const int64_t gi = i0 + ii, gr = r0 + rr;
-      As[rr][ii] = (gi < M && gr < K) ? Num<T>::to_f(X[gi * ldx + gr]) : 0.f;
+      pa[u] = (gi < M && gr < K) ? Num<T>::to_f(X[gi * ldx + gr]) : 0.f;
       const int64_t gj = j0 + ii;
-      Bs[rr][ii] = (gj < N && gr < K) ? W[gj * K + gr] : 0.f;
+      pb[u] = (gj < N && gr < K) ? W[gj * K + gr] : 0.f;
+    }
+  };
+  if (K > 0) gload(0);
+  for (int64_t r0 = 0; r0 < K; r0 += GB_K) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = t + u * 256;
+      const int rr = idx % GB_K, ii = idx / GB_K;
+      As[rr][ii] = pa[u];
+      Bs[rr][ii] = pb[u];
     }
     __syncthreads();
+    if (r0 + GB_K < K) gload(r0 + GB_K);
 #pragma unroll
     for (int k = 0; k < GB_K; ++k) {
       float a[4], b[4];
