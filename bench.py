@@ -303,6 +303,26 @@ def run_b200(args, rank, world, local_rank):
     if last != last:
         raise RuntimeError("bench.py: loss is NaN")
 
+    # ---- optimizer step, reported separately (the metric is forward + backward; train.py:111-123)
+    opt_info = None
+    if world == 1:
+        from modulus_b200.optim import FusedAdam
+        opt = FusedAdam(model.parameters(), lr=0.0)  # lr 0: the measured weights stay what the timed regions used
+        for _ in range(3):
+            opt.step()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l_opt = lib.mgn_launch_count()
+        o0.record()
+        for _ in range(10):
+            opt.step()
+        o1.record()
+        torch.cuda.synchronize()
+        n_par = sum(p.numel() for p in model.parameters() if p.requires_grad)
+        opt_info = {"impl": "modulus_b200.optim.FusedAdam (mgn_adam_multi_step)", "ms_per_step": o0.elapsed_time(o1) / 10,
+                    "launches_per_step": int((lib.mgn_launch_count() - l_opt) // 10), "parameters": n_par,
+                    "tensors": sum(1 for p in model.parameters() if p.requires_grad),
+                    "algorithmic_bytes": 28 * n_par}
+
     if rank != 0:
         return
     b = 2 if use_bf16 else 4
@@ -353,7 +373,7 @@ def run_b200(args, rank, world, local_rank):
         "e2e": {"value": E_glob / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
-        "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "clocks": clk,
+        "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "clocks": clk, "optimizer_step": opt_info,
         "kernel_shares": {k: round(v["ms"], 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]},
     }
     print(json.dumps(line), flush=True)
