@@ -37,36 +37,15 @@ class MeshGraphEncoder(nn.Module):
     ):
         super().__init__()
         self.aggregation = aggregation
+        # construction order (edge MLP first) fixes the RNG stream, hence the initial weights, to the reference's
+        shared = dict(hidden_dim=hidden_dim, hidden_layers=hidden_layers, activation_fn=activation_fn,
+                      norm_type=norm_type, recompute_activation=recompute_activation)
         MLP = MeshGraphEdgeMLPSum if do_concat_trick else MeshGraphEdgeMLPConcat
-        self.edge_mlp = MLP(
-            efeat_dim=input_dim_edges,
-            src_dim=input_dim_src_nodes,
-            dst_dim=input_dim_dst_nodes,
-            output_dim=output_dim_edges,
-            hidden_dim=hidden_dim,
-            hidden_layers=hidden_layers,
-            activation_fn=activation_fn,
-            norm_type=norm_type,
-            recompute_activation=recompute_activation,
-        )
-        self.src_node_mlp = MeshGraphMLP(
-            input_dim=input_dim_src_nodes,
-            output_dim=output_dim_src_nodes,
-            hidden_dim=hidden_dim,
-            hidden_layers=hidden_layers,
-            activation_fn=activation_fn,
-            norm_type=norm_type,
-            recompute_activation=recompute_activation,
-        )
-        self.dst_node_mlp = MeshGraphMLP(
-            input_dim=input_dim_dst_nodes + output_dim_edges,
-            output_dim=output_dim_dst_nodes,
-            hidden_dim=hidden_dim,
-            hidden_layers=hidden_layers,
-            activation_fn=activation_fn,
-            norm_type=norm_type,
-            recompute_activation=recompute_activation,
-        )
+        self.edge_mlp = MLP(efeat_dim=input_dim_edges, src_dim=input_dim_src_nodes, dst_dim=input_dim_dst_nodes,
+                            output_dim=output_dim_edges, **shared)
+        self.src_node_mlp = MeshGraphMLP(input_dim=input_dim_src_nodes, output_dim=output_dim_src_nodes, **shared)
+        self.dst_node_mlp = MeshGraphMLP(input_dim=input_dim_dst_nodes + output_dim_edges,
+                                         output_dim=output_dim_dst_nodes, **shared)
 
     def forward(self, g2m_efeat: Tensor, grid_nfeat: Tensor, mesh_nfeat: Tensor, graph) -> Tuple[Tensor, Tensor]:
         dt = compute_dtype(g2m_efeat)
