@@ -23,8 +23,11 @@ gemm_simt_kernel(const TA* __restrict__ A, int64_t sa_i, int64_t sa_r, const TB*
   __shared__ float Bs[GB_K][GB_N + 4];
   const int t = threadIdx.x;
   const int ti = t / 16, tj = t % 16;  // 16x16 threads, 4x4 each
-  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * GB_M;
-  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * GB_N;
+  // grid.x is a linear tile id, column tile fastest: CTAs sharing a row tile of A are adjacent, and the row-tile
+  // count is not bound by the 65 535 limit of grid.y (6 M-edge tables have 94 k row tiles)
+  const int64_t nj = (J + GB_N - 1) / GB_N;
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) / nj) * GB_M;
+  const int64_t j0 = (static_cast<int64_t>(blockIdx.x) % nj) * GB_N;
   const int64_t r_begin = static_cast<int64_t>(blockIdx.z) * r_chunk;
   const int64_t r_end = min(R, r_begin + r_chunk);
   float acc[4][4];
@@ -103,8 +106,9 @@ linear_fwd_kernel(const T* __restrict__ X, int64_t ldx, const float* __restrict_
   __shared__ float Bs[GB_K][GB_N + 4];
   const int t = threadIdx.x;
   const int ti = t / 16, tj = t % 16;
-  const int64_t i0 = static_cast<int64_t>(blockIdx.y) * GB_M;
-  const int64_t j0 = static_cast<int64_t>(blockIdx.x) * GB_N;
+  const int64_t nj = (N + GB_N - 1) / GB_N;  // linear tile id on grid.x, column tile fastest (see gemm_simt_kernel)
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) / nj) * GB_M;
+  const int64_t j0 = (static_cast<int64_t>(blockIdx.x) % nj) * GB_N;
   float acc[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -338,7 +342,9 @@ template <typename T>
 static int linear_fwd_t(const void* x, int64_t ldx, int64_t M, int64_t K, const float* w, const float* b, int64_t N,
                         int act, void* y_pre, void* h, int64_t ldh, cudaStream_t st) {
   if (M == 0 || N == 0) return MGN_OK;
-  dim3 grid(static_cast<unsigned>((N + GB_N - 1) / GB_N), static_cast<unsigned>((M + GB_M - 1) / GB_M), 1);
+  const int64_t n_tiles = ((N + GB_N - 1) / GB_N) * ((M + GB_M - 1) / GB_M);
+  if (n_tiles > 0x7fffffffLL) return MGN_EUNSUPPORTED;
+  dim3 grid(static_cast<unsigned>(n_tiles), 1, 1);
   linear_fwd_kernel<T><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const T*>(x), ldx, w, b, M, N, K, act,
                                              static_cast<T*>(y_pre), static_cast<T*>(h), ldh);
   return mgn_launch_status();
@@ -355,7 +361,6 @@ extern "C" int mgn_linear_fwd(int dtype, const void* x, int64_t ldx, int64_t M, 
   if (M == 0) return MGN_OK;
   MGN_CHECK_ARG(x && w && (y_pre || h));
   MGN_CHECK_ARG(act >= MGN_ACT_NONE && act <= MGN_ACT_ELU);
-  if (M > int64_t(65535) * GB_M) return MGN_EUNSUPPORTED;
   if (dtype == MGN_F32) return linear_fwd_t<float>(x, ldx, M, K, w, b, N, act, y_pre, h, ldh, as_stream(stream));
   if (dtype == MGN_BF16) return linear_fwd_t<bf16>(x, ldx, M, K, w, b, N, act, y_pre, h, ldh, as_stream(stream));
   return MGN_EINVAL;
@@ -414,9 +419,10 @@ extern "C" int mgn_linear_bwd_data(int dtype, const void* g_y, int64_t M, int64_
   MGN_CHECK_ARG(M >= 0 && N >= 0 && K >= 0 && ldgx >= K);
   if (M == 0 || K == 0) return MGN_OK;
   MGN_CHECK_ARG(g_y && w && g_x);
-  if (M > int64_t(65535) * GB_M) return MGN_EUNSUPPORTED;
   cudaStream_t st = as_stream(stream);
-  dim3 grid(static_cast<unsigned>((K + GB_N - 1) / GB_N), static_cast<unsigned>((M + GB_M - 1) / GB_M), 1);
+  const int64_t n_tiles = ((K + GB_N - 1) / GB_N) * ((M + GB_M - 1) / GB_M);
+  if (n_tiles > 0x7fffffffLL) return MGN_EUNSUPPORTED;
+  dim3 grid(static_cast<unsigned>(n_tiles), 1, 1);
   // C[m,k] = sum_n g_y[m,n] W[n,k]:  A(i=m, r=n) = g_y[m*N+n],  B(r=n, j=k) = W[n*K+k]
   if (dtype == MGN_F32)
     gemm_simt_kernel<float, float, float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const float*>(g_y), N, 1, w, K, 1, M, K,
@@ -465,8 +471,7 @@ extern "C" int mgn_linear_bwd_weight(int dtype, const void* g_y, const void* x, 
   splits = (M + r_chunk - 1) / r_chunk;
   float* part_w = static_cast<float*>(workspace);
   float* part_b = part_w + splits * N * K;
-  dim3 grid(static_cast<unsigned>((K + GB_N - 1) / GB_N), static_cast<unsigned>((N + GB_M - 1) / GB_M),
-            static_cast<unsigned>(splits));
+  dim3 grid(static_cast<unsigned>(((K + GB_N - 1) / GB_N) * ((N + GB_M - 1) / GB_M)), 1, static_cast<unsigned>(splits));
   // C[n,k] = sum_m g_y[m,n] x[m,k]:  A(i=n, r=m) = g_y[m*N+n],  B(r=m, j=k) = x[m*ldx+k]
   if (dtype == MGN_F32)
     gemm_simt_kernel<float, float, float><<<grid, 256, 0, MGN_ST(st)>>>(static_cast<const float*>(g_y), 1, N,
