@@ -24,8 +24,8 @@ def compute_dtype(x: Tensor) -> torch.dtype:
     """fp32 tensors run the fp32 kernels; under `torch.autocast(dtype=bfloat16)` (the reference's
     AMP switch, examples/cfd/vortex_shedding_mgn/train.py:153) or for bf16 inputs the bf16 kernels
     (bf16 storage, fp32 accumulate, fp32 LayerNorm statistics)."""
-    if torch.is_autocast_enabled():
-        dt = torch.get_autocast_gpu_dtype()
+    if torch.is_autocast_enabled("cuda"):
+        dt = torch.get_autocast_dtype("cuda")
         if dt != torch.bfloat16:
             raise NotImplementedError(f"modulus_b200 supports bfloat16 autocast only (got {dt})")
         return dt
