@@ -387,3 +387,45 @@ def test_capture_after_eager_steps_on_the_default_stream(use_amp):
         assert torch.isfinite(out).all()
     finally:
         gc.enable()
+
+
+# ------------------------------------------------------------------------------ DevicePrefetcher
+def test_prefetcher_has_no_cpu_path():
+    from modulus_b200.prefetch import DevicePrefetcher
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DevicePrefetcher("cpu")
+
+
+@pytest.mark.gpu
+def test_prefetcher_stages_batches_in_order_while_compute_runs():
+    from modulus_b200.prefetch import DevicePrefetcher
+
+    g = torch.Generator().manual_seed(0)
+    batches = [(torch.randn(300_000, 7, generator=g).pin_memory(), torch.randn(50_000, 3, generator=g).pin_memory())
+               for _ in range(5)]
+    pf = DevicePrefetcher(DEV)
+    with pytest.raises(RuntimeError, match="nothing staged"):
+        pf.take()
+    pf.stage(*batches[0])
+    sums = []
+    ptrs = set()
+    for i in range(len(batches)):
+        a, b = pf.take()
+        if i + 1 < len(batches):
+            pf.stage(*batches[i + 1])
+        x = a
+        for _ in range(20):                       # keep the compute stream busy while the next copy runs
+            x = x * 1.0001 + 0.0
+        sums.append((a.double().sum() + b.double().sum() + 0 * x.double().sum()))
+        ptrs.add(a.data_ptr())
+        pf.release()
+    torch.cuda.synchronize()
+    for s, (ha, hb) in zip(sums, batches):
+        assert abs(float(s) - float(ha.double().sum() + hb.double().sum())) < 1e-6 * float(ha.double().abs().sum())
+    assert len(ptrs) == 2                         # two static slots, reused
+    assert pf.h2d_bytes == sum(a.numel() * 4 + b.numel() * 4 for a, b in batches)
+    pf.stage(*batches[0])
+    pf.stage(*batches[1])
+    with pytest.raises(RuntimeError, match="every slot"):
+        pf.stage(*batches[2])
