@@ -39,6 +39,12 @@ class DevicePrefetcher:
         self.taken = 0    # batches handed out so far
         self.h2d_bytes = 0
 
+    def reserve(self, *host: Tensor) -> None:
+        """Allocate the device buffers of every slot for batches shaped like `host` (no copy), so that no step pays
+        for a cudaMalloc."""
+        for slot in range(len(self.buffers)):
+            self.buffers[slot] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host)
+
     def stage(self, *host: Tensor) -> None:
         if self.staged - self.taken >= len(self.buffers):
             raise RuntimeError("DevicePrefetcher: every slot holds a batch that has not been taken yet")
