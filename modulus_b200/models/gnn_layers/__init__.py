@@ -8,6 +8,7 @@ from .distributed_graph import (  # noqa: F401
     partition_graph_with_matrix_decomposition,
 )
 from .graph import CuGraphCSC  # noqa: F401
+from .halo_partition import HaloPartition, partition_ids_by_slabs, partition_with_halo  # noqa: F401
 from .mesh_edge_block import MeshEdgeBlock  # noqa: F401
 from .mesh_graph_decoder import MeshGraphDecoder  # noqa: F401
 from .mesh_graph_encoder import MeshGraphEncoder  # noqa: F401

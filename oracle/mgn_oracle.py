@@ -288,3 +288,45 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float =
     bc2 = 1.0 - beta2 ** step
     denom = (v.sqrt() / (bc2 ** 0.5)).add_(eps)
     p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+def khop_halo_partition(offsets: Tensor, indices: Tensor, part_id: Tensor, num_partitions: int, halo_hops: int):
+    """Pure-Python restatement of the k-hop-halo partitions the reference obtains from
+    `dgl.metis_partition(graph, k, extra_cached_hops=halo_hops, reshuffle=True)`
+    (examples/cfd/external_aerodynamics/xaeronet/surface/preprocessor.py:129-155; DGL v2.4
+    `partition_graph_with_halo`, unpinned third party): starting from the nodes a piece owns, each hop adds all
+    in-edges of the previous hop's nodes and their not-yet-present sources.  The node assignment (METIS in the
+    reference) is an input.  Returns, per piece, python lists: node_ids (inner ascending, then halo ascending),
+    inner flags, global edge rows and local (src, dst) pairs in local-CSC order.  Small graphs only."""
+    off = offsets.tolist()
+    idx = indices.tolist()
+    pid = part_id.tolist()
+    out = []
+    for p in range(num_partitions):
+        inner = [v for v in range(len(pid)) if pid[v] == p]
+        members = set(inner)
+        with_edges = set()
+        frontier = list(inner)
+        for _ in range(halo_hops):
+            nxt = []
+            for v in frontier:
+                with_edges.add(v)
+                for e in range(off[v], off[v + 1]):
+                    u = idx[e]
+                    if u not in members:
+                        members.add(u)
+                        nxt.append(u)
+            frontier = nxt
+        halo = sorted(members - set(inner))
+        nodes = inner + halo
+        local = {v: i for i, v in enumerate(nodes)}
+        edge_rows, src_l, dst_l = [], [], []
+        for v in nodes:
+            if v in with_edges:
+                for e in range(off[v], off[v + 1]):
+                    edge_rows.append(e)
+                    src_l.append(local[idx[e]])
+                    dst_l.append(local[v])
+        out.append(dict(node_ids=nodes, inner=[True] * len(inner) + [False] * len(halo), edge_ids=edge_rows,
+                        src=src_l, dst=dst_l))
+    return out
