@@ -330,3 +330,32 @@ def khop_halo_partition(offsets: Tensor, indices: Tensor, part_id: Tensor, num_p
         out.append(dict(node_ids=nodes, inner=[True] * len(inner) + [False] * len(halo), edge_ids=edge_rows,
                         src=src_l, dst=dst_l))
     return out
+
+
+def rollout_reference_loop(model_fn, frames_x: Sequence[Tensor], edge_features: Tensor, mask: Tensor,
+                           stats: Dict[str, Tensor]) -> List[Tensor]:
+    """The prediction loop of examples/cfd/vortex_shedding_mgn/inference.py:90-150 restated statement by statement
+    for ONE trajectory: `frames_x[i]` is the dataset's (normalised) node-feature frame i, `model_fn(x, efeat)` the
+    network.  Returns the list of de-normalised predictions (u, v, p) the reference stores in `self.pred`."""
+    def denorm(x, mu, std):  # VortexSheddingDataset.denormalize (vortex_shedding_dataset.py:351-355)
+        return x * std + mu
+
+    def norm(x, mu, std):    # normalize_node (:335-340)
+        return (x - mu.expand(x.size())) / std.expand(x.size())
+
+    preds: List[Tensor] = []
+    for i, x in enumerate(frames_x):
+        x = x.clone()
+        x[:, 0:2] = denorm(x[:, 0:2], stats["velocity_mean"], stats["velocity_std"])
+        invar = x.clone()
+        if i != 0:
+            invar[:, 0:2] = preds[i - 1][:, 0:2].clone()
+        invar[:, 0:2] = norm(invar[:, 0:2], stats["velocity_mean"], stats["velocity_std"])
+        pred_i = model_fn(invar, edge_features).detach().clone()
+        pred_i[:, 0:2] = denorm(pred_i[:, 0:2], stats["velocity_diff_mean"], stats["velocity_diff_std"])
+        pred_i[:, 2] = denorm(pred_i[:, 2], stats["pressure_mean"], stats["pressure_std"])
+        invar[:, 0:2] = denorm(invar[:, 0:2], stats["velocity_mean"], stats["velocity_std"])
+        m = torch.cat((mask, mask), dim=-1)
+        pred_i[:, 0:2] = torch.where(m, pred_i[:, 0:2], torch.zeros_like(pred_i[:, 0:2]))
+        preds.append(torch.cat(((pred_i[:, 0:2] + invar[:, 0:2]), pred_i[:, [2]]), dim=-1))
+    return preds
