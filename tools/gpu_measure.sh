@@ -14,4 +14,6 @@ tail -2 gpurun_out/ncu_bench.log
 for k in edge_bwd2_kernel edge_fwd3_kernel mlp3_bwd_tc_kernel mlp3_fwd2_tc_kernel segment_sum_batch_kernel node_gemm_tc_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -c 1 -f -o gpurun_out/r01_full_$k python tools/prof_kernels.py 1000 1000 1 > gpurun_out/ncu_$k.log 2>&1
 done
+timeout 300 python tools/bench_train_step.py > gpurun_out/train_step.md 2> gpurun_out/train_step.err; tail -12 gpurun_out/train_step.md
+timeout 300 python bench.py --workload c1 --no-cpu --steps 5 > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err; tail -c 600 gpurun_out/bench_c1.json
 ls -la gpurun_out | head -30
