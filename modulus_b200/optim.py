@@ -2,7 +2,8 @@
 
 The reference's recipe uses `apex.optimizers.FusedAdam` when installed and `torch.optim.Adam` otherwise
 (examples/cfd/vortex_shedding_mgn/train.py:111-123), with `GradScaler.step` deciding whether the step is
-skipped under AMP (:161-163).  A default MeshGraphNet has 263 parameter tensors; torch's foreach Adam
+skipped under AMP (:161-163).  A default MeshGraphNet has 262 parameter tensors (263 state_dict entries with its
+one buffer); torch's foreach Adam
 issues ~10 launches over them, the single-tensor path ~2 000.  Here a device-resident pointer table
 (parameters, gradients, both moments) and a chunk map are built once and `mgn_adam_multi_step` updates
 every tensor in one launch (include/mgn_b200.h).  The step counter lives on the device, so the call never
