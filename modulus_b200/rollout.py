@@ -12,7 +12,7 @@ integrate) plus two small device copies, and nothing synchronises until the call
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional
+from typing import Callable, Dict
 
 import torch
 from torch import Tensor
