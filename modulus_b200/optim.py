@@ -169,6 +169,9 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        for group in self.param_groups:  # flags a torch.optim.Adam checkpoint may carry into the groups
+            if group.get("amsgrad", False) or group.get("maximize", False):
+                raise RuntimeError("FusedAdam does not support amsgrad / maximize (found in a parameter group)")
         tables = [self._tables.get(gi) or self._init_group(gi, group) for gi, group in enumerate(self.param_groups)]
         lib = _lib.load()
         stream = torch.cuda.current_stream().cuda_stream

@@ -72,6 +72,9 @@ def test_fused_adam_argument_errors():
     w.grad = torch.ones(4)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         opt.step()
+    opt.param_groups[0]["maximize"] = True      # e.g. carried in by load_state_dict from torch.optim.Adam(maximize=True)
+    with pytest.raises(RuntimeError, match="maximize"):
+        opt.step()
 
 
 # ------------------------------------------------------------------------------ CUDA path (GPU)
