@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for A/B builds of kernel variants (e.g. MGN_NVCC_EXTRA="-DMGN_WAIT_HINT=20000"); part of the digest
+NVCC_FLAGS += os.environ.get("MGN_NVCC_EXTRA", "").split()
+
+
 def sources():
     return sorted(CSRC.glob("*.cu"))
 

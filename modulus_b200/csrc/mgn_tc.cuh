@@ -217,6 +217,24 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+#ifdef MGN_WAIT_HINT
+// A/B switch for round 2 (profiles/r01_issue_slots.md): try_wait with a suspend-time hint of MGN_WAIT_HINT ns, so the
+// hardware parks a waiting warp instead of returning to the polling loop every ~200 cycles.  Off by default: build
+// with MGN_NVCC_EXTRA="-DMGN_WAIT_HINT=20000" python -m modulus_b200.build to try it.
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(static_cast<uint32_t>(MGN_WAIT_HINT))
+      : "memory");
+  return ok;
+}
+#endif
 // Bounded wait: a wrong descriptor must never hang the GPU box.  Returns false on
 // timeout (callers flag an error and bail out).
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {

@@ -21,6 +21,16 @@ struct RowSrc {  // row r of the tile source lives at tab[(idx ? idx[r] : r) * l
 };
 
 __device__ __forceinline__ bool wait_clk(uint64_t* bar, uint32_t parity) {
+#ifdef MGN_WAIT_HINT
+  // variant under test: hinted try_wait, clock tested once per 256 iterations (~6 instead of ~16 instructions per turn)
+  if (mbar_try_wait_hint(bar, parity)) return true;
+  const long long t0h = clock64();
+  uint32_t spins = 0;
+  while (!mbar_try_wait_hint(bar, parity)) {
+    if ((++spins & 255u) == 0 && clock64() - t0h > 400000000LL) return false;
+  }
+  return true;
+#endif
   if (mbar_try_wait(bar, parity)) return true;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
