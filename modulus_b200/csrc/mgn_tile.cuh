@@ -35,6 +35,9 @@ __device__ __forceinline__ bool wait_clk(uint64_t* bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 400000000LL) return false;  // ~0.2 s: a wrong descriptor must not hang the box
+#ifdef MGN_WAIT_SLEEP
+    __nanosleep(MGN_WAIT_SLEEP);  // second A/B switch: back-off between polls (-DMGN_WAIT_SLEEP=ns), off by default
+#endif
   }
   return true;
 }
