@@ -3,10 +3,10 @@
 Public names, argument lists, the `GraphPartition` fields and every index map are those of
 the reference (physicsnemo/models/gnn_layers/distributed_graph.py:35-1197); maps are
 bit-exact (tests/test_partition.py compares against the reference's known-answer tests and
-against partitions produced by the unmodified reference).  The construction is vectorised:
-the reference expands every destination's edge range with a Python loop
-(`for i in range(len(offset_start))`, :306-334), here one repeat_interleave does it, so an
-8 M-node mesh partitions in seconds instead of minutes.
+against partitions produced by the unmodified reference).  The construction is NOT the reference's
+(loops over ranks and destination nodes, every rank building all P partitions): one keyed sort / unique
+pass over the edge list yields every rank's halo sizes and this rank's own arrays (see `_HaloPairs`), on
+the CPU or on the graph's device, so an 8 M-node mesh partitions in seconds instead of minutes.
 """
 from __future__ import annotations
 
@@ -87,15 +87,75 @@ class GraphPartition:
         return self
 
 
-def _expand_ranges(start: torch.Tensor, end: torch.Tensor, dtype, device) -> torch.Tensor:
-    """cat([arange(start[i], end[i]) for i]) without the Python loop."""
-    deg = (end - start).to(torch.int64)
-    total = int(deg.sum().item())
-    if total == 0:
-        return torch.empty(0, dtype=dtype, device=device)
-    seg_start = torch.cumsum(deg, 0) - deg
-    base = torch.repeat_interleave(start.to(torch.int64) - seg_start, deg)
-    return (torch.arange(total, dtype=torch.int64, device=device) + base).to(dtype)
+# ----------------------------------------------------------------------------------------
+# Partitioning as ONE keyed pass over the edge list
+# ----------------------------------------------------------------------------------------
+# Every partitioner below reduces to the same question: which (rank, source id) pairs occur, i.e. which
+# source rows does each rank's edge set reference.  Edge e belongs to rank own(dst(e)); the pair is packed
+# into one integer key  own(dst(e)) * n_src + src(e), and a single sorted `unique` over the E keys gives,
+# for all ranks at once, the referenced sources in (rank, source id) order.  The reference's local source
+# numbering "[rows owned by rank 0 | rank 1 | ...], each block ascending" (distributed_graph.py:336-368)
+# is then the position after a stable regrouping of that list by (rank, owner(source)); the P x P `sizes`
+# table is a bincount of (owner, rank); a rank's `scatter_indices` are slices of the same list.  Only the
+# calling rank's own arrays are materialised.  All of it is sort / unique / bincount / searchsorted on
+# whatever device the graph lives on (no per-node or per-rank Python loops over graph data).
+_ERR_SIZES = ("error in graph partition: list containing sizes of exchanged indices does not match the tensor "
+              "of indices to be exchanged")
+
+
+class _HaloPairs:
+    """The (rank, source) pairs of a partitioned edge list, grouped by (rank, owner(source), source id)."""
+
+    def __init__(self, edge_rank: torch.Tensor, edge_src: torch.Tensor, src_owner: torch.Tensor, n_src: int, P: int):
+        key = edge_rank.to(torch.int64) * n_src + edge_src.to(torch.int64)
+        self.keys = torch.unique(key, sorted=True)                     # (rank, source) ascending
+        self.rank = torch.div(self.keys, n_src, rounding_mode="floor")
+        self.src = self.keys - self.rank * n_src
+        self.owner = src_owner.to(torch.int64)[self.src]
+        group = self.rank * P + self.owner
+        # rows of the list regrouped by (rank, owner); within a group the source ids stay ascending
+        self.order = torch.sort(group, stable=True).indices
+        counts = torch.bincount(group, minlength=P * P).reshape(P, P)   # [rank, owner]
+        self.counts = counts
+        self.sizes = counts.t().tolist()                               # sizes[owner][rank]
+        per_rank = counts.sum(dim=1)
+        self.rank_start = torch.cumsum(per_rank, 0) - per_rank         # first list row of every rank
+        self.n_src, self.P = n_src, P
+
+    def local_ids(self, rank: int) -> torch.Tensor:
+        """local source id of every list row of `rank`, indexed by its position in the (rank, source)-sorted list"""
+        lo = int(self.rank_start[rank])
+        hi = lo + int(self.counts[rank].sum())
+        rows = self.order[lo:hi]                                        # list rows of this rank in (owner, source) order
+        lid = torch.empty(hi - lo, dtype=torch.int64, device=rows.device)
+        lid[rows - lo] = torch.arange(hi - lo, dtype=torch.int64, device=rows.device)
+        return lid
+
+    def edge_local_src(self, rank: int, edge_src: torch.Tensor) -> torch.Tensor:
+        """local source id of each of `rank`'s edges (given their global source ids)"""
+        lo = int(self.rank_start[rank])
+        pos = torch.searchsorted(self.keys, rank * self.n_src + edge_src.to(torch.int64)) - lo
+        return self.local_ids(rank)[pos]
+
+    def sources_of(self, rank: int, owner: int) -> torch.Tensor:
+        """global ids (ascending) of the sources owned by `owner` that `rank`'s edges reference"""
+        c = self.counts[rank]
+        lo = int(self.rank_start[rank]) + int(c[:owner].sum())
+        return self.src[self.order[lo: lo + int(c[owner])]]
+
+
+def _rank_major(mapping: torch.Tensor, P: int):
+    """ids grouped by rank (ascending inside a rank), the per-rank counts and the inverse permutation"""
+    order = torch.sort(mapping.to(torch.int64), stable=True).indices
+    counts = torch.bincount(mapping.to(torch.int64), minlength=P)
+    inverse = torch.empty_like(order)
+    inverse[order] = torch.arange(order.numel(), dtype=torch.int64, device=order.device)
+    return order, counts, inverse
+
+
+def _edge_destinations(global_offsets: torch.Tensor) -> torch.Tensor:
+    deg = (global_offsets[1:] - global_offsets[:-1]).to(torch.int64)
+    return torch.repeat_interleave(torch.arange(deg.numel(), dtype=torch.int64, device=deg.device), deg)
 
 
 def partition_graph_with_id_mapping(
@@ -107,124 +167,67 @@ def partition_graph_with_id_mapping(
     partition_rank: int,
     device: torch.device,
 ) -> GraphPartition:
-    """Partition a global CSC graph given id -> rank maps for the source and destination id spaces
-    (reference: distributed_graph.py:154-398).  Every rank derives all P partitions' sizes (needed
-    for the all-to-all) and keeps its own local graph."""
-    graph_partition = GraphPartition(partition_size=partition_size, partition_rank=partition_rank, device=device)
+    """Partition a global CSC graph given id -> rank maps of the source and destination id spaces.  Same
+    result, field by field and bit for bit, as the reference's distributed_graph.py:154-398 (checked by
+    tests/test_partition.py against partitions the unmodified reference produced); built by the keyed pass
+    described above instead of the reference's loops over ranks and destination nodes."""
+    P, me = partition_size, partition_rank
+    gp = GraphPartition(partition_size=P, partition_rank=me, device=device)
+    idx_dtype, map_dtype = global_indices.dtype, mapping_src_ids_to_ranks.dtype
+    dst_dtype = mapping_dst_ids_to_ranks.dtype
 
-    dst_nodes_in_each_partition = [None] * partition_size
-    src_nodes_in_each_partition = [None] * partition_size
-    num_dst_nodes_in_each_partition = [None] * partition_size
-    num_src_nodes_in_each_partition = [None] * partition_size
+    dst_order, dst_counts, dst_inverse = _rank_major(mapping_dst_ids_to_ranks, P)
+    src_order, src_counts, src_inverse = _rank_major(mapping_src_ids_to_ranks, P)
+    for r in range(P):  # same complaints, in the same order, as the reference
+        if int(dst_counts[r]) == 0:
+            raise RuntimeError(f"Aborting partitioning, rank {r} has 0 destination nodes to work on.")
+        if int(src_counts[r]) == 0:
+            raise RuntimeError(f"Aborting partitioning, rank {r} has 0 source nodes to work on.")
+    gp.num_dst_nodes_in_each_partition = dst_counts.tolist()
+    gp.num_src_nodes_in_each_partition = src_counts.tolist()
+    gp.map_concatenated_local_dst_ids_to_global = dst_order.to(dst_dtype)
+    gp.map_global_dst_ids_to_concatenated_local = dst_inverse.to(dst_dtype)
+    gp.map_concatenated_local_src_ids_to_global = src_order.to(map_dtype)
+    gp.map_global_src_ids_to_concatenated_local = src_inverse.to(map_dtype)
+    src_start = torch.cumsum(src_counts, 0) - src_counts
+    dst_start = torch.cumsum(dst_counts, 0) - dst_counts
+    # row of a source inside its owner's partitioned table
+    src_row_in_partition = src_inverse - src_start[mapping_src_ids_to_ranks.to(torch.int64)]
 
-    dtype = global_indices.dtype
-    input_device = global_indices.device
+    # edges: CSC order is destination-major, so a stable regrouping by the destination's rank is the
+    # concatenation of every rank's CSC ranges
+    edge_rank = mapping_dst_ids_to_ranks.to(torch.int64)[_edge_destinations(global_offsets)]
+    edge_order, edge_counts, edge_inverse = _rank_major(edge_rank, P)
+    gp.map_concatenated_local_edge_ids_to_global = edge_order.to(idx_dtype)
+    gp.map_global_edge_ids_to_concatenated_local = edge_inverse.to(idx_dtype)
+    gp.num_indices_in_each_partition = edge_counts.tolist()
 
-    graph_partition.map_concatenated_local_src_ids_to_global = torch.empty_like(mapping_src_ids_to_ranks)
-    graph_partition.map_concatenated_local_dst_ids_to_global = torch.empty_like(mapping_dst_ids_to_ranks)
-    graph_partition.map_concatenated_local_edge_ids_to_global = torch.empty_like(global_indices)
-    graph_partition.map_global_src_ids_to_concatenated_local = torch.empty_like(mapping_src_ids_to_ranks)
-    graph_partition.map_global_dst_ids_to_concatenated_local = torch.empty_like(mapping_dst_ids_to_ranks)
-    graph_partition.map_global_edge_ids_to_concatenated_local = torch.empty_like(global_indices)
-    _map_global_src_ids_to_local = torch.empty_like(mapping_src_ids_to_ranks)
+    n_src = int(mapping_src_ids_to_ranks.numel())
+    pairs = _HaloPairs(edge_rank, global_indices, mapping_src_ids_to_ranks, n_src, P)
+    for q in range(P):
+        for r in range(P):
+            gp.sizes[q][r] = pairs.sizes[q][r]
+    # rows this rank sends to each peer
+    gp.scatter_indices = [src_row_in_partition[pairs.sources_of(r, me)].to(torch.int64).clone() for r in range(P)]
 
-    _src_id_offset = 0
-    _dst_id_offset = 0
-    _edge_id_offset = 0
+    # this rank's local graph
+    e_lo = int(edge_counts[:me].sum())
+    my_edges = edge_order[e_lo: e_lo + int(edge_counts[me])]
+    my_dst = dst_order[int(dst_start[me]): int(dst_start[me]) + int(dst_counts[me])]
+    degree = global_offsets[my_dst + 1] - global_offsets[my_dst]
+    gp.local_offsets = torch.cat([torch.zeros(1, dtype=idx_dtype, device=global_indices.device), degree.cumsum(dim=0)])
+    gp.local_indices = pairs.edge_local_src(me, global_indices[my_edges]).to(map_dtype)
+    gp.num_local_indices = int(my_edges.numel())
+    gp.num_local_dst_nodes = int(dst_counts[me])
+    gp.num_local_src_nodes = int(pairs.counts[me].sum())
+    gp.map_partitioned_src_ids_to_global = src_order[int(src_start[me]): int(src_start[me]) + int(src_counts[me])]
+    gp.map_partitioned_dst_ids_to_global = my_dst
+    gp.map_partitioned_edge_ids_to_global = my_edges.to(idx_dtype)
 
-    for rank in range(partition_size):
-        dst_nodes_in_each_partition[rank] = torch.nonzero(mapping_dst_ids_to_ranks == rank).view(-1)
-        src_nodes_in_each_partition[rank] = torch.nonzero(mapping_src_ids_to_ranks == rank).view(-1)
-        num_nodes = dst_nodes_in_each_partition[rank].numel()
-        if num_nodes == 0:
-            raise RuntimeError(f"Aborting partitioning, rank {rank} has 0 destination nodes to work on.")
-        num_dst_nodes_in_each_partition[rank] = num_nodes
-
-        num_nodes = src_nodes_in_each_partition[rank].numel()
-        num_src_nodes_in_each_partition[rank] = num_nodes
-        if num_nodes == 0:
-            raise RuntimeError(f"Aborting partitioning, rank {rank} has 0 source nodes to work on.")
-
-        ids = src_nodes_in_each_partition[rank]
-        mapped_ids = torch.arange(start=_src_id_offset, end=_src_id_offset + ids.numel(), dtype=dtype,
-                                  device=input_device)
-        _map_global_src_ids_to_local[ids] = (mapped_ids - _src_id_offset).to(_map_global_src_ids_to_local.dtype)
-        graph_partition.map_global_src_ids_to_concatenated_local[ids] = mapped_ids.to(
-            graph_partition.map_global_src_ids_to_concatenated_local.dtype)
-        graph_partition.map_concatenated_local_src_ids_to_global[mapped_ids] = ids.to(
-            graph_partition.map_concatenated_local_src_ids_to_global.dtype)
-        _src_id_offset += ids.numel()
-
-        ids = dst_nodes_in_each_partition[rank]
-        mapped_ids = torch.arange(start=_dst_id_offset, end=_dst_id_offset + ids.numel(), dtype=dtype,
-                                  device=input_device)
-        graph_partition.map_global_dst_ids_to_concatenated_local[ids] = mapped_ids.to(
-            graph_partition.map_global_dst_ids_to_concatenated_local.dtype)
-        graph_partition.map_concatenated_local_dst_ids_to_global[mapped_ids] = ids.to(
-            graph_partition.map_concatenated_local_dst_ids_to_global.dtype)
-        _dst_id_offset += ids.numel()
-
-    graph_partition.num_src_nodes_in_each_partition = num_src_nodes_in_each_partition
-    graph_partition.num_dst_nodes_in_each_partition = num_dst_nodes_in_each_partition
-
-    for rank in range(partition_size):
-        offset_start = global_offsets[dst_nodes_in_each_partition[rank]].view(-1)
-        offset_end = global_offsets[dst_nodes_in_each_partition[rank] + 1].view(-1)
-        degree = offset_end - offset_start
-        local_offsets = degree.view(-1).cumsum(dim=0)
-        local_offsets = torch.cat([torch.zeros(1, dtype=dtype, device=input_device), local_offsets])
-
-        # all in-edges of the owned destinations, destination-major, in CSC order
-        partitioned_edge_ids = _expand_ranges(offset_start, offset_end, dtype, input_device)
-
-        ids = partitioned_edge_ids
-        mapped_ids = torch.arange(_edge_id_offset, _edge_id_offset + ids.numel(), device=ids.device, dtype=ids.dtype)
-        graph_partition.map_global_edge_ids_to_concatenated_local[ids] = mapped_ids
-        graph_partition.map_concatenated_local_edge_ids_to_global[mapped_ids] = ids
-        _edge_id_offset += ids.numel()
-
-        partitioned_src_ids = global_indices[partitioned_edge_ids]
-
-        global_src_ids_on_rank, inverse_mapping = partitioned_src_ids.unique(sorted=True, return_inverse=True)
-        remote_local_src_ids_on_rank = _map_global_src_ids_to_local[global_src_ids_on_rank]
-
-        # local source id = position in [ids owned by rank 0 | rank 1 | ...], each block sorted
-        owner = mapping_src_ids_to_ranks[global_src_ids_on_rank]
-        _num_local_indices = 0
-        local_id_of_unique = torch.empty_like(global_src_ids_on_rank)
-        for rank_offset in range(partition_size):
-            mask = owner == rank_offset
-            if partition_rank == rank_offset:
-                graph_partition.scatter_indices[rank] = (
-                    remote_local_src_ids_on_rank[mask].detach().clone().to(dtype=torch.int64)
-                )
-            numel_mask = int(mask.sum().item())
-            graph_partition.sizes[rank_offset][rank] = numel_mask
-            local_id_of_unique[mask] = torch.arange(
-                _num_local_indices, _num_local_indices + numel_mask, device=input_device, dtype=dtype
-            ).to(local_id_of_unique.dtype)
-            _num_local_indices += numel_mask
-
-        local_indices = local_id_of_unique[inverse_mapping].to(mapping_src_ids_to_ranks.dtype)
-        graph_partition.num_indices_in_each_partition[rank] = local_indices.size(0)
-
-        if rank == partition_rank:
-            graph_partition.local_offsets = local_offsets
-            graph_partition.local_indices = local_indices
-            graph_partition.num_local_indices = graph_partition.local_indices.size(0)
-            graph_partition.num_local_dst_nodes = num_dst_nodes_in_each_partition[rank]
-            graph_partition.num_local_src_nodes = global_src_ids_on_rank.size(0)
-            graph_partition.map_partitioned_src_ids_to_global = src_nodes_in_each_partition[rank]
-            graph_partition.map_partitioned_dst_ids_to_global = dst_nodes_in_each_partition[rank]
-            graph_partition.map_partitioned_edge_ids_to_global = partitioned_edge_ids
-
-    for r in range(graph_partition.partition_size):
-        err_msg = "error in graph partition: list containing sizes of exchanged indices does not match the tensor of indices to be exchanged"
-        if graph_partition.sizes[graph_partition.partition_rank][r] != graph_partition.scatter_indices[r].numel():
-            raise AssertionError(err_msg)
-
-    graph_partition = graph_partition.to(device=device)
-    return graph_partition
+    for r in range(P):
+        if gp.sizes[me][r] != gp.scatter_indices[r].numel():
+            raise AssertionError(_ERR_SIZES)
+    return gp.to(device=device)
 
 
 def partition_graph_with_matrix_decomposition(
@@ -236,70 +239,59 @@ def partition_graph_with_matrix_decomposition(
     partition_rank: int,
     device: torch.device,
 ) -> GraphPartition:
-    """1-D row decomposition of a square adjacency matrix given contiguous node ranges
-    `partition_book` (reference: distributed_graph.py:401-562)."""
-    graph_partition = GraphPartition(partition_size=partition_size, partition_rank=partition_rank, device=device)
+    """1-D row decomposition of a square adjacency matrix over the contiguous node ranges of
+    `partition_book` (reference: distributed_graph.py:401-562).  Here the local source space of a rank is
+    simply its referenced sources in ascending global id (owners are contiguous ranges, so that IS the
+    rank-grouped order) and the partitioned source table is that same list; the concatenated <-> global maps
+    are identities.  Served by the same keyed pass."""
+    P, me = partition_size, partition_rank
+    gp = GraphPartition(partition_size=P, partition_rank=me, device=device, matrix_decomp=True)
     dtype = global_indices.dtype
-    num_edges = global_indices.size(0)
-    node_offset = partition_book[partition_rank]
-    num_local_nodes = partition_book[partition_rank + 1] - partition_book[partition_rank]
-    edge_partition_offset = global_offsets[node_offset]
-    if node_offset + num_local_nodes > num_nodes:
+    book = partition_book.to(device=global_indices.device, dtype=torch.int64)
+    node_lo, node_hi = int(book[me]), int(book[me + 1])
+    if node_hi > num_nodes:
         raise ValueError("Invalid node offset and number of local nodes")
+    ids = torch.arange(num_nodes, dtype=torch.int64, device=global_indices.device)
+    owner = torch.bucketize(ids, book, right=True) - 1
+    edge_rank = owner[_edge_destinations(global_offsets)]
+    pairs = _HaloPairs(edge_rank, global_indices, owner, num_nodes, P)
 
-    local_offsets = global_offsets[node_offset: node_offset + num_local_nodes + 1].to(device=device, non_blocking=True)
-    graph_partition.local_offsets = local_offsets - edge_partition_offset
-    graph_partition.num_local_dst_nodes = num_local_nodes
+    e_lo, e_hi = int(global_offsets[node_lo]), int(global_offsets[node_hi])
+    gp.local_offsets = global_offsets[node_lo: node_hi + 1] - global_offsets[node_lo]
+    gp.local_indices = pairs.edge_local_src(me, global_indices[e_lo:e_hi])
+    gp.num_local_indices = e_hi - e_lo
+    gp.num_local_dst_nodes = node_hi - node_lo
+    gp.num_local_src_nodes = int(pairs.counts[me].sum())
+    gp.map_partitioned_src_ids_to_global = torch.cat([pairs.sources_of(me, q) for q in range(P)]).to(dtype)
+    gp.scatter_indices = [(pairs.sources_of(r, me) - node_lo).to(dtype) for r in range(P)]
+    edges_per_rank = global_offsets.to(torch.int64)[book[1:]] - global_offsets.to(torch.int64)[book[:-1]]
+    gp.num_indices_in_each_partition = edges_per_rank.tolist()
+    gp.num_dst_nodes_in_each_partition = (book[1:] - book[:-1]).tolist()
+    gp.num_src_nodes_in_each_partition = pairs.counts.sum(dim=1).tolist()
+    for q in range(P):
+        for r in range(P):
+            gp.sizes[q][r] = pairs.sizes[q][r]
 
-    partition_book = partition_book.to(device=device)
-    for to_partition in range(partition_size):
-        local_indices = global_indices[
-            global_offsets[partition_book[to_partition]]: global_offsets[partition_book[to_partition + 1]]
-        ].to(device=device, non_blocking=True)
-        global_src_node_at_partition, inverse_indices = local_indices.unique(sorted=True, return_inverse=True)
-        global_src_node_at_partition_rank = (
-            torch.bucketize(global_src_node_at_partition, partition_book, right=True) - 1
-        )
-        src_node_indices = torch.nonzero(global_src_node_at_partition_rank == partition_rank, as_tuple=False).squeeze(1)
-        graph_partition.scatter_indices[to_partition] = global_src_node_at_partition[src_node_indices] - node_offset
-        graph_partition.num_indices_in_each_partition[to_partition] = local_indices.size(0)
-        graph_partition.num_dst_nodes_in_each_partition[to_partition] = (
-            partition_book[to_partition + 1] - partition_book[to_partition]
-        )
-        graph_partition.num_src_nodes_in_each_partition[to_partition] = global_src_node_at_partition.size(0)
+    gp.map_partitioned_dst_ids_to_global = torch.arange(node_lo, node_hi, dtype=dtype, device=device)
+    gp.map_partitioned_edge_ids_to_global = torch.arange(e_lo, e_hi, dtype=dtype, device=device)
+    node_identity = torch.arange(num_nodes, dtype=dtype, device=device)
+    edge_identity = torch.arange(global_indices.size(0), dtype=dtype, device=device)
+    gp.map_concatenated_local_src_ids_to_global = node_identity
+    gp.map_concatenated_local_dst_ids_to_global = node_identity
+    gp.map_global_src_ids_to_concatenated_local = node_identity
+    gp.map_global_dst_ids_to_concatenated_local = node_identity
+    gp.map_concatenated_local_edge_ids_to_global = edge_identity
+    gp.map_global_edge_ids_to_concatenated_local = edge_identity
 
-        if to_partition == partition_rank:
-            graph_partition.local_indices = inverse_indices
-            graph_partition.num_local_indices = graph_partition.local_indices.size(0)
-            graph_partition.num_local_src_nodes = global_src_node_at_partition.size(0)
-            graph_partition.map_partitioned_src_ids_to_global = global_src_node_at_partition
+    for r in range(P):
+        if gp.sizes[me][r] != gp.scatter_indices[r].numel():
+            raise AssertionError(_ERR_SIZES)
+    return gp.to(device=device)
 
-        for from_partition in range(partition_size):
-            graph_partition.sizes[from_partition][to_partition] = torch.count_nonzero(
-                global_src_node_at_partition_rank == from_partition
-            )
 
-    graph_partition.map_partitioned_dst_ids_to_global = torch.arange(
-        node_offset, node_offset + num_local_nodes, dtype=dtype, device=device
-    )
-    graph_partition.map_partitioned_edge_ids_to_global = torch.arange(
-        edge_partition_offset, edge_partition_offset + graph_partition.num_local_indices, dtype=dtype, device=device
-    )
-    graph_partition.map_concatenated_local_src_ids_to_global = torch.arange(num_nodes, dtype=dtype, device=device)
-    graph_partition.map_concatenated_local_edge_ids_to_global = torch.arange(num_edges, dtype=dtype, device=device)
-    graph_partition.map_concatenated_local_dst_ids_to_global = graph_partition.map_concatenated_local_src_ids_to_global
-    graph_partition.map_global_src_ids_to_concatenated_local = graph_partition.map_concatenated_local_src_ids_to_global
-    graph_partition.map_global_dst_ids_to_concatenated_local = graph_partition.map_concatenated_local_src_ids_to_global
-    graph_partition.map_global_edge_ids_to_concatenated_local = graph_partition.map_concatenated_local_edge_ids_to_global
-    graph_partition.matrix_decomp = True
-
-    for r in range(graph_partition.partition_size):
-        err_msg = "error in graph partition: list containing sizes of exchanged indices does not match the tensor of indices to be exchanged"
-        if graph_partition.sizes[graph_partition.partition_rank][r] != graph_partition.scatter_indices[r].numel():
-            raise AssertionError(err_msg)
-
-    graph_partition = graph_partition.to(device=device)
-    return graph_partition
+def _chunk_owner(n: int, P: int, like: torch.Tensor) -> torch.Tensor:
+    per_rank = (n + P - 1) // P
+    return torch.arange(n, dtype=like.dtype, device=like.device) // per_rank
 
 
 def partition_graph_nodewise(
@@ -310,36 +302,34 @@ def partition_graph_nodewise(
     device: torch.device,
     matrix_decomp: bool = False,
 ) -> GraphPartition:
-    """Equal-size chunks of the source and destination id spaces: owner(v) = v // ceil(N / P)
-    (reference: distributed_graph.py:565-666)."""
-    num_global_src_nodes = global_indices.max().item() + 1
-    num_global_dst_nodes = global_offsets.size(0) - 1
-    num_dst_nodes_per_partition = (num_global_dst_nodes + partition_size - 1) // partition_size
-
+    """Equal chunks of both id spaces: owner(v) = v // ceil(n / P) (reference: distributed_graph.py:565-666)."""
+    n_src = int(global_indices.max()) + 1
+    n_dst = int(global_offsets.numel()) - 1
     if matrix_decomp:
-        if num_global_src_nodes != num_global_dst_nodes:
+        if n_src != n_dst:
             raise ValueError("Must be square adj. matrix (num_src=num_dst) for matrix decomposition")
-        partition_book = torch.arange(0, num_global_dst_nodes, num_dst_nodes_per_partition, dtype=global_indices.dtype)
-        partition_book = torch.cat([partition_book, torch.tensor([num_global_dst_nodes], dtype=global_indices.dtype)])
-        return partition_graph_with_matrix_decomposition(
-            global_offsets, global_indices, num_global_dst_nodes, partition_book, partition_size, partition_rank,
-            device,
-        )
-
-    num_src_nodes_per_partition = (num_global_src_nodes + partition_size - 1) // partition_size
-
-    mapping_dst_ids_to_ranks = (
-        torch.arange(num_global_dst_nodes, dtype=global_offsets.dtype, device=global_offsets.device)
-        // num_dst_nodes_per_partition
-    )
-    mapping_src_ids_to_ranks = (
-        torch.arange(num_global_src_nodes, dtype=global_offsets.dtype, device=global_offsets.device)
-        // num_src_nodes_per_partition
-    )
+        per_rank = (n_dst + partition_size - 1) // partition_size
+        book = torch.tensor(list(range(0, n_dst, per_rank)) + [n_dst], dtype=global_indices.dtype)
+        return partition_graph_with_matrix_decomposition(global_offsets, global_indices, n_dst, book, partition_size,
+                                                         partition_rank, device)
     return partition_graph_with_id_mapping(
-        global_offsets, global_indices, mapping_src_ids_to_ranks, mapping_dst_ids_to_ranks, partition_size,
-        partition_rank, device,
-    )
+        global_offsets, global_indices, _chunk_owner(n_src, partition_size, global_offsets),
+        _chunk_owner(n_dst, partition_size, global_offsets), partition_size, partition_rank, device)
+
+
+def _bbox_owner(coordinates: torch.Tensor, lo: List[List[Optional[float]]], hi: List[List[Optional[float]]],
+                like: torch.Tensor) -> torch.Tensor:
+    """rank of every point: the LAST box (in rank order) with lo <= x < hi on every bounded axis; 0 if none"""
+    P, dim = len(lo), coordinates.size(-1)
+    inf = float("inf")
+    lo_t = torch.tensor([[-inf if v is None else v for v in row] for row in lo], dtype=coordinates.dtype,
+                        device=coordinates.device)
+    hi_t = torch.tensor([[inf if v is None else v for v in row] for row in hi], dtype=coordinates.dtype,
+                        device=coordinates.device)
+    x = coordinates[:, None, :dim]
+    inside = ((x >= lo_t[None]) & (x < hi_t[None])).all(dim=-1)          # [n, P]
+    ranks = torch.arange(1, P + 1, device=coordinates.device)
+    return ((inside * ranks[None]).amax(dim=1) - 1).clamp_min(0).to(like.dtype)
 
 
 def partition_graph_by_coordinate_bbox(
@@ -353,43 +343,23 @@ def partition_graph_by_coordinate_bbox(
     partition_rank: int,
     device: torch.device,
 ) -> GraphPartition:
-    """Assign nodes to ranks by axis-aligned boxes ``min <= x < max`` (None = unbounded); boxes are
-    applied in rank order, so the LAST matching box wins and unmatched points stay on rank 0
-    (reference: distributed_graph.py:669-882)."""
+    """Nodes go to ranks by axis-aligned boxes ``min <= x < max`` (None = unbounded).  The reference assigns
+    box after box in rank order (distributed_graph.py:848-869), so overlapping boxes resolve to the last one
+    and points in no box stay on rank 0; `_bbox_owner` states that rule directly."""
     dim = src_coordinates.size(-1)
     if dst_coordinates.size(-1) != dim:
         raise ValueError()
-    if len(coordinate_separators_min) != partition_size:
-        a, b = len(coordinate_separators_min), partition_size
-        raise ValueError(f"Expected len(coordinate_separators_min) == partition_size, but got {a} and {b} respectively")
-    if len(coordinate_separators_max) != partition_size:
-        a, b = len(coordinate_separators_max), partition_size
-        raise ValueError(f"Expected len(coordinate_separators_max) == partition_size, but got {a} and {b} respectively")
-
-    num_global_src_nodes = global_indices.max().item() + 1
-    num_global_dst_nodes = global_offsets.size(0) - 1
-
-    mapping_dst_ids_to_ranks = torch.zeros(num_global_dst_nodes, dtype=global_offsets.dtype, device=global_offsets.device)
-    mapping_src_ids_to_ranks = torch.zeros(num_global_src_nodes, dtype=global_offsets.dtype, device=global_offsets.device)
-
-    def _assign_ranks(mapping, coordinates):
-        for p in range(partition_size):
-            mask = torch.ones_like(mapping).to(dtype=torch.bool)
-            for d in range(dim):
-                min_val, max_val = coordinate_separators_min[p][d], coordinate_separators_max[p][d]
-                if min_val is not None:
-                    mask = mask & (coordinates[:, d] >= min_val)
-                if max_val is not None:
-                    mask = mask & (coordinates[:, d] < max_val)
-            mapping[mask] = p
-
-    _assign_ranks(mapping_src_ids_to_ranks, src_coordinates)
-    _assign_ranks(mapping_dst_ids_to_ranks, dst_coordinates)
-
+    for name, seps in (("coordinate_separators_min", coordinate_separators_min),
+                       ("coordinate_separators_max", coordinate_separators_max)):
+        if len(seps) != partition_size:
+            raise ValueError(f"Expected len({name}) == partition_size, but got {len(seps)} and {partition_size} respectively")
+    n_src = int(global_indices.max()) + 1
+    n_dst = int(global_offsets.numel()) - 1
     return partition_graph_with_id_mapping(
-        global_offsets, global_indices, mapping_src_ids_to_ranks, mapping_dst_ids_to_ranks, partition_size,
-        partition_rank, device,
-    )
+        global_offsets, global_indices,
+        _bbox_owner(src_coordinates[:n_src], coordinate_separators_min, coordinate_separators_max, global_offsets),
+        _bbox_owner(dst_coordinates[:n_dst], coordinate_separators_min, coordinate_separators_max, global_offsets),
+        partition_size, partition_rank, device)
 
 
 class DistributedGraph:

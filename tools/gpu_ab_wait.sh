@@ -4,7 +4,7 @@
 set -x
 mkdir -p gpurun_out
 timeout 300 python tools/prof_kernels.py 1000 1000 3 > gpurun_out/ab_wait_default.txt 2>&1; head -8 gpurun_out/ab_wait_default.txt
-for v in "-DMGN_WAIT_HINT=20000" "-DMGN_WAIT_HINT=1000000" "-DMGN_WAIT_SLEEP=32" "-DMGN_WAIT_SLEEP=100"; do
+for v in "-DMGN_WAIT_HINT=20000" "-DMGN_WAIT_SLEEP=32" "-DMGN_WAIT_SLEEP=200"; do
   tag=$(echo "$v" | tr -c 'A-Za-z0-9\n' '_')
   MGN_NVCC_EXTRA="$v" timeout 300 python -m modulus_b200.build || continue
   MGN_NVCC_EXTRA="$v" timeout 300 python tools/prof_kernels.py 1000 1000 3 > gpurun_out/ab_wait$tag.txt 2>&1; head -8 gpurun_out/ab_wait$tag.txt
