@@ -159,6 +159,7 @@ class DistributedManager:
         os.environ["MASTER_PORT"] = str(port)
         DistributedManager._shared_state["_is_initialized"] = True
         m = DistributedManager()
+        m._is_initialized = True  # (the first instantiation fills in defaults, this flag among them)
         m._rank, m._world_size = rank, world_size
         m._local_rank = local_rank if local_rank is not None else (
             rank % torch.cuda.device_count() if torch.cuda.is_available() else 0)

@@ -27,13 +27,20 @@ from .manager import DistributedManager
 
 
 # ----------------------------------------------------------------------------------------
-# transport helper: list-based all_to_all that also works on gloo (CPU test harness)
+# transport.  NCCL is the product transport (one all_to_all_single over NVLink).  Any other backend
+# (gloo: the CPU test harness, and the single-device multi-process emulation of tests/test_gpu_dist.py, where
+# several ranks share one GPU, which NCCL refuses) gets a point-to-point realisation; device tensors are staged
+# through host memory there, because gloo moves host buffers only.  Nothing else differs between the two.
 # ----------------------------------------------------------------------------------------
 def _backend_has_alltoall(group) -> bool:
     try:
         return dist.get_backend(group) == "nccl"
     except Exception:
         return False
+
+
+def _host_staged(group, *tensors) -> bool:
+    return (not _backend_has_alltoall(group)) and any(t.is_cuda for t in tensors if t is not None)
 
 
 def all_to_all_list(x_recv: List[torch.Tensor], x_send: List[torch.Tensor], group=None) -> None:
@@ -44,18 +51,25 @@ def all_to_all_list(x_recv: List[torch.Tensor], x_send: List[torch.Tensor], grou
     rank = dist.get_rank(group=group)
     size = dist.get_world_size(group=group)
     ranks = dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)
+    staged = _host_staged(group, *x_recv, *x_send)
+    recv_bufs = [torch.empty(t.shape, dtype=t.dtype) for t in x_recv] if staged else x_recv
     x_recv[rank].copy_(x_send[rank])
     ops_ = []
     for r in range(size):
         if r == rank:
             continue
         if x_send[r].numel() > 0:
-            ops_.append(dist.P2POp(dist.isend, x_send[r].contiguous(), ranks[r], group=group))
+            ops_.append(dist.P2POp(dist.isend, x_send[r].contiguous().cpu() if staged else x_send[r].contiguous(),
+                                   ranks[r], group=group))
         if x_recv[r].numel() > 0:
-            ops_.append(dist.P2POp(dist.irecv, x_recv[r], ranks[r], group=group))
+            ops_.append(dist.P2POp(dist.irecv, recv_bufs[r], ranks[r], group=group))
     if ops_:
         for req in dist.batch_isend_irecv(ops_):
             req.wait()
+    if staged:
+        for r in range(size):
+            if r != rank and x_recv[r].numel() > 0:
+                x_recv[r].copy_(recv_bufs[r])
 
 
 def all_to_all_rows(send: torch.Tensor, send_splits: Sequence[int], recv_splits: Sequence[int],
@@ -68,6 +82,25 @@ def all_to_all_rows(send: torch.Tensor, send_splits: Sequence[int], recv_splits:
         all_to_all_list(list(torch.split(recv, list(recv_splits), dim=0)),
                         list(torch.split(send, list(send_splits), dim=0)), group=group)
     return recv
+
+
+def all_to_all_rows_async(send: torch.Tensor, send_splits: Sequence[int], recv_splits: Sequence[int], group=None):
+    """(work, recv): the exchange is in flight on NCCL's stream until work.wait(); `work` is None when the
+    transport completed it synchronously."""
+    if _backend_has_alltoall(group):
+        recv = send.new_empty((int(sum(recv_splits)),) + tuple(send.shape[1:]))
+        work = dist.all_to_all_single(recv, send, list(recv_splits), list(send_splits), group=group, async_op=True)
+        return work, recv
+    return None, all_to_all_rows(send, send_splits, recv_splits, group=group)
+
+
+def _all_reduce_sum(t: torch.Tensor, group=None) -> None:
+    if _host_staged(group, t):
+        h = t.cpu()
+        dist.all_reduce(h, group=group)
+        t.copy_(h)
+    else:
+        dist.all_reduce(t, group=group)
 
 
 # ----------------------------------------------------------------------------------------
@@ -201,7 +234,10 @@ def all_gather_v_wrapper(tensor, sizes: Optional[List[int]] = None, dim: int = 0
         if sizes is not None:
             shape[dim] = sizes[r]
         tensor_list.append(torch.empty(shape, dtype=tensor.dtype, device=tensor.device))
-    dist.all_gather(tensor_list, tensor.contiguous(), group=group)
+    if _backend_has_alltoall(group):
+        dist.all_gather(tensor_list, tensor.contiguous(), group=group)
+    else:  # gloo's all_gather wants equal shapes: every rank sends its block to every peer instead
+        all_to_all_list(tensor_list, [tensor.contiguous()] * comm_size, group=group)
     return torch.cat(tensor_list, dim=dim).contiguous()
 
 
@@ -291,10 +327,10 @@ def _reduce(input_, use_fp32=True, group=None):
     if use_fp32 and (input_.dtype.itemsize < 4) and input_.dtype.is_floating_point:
         dtype = input_.dtype
         inputf_ = input_.float()
-        dist.all_reduce(inputf_, group=group)
+        _all_reduce_sum(inputf_, group=group)
         input_ = inputf_.to(dtype)
     else:
-        dist.all_reduce(input_, group=group)
+        _all_reduce_sum(input_, group=group)
     return input_
 
 
@@ -318,7 +354,7 @@ def mark_module_as_shared(module: nn.Module, process_group: Optional[str], recur
         grads = [p.grad for p in params]
         acc = torch.float32 if use_fp32_reduction else None
         flat = torch.cat([g.reshape(-1).to(acc or g.dtype) for g in grads])
-        dist.all_reduce(flat, group=group)
+        _all_reduce_sum(flat, group=group)
         off = 0
         for g in grads:
             n = g.numel()
@@ -365,7 +401,7 @@ def reduce_shared_gradients(module: nn.Module, process_group: Optional[str] = No
     if not grads:
         return
     flat = torch.cat([g.reshape(-1).float() for g in grads])
-    dist.all_reduce(flat, group=group)
+    _all_reduce_sum(flat, group=group)
     off = 0
     for g in grads:
         n = g.numel()

@@ -136,57 +136,41 @@ class HaloContext:
         # received halo gradients touch only the few partition rows this rank sends out: group them by those rows
         self.sent_rows, inv = torch.unique(self.send_idx_remote.long(), return_inverse=True)
         self.acc_remote = ops._group_by_key(inv.to(torch.int32).contiguous(), int(self.sent_rows.numel()))
-        self.remote_only = du._backend_has_alltoall(self.group)
+        self.remote_only = True  # (the transport, NCCL or the point-to-point stand-in, is the same for both protocols)
 
-    # forward: pack -> all-to-all (async) ; returns (work, recv buffer [n_src_local, H], packed keep-alive)
+    # forward: pack -> all-to-all (in flight) ; returns (work, recv buffer [n_src_local, H], packed keep-alive)
     def start_fwd(self, P: Tensor):
         from .distributed import utils as du
-        import torch.distributed as dist
 
         xp = self.xplan
         packed = ops.gather_rows(P, 0, H, xp.send_idx, xp.send_idx.numel())
-        if du._backend_has_alltoall(self.group):
-            recv = packed.new_empty((int(sum(xp.recv_splits)), H))
-            work = dist.all_to_all_single(recv, packed, list(xp.recv_splits), list(xp.send_splits), group=self.group,
-                                          async_op=True)
-            return work, recv, packed
-        recv = du.all_to_all_rows(packed, xp.send_splits, xp.recv_splits, group=self.group)
-        return None, recv, packed
+        work, recv = du.all_to_all_rows_async(packed, xp.send_splits, xp.recv_splits, group=self.group)
+        return work, recv, packed
 
     # backward: gradients of the received rows travel back and are summed (fixed order) into out[:, col0:col0+H]
     def start_bwd(self, g_rows: Tensor):
         from .distributed import utils as du
-        import torch.distributed as dist
 
         xp = self.xplan
-        if du._backend_has_alltoall(self.group):
-            recv = g_rows.new_empty((int(sum(xp.send_splits)), H))
-            work = dist.all_to_all_single(recv, g_rows, list(xp.send_splits), list(xp.recv_splits), group=self.group,
-                                          async_op=True)
-            return work, recv
-        return None, du.all_to_all_rows(g_rows, xp.recv_splits, xp.send_splits, group=self.group)
+        return du.all_to_all_rows_async(g_rows, xp.recv_splits, xp.send_splits, group=self.group)
 
     # remote-only variants: only halo rows are packed / sent / accumulated
     def start_fwd_remote(self, P: Tensor):
-        import torch.distributed as dist
+        from .distributed import utils as du
 
         n = int(self.send_idx_remote.numel())
         packed = ops.gather_rows(P, 0, H, self.send_idx_remote, n) if n > 0 else P.new_empty((0, H))
-        recv = P.new_empty((self.halo_rows, H))
-        work = dist.all_to_all_single(recv, packed, list(self.recv_splits_r), list(self.send_splits_r), group=self.group,
-                                      async_op=True)
+        work, recv = du.all_to_all_rows_async(packed, self.send_splits_r, self.recv_splits_r, group=self.group)
         return work, recv, packed
 
     def start_bwd_remote(self, g_halo: Tensor):
-        import torch.distributed as dist
+        from .distributed import utils as du
 
-        recv = g_halo.new_empty((int(self.send_idx_remote.numel()), H))
-        work = dist.all_to_all_single(recv, g_halo, list(self.send_splits_r), list(self.recv_splits_r), group=self.group,
-                                      async_op=True)
-        return work, recv
+        return du.all_to_all_rows_async(g_halo, self.recv_splits_r, self.send_splits_r, group=self.group)
 
     def finish_bwd_remote(self, work, recv: Tensor, out: Tensor, out_col0: int):
-        work.wait()
+        if work is not None:
+            work.wait()
         if recv.shape[0] > 0:  # fixed-order sums per sent row, then one add per (unique) row
             offsets, ids = self.acc_remote
             part = ops.segment_sum(recv, 0, H, offsets, ids, int(self.sent_rows.numel()))
@@ -256,7 +240,8 @@ class FusedProcessorFn(torch.autograd.Function):
 
                 if remote_only:
                     run(1, P_ext, halo.src_ext[halo.e0:halo.e1])  # interior edges (own sources) overlap the exchange
-                    work.wait()
+                    if work is not None:
+                        work.wait()
                     if halo.halo_rows > 0:
                         P_ext[N:, :H].copy_(recv_r)
                     run(0, P_ext, halo.src_ext[:halo.e0])
@@ -368,20 +353,44 @@ class FusedProcessorFn(torch.autograd.Function):
         return (g_n, g_e, None, None, None, None, *grads)
 
 
+def _partition_eligible(graph, plan: GraphPlan) -> bool:
+    """Partition-level half of `processor_eligible`, decided ONCE per graph and identically on every rank: the fused
+    and the generic path issue different collectives, so a rank-local decision could hang the group.  Needs a square
+    graph partitioned identically on both id spaces (one owned node table serves sources and destinations) and no
+    rank without edges; the rank-local verdict is min-reduced over the partition group."""
+    ok = plan.extra.get("fused_partition_ok")
+    if ok is None:
+        import torch.distributed as dist
+
+        from .distributed import utils as du
+
+        gp = graph.dist_graph.graph_partition
+        ok = (not gp.matrix_decomp
+              and list(map(int, gp.num_src_nodes_in_each_partition)) == list(map(int, gp.num_dst_nodes_in_each_partition))
+              and all(int(n) > 0 for n in gp.num_indices_in_each_partition)
+              and torch.equal(gp.map_partitioned_src_ids_to_global, gp.map_partitioned_dst_ids_to_global))
+        group = graph.dist_graph.process_group
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group=group) > 1:
+            flag = torch.tensor([1.0 if ok else 0.0], device=plan.src.device)
+            if du._host_staged(group, flag):
+                flag = flag.cpu()
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            ok = bool(flag.item() > 0.5)
+        plan.extra["fused_partition_ok"] = ok
+    return ok
+
+
 def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPlan, dt: torch.dtype) -> bool:
     """Conditions under which the fused tcgen05 path computes exactly what the generic path does."""
     from .models.gnn_layers.mesh_graph_mlp import MeshGraphEdgeMLPConcat
     from .models.layers.activations import activation_name
 
-    if dt != BF16 or not plan.is_csc_ordered or plan.n_edges == 0:
+    if dt != BF16 or not plan.is_csc_ordered:
         return False
     if getattr(graph, "is_distributed", False):
-        gp = graph.dist_graph.graph_partition
-        r = gp.partition_rank
-        # square graphs partitioned identically on both id spaces: one owned node table serves src and dst
-        if int(gp.num_src_nodes_in_each_partition[r]) != int(gp.num_dst_nodes_in_each_partition[r]):
+        if not _partition_eligible(graph, plan):
             return False
-    elif plan.n_src != plan.n_dst:
+    elif plan.n_src != plan.n_dst or plan.n_edges == 0:
         return False
     if nfeat.shape[1] != H or efeat.shape[1] != H or nfeat.shape[0] != plan.n_dst:
         return False
