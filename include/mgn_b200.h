@@ -3,7 +3,9 @@
  * Drop-in boundary for NVIDIA PhysicsNeMo's MeshGraphNet hot path.  Every entry point takes
  * plain device pointers, sizes, a dtype enum and a CUDA stream; no torch types.  The library
  * never allocates user-visible memory (outputs and workspaces are caller-provided), keeps no
- * mutable global state, never synchronises the host and is CUDA-graph capturable.
+ * mutable global state (the only statics are write-once per-device caches: SM count, kernel attributes, and the
+ * launch counter), never synchronises the host and is CUDA-graph capturable.  Profiling hooks exist only in builds
+ * made with -DMGN_DEBUG_HOOKS (include/mgn_b200_debug.h); the product library does not export them.
  *
  * Return value of every function: 0 = ok, <0 = argument error (MGN_E*), >0 = cudaError_t.
  *
@@ -50,6 +52,9 @@ enum {
 };
 
 int mgn_version(void);
+/* sha256 of the sources + flags this binary was built from (modulus_b200/build.py); the loader refuses a library whose
+ * digest differs from the sources next to it, so a stale .so can never be bound to a newer header. */
+const char* mgn_build_digest(void);
 const char* mgn_error_string(int code);
 /* kernels launched by this library since it was loaded (all streams, all entry points) */
 int64_t mgn_launch_count(void);
@@ -159,37 +164,8 @@ int mgn_add(int dtype, const void* a, const void* b, void* out, int64_t n, mgn_s
 /* ------------------------------------------------------------------------------------------
  * Fused tensor-core path (bf16 storage, hidden width 128, ReLU): tcgen05.mma + TMEM.
  * ---------------------------------------------------------------------------------------- */
-/* Fused MeshGraphMLP forward over 128-row tiles:
- *     A   = [ tab0[idx0[r]] | tab1[idx1[r]] | tab2[idx2[r]] ]   (n_tab tables of [*,128] bf16; idxK NULL = row r)
- *           or, encoder mode (small_in > 0), the raw [M, small_in] features zero-padded to 64 columns
- *     out = [LayerNorm]( W3 relu(W2 relu(W1 A + b1) + b2) + b3 ) [* gamma + beta] [+ residual]
- * Replaces MeshEdgeBlock.forward (mesh_edge_block.py:88-96 = concat_efeat utils.py:151 + MeshGraphMLP
- * mesh_graph_mlp.py:200-203 + residual), the MLP half of MeshNodeBlock.forward (mesh_node_block.py:88-91)
- * and the encoder/decoder MLPs (meshgraphnet.py:213-216).  gamma == NULL: no LayerNorm (decoder).
- * h1_save / h2_save (nullable): hidden activations [M,128] bf16 kept for the backward kernels.
- * status (nullable, device int): OR-ed with a nonzero code if the kernel detected an internal timeout. */
-int mgn_mlp3_fwd_tc(const void* tab0, const int32_t* idx0, const void* tab1, const int32_t* idx1,
-                    const void* tab2, const int32_t* idx2, int n_tab, const void* small_x, int small_in,
-                    int small_is_f32, int64_t M, const float* w1, const float* b1, const float* w2,
-                    const float* b2, const float* w3, const float* b3, const float* gamma,
-                    const float* beta, int n_out, float eps, const void* residual, void* out,
-                    int64_t ld_out, void* h1_save, void* h2_save, int* status, mgn_stream_t stream);
-
-/* Same fused forward with the first Linear split the way the reference's "concat trick" does
- * (MeshGraphEdgeMLPSum, mesh_graph_mlp.py:278-458: per-node partial products gathered and summed per edge):
- *     z1  = A W1^T + G + b1,   A = a_tab[a_idx[r]] [*,128],   G = g1_tab[g1_idx[r]] (+ g2_tab[g2_idx[r]])
- *     out = [LayerNorm]( W3 relu(W2 relu(z1) + b2) + b3 ) [+ residual]
- * g*_tab rows are [*, g*_ld] bf16 read from column g*_col0 (128 columns); w1 is read with row stride ld_w1.
- * Edge block:  A = efeat, G = P[src][0:128] + P[dst][128:256] with P = nfeat [W1_src; W1_dst]^T.
- * Node block:  A = agg,   G = P[r][256:384]                   with P = nfeat W1_nfeat^T. */
-int mgn_mlp3_fwd_tc_g(const void* a_tab, const int32_t* a_idx, const void* g1_tab, const int32_t* g1_idx,
-                      int64_t g1_ld, int64_t g1_col0, const void* g2_tab, const int32_t* g2_idx,
-                      int64_t g2_ld, int64_t g2_col0, int64_t M, const float* w1, int64_t ld_w1,
-                      const float* b1, const float* w2, const float* b2, const float* w3, const float* b3,
-                      const float* gamma, const float* beta, int n_out, float eps, const void* residual,
-                      void* out, int64_t ld_out, int* status, mgn_stream_t stream);
-
-/* Second-generation fused forward (same maths as mgn_mlp3_fwd_tc_g; all operand rows staged by cp.async, output
+/* Fused MeshGraphMLP forward over 128-row tiles with the first Linear split the way the reference's "concat trick" does
+ * (MeshGraphEdgeMLPSum, mesh_graph_mlp.py:278-458: per-node partial products gathered and summed per edge; all operand rows staged by cp.async, output
  * tile leaves through coalesced stores, next tile prefetched while the current one computes):
  *     z1  = A W1^T + b1 + g1_tab[g1_idx[r]] + g2_tab[g2_idx[r]]     (A = a_tab[a_idx[r]] or raw small_x)
  *     out = [LayerNorm]( W3 relu(W2 relu(z1) + b2) + b3 ) + residual
@@ -203,7 +179,6 @@ int mgn_mlp3_fwd2_tc(const void* a_tab, const int32_t* a_idx, const void* small_
                      int64_t ld_w1, const float* b1, const float* w2, const float* b2, const float* w3,
                      const float* b3, const float* gamma, const float* beta, int n_out, float eps, void* out,
                      int64_t ld_out, int* status, mgn_stream_t stream);
-int mgn_debug_set_fwd2_timing(void* dev_buf);
 
 /* Fused MeshGraphMLP backward over 128-row tiles (forward hiddens are recomputed, nothing but the
  * layer inputs is read back):
@@ -287,17 +262,12 @@ int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, co
                           const int32_t* csc_offsets, const int32_t* dst_idx, int64_t n_dst, void* gz1_agg,
                           int64_t ld_agg, void* agg_workspace, size_t agg_workspace_bytes, int* status,
                           mgn_stream_t stream);
-int mgn_debug_set_edge_bwd2_timing(void* dev_buf);
 
 /* Node-level plain GEMMs of the fused path (bf16 rows, fp32 weights read in place):
- *   mgn_linear_tc : out[M,128] (row stride ld_out) = [x0 | x1 | x2][M, 128*n_tab] W^T + bias (+ residual[M,128])
- *                   x_k are [M,128] column blocks with row stride ld_k; W is [128, 128*n_tab] with row stride ld_w
+ *   mgn_node_gemm_tc / mgn_linear128_tc : out = x W^T (+ residual) over [M,128] column blocks
  *   mgn_wgrad_tc  : out[128*n_blocks, 128] (fp32, row stride ld_out) = G[M, 128*n_blocks]^T X[M,128]
  * They replace the cuBLAS GEMMs autograd runs for the node-row column blocks of the first Linear
  * (mesh_graph_mlp.py:142-168 / the lin_src, lin_dst products of MeshGraphEdgeMLPSum :396-405). */
-int mgn_linear_tc(const void* x0, int64_t ld0, const void* x1, int64_t ld1, const void* x2, int64_t ld2,
-                  int n_tab, int64_t M, const float* w, int64_t ld_w, const float* bias,
-                  const void* residual, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
 /* out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); second-generation
  * pipeline (cp.async staging, coalesced stores).  Wider products are issued per 128-column block. */
 int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,
@@ -337,14 +307,6 @@ int mgn_adam_multi_step(void* const* params, const void* const* grads, void* con
  *           (datapipes/gnn/vortex_shedding_dataset.py:324-349). */
 int mgn_edge_features(const float* pos, int dim, const int32_t* src, const int32_t* dst, int64_t n_edges,
                       const float* mu, const float* sd, float* out, mgn_stream_t stream);
-
-/* Debug hook (not part of the drop-in surface): dev_buf = 96 x int64 that CTA 0 of subsequent
- * mgn_mlp3_bwd_tc launches fills with per-role, per-phase cycle counts; NULL disables. */
-int mgn_debug_set_bwd_timing(void* dev_buf);
-/* A/B hook: 0 routes mgn_edge_block_fwd*_tc to the second-generation (one tile in flight) kernel, 1 (default) to the
- * two-tiles-in-flight kernel. */
-int mgn_debug_set_edge_fwd3(int on);
-int mgn_debug_set_fwd_timing(void* dev_buf);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,9 @@ def _parse_header(text: str):
 
 
 PROTOTYPES = _parse_header(HEADER.read_text())
+# profiling hooks: bound only when the library was built with -DMGN_DEBUG_HOOKS (tools/prof_kernels.py)
+DEBUG_HEADER = HEADER.parent / "mgn_b200_debug.h"
+DEBUG_PROTOTYPES = _parse_header(DEBUG_HEADER.read_text()) if DEBUG_HEADER.exists() else {}
 
 _lib = None
 
@@ -74,8 +77,34 @@ def load() -> ctypes.CDLL:
             fn = getattr(lib, name)  # AttributeError => header/library mismatch
             fn.restype = restype
             fn.argtypes = argtypes
+        for name, (restype, argtypes) in DEBUG_PROTOTYPES.items():
+            fn = getattr(lib, name, None)
+            if fn is not None:
+                fn.restype = restype
+                fn.argtypes = argtypes
+        _verify_digest(lib)
         _lib = lib
     return _lib
+
+
+def _verify_digest(lib) -> None:
+    """The library must have been built from the sources next to it (same header the prototypes above were parsed
+    from).  A mismatch is a stale build: calling it would be undefined behaviour, so it is an error, not a warning."""
+    import os
+
+    from . import build
+
+    if os.environ.get("MGN_ALLOW_STALE_LIB") == "1" or not build.CSRC.exists():
+        return
+    have, want = lib.mgn_build_digest().decode(), build._digest()
+    if have != want:
+        raise MGNError(
+            f"{LIB_PATH} was built from different sources or flags (library {have[:12]}, sources {want[:12]}): "
+            "rebuild it with `python -m modulus_b200.build`")
+
+
+def has_debug_hooks() -> bool:
+    return all(hasattr(load(), n) for n in DEBUG_PROTOTYPES)
 
 
 def check(rc: int, what: str = "") -> None:
@@ -108,13 +137,6 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
     """(bound, amount) of ONE call from its arguments: ("hbm", algorithmic bytes) for the
     gather / scatter / elementwise entry points, ("tensor", useful flops) for the dense ones.
     Formulas: DESIGN.md section 'Kernels and their rooflines' (SURVEY 8d)."""
-    if name == "mgn_mlp3_fwd_tc":
-        n_tab, small_in, M, n_out = a[6], a[8], a[10], a[19]
-        k1 = small_in if small_in > 0 else 128 * n_tab
-        return "tensor", 2.0 * M * (k1 * 128 + 128 * 128 + 128 * n_out)
-    if name == "mgn_mlp3_fwd_tc_g":
-        M, g2 = a[10], a[6]
-        return "tensor", (10.0 if g2 else 8.0) * 128 * 128 * M  # useful flops of the concat formulation (SURVEY 8d)
     if name == "mgn_edge_block_bwd_tc":
         return "tensor", 20.0 * 128 * 128 * a[6]  # useful flops of the reference formulation (dgrad + wgrad = 2 x forward)
     if name == "mgn_mlp3_bwd_tc":
@@ -142,9 +164,6 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
         return "hbm", 2.0 * M * 128 * (kb + nb + (1 if res else 0))  # one pass over x, (residual,) out
     if name == "mgn_linear128_tc":
         return "tensor", 2.0 * a[2] * 128 * 128
-    if name == "mgn_linear_tc":
-        n_tab, M = a[6], a[7]
-        return "tensor", 2.0 * M * 128 * 128 * n_tab
     if name == "mgn_wgrad_tc":
         jb, M = a[2], a[5]
         return "tensor", 2.0 * M * 128 * 128 * jb

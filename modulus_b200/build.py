@@ -35,8 +35,13 @@ def sources():
 
 
 def _digest() -> str:
+    """sha256 over every source the library is made of and the compiler flags.  It is compiled INTO the library
+    (mgn_build_digest()); `_lib.load()` recomputes it from the sources next to it and refuses a library that was built
+    from anything else, so a stale binary can never be bound to prototypes parsed from a newer header."""
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + [ROOT.parent / "include" / "mgn_b200.h"]):
+    inc = ROOT.parent / "include"
+    for p in sorted(list(CSRC.glob("*.cu")) + list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+                    + [inc / "mgn_b200.h", inc / "mgn_b200_debug.h"]):
         h.update(p.name.encode())
         h.update(p.read_bytes())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -46,9 +51,8 @@ def _digest() -> str:
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     LIBDIR.mkdir(exist_ok=True)
-    stamp = LIBDIR / "libmgn_b200.sha256"
     dig = _digest()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text().strip() == dig:
+    if not force and LIB.exists() and embedded_digest() == dig:
         return LIB
     if not os.path.exists(nvcc):
         if LIB.exists():  # GPU box without a toolchain mismatch: use the prebuilt library
@@ -62,6 +66,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         obj = objdir / (src.stem + ".o")
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if src.name == "mgn_misc.cu":
+            cmd.insert(1, f'-DMGN_BUILD_DIGEST="MGNDIGEST:{dig}"')
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -75,9 +81,19 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc failed")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs)]
     subprocess.run(cmd, check=True)
-    stamp.write_text(dig)
+    for stale in objdir.glob("*.o"):  # objects of sources that no longer exist
+        if stale not in objs:
+            stale.unlink()
     return LIB
 
 
-if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+def embedded_digest() -> str:
+    """digest string compiled into the built library ('' when absent).  Read from the file's bytes (the string is stored
+    behind the marker "MGNDIGEST:"), not through dlopen: a handle opened here would shadow the rebuilt library."""
+    import re
+
+    try:
+        m = re.search(rb"MGNDIGEST:([0-9a-f]{64})", LIB.read_bytes())
+    except OSError:
+        return ""
+    return m.group(1).decode() if m else ""

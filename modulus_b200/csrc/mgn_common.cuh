@@ -32,15 +32,29 @@ static inline cudaStream_t count_launch(cudaStream_t s) {
 }
 #define MGN_ST(s) ::mgn::count_launch(s)
 
+// Per-device caches: the library may be called for several devices of one process (the caller selects the device,
+// e.g. `with torch.cuda.device(t.device)`); function attributes and the SM count belong to the CURRENT device.
+constexpr int kMaxDevices = 64;
+static inline int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+struct PerDeviceFlag {  // `static PerDeviceFlag f; bool& done = f.get();`
+  bool done[kMaxDevices] = {};
+  bool& get() { return done[current_device_slot()]; }
+};
+
 static inline int num_sms() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
+  static int n[kMaxDevices] = {};
+  const int slot = current_device_slot();
+  if (n[slot] == 0) {
+    int dev = 0, v = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[slot] = v > 0 ? v : 148;
   }
-  return n;
+  return n[slot];
 }
 
 template <typename T> struct Num;

@@ -683,11 +683,15 @@ static int bwd2_grid(int64_t M) {
   return static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
 }
 
+#ifdef MGN_DEBUG_HOOKS
 static long long* g_bwd2_timing = nullptr;
 extern "C" int mgn_debug_set_edge_bwd2_timing(void* dev_buf) {
   g_bwd2_timing = static_cast<long long*>(dev_buf);
   return MGN_OK;
 }
+#else
+static constexpr long long* g_bwd2_timing = nullptr;
+#endif
 
 extern "C" size_t mgn_edge_block_bwd_tc_workspace_bytes(int64_t n_edges) {
   if (n_edges <= 0) return 0;
@@ -743,7 +747,8 @@ extern "C" int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const vo
     p.agg_part = static_cast<float*>(agg_workspace);
     p.agg_part_v = reinterpret_cast<int32_t*>(p.agg_part + 2 * n_tiles_ * bwd2::kH);
   }
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(bwd2::edge_bwd2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd2::Smem::kTotal);
     if (ce == cudaSuccess)

@@ -485,8 +485,12 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
 
 }  // namespace fwd3
 
+#ifdef MGN_DEBUG_HOOKS
 static long long* g_fwd3_timing = nullptr;
 void edge_fwd3_set_timing(long long* buf) { g_fwd3_timing = buf; }
+#else
+static constexpr long long* g_fwd3_timing = nullptr;
+#endif
 
 int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   fwd3::Params p{};
@@ -494,7 +498,8 @@ int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   p.timing = g_fwd3_timing;
   if (tma_make_rows_map(&p.m_a, args.a, args.M, 128, 128) != 0) return MGN_EINVAL;
   if (tma_make_rows_map(&p.m_out, args.out, args.M, 128, 128) != 0) return MGN_EINVAL;
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
     if (e != cudaSuccess) return static_cast<int>(e);

@@ -5,7 +5,13 @@ namespace mgn {
 unsigned long long g_mgn_launches = 0;
 }
 
-extern "C" int mgn_version(void) { return 101; }
+extern "C" int mgn_version(void) { return 200; }
+
+#ifndef MGN_BUILD_DIGEST
+#define MGN_BUILD_DIGEST "MGNDIGEST:unknown"
+#endif
+// "MGNDIGEST:<sha256>": the marker lets build.py find the digest in the file without loading it
+extern "C" const char* mgn_build_digest(void) { return MGN_BUILD_DIGEST + 10; }
 
 extern "C" int64_t mgn_launch_count(void) {
   return static_cast<int64_t>(__atomic_load_n(&mgn::g_mgn_launches, __ATOMIC_RELAXED));

@@ -864,7 +864,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
 template <int KP>
 static int launch(Params& p, int grid, cudaStream_t st) {
   using L = Smem<KP>;
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp3_bwd_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -885,12 +886,16 @@ static int bwd_grid(int64_t M) {
   return static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
 }
 
+#ifdef MGN_DEBUG_HOOKS
 static long long* g_bwd_timing = nullptr;
 /* debug hook: device buffer of 96 int64 that CTA 0 of the next backward launches fills with per-phase cycles */
 extern "C" int mgn_debug_set_bwd_timing(void* dev_buf) {
   g_bwd_timing = static_cast<long long*>(dev_buf);
   return MGN_OK;
 }
+#else
+static constexpr long long* g_bwd_timing = nullptr;
+#endif
 
 extern "C" size_t mgn_mlp3_bwd_tc_workspace_bytes(int64_t M) {
   if (M <= 0) return 0;

@@ -572,12 +572,17 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+#ifdef MGN_DEBUG_HOOKS
 static long long* g_timing = nullptr;
+#else
+static constexpr long long* g_timing = nullptr;
+#endif
 
 template <int KP>
 static int launch(Params& p, cudaStream_t st) {
   using L = Smem<KP>;
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(mlp3_fwd2_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return static_cast<int>(e);
@@ -599,20 +604,15 @@ static int launch(Params& p, cudaStream_t st) {
 
 using namespace mgn;
 
+#ifdef MGN_DEBUG_HOOKS
 extern "C" int mgn_debug_set_fwd2_timing(void* dev_buf) {
   edge_fwd3_set_timing(static_cast<long long*>(dev_buf));  // (the edge-block kernel fills the first 6 slots)
   fwd2::g_timing = static_cast<long long*>(dev_buf);
   return MGN_OK;
 }
+#endif
 
 extern "C" size_t mgn_mlp3_fwd2_agg_workspace_bytes(int64_t M) { return agg::workspace_bytes(M); }
-
-static int g_use_fwd3 = 1;
-/* debug / A-B hook: 0 routes mgn_edge_block_fwd*_tc back to the second-generation kernel */
-extern "C" int mgn_debug_set_edge_fwd3(int on) {
-  g_use_fwd3 = on;
-  return MGN_OK;
-}
 
 struct AggArgs {
   const int32_t* seg_off = nullptr;
@@ -688,7 +688,7 @@ static int fwd2_run(const void* a_tab, const int32_t* a_idx, const void* small_x
   int rc;
   // the edge block proper (gathered source / destination projections, LayerNorm, residual = input, destination sums)
   // runs on the two-tiles-in-flight kernel (mgn_edge_fwd3_tc.cu)
-  const bool edge3 = g_use_fwd3 && ag.seg_off != nullptr && small_in <= 0 && a_tab != nullptr && a_idx == nullptr &&
+  const bool edge3 = ag.seg_off != nullptr && small_in <= 0 && a_tab != nullptr && a_idx == nullptr &&
                      g1_tab != nullptr && g1_idx != nullptr && g2_tab != nullptr && g2_idx != nullptr && res_is_a &&
                      gamma != nullptr && n_out == fwd2::kH && ld_out == fwd2::kH && ld_w1 >= fwd2::kH &&
                      (reinterpret_cast<uintptr_t>(a_tab) & 15) == 0;

@@ -212,7 +212,8 @@ extern "C" int mgn_node_gemm_tc(const void* x, int64_t ld_x, int kb, int64_t M, 
   e |= tma_make_rows_map(&p.m_out, out, M, ld_out, 128, 128 * nb);
   if (residual) e |= tma_make_rows_map(&p.m_res, residual, M, 128, 128, 128);
   if (e != 0) return MGN_EINVAL;
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t ce = cudaFuncSetAttribute(ng::node_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ng::Smem::kTotal);
     if (ce != cudaSuccess) return static_cast<int>(ce);

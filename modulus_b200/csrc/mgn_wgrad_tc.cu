@@ -193,7 +193,8 @@ extern "C" int mgn_wgrad_tc(const void* g, int64_t ld_g, int n_blocks, const voi
   MGN_CHECK_ARG(ld_g % 8 == 0 && ld_x % 8 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 &&
                 (reinterpret_cast<uintptr_t>(x) & 15) == 0);
   if (workspace == nullptr || workspace_bytes < mgn_wgrad_tc_workspace_bytes(M, n_blocks)) return MGN_EWORKSPACE;
-  static bool configured = false;
+  static PerDeviceFlag configured_flag;
+  bool& configured = configured_flag.get();
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(wg::wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg::Smem::kTotal);
     if (e != cudaSuccess) return static_cast<int>(e);

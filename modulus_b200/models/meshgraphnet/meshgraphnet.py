@@ -141,7 +141,9 @@ class MeshGraphNet(nn.Module):
     def forward(self, node_features: Tensor, edge_features: Tensor, graph, **kwargs) -> Tensor:
         ops.require_cuda(node_features, edge_features)
         if isinstance(graph, (list, tuple)):
-            raise NotImplementedError("lists of graphs (neighbor-sampling blocks) are not supported")
+            # (the reference's annotation admits List[DGLGraph], meshgraphnet.py:210, but its blocks hand the list to
+            #  concat_efeat, which only accepts a DGLGraph or CuGraphCSC, utils.py:196-229: no caller can use one)
+            raise NotImplementedError("lists of graphs are not supported by the MeshGraphNet blocks")
         edge_features = self.edge_encoder(edge_features)
         node_features = self.node_encoder(node_features)
         x = self.processor(node_features, edge_features, graph)
@@ -228,6 +230,7 @@ class MeshGraphNetProcessor(nn.Module):
             if fused.processor_eligible(self, node_features, edge_features, graph, plan, dt):
                 # bf16 / hidden 128 / ReLU / sum: fused tcgen05 kernels with in-kernel recompute (checkpoint
                 # segments only trade memory for recompute in the reference; nothing to do here)
+                ops.tc_poll(node_features.device)  # deferred look at the kernels' stall flag (no synchronisation)
                 return fused.processor_forward(self, node_features, edge_features, plan, graph)
         with self.checkpoint_offload_ctx:
             for segment_start, segment_end in self.checkpoint_segments:

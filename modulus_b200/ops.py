@@ -32,7 +32,16 @@ def _dt(t: Tensor) -> int:
 
 
 def _p(t: Optional[Tensor]):
-    return None if t is None else t.data_ptr()
+    """Raw pointer of a tensor argument.  The library launches on the CURRENT device and on its current stream
+    (`_stream()`), so a tensor that lives elsewhere would be touched from the wrong context with no stream ordering:
+    that is refused here, at the one place every pointer passes through."""
+    if t is None:
+        return None
+    if t.is_cuda and t.device.index != torch.cuda.current_device():
+        raise RuntimeError(
+            f"modulus_b200: tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+            "run the model under `with torch.cuda.device(tensor.device):` or call torch.cuda.set_device first")
+    return t.data_ptr()
 
 
 def _stream() -> int:
@@ -228,6 +237,12 @@ class SumEfeatFn(torch.autograd.Function):
         E, D = plan.n_edges, efeat.shape[1]
         if efeat.shape[0] != E or src_feat.shape[1] != D or dst_feat.shape[1] != D:
             raise ValueError("sum_efeat: shape mismatch")
+        if src_feat.shape[0] < plan.n_src or dst_feat.shape[0] < plan.n_dst:
+            raise ValueError(
+                f"sum_efeat: node tables have ({src_feat.shape[0]}, {dst_feat.shape[0]}) rows, the graph needs "
+                f"(n_src={plan.n_src}, n_dst={plan.n_dst})")
+        if not (efeat.dtype == src_feat.dtype == dst_feat.dtype):
+            raise TypeError("sum_efeat: all feature tables must share one dtype")
         out = torch.empty_like(efeat)
         call("mgn_sum_efeat_fwd", _dt(efeat), _p(efeat), _p(src_feat), _p(dst_feat), D, _p(plan.src), _p(plan.dst),
              E, _p(out), _stream())
@@ -467,9 +482,14 @@ TC_HIDDEN = 128
 _STATUS = {}
 
 
+TC_CHECK_EVERY = 50  # fused forward passes between two non-blocking looks at the status word (see tc_poll)
+_POLL = {}
+
+
 def tc_status(device) -> Tensor:
-    """Device int the fused kernels OR an error code into (internal pipeline timeout).  Checked by
-    `tc_check()`; never read on the hot path."""
+    """Device int the fused kernels OR an error code into (bounded mbarrier wait ran out = a pipeline stall that left
+    partial outputs).  Never read synchronously on the hot path; surfaced by `tc_poll` (every model forward),
+    `tc_found_inf` (skips the optimizer step on the device) and `tc_check` (explicit, synchronising)."""
     key = torch.device(device).index or 0
     if key not in _STATUS:
         _STATUS[key] = torch.zeros(1, dtype=torch.int32, device=device)
@@ -483,43 +503,40 @@ def tc_check(device="cuda") -> None:
         raise _lib.MGNError(f"libmgn_b200: fused tensor-core kernel reported internal status {code}")
 
 
-def mlp3_fwd_tc(tabs: Sequence[Tensor], idxs: Sequence[Optional[Tensor]], M: int,
-                w1, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
-                residual: Optional[Tensor] = None, n_out: int = TC_HIDDEN,
-                small_x: Optional[Tensor] = None, save_hidden: bool = False):
-    """Raw call of the fused forward kernel (see include/mgn_b200.h: mgn_mlp3_fwd_tc)."""
-    dev = (small_x if small_x is not None else tabs[0]).device
-    out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
-    h1 = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if save_hidden else None
-    h2 = torch.empty((M, TC_HIDDEN), dtype=torch.bfloat16, device=dev) if save_hidden else None
-    t = list(tabs) + [None] * (3 - len(tabs))
-    ix = list(idxs) + [None] * (3 - len(idxs))
-    small_in = 0 if small_x is None else small_x.shape[1]
-    small_f32 = int(small_x is not None and small_x.dtype == torch.float32)
-    call("mgn_mlp3_fwd_tc", _p(t[0]), _p(ix[0]), _p(t[1]), _p(ix[1]), _p(t[2]), _p(ix[2]), len(tabs),
-         _p(small_x), small_in, small_f32, M, _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta),
-         n_out, eps, _p(residual), _p(out), n_out, _p(h1), _p(h2), _p(tc_status(dev)), _stream())
-    return out, h1, h2
+def tc_poll(device) -> None:
+    """Production-path check without a per-step synchronisation: every TC_CHECK_EVERY calls the status word is copied
+    to pinned host memory asynchronously; the copy started at the PREVIOUS poll is inspected (its event has long
+    completed), so a stalled kernel is reported at most 2 x TC_CHECK_EVERY steps later instead of never.  Not taken
+    while a CUDA graph is being captured."""
+    dev = torch.device(device)
+    key = dev.index or 0
+    st = _POLL.get(key)
+    if st is None:
+        st = _POLL[key] = {"n": 0, "host": torch.zeros(1, dtype=torch.int32).pin_memory(), "event": None}
+    st["n"] += 1
+    if st["n"] % TC_CHECK_EVERY != 0 or torch.cuda.is_current_stream_capturing():
+        return
+    if st["event"] is not None and st["event"].query():
+        code = int(st["host"][0])
+        if code != 0:
+            st["event"] = None
+            tc_status(dev).zero_()
+            raise _lib.MGNError(f"libmgn_b200: fused tensor-core kernel reported internal status {code} "
+                                "(pipeline stall: outputs of a recent step are incomplete)")
+    st["host"].copy_(tc_status(dev), non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record()
+    st["event"] = ev
+
+
+def tc_found_inf(device) -> Tensor:
+    """fp32 [1] device flag, nonzero when a fused kernel has reported a stall since the last check: pass it as
+    `found_inf` to FusedAdam.step (optim.py does so by default) and the update is skipped on the device."""
+    return (tc_status(device) != 0).to(torch.float32)
 
 
 def _ws(nbytes: int, dev) -> Tensor:
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
-
-
-def mlp3_fwd_tc_g(a: Tensor, a_idx: Optional[Tensor], g1: Optional[Tensor], g1_idx: Optional[Tensor], g1_col0: int,
-                  g2: Optional[Tensor], g2_idx: Optional[Tensor], g2_col0: int, M: int,
-                  w1: Tensor, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
-                  residual: Optional[Tensor] = None, n_out: int = TC_HIDDEN, out: Optional[Tensor] = None) -> Tensor:
-    """Fused forward with additive gathered rows (include/mgn_b200.h: mgn_mlp3_fwd_tc_g).  `w1` may be a
-    column-block view of the full first-layer weight (row stride = w1.stride(0))."""
-    dev = a.device
-    if out is None:
-        out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
-    call("mgn_mlp3_fwd_tc_g", _p(a), _p(a_idx), _p(g1), _p(g1_idx), 0 if g1 is None else g1.stride(0), g1_col0,
-         _p(g2), _p(g2_idx), 0 if g2 is None else g2.stride(0), g2_col0, M, _p(w1), w1.stride(0), _p(b1), _p(w2),
-         _p(b2), _p(w3), _p(b3), _p(gamma), _p(beta), n_out, eps, _p(residual), _p(out), out.stride(0),
-         _p(tc_status(dev)), _stream())
-    return out
 
 
 def mlp3_fwd2_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[Tensor],
@@ -528,7 +545,7 @@ def mlp3_fwd2_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional
                  w1: Tensor, b1, w2, b2, w3, b3, gamma=None, beta=None, eps: float = 1e-5,
                  residual: Optional[Tensor] = None, res_is_a: bool = False, n_out: int = TC_HIDDEN,
                  out: Optional[Tensor] = None) -> Tensor:
-    """Second-generation fused forward (include/mgn_b200.h: mgn_mlp3_fwd2_tc)."""
+    """Fused forward of the node / encoder / decoder forms (include/mgn_b200.h: mgn_mlp3_fwd2_tc)."""
     dev = (small_x if small_x is not None else a).device
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.bfloat16, device=dev)
@@ -650,7 +667,7 @@ def mlp3_bwd_tc(a: Optional[Tensor], a_idx: Optional[Tensor], small_x: Optional[
 # ----------------------------------------------------------------------------------------
 def linear_tc(x: Tensor, w: Tensor, out: Optional[Tensor] = None, residual: Optional[Tensor] = None) -> Tensor:
     """out[M, Nout] = x[M, K] w[Nout, K]^T (+ residual); K, Nout multiples of 128 (K <= 384).  tcgen05 GEMM
-    (include/mgn_b200.h: mgn_linear_tc), one launch per 128 output columns."""
+    (include/mgn_b200.h: mgn_node_gemm_tc; mgn_linear128_tc per 128-column block for the wider products)."""
     M, K = x.shape
     n_out = w.shape[0]
     if K % TC_HIDDEN or n_out % TC_HIDDEN or K > 3 * TC_HIDDEN or w.shape[1] != K or x.dtype != torch.bfloat16:

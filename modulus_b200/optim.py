@@ -178,6 +178,12 @@ class FusedAdam(torch.optim.Optimizer):
         for tab, group in zip(tables, self.param_groups):
             if not tab.params:
                 continue
+            # a fused tensor-core kernel that reported a pipeline stall left partial gradients behind: such a step is
+            # skipped ON THE DEVICE (same mechanism as an inf/nan under GradScaler), and ops.tc_poll raises soon after
+            from . import ops
+
+            stalled = ops.tc_found_inf(tab.params[0].device)
+            found_inf = stalled if found_inf is None else torch.maximum(found_inf.to(torch.float32).reshape(1), stalled)
             tab.refresh()
             lr = group["lr"]
             lr_dev = lr if isinstance(lr, Tensor) else None

@@ -109,3 +109,26 @@ def test_product_never_imports_the_oracle():
     for p in root.rglob("*.py"):
         txt = p.read_text()
         assert "import oracle" not in txt and "from oracle" not in txt, p
+
+
+def test_library_carries_the_digest_of_its_sources_and_stale_builds_are_refused(monkeypatch):
+    """The built library embeds the sha256 of the sources + flags it was made from; the loader recomputes it from the
+    sources next to it and refuses anything else (a stale .so bound to a newer header is undefined behaviour)."""
+    from modulus_b200 import build
+
+    lib = _lib.load()
+    assert lib.mgn_build_digest().decode() == build._digest() == build.embedded_digest()
+    monkeypatch.setattr(build, "_digest", lambda: "0" * 64)
+    with pytest.raises(_lib.MGNError, match="rebuild"):
+        _lib._verify_digest(lib)
+
+
+def test_product_library_has_no_process_global_debug_switches():
+    """Profiling hooks (include/mgn_b200_debug.h) exist only in -DMGN_DEBUG_HOOKS builds."""
+    import os
+
+    if "MGN_DEBUG_HOOKS" in os.environ.get("MGN_NVCC_EXTRA", ""):
+        pytest.skip("debug build")
+    lib = _lib.load()
+    assert _lib.DEBUG_PROTOTYPES and not any(hasattr(lib, n) for n in _lib.DEBUG_PROTOTYPES)
+    assert not any("debug" in n for n in _lib.PROTOTYPES)

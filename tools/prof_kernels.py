@@ -1,4 +1,5 @@
-"""Stand-alone launches of the fused edge-block kernels at the c2 size (for ncu captures and timing)."""
+"""Stand-alone launches of the fused kernels (for ncu captures and timing): python tools/prof_kernels.py NX NY REPS.
+Phase breakdowns need a library built with MGN_NVCC_EXTRA=-DMGN_DEBUG_HOOKS."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,24 +21,12 @@ b1, b2, b3, gamma, beta = r(128) * .1, r(128) * .1, r(128) * .1, 1 + .1 * r(128)
 gw1 = torch.empty(128, 384, device=DEV); gw2 = torch.empty(128, 128, device=DEV); gw3 = torch.empty(128, 128, device=DEV)
 gb = [torch.empty(128, device=DEV) for _ in range(5)]
 
-def fwd():
-    return ops.mlp3_fwd_tc_g(efeat, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta,
-                             residual=efeat)
-
 def fwd2():
     return ops.mlp3_fwd2_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, E, w1[:, :128], b1, w2, b2, w3, b3,
                             gamma, beta, res_is_a=True)
 
 def eblk():
     return ops.edge_block_fwd_tc(efeat, P, plan.src, plan.dst, plan.csc_offsets, N, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta)
-
-def eblk2():
-    from modulus_b200 import _lib as L
-    L.call("mgn_debug_set_edge_fwd3", 0)
-    try:
-        return eblk()
-    finally:
-        L.call("mgn_debug_set_edge_fwd3", 1)
 
 def bwd():
     return ops.mlp3_bwd_tc(efeat, None, None, P, plan.src, 0, P, plan.dst, 128, g_e, g_agg, plan.dst, E,
@@ -78,7 +67,7 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
-for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg", eblk2), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("segsum csc", agg), ("segsum csr", csr),
+for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
@@ -93,8 +82,11 @@ for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd2+agg",
     print(f"{name:12s} N={N} E={E}: {ms:.3f} ms  ({E / ms / 1e3:.1f} M edges/s)", flush=True)
 ops.tc_check(DEV)
 
-# per-phase cycle breakdown of CTA 0 of the backward kernel
+# per-phase cycle breakdown of CTA 0 (only in a library built with -DMGN_DEBUG_HOOKS, see include/mgn_b200_debug.h)
 from modulus_b200 import _lib
+if not _lib.has_debug_hooks():
+    print("(no phase breakdown: build with MGN_NVCC_EXTRA=-DMGN_DEBUG_HOOKS for it)")
+    sys.exit(0)
 tbuf = torch.zeros(96, dtype=torch.int64, device=DEV)
 _lib.call("mgn_debug_set_bwd_timing", tbuf.data_ptr())
 bwd(); torch.cuda.synchronize()
