@@ -17,9 +17,13 @@ the timed region), roofline (dominant kernel, CUDA-event durations recorded insi
 region against algorithmic bytes/flops), cpu_baseline (oracle port on the host cores, bounded
 sample), clocks, gpu_launches.
 
---impl reference times the CPU implementation of the same path (oracle/mgn_oracle.py: the
-reference's algorithm restated in plain torch, pinned to the reference's golden vectors in
-tests/test_oracle.py; /root/reference itself is not present on the GPU box).
+--impl reference times the reference's own CPU implementation of the same path on the host cores: the UNMODIFIED
+physicsnemo MeshGraphNet staged under oracle/_ref by oracle/stage_reference.py (cpu_baseline.kind "reference"; absent
+third-party imports served by oracle/ref_shim), or, where that was not staged, the oracle port oracle/mgn_oracle.py
+(kind "port"; pinned to the reference's golden vectors in tests/test_oracle.py).  Each step is a bounded sample of the
+SAME workload (same mesh generator, same MeshGraphNet dimensions, fewer mesh rows), plus one full-size step of c2.
+
+The line also carries `parity`: an in-run check of the CUDA path against the oracle on a 10k-node mesh.
 """
 from __future__ import annotations
 
@@ -50,7 +54,9 @@ WORKLOADS = {
 
 def load_traffic(kernel, workload):
     """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/r01_ncu_traffic.json)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if not os.path.exists(p):
+        p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if not os.path.exists(p):
         return None
     try:
@@ -126,49 +132,90 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------
-# CPU arm (oracle port) -- the reference's algorithm on the host cores
+# CPU arm -- the reference's own implementation (staged, unmodified) or the oracle port, on the host cores
 # ------------------------------------------------------------------------------------------
-def cpu_step_rate(sample_nx: int, sample_ny: int, d_n, d_e, d_out, reps: int, warmup: int, threads: int):
+# bounded sample of a workload: same generator and model dimensions, fewer mesh rows (about 40k nodes / 240k edges,
+# 2-3 s of CPU work per step); c1 is small enough to run whole
+SAMPLE_ROWS = {"c1": 42, "c2": 126, "c3": 40}
+
+
+def cpu_inputs(workload: str, rows=None):
     import torch
-    from modulus_b200.mesh import triangle_grid_mesh
+    from modulus_b200 import mesh as meshgen
+
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[workload]
+    rows = gargs[0] if rows is None else rows
+    mesh = getattr(meshgen, gen)(rows, gargs[1])
+    n, E = mesh["num_nodes"], int(mesh["indices"].numel())
+    g = torch.Generator().manual_seed(1)
+    nf, tgt = torch.randn(n, d_n, generator=g), torch.randn(n, d_out, generator=g)
+    ef = mesh["edge_features"]
+    ef = (ef[:, :d_e] if ef.shape[1] >= d_e else torch.cat([ef, ef[:, :1].expand(-1, d_e - ef.shape[1])], 1)).contiguous()
+    return mesh, n, E, nf, ef, tgt, f"{gen}({rows},{gargs[1]})"
+
+
+CPU_BUDGET_S = 150.0  # the CPU legs stop adding timed repetitions once this much wall time is spent
+
+
+def cpu_step_rate(workload: str, rows, reps: int, warmup: int, threads: int):
+    """(edges/s, s per step, nodes, edges, kind, mesh name, reps done) of the CPU implementation on `rows` mesh rows of
+    `workload`; at most `reps` timed steps, fewer when CPU_BUDGET_S runs out (slow hosts)."""
+    import torch
     from oracle import mgn_oracle as O  # CPU baseline leg only
+    from oracle import ref_runner as R
 
     torch.set_num_threads(threads)
-    mesh = triangle_grid_mesh(sample_nx, sample_ny)
-    n, E = mesh["num_nodes"], int(mesh["indices"].numel())
-    src, dst = O.coo_from_csc(mesh["offsets"], mesh["indices"])
-    torch.manual_seed(0)
-    sd = O.make_state_dict(d_n, d_e, d_out, processor_size=L, hidden=H)
-    nf, tgt = torch.randn(n, d_n), torch.randn(n, d_out)
-    ef = mesh["edge_features"][:, :d_e].contiguous() if mesh["edge_features"].shape[1] >= d_e else torch.randn(E, d_e)
-    times = []
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[workload]
+    mesh, n, E, nf, ef, tgt, name = cpu_inputs(workload, rows)
+    if R.available():
+        model, graph = R.build(d_n, d_e, d_out, mesh["offsets"], mesh["indices"], processor_size=L, seed=0)
+        kind, one = "reference", (lambda: R.step(model, graph, nf, ef, tgt))
+    else:
+        src, dst = O.coo_from_csc(mesh["offsets"], mesh["indices"])
+        torch.manual_seed(0)
+        sd = O.make_state_dict(d_n, d_e, d_out, processor_size=L, hidden=H)
+        kind, one = "port", (lambda: O.step_fwd_bwd(sd, nf, ef, src, dst, tgt, processor_size=L))
+    times, t_start = [], time.perf_counter()
     for i in range(warmup + reps):
         t0 = time.perf_counter()
-        O.step_fwd_bwd(sd, nf, ef, src, dst, tgt, processor_size=L)
-        dt = time.perf_counter() - t0
+        one()
         if i >= warmup:
-            times.append(dt)
+            times.append(time.perf_counter() - t0)
+            if time.perf_counter() - t_start > CPU_BUDGET_S:
+                break
     t = sum(times) / len(times)
-    return E / t, t, n, E
+    return E / t, t, n, E, kind, name, len(times)
+
+
+def _cpu_desc(kind, name, n, E, t, reps, warmup):
+    what = ("unmodified physicsnemo MeshGraphNet (oracle/_ref + oracle/ref_shim)" if kind == "reference"
+            else "oracle port (oracle/mgn_oracle.py)")
+    return (f"{what} on {name}: {n} nodes / {E} edges, 15 layers, hidden 128, fp32, torch CPU, {reps} reps after "
+            f"{warmup} warm-up, {t:.2f} s per step")
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[args.workload]
     threads = os.cpu_count() or 1
-    # bounded sample of the workload: a 200x200 triangle mesh (40k nodes, ~238k edges) per step, ~2.6 s on 16 cores
-    nx, ny = (42, 45) if args.workload == "c1" else (200, 200)
-    rate, t, n, E = cpu_step_rate(nx, ny, d_n, d_e, d_out, reps=max(args.steps, 1), warmup=min(args.warmup, 1),
-                                  threads=threads)
-    sample = f"triangle_grid_mesh({nx},{ny}): {n} nodes / {E} edges, 15 layers, hidden 128, fp32, torch CPU"
+    rows = SAMPLE_ROWS[args.workload]
+    reps, warm = max(args.steps, 1), min(args.warmup, 1)
+    rate, t, n, E, kind, name, reps = cpu_step_rate(args.workload, rows, reps, warm, threads)
+    sample = _cpu_desc(kind, name, n, E, t, reps, warm)
+    full = None
+    if not args.no_full_size and args.workload != "c1":
+        # like-for-like at a BASELINE size: ONE step of the whole c2 mesh (100k nodes / 600k edges), no warm-up
+        r2, t2, n2, E2, _, name2, _ = cpu_step_rate("c2", None, 1, 0, threads)
+        full = {"workload": workload_name("c2", 1), "value": r2, "unit": UNIT, "s_per_step": t2, "nodes": n2, "edges": E2,
+                "note": "whole configs[1] mesh, one step"}
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, 1), "sample": sample},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "full_size_step": full,
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -183,6 +230,92 @@ def workload_name(w, world):
 # ------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------
+def parity_check(dev):
+    """In-run parity (last row): the CUDA path against the CPU oracle on the same seeded inputs and weights, a
+    10k-node / 59k-edge triangle mesh through all 15 layers.  fp32 path: output, input gradients and every weight gradient
+    within 1e-3 (north_star's 15-layer bar); fused bf16 path: output within 2e-2.  The oracle is the checker only."""
+    import torch
+    from modulus_b200.mesh import triangle_grid_mesh
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from oracle import mgn_oracle as O  # checker
+
+    mesh = triangle_grid_mesh(100, 100)
+    n = mesh["num_nodes"]
+    torch.manual_seed(0)
+    model = MeshGraphNet(6, 3, 3).to(dev)
+    g = torch.Generator().manual_seed(2)
+    nf, tgt, ef = torch.randn(n, 6, generator=g), torch.randn(n, 3, generator=g), mesh["edge_features"].clone()
+    graph = CuGraphCSC(mesh["offsets"].to(dev), mesh["indices"].to(dev), n, n)
+    src, dst = O.coo_from_csc(mesh["offsets"], mesh["indices"])
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref_out, _, ref_g = O.step_fwd_bwd(sd, nf, ef, src, dst, tgt, processor_size=L)
+
+    def rel(a, b):
+        return float((a.double().cpu() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    res = {"mesh": f"triangle_grid_mesh(100,100): {n} nodes / {int(src.numel())} edges, 15 layers, hidden 128",
+           "oracle": "oracle/mgn_oracle.py fp32 (pinned to the reference's goldens)"}
+    for name, bf16 in (("fp32", False), ("bf16", True)):
+        model.zero_grad(set_to_none=True)
+        x = nf.to(dev).requires_grad_(True)
+        e = ef.to(dev).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            out = model(x, e, graph)
+        torch.nn.functional.mse_loss(out.float(), tgt.to(dev)).backward()
+        torch.cuda.synchronize()
+        res[name + "_out"] = rel(out.float(), ref_out)
+        if not bf16:
+            res["fp32_grad_inputs"] = max(rel(x.grad, ref_g["__node_features"]), rel(e.grad, ref_g["__edge_features"]))
+            res["fp32_grad_weights_max"] = max(rel(p.grad, ref_g[k]) for k, p in model.named_parameters())
+    res["tolerances"] = {"fp32": 1e-3, "bf16_out": 2e-2}
+    res["ok"] = bool(res["fp32_out"] < 1e-3 and res["fp32_grad_inputs"] < 1e-3 and res["fp32_grad_weights_max"] < 1e-3
+                     and res["bf16_out"] < 2e-2)
+    return res
+
+
+def side_rate(workload, dev, peaks, steps=10, warmup=3):
+    """fwd+bwd rate of another BASELINE configuration on this GPU (inputs resident), for the record next to the headline"""
+    import torch
+    from modulus_b200 import mesh as meshgen
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+
+    gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[workload]
+    mesh = getattr(meshgen, gen)(*gargs, device=dev)
+    n, E = mesh["num_nodes"], int(mesh["indices"].numel())
+    torch.manual_seed(0)
+    model = MeshGraphNet(d_n, d_e, d_out).to(dev)
+    graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n, n)
+    g = torch.Generator().manual_seed(1)
+    nf, tgt = torch.randn(n, d_n, generator=g).to(dev), torch.randn(n, d_out, generator=g).to(dev)
+    ef = mesh["edge_features"]
+    ef = (ef[:, :d_e] if ef.shape[1] >= d_e else torch.cat([ef, ef[:, :1].expand(-1, d_e - ef.shape[1])], 1)).float().contiguous()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == "bf16"):
+            pred = model(nf, ef, graph)
+        torch.nn.functional.mse_loss(pred.float(), tgt).backward()
+
+    for _ in range(warmup):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    b = 2 if dtype == "bf16" else 4
+    return {"workload": workload_name(workload, 1), "value": E / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+            "steps": steps, "warmup": warmup, "dtype": dtype,
+            "hbm_frac": step_bytes(n, E, b) / (ms * 1e-3) / 1e9 / peaks["hbm"],
+            "tensor_frac": step_flops(n, E, d_n, d_e, d_out) / (ms * 1e-3) / 1e12 / peaks["tc_sust"],
+            "l2": "edge table %.0f MB: %s the 126 MB L2" % (E * H * b / 1e6, "exceeds" if E * H * b > 126e6 else "fits")}
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -346,6 +479,12 @@ def run_b200(args, rank, world, local_rank):
 
     if rank != 0:
         return
+    parity = side = None
+    if not args.no_extra:
+        del nf_d, ef_d, tgt_d
+        parity = parity_check(dev)
+        if world == 1 and args.workload == "c3":
+            side = {"c2": side_rate("c2", dev, peaks)}
     b = 2 if use_bf16 else 4
     N1, E1 = n_glob // world, E_glob // world  # per-rank work (weak scaling)
     flops, bytes_ = step_flops(N1, E1, d_n, d_e, d_out), step_bytes(N1, E1, b)
@@ -378,10 +517,9 @@ def run_b200(args, rank, world, local_rank):
     cpu = None
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        rate, t, n_s, E_s = cpu_step_rate(200, 200, d_n, d_e, d_out, reps=4, warmup=1, threads=threads)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"oracle step on triangle_grid_mesh(200,200): {n_s} nodes / {E_s} edges, 15 layers, hidden 128, "
-                         f"fp32, 4 reps after 1 warm-up, {t:.2f} s per step ({5 * t:.0f} s of CPU work)"}
+        rate, t, n_s, E_s, kind, name, reps = cpu_step_rate(args.workload, SAMPLE_ROWS[args.workload], 4, 1, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": _cpu_desc(kind, name, n_s, E_s, t, reps, 1) + f" ({(reps + 1) * t:.0f} s of CPU work)"}
     line = {
         "metric": METRIC, "value": E_glob / (t_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
@@ -395,6 +533,7 @@ def run_b200(args, rank, world, local_rank):
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),
         "roofline": roof, "whole_step": whole, "cpu_baseline": cpu, "clocks": clk, "optimizer_step": opt_info,
+        "parity": parity, "other_configs": side,
         "kernel_shares": {k: round(v["ms"], 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]},
     }
     print(json.dumps(line), flush=True)
@@ -408,6 +547,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-full-size", action="store_true", help="reference arm: skip the one full-size c2 step")
+    ap.add_argument("--no-extra", action="store_true", help="skip the c2 side measurement and the in-run parity check")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -423,8 +564,6 @@ def main():
         import torch.distributed as dist
         import torch
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # (NCCL prints its version banner on stdout; stdout carries one JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     try:
