@@ -1,0 +1,109 @@
+"""Matched-rounding oracle of the fused bf16 path (the bar for bf16 GRADIENTS).
+
+TEST INFRASTRUCTURE (see oracle/mgn_oracle.py for the rules: only tests/, smoke() and bench.py's checker legs import it).
+
+Why it exists.  north_star asks the bf16 path to stay within 2e-2 of the reference.  For outputs that is checked against
+the fp32 reference directly.  For gradients it cannot be: a ReLU pre-activation within bf16 rounding distance of zero flips
+its mask between ANY bf16 evaluation and an fp32 one, and the reference's own `torch.autocast(bfloat16)` path is 0.13-0.22
+off its fp32 gradients on the golden cases (tests/test_gpu_ops.py).  What CAN be held to 2e-2 is: the CUDA path
+against the same algorithm evaluated in float64 with bf16 rounding applied exactly where the kernels store bf16 -- forward
+(straight-through rounding, so ReLU masks follow the stored bf16 activations) and backward (gradients rounded where the
+kernels write them).  Everything between two storage points is exact here and fp32-accumulated in the kernels.
+
+Pin.  With both roundings switched off this file computes, in float64, exactly what oracle/mgn_oracle.step_fwd_bwd computes
+(tests/test_oracle.py::test_matched_rounding_oracle_reduces_to_the_plain_oracle), and that one is pinned to the reference's
+golden vectors.  The rounding points below restate modulus_b200/fused.py + the kernels' documented storage points
+(DESIGN.md 3-5); the reference lines of the underlying algorithm are cited in oracle/mgn_oracle.py.
+
+Storage points (H = 128):
+  forward   bf16: weights as read by the tensor cores; encoder inputs; h1, h2 of every MLP; LayerNorm(+residual) outputs
+            (efeat_l, nfeat_l); P_l = nfeat_l Wp^T; agg_l = sum by destination; decoder output
+  backward  bf16: g_out = g_e + g_agg[dst]; g_y (LayerNorm backward); g_z2, g_z1; g_efeat; g_agg; the three column blocks
+            of T (CSR / CSC sums of g_z1, node g_z1); g_nfeat = g_n + T Wp
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+H = 128
+
+
+def _bf(x: Tensor) -> Tensor:
+    return x.to(torch.float32).to(torch.bfloat16).to(x.dtype)
+
+
+class _GradRound(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _bf(g)
+
+
+class Rounding:
+    def __init__(self, fwd: bool = True, bwd: bool = True):
+        self.fwd, self.bwd = fwd, bwd
+
+    def s(self, x: Tensor) -> Tensor:  # stored as bf16 in the forward pass (straight-through)
+        return x + (_bf(x.detach()) - x.detach()) if self.fwd else x
+
+    def g(self, x: Tensor) -> Tensor:  # the gradient arriving at x is stored as bf16
+        return _GradRound.apply(x) if self.bwd else x
+
+
+def _mlp(R: Rounding, p: Dict[str, Tensor], pre: str, x: Tensor, extra=None, w1_cols=None, norm: bool = True) -> Tensor:
+    """Linear-ReLU-Linear-ReLU-Linear(-LayerNorm) with the kernels' storage points.  `extra` is added to the first
+    pre-activation (the gathered projection rows); `w1_cols` selects the column block of W1 that multiplies x."""
+    w1 = p[f"{pre}.model.0.weight"]
+    if w1_cols is not None:
+        w1 = w1[:, w1_cols[0]:w1_cols[1]]
+    z1 = x @ R.s(w1).T + p[f"{pre}.model.0.bias"]
+    if extra is not None:
+        z1 = z1 + extra
+    h1 = R.s(F.relu(R.g(z1)))
+    h2 = R.s(F.relu(R.g(h1 @ R.s(p[f"{pre}.model.2.weight"]).T + p[f"{pre}.model.2.bias"])))
+    y = R.g(h2 @ R.s(p[f"{pre}.model.4.weight"]).T + p[f"{pre}.model.4.bias"])
+    if norm:
+        y = F.layer_norm(y, (y.shape[-1],), p[f"{pre}.model.5.weight"], p[f"{pre}.model.5.bias"], 1e-5)
+    return y
+
+
+def forward(R: Rounding, p: Dict[str, Tensor], nf: Tensor, ef: Tensor, src: Tensor, dst: Tensor, L: int) -> Tensor:
+    """The fused path's algebra (modulus_b200/fused.py: first Linear split by input block, P = nfeat Wp^T)."""
+    n = nf.shape[0]
+    e = R.g(R.s(_mlp(R, p, "edge_encoder", R.s(ef))))
+    v = R.g(R.s(_mlp(R, p, "node_encoder", R.s(nf))))
+    for l in range(L):
+        pe, pn = f"processor.processor_layers.{2 * l}.edge_mlp", f"processor.processor_layers.{2 * l + 1}.node_mlp"
+        w1e, w1n = p[f"{pe}.model.0.weight"], p[f"{pn}.model.0.weight"]
+        wp = torch.cat([w1e[:, H:2 * H], w1e[:, 2 * H:3 * H], w1n[:, H:2 * H]], dim=0)       # [3H, H]
+        P = R.g(R.s(v @ R.s(wp).T))                                                         # [N, 3H]
+        e_in = R.g(e)  # what the edge block's own backward returns (g_efeat) is rounded before it meets g_agg[dst]
+        y = _mlp(R, p, pe, e_in, extra=P[src, :H] + P[dst, H:2 * H], w1_cols=(0, H))
+        e = R.g(R.s(y + e_in))
+        agg = R.g(R.s(torch.zeros((n, H), dtype=e.dtype).index_add(0, dst, e)))
+        y = _mlp(R, p, pn, agg, extra=P[:, 2 * H:], w1_cols=(0, H))
+        v = R.g(R.s(y + v))
+    return R.g(R.s(_mlp(R, p, "node_decoder", v, norm=False)))
+
+
+def step_fwd_bwd(sd: Dict[str, Tensor], nf: Tensor, ef: Tensor, src: Tensor, dst: Tensor, tgt: Tensor, L: int,
+                 round_fwd: bool = True, round_bwd: bool = True):
+    """zero_grad -> forward -> MSE -> backward in float64.  Returns (prediction, loss, {name: grad}) with the input
+    gradients under "__node_features" / "__edge_features" (same convention as oracle/mgn_oracle.step_fwd_bwd)."""
+    R = Rounding(round_fwd, round_bwd)
+    leaves = {k: t.detach().double().requires_grad_(True) for k, t in sd.items() if t.is_floating_point()}
+    x = nf.detach().double().requires_grad_(True)
+    a = ef.detach().double().requires_grad_(True)
+    pred = forward(R, leaves, x, a, src.long(), dst.long(), L)
+    loss = F.mse_loss(pred, tgt.double())
+    loss.backward()
+    grads = {k: t.grad for k, t in leaves.items()}
+    grads["__node_features"], grads["__edge_features"] = x.grad, a.grad
+    return pred.detach(), loss.detach(), grads

@@ -1,0 +1,73 @@
+"""Oracle comparison AT the sizes BASELINE.json names (not only on the 156-node golden mesh):
+
+  c1  vortex_shedding_mgn size: 1 890-node triangle mesh, MeshGraphNet(6,3,3), fp32, 15 layers  (configs[0])
+  c2  100k-node / 600k-edge 2-D triangle mesh, 15 layers, hidden 128                            (configs[1])
+
+The CPU side is the staged UNMODIFIED reference (oracle/_ref, when the build container staged it) or the oracle port --
+the two agree bit for bit (tests/test_oracle.py) -- run once per size in fp32.  Bars are north_star's: fp32 path outputs and
+gradients within 1e-3 after 15 layers, fused bf16 path outputs within 2e-2.  c3 (1 M nodes) is minutes of CPU per step and
+is covered by size-independent properties in tests/test_gpu_fullsize.py."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _cpu_step(model, mesh, nf, ef, tgt, L):
+    """(output, {param name: grad}, grad of node features, which CPU implementation ran)"""
+    from oracle import mgn_oracle as O, ref_runner as R
+
+    torch.set_num_threads(max(torch.get_num_threads(), 1))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    if R.available():
+        ref, graph = R.build(nf.shape[1], ef.shape[1], tgt.shape[1], mesh["offsets"], mesh["indices"], processor_size=L)
+        ref.load_state_dict(sd)
+        x = nf.clone().requires_grad_(True)
+        ref.zero_grad(set_to_none=True)
+        out = ref(x, ef, graph)
+        torch.nn.functional.mse_loss(out, tgt).backward()
+        return out.detach(), {k: p.grad for k, p in ref.named_parameters()}, x.grad, "reference"
+    src, dst = O.coo_from_csc(mesh["offsets"], mesh["indices"])
+    out, _, g = O.step_fwd_bwd(sd, nf, ef, src, dst, tgt, processor_size=L)
+    return out, g, g["__node_features"], "port"
+
+
+@pytest.mark.parametrize("size", ["c1", "c2"])
+def test_model_against_cpu_reference_at_baseline_size(size):
+    from modulus_b200 import ops
+    from modulus_b200.mesh import triangle_grid_mesh
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+
+    L = 15
+    mesh = triangle_grid_mesh(*((42, 45) if size == "c1" else (316, 317)))
+    n = mesh["num_nodes"]
+    torch.manual_seed(0)
+    model = MeshGraphNet(6, 3, 3, processor_size=L).to(DEV)
+    g = torch.Generator().manual_seed(4)
+    nf, tgt, ef = torch.randn(n, 6, generator=g), torch.randn(n, 3, generator=g), mesh["edge_features"].clone()
+    ref_out, ref_grads, ref_gnf, kind = _cpu_step(model, mesh, nf, ef, tgt, L)
+    graph = CuGraphCSC(mesh["offsets"].to(DEV), mesh["indices"].to(DEV), n, n)
+
+    def step(bf16):
+        model.zero_grad(set_to_none=True)
+        x = nf.to(DEV).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=bf16):
+            out = model(x, ef.to(DEV), graph)
+        torch.nn.functional.mse_loss(out.float(), tgt.to(DEV)).backward()
+        return out.float(), x.grad
+
+    out32, gnf32 = step(False)
+    assert _rel(out32, ref_out) < 1e-3, (kind, _rel(out32, ref_out))
+    assert _rel(gnf32, ref_gnf) < 1e-3
+    worst = max(((k, _rel(p.grad, ref_grads[k])) for k, p in model.named_parameters()), key=lambda kv: kv[1])
+    assert worst[1] < 1e-3, (kind, worst)
+    out16, _ = step(True)
+    ops.tc_check(DEV)
+    assert _rel(out16, ref_out) < 2e-2, (kind, _rel(out16, ref_out))
