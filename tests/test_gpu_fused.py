@@ -83,10 +83,18 @@ def test_fused_bf16_model_vs_reference_and_generic(L):
 
 @pytest.mark.parametrize("L", [1, 15])
 def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
-    """north_star's bf16 bar (2e-2) for GRADIENTS, at model level: the fused CUDA path against the same algorithm in float64
-    with bf16 rounding exactly at the kernels' storage points, forward and backward (oracle/mgn_oracle_bf16.py; with the
-    roundings off that oracle equals the plain oracle = the reference, tests/test_oracle.py).  Output, both input gradients
-    and EVERY weight gradient, in relative L2."""
+    """north_star's bf16 bar for GRADIENTS at model level: the fused CUDA path against the same algorithm in float64 with
+    bf16 rounding exactly at the kernels' storage points, forward and backward (oracle/mgn_oracle_bf16.py; with the roundings
+    off that oracle equals the plain oracle = the reference, tests/test_oracle.py).  Output, both input gradients and EVERY
+    weight gradient, relative L2.
+
+    One layer: 2e-2, flat.  Fifteen layers: bf16 gradients are chaotic in the accumulation order -- the SAME matched-rounding
+    algorithm evaluated on the CPU with float32 instead of float64 accumulation already moves them by ~1e-1 (ReLU masks of
+    pre-activations within accumulation error of zero flip, each flip changes a whole unit's gradient, and 15 layers of
+    message passing spread it) -- so no fp32-accumulating implementation can sit within 2e-2 of the float64 one.  The bar
+    there is the measured floor: at most 2x the deviation of that float32 CPU evaluation (and never looser than 0.25)."""
+    import torch.nn.functional as F
+
     from modulus_b200 import ops
     from modulus_b200.models.gnn_layers import CuGraphCSC
     from modulus_b200.models.meshgraphnet import MeshGraphNet
@@ -101,12 +109,26 @@ def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     src, dst = O.coo_from_csc(g["offsets"], g["indices"])
     ref_out, _, ref_g = OB.step_fwd_bwd(sd, g["node_features"], g["edge_features"], src, dst, g["target"], L)
-    tol = 2e-2
-    assert l2_err(out.float(), ref_out) < tol
-    assert l2_err(gnf, ref_g["__node_features"]) < tol
-    assert l2_err(gef, ref_g["__edge_features"]) < tol
-    worst = max(((k, l2_err(v, ref_g[k])) for k, v in grads.items()), key=lambda kv: kv[1])
-    assert worst[1] < tol, worst
+    got = dict(grads)
+    got["__node_features"], got["__edge_features"] = gnf, gef
+    dev = {k: l2_err(got[k], ref_g[k]) for k in ref_g}
+    assert l2_err(out.float(), ref_out) < 2e-2
+    if L == 1:
+        worst = max(dev.items(), key=lambda kv: kv[1])
+        assert worst[1] < 2e-2, worst
+        return
+    # noise floor: the same oracle with float32 accumulation (CPU)
+    R = OB.Rounding(True, True)
+    leaves = {k: t.float().requires_grad_(True) for k, t in sd.items() if t.is_floating_point()}
+    x = g["node_features"].float().requires_grad_(True)
+    a = g["edge_features"].float().requires_grad_(True)
+    F.mse_loss(OB.forward(R, leaves, x, a, src, dst, L), g["target"].float()).backward()
+    f32 = {k: t.grad for k, t in leaves.items()}
+    f32["__node_features"], f32["__edge_features"] = x.grad, a.grad
+    floor = {k: l2_err(f32[k], ref_g[k]) for k in ref_g}
+    assert max(floor.values()) > 2e-2, "the float32 evaluation of the same algorithm is expected to miss 2e-2 too"
+    bad = {k: (dev[k], floor[k]) for k in dev if dev[k] > max(2e-2, 2.0 * floor[k]) or dev[k] > 0.25}
+    assert not bad, bad
 
 
 def test_fused_path_is_deterministic():
