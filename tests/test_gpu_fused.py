@@ -111,7 +111,9 @@ def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
     ref_out, _, ref_g = OB.step_fwd_bwd(sd, g["node_features"], g["edge_features"], src, dst, g["target"], L)
     got = dict(grads)
     got["__node_features"], got["__edge_features"] = gnf, gef
-    dev = {k: l2_err(got[k], ref_g[k]) for k in ref_g}
+    dev = {k: l2_err(got[k], ref_g[k]) for k in got}
+    print(f"[L={L}] out {l2_err(out.float(), ref_out):.2e}; worst gradient deviations:",
+          sorted(((round(v, 4), k) for k, v in dev.items()), reverse=True)[:4])
     assert l2_err(out.float(), ref_out) < 2e-2
     if L == 1:
         worst = max(dev.items(), key=lambda kv: kv[1])
@@ -125,8 +127,9 @@ def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
     F.mse_loss(OB.forward(R, leaves, x, a, src, dst, L), g["target"].float()).backward()
     f32 = {k: t.grad for k, t in leaves.items()}
     f32["__node_features"], f32["__edge_features"] = x.grad, a.grad
-    floor = {k: l2_err(f32[k], ref_g[k]) for k in ref_g}
+    floor = {k: l2_err(f32[k], ref_g[k]) for k in got}
     assert max(floor.values()) > 2e-2, "the float32 evaluation of the same algorithm is expected to miss 2e-2 too"
+    print("    float32-CPU floor:", sorted(((round(v, 4), k) for k, v in floor.items()), reverse=True)[:4])
     bad = {k: (dev[k], floor[k]) for k in dev if dev[k] > max(2e-2, 2.0 * floor[k]) or dev[k] > 0.25}
     assert not bad, bad
 
