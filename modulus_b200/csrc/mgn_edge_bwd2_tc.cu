@@ -102,8 +102,15 @@ __device__ __forceinline__ void tma_tile(uint8_t* buf, const CUtensorMap* map, l
 // node block.  Compile-time: a run-time flag in the last epilogue pass costs the edge instance 9 % through spills.
 // kAgg: the reducer warps also sum the g_z1 tile by destination segment (they have the slack for it in this kernel:
 // no projection-row gathers).
+// Register budget: __launch_bounds__(448, 1) makes ptxas budget for 512 threads (128 registers); 14 warps x 144 x 32 also
+// fit the register file, -DMGN_MAXNREG=144 asks for that instead (A/B switch).
+#ifdef MGN_MAXNREG
+#define MGN_BWD2_BOUNDS __maxnreg__(MGN_MAXNREG)
+#else
+#define MGN_BWD2_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
 template <bool kAddGout, bool kAgg>
-__global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_constant__ Params p) {
+__global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if ((smem_u32(smem) & 1023u) != 0) {
@@ -452,9 +459,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[32 * hh + 2 * j], 0.f),
-                             fmaxf(__uint_as_float(v[2 * j + 1]) + b2[32 * hh + 2 * j + 1], 0.f));
+        for (int j = 0; j < 16; ++j)  // relu(round(x)) == round(relu(x)): FADD2 + F2FP + HMNMX2 per pair
+          o[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
         row_store32p(bH2, row, c0 + 32 * hh, o);
       }
       MGN_EPI_DONE(B_E + 0);
@@ -466,31 +472,40 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
       MGN_T(3);
       tc_fence_after_sync();
       {
-        float s_y = 0.f, s_yy = 0.f, s_g = 0.f, s_gy = 0.f;
+        // g_out = go1 (+ go2) -> X; LayerNorm statistics of y = acc + b3 and of ghat = g_out * gamma.  All fp32 arithmetic
+        // runs two lanes per instruction (f2_*); the go1 + go2 sum is one packed bf16 add per pair.
+        float s_y, s_yy, s_g, s_gy;
+        {
+          uint64_t sy2 = 0ull, syy2 = 0ull, sg2 = 0ull, sgy2 = 0ull;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          const int cc = c0 + 32 * hh;
-          uint32_t v[32];
-          tmem_ld32(t_acc + 32 * hh, v);
-          uint32_t go[16];
-          row_load32p(bX, row, cc, go);
-          if (has_go2) {
-            uint32_t g2[16];
-            row_load32p(bA, row, cc, g2);
+          for (int hh = 0; hh < 2; ++hh) {
+            const int cc = c0 + 32 * hh;
+            uint32_t v[32];
+            tmem_ld32(t_acc + 32 * hh, v);
+            uint32_t go[16];
+            row_load32p(bX, row, cc, go);
+            if (has_go2) {
+              uint32_t g2[16];
+              row_load32p(bA, row, cc, g2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
-            row_store32p(bX, row, cc, go);
-          }
-          tmem_ld_wait();
+              for (int j = 0; j < 16; ++j) go[j] = add_bf16x2(go[j], g2[j]);
+              row_store32p(bX, row, cc, go);
+            }
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = __uint_as_float(v[j]) + b3[32 * hh + j];
-            const float gh = ((j & 1) ? bf_hi(go[j >> 1]) : bf_lo(go[j >> 1])) * gam[32 * hh + j];
-            s_y += y;
-            s_yy = fmaf(y, y, s_yy);
-            s_g += gh;
-            s_gy = fmaf(gh, y, s_gy);
+            for (int j = 0; j < 16; ++j) {
+              const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 32 * hh + 2 * j));
+              const uint64_t gh2 = f2_mul(f2_from_bf16x2(go[j]), f2_ld(gam + 32 * hh + 2 * j));
+              sy2 = f2_add(sy2, y2);
+              syy2 = f2_fma(y2, y2, syy2);
+              sg2 = f2_add(sg2, gh2);
+              sgy2 = f2_fma(gh2, y2, sgy2);
+            }
           }
+          s_y = f2_lo(sy2) + f2_hi(sy2);
+          s_yy = f2_lo(syy2) + f2_hi(syy2);
+          s_g = f2_lo(sg2) + f2_hi(sg2);
+          s_gy = f2_lo(sgy2) + f2_hi(sgy2);
         }
         *reinterpret_cast<float4*>(bA + xch_own) = make_float4(s_y, s_yy, s_g, s_gy);
         MGN_ROW_SYNC();
@@ -507,6 +522,11 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
         const float rstd = rsqrtf(var + p.eps);
         const float m1 = s_g * (1.f / kH);
         const float m2 = (s_gy - mu * s_g) * rstd * (1.f / kH);  // mean(ghat * xhat)
+        // g_y = rstd (ghat - m1 - xhat m2) with xhat = rstd (y - mu), expanded so that each element is two FMAs:
+        //   g_y = rstd * ghat - k2 * y + k0,   k2 = rstd^2 m2,   k0 = k2 mu - rstd m1;   xhat = rstd * y - rstd mu
+        const float k2 = rstd * rstd * m2;
+        const uint64_t A2 = f2_splat(rstd), NK2 = f2_splat(-k2), K0 = f2_splat(fmaf(k2, mu, -rstd * m1)),
+                       NAMU = f2_splat(-rstd * mu);
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = c0 + 32 * hh;
@@ -522,14 +542,13 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int c = 16 * h + 2 * j;  // column within this 32-column half
-              const float g0 = bf_lo(go[c >> 1]), g1v = bf_hi(go[c >> 1]);
-              const float x0 = (__uint_as_float(v[c]) + b3[32 * hh + c] - mu) * rstd;
-              const float x1 = (__uint_as_float(v[c + 1]) + b3[32 * hh + c + 1] - mu) * rstd;
-              const float y0 = rstd * (g0 * gam[32 * hh + c] - m1 - x0 * m2);
-              const float y1 = rstd * (g1v * gam[32 * hh + c + 1] - m1 - x1 * m2);
-              o[j] = pack_bf16x2(y0, y1);
-              t[2 * j] = g0 * x0;  // gamma-gradient contribution of this row
-              t[2 * j + 1] = g1v * x1;
+              const uint64_t y2 = f2_add(f2_packu(v[c], v[c + 1]), f2_ld(b3 + 32 * hh + c));
+              const uint64_t g2 = f2_from_bf16x2(go[c >> 1]);
+              const uint64_t gh2 = f2_mul(g2, f2_ld(gam + 32 * hh + c));
+              o[j] = f2_to_bf16x2(f2_fma(A2, gh2, f2_fma(NK2, y2, K0)));
+              const uint64_t tt = f2_mul(g2, f2_fma(A2, y2, NAMU));  // gamma-gradient contribution g_out * xhat
+              t[2 * j] = f2_lo(tt);
+              t[2 * j + 1] = f2_hi(tt);
             }
             uint8_t* base = bA + ch * kPB;
             const int c8 = 4 * hh + 2 * h;
@@ -556,9 +575,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
           row_load32p(bH2, row, c0 + 32 * hh, hq[hh]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+          for (int j = 0; j < 16; ++j)  // F2FP + HSET2 + LOP3 per pair
+            hq[hh][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[hh][j]);
         }
         MGN_W(B_W3, par);
         row_store32p(bH2, row, c0, hq[0]);
@@ -579,9 +597,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
           row_load32p(bH1, row, c0 + 32 * hh, hq[hh]);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+          for (int j = 0; j < 16; ++j)  // F2FP + HSET2 + LOP3 per pair
+            hq[hh][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[hh][j]);
         }
         MGN_W(B_W2, par);
         row_store32p(bH1, row, c0, hq[0]);
@@ -602,8 +619,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_bwd2_kernel(const __grid_con
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + (kAddGout ? bf_lo(go[j]) : 0.f),
-                                __uint_as_float(v[2 * j + 1]) + (kAddGout ? bf_hi(go[j]) : 0.f));
+            go[j] = kAddGout ? f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_from_bf16x2(go[j])))
+                             : pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           row_store32p(bX, row, c0 + 32 * hh, go);
         }
       }

@@ -60,7 +60,12 @@ struct Smem {
 // one completion are kept per slot: a parity wait cannot tell two completions from none.)
 enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_NUM = 17 };
 
-__global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_constant__ Params p) {
+#ifdef MGN_MAXNREG
+#define MGN_FWD3_BOUNDS __maxnreg__(MGN_MAXNREG)
+#else
+#define MGN_FWD3_BOUNDS __launch_bounds__(kThreads, 1)
+#endif
+__global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const Args& a = p.a;
@@ -324,22 +329,15 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 bb = reinterpret_cast<const float4*>(b1 + 32 * hh)[u];
+        for (int u = 0; u < 8; ++u) {  // two fp32 lanes per instruction (mgn_tile.cuh); relu after the bf16 rounding
           const uint4 gd = gq[4 * hh + (u >> 1)];
           const uint32_t d0 = (u & 1) ? gd.z : gd.x, d1 = (u & 1) ? gd.w : gd.y;
-          float z0 = __uint_as_float(v[4 * u]) + bb.x, z1 = __uint_as_float(v[4 * u + 1]) + bb.y;
-          float z2 = __uint_as_float(v[4 * u + 2]) + bb.z, z3 = __uint_as_float(v[4 * u + 3]) + bb.w;
-          z0 += bf_lo(ga[2 * u]);
-          z1 += bf_hi(ga[2 * u]);
-          z2 += bf_lo(ga[2 * u + 1]);
-          z3 += bf_hi(ga[2 * u + 1]);
-          z0 += bf_lo(d0);
-          z1 += bf_hi(d0);
-          z2 += bf_lo(d1);
-          z3 += bf_hi(d1);
-          pk[2 * u] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-          pk[2 * u + 1] = pack_bf16x2(fmaxf(z2, 0.f), fmaxf(z3, 0.f));
+          uint64_t za = f2_add(f2_packu(v[4 * u], v[4 * u + 1]), f2_ld(b1 + 32 * hh + 4 * u));
+          uint64_t zb = f2_add(f2_packu(v[4 * u + 2], v[4 * u + 3]), f2_ld(b1 + 32 * hh + 4 * u + 2));
+          za = f2_add(f2_add(za, f2_from_bf16x2(ga[2 * u])), f2_from_bf16x2(d0));
+          zb = f2_add(f2_add(zb, f2_from_bf16x2(ga[2 * u + 1])), f2_from_bf16x2(d1));
+          pk[2 * u] = relu_bf16x2(f2_to_bf16x2(za));
+          pk[2 * u + 1] = relu_bf16x2(f2_to_bf16x2(zb));
         }
         tmem_st16(t_h + 16 * hh, pk);
         if (a.h1_out != nullptr) row_store32p(bG1, row, c0 + 32 * hh, pk);  // over this thread's own consumed G1 span
@@ -390,12 +388,8 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
           tmem_ld_wait();
           uint32_t pk[16];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 bb = reinterpret_cast<const float4*>(b2 + 32 * hh)[u];
-            pk[2 * u] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * u]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * u + 1]) + bb.y, 0.f));
-            pk[2 * u + 1] =
-                pack_bf16x2(fmaxf(__uint_as_float(v[4 * u + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * u + 3]) + bb.w, 0.f));
-          }
+          for (int j = 0; j < 16; ++j)
+            pk[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
           tmem_st16(t_h + 16 * hh, pk);
         }
         tmem_st_wait();
@@ -416,20 +410,23 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
         MGN_W(B_M3, par);
         MGN_T(4);
         tc_fence_after_sync();
-        float s = 0.f, ss = 0.f;
+        float s, ss;
+        {
+          uint64_t s2 = 0ull, ss2 = 0ull;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + 32 * hh, v);
-          tmem_ld_wait();
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + 32 * hh, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
-            const float y0 = __uint_as_float(v[4 * u]) + bb.x, y1 = __uint_as_float(v[4 * u + 1]) + bb.y;
-            const float y2 = __uint_as_float(v[4 * u + 2]) + bb.z, y3 = __uint_as_float(v[4 * u + 3]) + bb.w;
-            s += (y0 + y1) + (y2 + y3);
-            ss = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, ss))));
+            for (int j = 0; j < 16; ++j) {
+              const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 32 * hh + 2 * j));
+              s2 = f2_add(s2, y2);
+              ss2 = f2_fma(y2, y2, ss2);
+            }
           }
+          s = f2_lo(s2) + f2_hi(s2);
+          ss = f2_lo(ss2) + f2_hi(ss2);
         }
         tmem_st2(t_x + ch * 2, __float_as_uint(s), __float_as_uint(ss));
         tmem_st_wait();
@@ -450,19 +447,13 @@ __global__ void __launch_bounds__(kThreads, 1) edge_fwd3_kernel(const __grid_con
           row_load32p(bAcur, row, cc, r);
           tmem_ld_wait();
           uint32_t o[16];
+          const uint64_t NMU = f2_splat(-mu), RS = f2_splat(rstd);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
-            const float4 gg = reinterpret_cast<const float4*>(gam + 32 * hh)[u];
-            const float4 be = reinterpret_cast<const float4*>(bet + 32 * hh)[u];
-            float y[4] = {__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
-                          __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w};
-            y[0] = (y[0] - mu) * rstd * gg.x + be.x + bf_lo(r[2 * u]);
-            y[1] = (y[1] - mu) * rstd * gg.y + be.y + bf_hi(r[2 * u]);
-            y[2] = (y[2] - mu) * rstd * gg.z + be.z + bf_lo(r[2 * u + 1]);
-            y[3] = (y[3] - mu) * rstd * gg.w + be.w + bf_hi(r[2 * u + 1]);
-            o[2 * u] = pack_bf16x2(y[0], y[1]);
-            o[2 * u + 1] = pack_bf16x2(y[2], y[3]);
+          for (int j = 0; j < 16; ++j) {  // ((y - mu) rstd) gamma + beta, + residual: five packed fp32 ops per pair
+            const int c = 32 * hh + 2 * j;
+            uint64_t y2 = f2_add(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + c)), NMU);
+            y2 = f2_fma(f2_mul(y2, RS), f2_ld(gam + c), f2_ld(bet + c));
+            o[j] = f2_to_bf16x2(f2_add(y2, f2_from_bf16x2(r[j])));
           }
           row_store32p(bAcur, row, cc, o);
         }

@@ -279,6 +279,60 @@ __device__ __forceinline__ void row_store32p(uint8_t* buf, int row, int col, con
     *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + u)) = make_uint4(w[4 * u], w[4 * u + 1], w[4 * u + 2], w[4 * u + 3]);
 }
 
+// ---- two fp32 lanes per instruction (sm_100a: add / mul / fma .f32x2 = SASS FADD2 / FMUL2 / FFMA2).  The fp32 pipe does
+// not get faster (tools/probe_ffma2.cu: 128 FMA / cycle / SM either way) but every pair costs ONE issue slot, and the
+// epilogue passes are issue-bound.  A pair is an even-aligned 64-bit register pair: packing is free when the compiler can
+// place the two halves next to each other (tcgen05.ld outputs, unpacked bf16x2 words).
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_packu(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ uint64_t f2_splat(float x) { return f2_pack(x, x); }
+__device__ __forceinline__ float f2_lo(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v)); }
+__device__ __forceinline__ float f2_hi(uint64_t v) { return __uint_as_float(static_cast<uint32_t>(v >> 32)); }
+__device__ __forceinline__ uint64_t f2_add(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// bf16x2 word -> fp32 pair (exact), fp32 pair -> bf16x2 word (round to nearest even, one F2FP)
+__device__ __forceinline__ uint64_t f2_from_bf16x2(uint32_t w) { return f2_packu(w << 16, w & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t f2_to_bf16x2(uint64_t v) { return pack_bf16x2(f2_lo(v), f2_hi(v)); }
+__device__ __forceinline__ uint64_t f2_ld(const float* p) { return *reinterpret_cast<const uint64_t*>(p); }  // 8-byte aligned
+
+// ---- packed bf16x2 helpers (one instruction each: HMNMX2 / HSET2 + LOP3 / HFMA2)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t w) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&w), z);
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// keep the halves of `w` whose counterpart in `h` is > 0 (ReLU mask from the stored activation), zero the others
+__device__ __forceinline__ uint32_t mask_pos_bf16x2(uint32_t w, uint32_t h) {
+  const __nv_bfloat162 z = __floats2bfloat162_rn(0.f, 0.f);
+  return w & __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&h), z);
+}
+// a + b per half with ONE rounding (= bf16(exact sum), what rounding the fp32 sum gives except in double-rounding ties)
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hadd2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+
 // warp transpose-reduce of 16 columns: on return lane L holds the sum over all 32 lanes of their v[L & 15]
 __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 #pragma unroll
