@@ -97,3 +97,7 @@ def embedded_digest() -> str:
     except OSError:
         return ""
     return m.group(1).decode() if m else ""
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
