@@ -452,6 +452,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       }
       MGN_T(0);
       tc_fence_after_sync();
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
@@ -463,6 +464,15 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
           o[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
         row_store32p(bH2, row, c0 + 32 * hh, o);
       }
+#else
+      tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)  // relu(round(x)) == round(relu(x)): FADD2 + F2FP + HMNMX2 per pair
+          o[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 16 * i + 2 * j))));
+        row_store16p(bH2, row, c0 + 16 * i, o);
+      });
+#endif
       MGN_EPI_DONE(B_E + 0);
       MGN_T(1);
       // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> X ; g_y -> A
@@ -475,6 +485,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         // g_out = go1 (+ go2) -> X; LayerNorm statistics of y = acc + b3 and of ghat = g_out * gamma.  All fp32 arithmetic
         // runs two lanes per instruction (f2_*); the go1 + go2 sum is one packed bf16 add per pair.
         float s_y, s_yy, s_g, s_gy;
+#ifdef MGN_NO_PIPE16
         {
           uint64_t sy2 = 0ull, syy2 = 0ull, sg2 = 0ull, sgy2 = 0ull;
 #pragma unroll 1
@@ -507,6 +518,36 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
           s_g = f2_lo(sg2) + f2_hi(sg2);
           s_gy = f2_lo(sgy2) + f2_hi(sgy2);
         }
+#else
+        {
+          uint64_t sy2 = 0ull, syy2 = 0ull, sg2 = 0ull, sgy2 = 0ull;
+          tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+            const int cc = c0 + 16 * i;
+            uint32_t go[8];
+            row_load16p(bX, row, cc, go);
+            if (has_go2) {
+              uint32_t g2[8];
+              row_load16p(bA, row, cc, g2);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) go[j] = add_bf16x2(go[j], g2[j]);
+              row_store16p(bX, row, cc, go);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 16 * i + 2 * j));
+              const uint64_t gh2 = f2_mul(f2_from_bf16x2(go[j]), f2_ld(gam + 16 * i + 2 * j));
+              sy2 = f2_add(sy2, y2);
+              syy2 = f2_fma(y2, y2, syy2);
+              sg2 = f2_add(sg2, gh2);
+              sgy2 = f2_fma(gh2, y2, sgy2);
+            }
+          });
+          s_y = f2_lo(sy2) + f2_hi(sy2);
+          s_yy = f2_lo(syy2) + f2_hi(syy2);
+          s_g = f2_lo(sg2) + f2_hi(sg2);
+          s_gy = f2_lo(sgy2) + f2_hi(sgy2);
+        }
+#endif
         *reinterpret_cast<float4*>(bA + xch_own) = make_float4(s_y, s_yy, s_g, s_gy);
         MGN_ROW_SYNC();
         {
@@ -527,6 +568,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         const float k2 = rstd * rstd * m2;
         const uint64_t A2 = f2_splat(rstd), NK2 = f2_splat(-k2), K0 = f2_splat(fmaf(k2, mu, -rstd * m1)),
                        NAMU = f2_splat(-rstd * mu);
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = c0 + 32 * hh;
@@ -559,6 +601,26 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
             else gg[2 + h] += cs;
           }
         }
+#else
+        tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+          uint32_t go[8];
+          row_load16p(bX, row, c0 + 16 * i, go);
+          float t[16];
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 16 * i + 2 * j));
+            const uint64_t g2 = f2_from_bf16x2(go[j]);
+            const uint64_t gh2 = f2_mul(g2, f2_ld(gam + 16 * i + 2 * j));
+            o[j] = f2_to_bf16x2(f2_fma(A2, gh2, f2_fma(NK2, y2, K0)));
+            const uint64_t tt = f2_mul(g2, f2_fma(A2, y2, NAMU));  // gamma-gradient contribution g_out * xhat
+            t[2 * j] = f2_lo(tt);
+            t[2 * j + 1] = f2_hi(tt);
+          }
+          row_store16p(bA, row, c0 + 16 * i, o);
+          gg[i] += warp_colsum16(t, lane);
+        });
+#endif
       }
       MGN_EPI_DONE(B_E + 1);
       MGN_T(4);
@@ -567,6 +629,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       tc_fence_after_sync();
       {
         // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+#ifdef MGN_NO_PIPE16
         uint32_t hq[2][16];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -581,6 +644,18 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         MGN_W(B_W3, par);
         row_store32p(bH2, row, c0, hq[0]);
         row_store32p(bH2, row, c0 + 32, hq[1]);
+#else
+        uint32_t hq[4][8];
+        tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+          row_load16p(bH2, row, c0 + 16 * i, hq[i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // F2FP + HSET2 + LOP3 per pair
+            hq[i][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[i][j]);
+        });
+        MGN_W(B_W3, par);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row_store16p(bH2, row, c0 + 16 * i, hq[i]);
+#endif
       }
       MGN_EPI_DONE(B_E + 2);
       MGN_T(5);
@@ -589,6 +664,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       tc_fence_after_sync();
       {
         // (the layer's weight-gradient MMAs still read this buffer: compute into registers, store once they are done)
+#ifdef MGN_NO_PIPE16
         uint32_t hq[2][16];
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
@@ -603,6 +679,18 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         MGN_W(B_W2, par);
         row_store32p(bH1, row, c0, hq[0]);
         row_store32p(bH1, row, c0 + 32, hq[1]);
+#else
+        uint32_t hq[4][8];
+        tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+          row_load16p(bH1, row, c0 + 16 * i, hq[i]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)  // F2FP + HSET2 + LOP3 per pair
+            hq[i][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[i][j]);
+        });
+        MGN_W(B_W2, par);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row_store16p(bH1, row, c0 + 16 * i, hq[i]);
+#endif
       }
       MGN_EPI_DONE(B_E + 3);
       MGN_T(6);
@@ -610,6 +698,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       MGN_W(B_MMA + 4, par);
       tc_fence_after_sync();
       {
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t v[32];
@@ -623,6 +712,17 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
                              : pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           row_store32p(bX, row, c0 + 32 * hh, go);
         }
+      #else
+        tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+          uint32_t go[8];
+          if (kAddGout) row_load16p(bX, row, c0 + 16 * i, go);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            go[j] = kAddGout ? f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_from_bf16x2(go[j])))
+                             : pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          row_store16p(bX, row, c0 + 16 * i, go);
+        });
+#endif
       }
       MGN_EPI_DONE(B_E + 4);
       MGN_T(7);

@@ -320,6 +320,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       for (int u = 0; u < 8; ++u) asm volatile("" : "+r"(gq[u].x), "+r"(gq[u].y), "+r"(gq[u].z), "+r"(gq[u].w));
       const uint32_t t_acc = tmem + (j % 3) * 128 + lane_off + c0;
       const uint32_t t_h = tmem + 384 + (j & 1) * 64 + lane_off + ch * 32;
+#ifdef MGN_NO_PIPE16
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
@@ -342,6 +343,23 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         tmem_st16(t_h + 16 * hh, pk);
         if (a.h1_out != nullptr) row_store32p(bG1, row, c0 + 32 * hh, pk);  // over this thread's own consumed G1 span
       }
+#else
+      tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {  // 16-column chunks, next chunk's TMEM load in flight
+        uint32_t ga[8];
+        row_load16p(bG1, row, c0 + 16 * i, ga);
+        const uint4 da = gq[2 * i], db = gq[2 * i + 1];
+        const uint32_t d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // two fp32 lanes per instruction; relu after the bf16 rounding
+          uint64_t z = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b1 + 16 * i + 2 * j));
+          z = f2_add(f2_add(z, f2_from_bf16x2(ga[j])), f2_from_bf16x2(d[j]));
+          pk[j] = relu_bf16x2(f2_to_bf16x2(z));
+        }
+        tmem_st8(t_h + 8 * i, pk);
+        if (a.h1_out != nullptr) row_store16p(bG1, row, c0 + 16 * i, pk);  // over this thread's own consumed G1 span
+      });
+#endif
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
@@ -381,6 +399,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         MGN_W(B_M2, par);
         MGN_T(0);
         tc_fence_after_sync();
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           uint32_t v[32];
@@ -392,6 +411,15 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
             pk[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
           tmem_st16(t_h + 16 * hh, pk);
         }
+#else
+        tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            pk[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 16 * i + 2 * j))));
+          tmem_st8(t_h + 8 * i, pk);
+        });
+#endif
         tmem_st_wait();
         tc_fence_before_sync();
         __syncwarp();
@@ -413,6 +441,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         float s, ss;
         {
           uint64_t s2 = 0ull, ss2 = 0ull;
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
           for (int hh = 0; hh < 2; ++hh) {
             uint32_t v[32];
@@ -425,6 +454,16 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
               ss2 = f2_fma(y2, y2, ss2);
             }
           }
+#else
+          tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 16 * i + 2 * j));
+              s2 = f2_add(s2, y2);
+              ss2 = f2_fma(y2, y2, ss2);
+            }
+          });
+#endif
           s = f2_lo(s2) + f2_hi(s2);
           ss = f2_lo(ss2) + f2_hi(ss2);
         }
@@ -438,6 +477,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         const float mu = (s + __uint_as_float(o0)) * (1.f / kH);
         const float var = fmaxf((ss + __uint_as_float(o1)) * (1.f / kH) - mu * mu, 0.f);
         const float rstd = rsqrtf(var + a.eps);
+#ifdef MGN_NO_PIPE16
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = c0 + 32 * hh;
@@ -457,6 +497,23 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           }
           row_store32p(bAcur, row, cc, o);
         }
+#else
+        {
+          const uint64_t NMU = f2_splat(-mu), RS = f2_splat(rstd);
+          tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
+            uint32_t r[8];
+            row_load16p(bAcur, row, c0 + 16 * i, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {  // ((y - mu) rstd) gamma + beta, + residual: five packed fp32 ops per pair
+              const int c = 16 * i + 2 * j;
+              uint64_t y2 = f2_add(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + c)), NMU);
+              y2 = f2_fma(f2_mul(y2, RS), f2_ld(gam + c), f2_ld(bet + c));
+              r[j] = f2_to_bf16x2(f2_add(y2, f2_from_bf16x2(r[j])));
+            }
+            row_store16p(bAcur, row, c0 + 16 * i, r);
+          });
+        }
+#endif
         fence_proxy_async_smem();  // the result tile leaves through the async proxy (TMA store)
         tc_fence_before_sync();
         __syncwarp();

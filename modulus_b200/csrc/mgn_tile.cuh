@@ -333,6 +333,42 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
+// 16 bf16 of this thread's row at column col (a multiple of 16) as 8 bf16x2 words
+__device__ __forceinline__ void row_load16p(const uint8_t* buf, int row, int col, uint32_t (&w)[8]) {
+  const uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + sw128_offset(row, c8));
+  const uint4 b = *reinterpret_cast<const uint4*>(base + sw128_offset(row, c8 + 1));
+  w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+  w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+}
+__device__ __forceinline__ void row_store16p(uint8_t* buf, int row, int col, const uint32_t (&w)[8]) {
+  uint8_t* base = buf + (col >> 6) * kPB;
+  const int c8 = (col & 63) >> 3;
+  *reinterpret_cast<uint4*>(base + sw128_offset(row, c8)) = make_uint4(w[0], w[1], w[2], w[3]);
+  *reinterpret_cast<uint4*>(base + sw128_offset(row, c8 + 1)) = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// One pass over this thread's 64 accumulator columns in four 16-column chunks, f(chunk, v[16]).  The tcgen05.ld of chunk
+// i + 1 is in flight while chunk i is processed: tcgen05.wait::ld waits for ALL outstanding loads, so the next load is
+// issued right after the wait and before the arithmetic of the chunk that just arrived.
+template <typename F>
+__device__ __forceinline__ void tmem_pass64(uint32_t taddr, F&& f) {
+  uint32_t va[16], vb[16];
+  tmem_ld16(taddr, va);
+  tmem_ld_wait();
+  tmem_ld16(taddr + 16, vb);
+  f(0, va);
+  tmem_ld_wait();
+  tmem_ld16(taddr + 32, va);
+  f(1, vb);
+  tmem_ld_wait();
+  tmem_ld16(taddr + 48, vb);
+  f(2, va);
+  tmem_ld_wait();
+  f(3, vb);
+}
+
 // warp transpose-reduce of 16 columns: on return lane L holds the sum over all 32 lanes of their v[L & 15]
 __device__ __forceinline__ float warp_colsum16(float (&v)[16], int lane) {
 #pragma unroll
