@@ -26,43 +26,66 @@ static inline size_t workspace_bytes(int64_t M) {
 // 128 threads (mt = 0..127): thread = (16-byte column chunk, segment lane); buf = result tile (two swizzled panels)
 // row0 / M / seg_id are relative to the rows this launch covers; row_base = position of its row 0 in the CSC order
 // (seg_off holds global positions), rec_base = index of its first tile's records (several launches over consecutive
-// row ranges share one record array in row order and one fix-up)
-__device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, long long M,
-                                                 const int32_t* __restrict__ seg_off, const int32_t* __restrict__ seg_id,
-                                                 bf16* __restrict__ out, long long ld_out, float* __restrict__ part,
-                                                 int32_t* __restrict__ part_v, int mt, long long row_base = 0,
-                                                 long long rec_base = 0) {
+// row ranges share one record array in row order and one fix-up).
+//
+// The index loads (first / last destination of the tile, then the bounds of this thread's first segment) are a chain of
+// two L2 round trips: `tile_segments_begin` issues them EARLY -- the callers run it before they wait for the tile --
+// and the loop fetches the bounds of its next segment before it sums the current one.
+struct TileSegs {
+  int v_first, v_last, nrows;
+  long long ob, oe;  // bounds of this thread's first segment (v_first + segment lane), if it has one
+};
+
+__device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long long M, const int32_t* __restrict__ seg_off,
+                                                        const int32_t* __restrict__ seg_id, int mt) {
+  TileSegs ts;
   const long long rem = M - row0;
-  const int nrows = rem < kRows ? static_cast<int>(rem) : kRows;
-  const int v_first = __ldg(seg_id + row0), v_last = __ldg(seg_id + row0 + nrows - 1);
+  ts.nrows = rem < kRows ? static_cast<int>(rem) : kRows;
+  ts.v_first = __ldg(seg_id + row0);
+  ts.v_last = __ldg(seg_id + row0 + ts.nrows - 1);
+  const int v = ts.v_first + (mt >> 4);
+  ts.ob = ts.oe = 0;
+  if (v <= ts.v_last) {
+    ts.ob = __ldg(seg_off + v);
+    ts.oe = __ldg(seg_off + v + 1);
+  }
+  return ts;
+}
+
+__device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, const TileSegs& ts,
+                                                 const int32_t* __restrict__ seg_off, bf16* __restrict__ out,
+                                                 long long ld_out, float* __restrict__ part, int32_t* __restrict__ part_v,
+                                                 int mt, long long row_base = 0, long long rec_base = 0) {
+  const int nrows = ts.nrows, v_first = ts.v_first, v_last = ts.v_last;
   const int chunk = mt & 15, sl = mt >> 4;
   const long long tile = rec_base + row0 / kRows;
   const uint8_t* col = buf + (chunk >> 3) * kPB;
   const long long g0 = row_base + row0;  // global position of the tile's first row
+  long long ob = ts.ob, oe = ts.oe;
   for (int v = v_first + sl; v <= v_last; v += 8) {
-    const long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
     const int b = static_cast<int>((ob > g0 ? ob : g0) - g0);
     const int e = static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0);
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (v + 8 <= v_last) {  // bounds of the next segment, in flight while this one is summed
+      ob = __ldg(seg_off + v + 8);
+      oe = __ldg(seg_off + v + 9);
+    }
+    uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 8 fp32 column sums as packed pairs (FADD2)
     for (int r = b; r < e; ++r) {
       const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));
-      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        acc[2 * k] += bf_lo(w[k]);
-        acc[2 * k + 1] += bf_hi(w[k]);
-      }
+      acc[0] = f2_add(acc[0], f2_from_bf16x2(t.x));
+      acc[1] = f2_add(acc[1], f2_from_bf16x2(t.y));
+      acc[2] = f2_add(acc[2], f2_from_bf16x2(t.z));
+      acc[3] = f2_add(acc[3], f2_from_bf16x2(t.w));
     }
     if (v == v_first || v == v_last) {
       const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);
       float4* d = reinterpret_cast<float4*>(part + rec * kH + chunk * 8);
-      d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-      d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      d[0] = make_float4(f2_lo(acc[0]), f2_hi(acc[0]), f2_lo(acc[1]), f2_hi(acc[1]));
+      d[1] = make_float4(f2_lo(acc[2]), f2_hi(acc[2]), f2_lo(acc[3]), f2_hi(acc[3]));
       if (chunk == 0) part_v[rec] = v;
     } else {
       *reinterpret_cast<uint4*>(out + static_cast<long long>(v) * ld_out + chunk * 8) =
-          make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                     pack_bf16x2(acc[6], acc[7]));
+          make_uint4(f2_to_bf16x2(acc[0]), f2_to_bf16x2(acc[1]), f2_to_bf16x2(acc[2]), f2_to_bf16x2(acc[3]));
     }
   }
   if (v_first == v_last && mt == 0) part_v[tile * 2 + 1] = -1;

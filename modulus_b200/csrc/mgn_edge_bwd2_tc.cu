@@ -20,6 +20,9 @@
 // layer-1 MMAs (go2) and the g_efeat store (go1).
 // Roles as in the generic kernel: warp 0 MMA issuer, warps 1-4 reducers (go2 gather, column sums), warps 5-12
 // epilogue, warp 13 loader (TMA).
+#ifdef MGN_BWD2_NO_PIPE16  // A/B switch: epilogue passes as two 32-column halves instead of four pipelined 16-column chunks
+#define MGN_NO_PIPE16
+#endif
 #include "mgn_common.cuh"
 #include "mgn_tc.cuh"
 #include "mgn_reduce.cuh"
@@ -302,6 +305,8 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       uint8_t* bX = MGN_BUF(R_X, it);
       uint8_t* bH1 = MGN_BUF(R_H1, it);
       uint8_t* bH2 = MGN_BUF(R_H2, it);
+      agg::TileSegs ts{};  // index loads of the tile's destination sums, issued before anything is waited for
+      if (kAgg) ts = agg::tile_segments_begin(row0, p.M, p.seg_off, p.seg_id, mt);
       // after E3: X = g_out (summed), A = g_y
       MGN_W(B_E + 1, par);
       colsum_tile(bX, mt, cs_beta);
@@ -314,7 +319,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
       MGN_W(B_E + 3, par);
       colsum_tile(bH1, mt, cs_b1);
-      if (kAgg) agg::tile_segment_sum(bH1, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
+      if (kAgg) agg::tile_segment_sum(bH1, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
       if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X once g_efeat has left

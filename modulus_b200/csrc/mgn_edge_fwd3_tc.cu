@@ -21,6 +21,9 @@
 // Warp roles (448 threads): warp 0 = MMA issuer + TMEM owner; warps 1-4 = movers (cp.async gather of the source
 // projections, destination sums of the result tile, mgn_agg.cuh); warps 5-12 = epilogue (two warps per TMEM lane
 // quarter, 64 columns each); warp 13 = loader (TMA: efeat tiles in, result tiles out).
+#ifdef MGN_FWD3_NO_PIPE16  // A/B switch: epilogue passes as two 32-column halves instead of four pipelined 16-column chunks
+#define MGN_NO_PIPE16
+#endif
 #include "mgn_common.cuh"
 #include "mgn_tc.cuh"
 #include "mgn_tile.cuh"
@@ -231,6 +234,9 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       }
       for (int k = 0; k < n_my; ++k) {
         const long long row0 = row_first + k * stride;
+        // (index loads of this tile's destination sums, issued before anything is waited for)
+        agg::TileSegs ts{};
+        if (a.seg_off != nullptr) ts = agg::tile_segments_begin(row0, a.M, a.seg_off, a.g2_idx, mt);
         if (k + 2 < n_my || (k + 1 < n_my && a.h1_out != nullptr)) {
           // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
           MGN_W(B_H1, (k + 1) & 1);
@@ -244,8 +250,8 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         // result tile k: destination sums from shared memory
         MGN_W(B_OUT + k % 3, (k / 3) & 1);
         if (a.seg_off != nullptr)
-          agg::tile_segment_sum(bA0 + (k % 3) * 2 * kPB, row0, a.M, a.seg_off, a.g2_idx, a.agg, a.ld_agg, a.agg_part,
-                                a.agg_part_v, mt, a.agg_row_base, a.agg_rec_base);
+          agg::tile_segment_sum(bA0 + (k % 3) * 2 * kPB, row0, ts, a.seg_off, a.agg, a.ld_agg, a.agg_part, a.agg_part_v, mt,
+                                a.agg_row_base, a.agg_rec_base);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AGG + k % 3]);
       }

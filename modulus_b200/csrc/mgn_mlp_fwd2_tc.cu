@@ -318,8 +318,9 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       }
       if (!direct_out && !p.tma_out) store_rows(bAcur, p.out, p.ld_out, row0, p.M, mt);
       if (p.seg_off != nullptr) {  // segmented sum of the result tile by destination
-        agg::tile_segment_sum(bAcur, row0, p.M, p.seg_off, p.seg_id, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt,
-                              p.agg_row_base, p.agg_rec_base);
+        const agg::TileSegs ts = agg::tile_segments_begin(row0, p.M, p.seg_off, p.seg_id, mt);
+        agg::tile_segment_sum(bAcur, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt, p.agg_row_base,
+                              p.agg_rec_base);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AGG]);
       }

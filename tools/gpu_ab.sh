@@ -8,7 +8,7 @@ for v in "$@"; do
   i=$((i+1))
   echo "=== variant $i: '$v'"
   MGN_NVCC_EXTRA="$v" timeout 300 python -m modulus_b200.build > /dev/null || { echo BUILD FAILED; continue; }
-  MGN_NVCC_EXTRA="$v" timeout 300 python tools/prof_kernels.py 1000 1000 3 > gpurun_out/ab_${tag}_$i.txt 2>&1
+  MGN_NVCC_EXTRA="$v" timeout 300 python tools/prof_kernels.py 1000 1000 15 > gpurun_out/ab_${tag}_$i.txt 2>&1
   grep -E "eblk|bwd edge|BWD2|FWD3|EPI|MMA|LOADER" gpurun_out/ab_${tag}_$i.txt | cut -c1-230
   MGN_NVCC_EXTRA="$v" timeout 400 python -m pytest tests/test_gpu_tc.py tests/test_gpu_fused.py -m gpu -x -q 2>&1 | tail -2
 done
