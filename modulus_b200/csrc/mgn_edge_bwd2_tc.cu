@@ -20,7 +20,9 @@
 // layer-1 MMAs (go2) and the g_efeat store (go1).
 // Roles as in the generic kernel: warp 0 MMA issuer, warps 1-4 reducers (go2 gather, column sums), warps 5-12
 // epilogue, warp 13 loader (TMA).
-#ifdef MGN_BWD2_NO_PIPE16  // A/B switch: epilogue passes as two 32-column halves instead of four pipelined 16-column chunks
+// Epilogue passes read the accumulator as two 32-column halves.  -DMGN_BWD2_PIPE16 selects four software-pipelined 16-column chunks
+// instead (tmem_pass64): fewer cycles per tile but not faster in wall time on a power-capped B200 (profiles/r02_ab_epilogue.md).
+#ifndef MGN_BWD2_PIPE16
 #define MGN_NO_PIPE16
 #endif
 #include "mgn_common.cuh"

@@ -21,7 +21,9 @@
 // Warp roles (448 threads): warp 0 = MMA issuer + TMEM owner; warps 1-4 = movers (cp.async gather of the source
 // projections, destination sums of the result tile, mgn_agg.cuh); warps 5-12 = epilogue (two warps per TMEM lane
 // quarter, 64 columns each); warp 13 = loader (TMA: efeat tiles in, result tiles out).
-#ifdef MGN_FWD3_NO_PIPE16  // A/B switch: epilogue passes as two 32-column halves instead of four pipelined 16-column chunks
+// Epilogue passes read the accumulator as two 32-column halves.  -DMGN_FWD3_PIPE16 selects four software-pipelined 16-column chunks
+// instead (tmem_pass64): fewer cycles per tile but not faster in wall time on a power-capped B200 (profiles/r02_ab_epilogue.md).
+#ifndef MGN_FWD3_PIPE16
 #define MGN_NO_PIPE16
 #endif
 #include "mgn_common.cuh"
