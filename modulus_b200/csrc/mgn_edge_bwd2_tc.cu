@@ -221,16 +221,6 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         MGN_W(B_E + 1, par);
         MGN_T(4);
         tc_fence_after_sync();
-#ifdef MGN_BWD2_WGRAD_FIRST  // A/B: weight-gradient MMAs ahead of the data-gradient MMAs (the pass then never waits for B_W*)
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
-        umma_commit(&bars[B_W3]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
-        umma_commit(&bars[B_MMA + 2]);
-#else
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aA + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW3, k, kPB), id_nn, k != 0);
@@ -239,22 +229,11 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         for (int j = 0; j < 8; ++j)
           umma_ss(tW3, umma_desc_mnmajor(aA, j, kPB), umma_desc_mnmajor(aH2, j, kPB), id_tn, (it | j) != 0);
         umma_commit(&bars[B_W3]);
-#endif
         MGN_T(5);
         // ---- layer 2: acc = g_z2 W2 ; gW2 += g_z2^T h1        (g_z2 in the H2 buffer)
         MGN_W(B_E + 2, par);
         MGN_T(6);
         tc_fence_after_sync();
-#ifdef MGN_BWD2_WGRAD_FIRST
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
-        umma_commit(&bars[B_W2]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
-        umma_commit(&bars[B_MMA + 3]);
-#else
 #pragma unroll
         for (int k = 0; k < 8; ++k)
           umma_ss(tAcc, umma_desc_kmajor(aH2 + (k >> 2) * kPB, k & 3), umma_desc_mnmajor(aW2, k, kPB), id_nn, k != 0);
@@ -263,7 +242,6 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         for (int j = 0; j < 8; ++j)
           umma_ss(tW2, umma_desc_mnmajor(aH2, j, kPB), umma_desc_mnmajor(aH1, j, kPB), id_tn, (it | j) != 0);
         umma_commit(&bars[B_W2]);
-#endif
         MGN_T(7);
         // ---- layer 1: acc = g_z1 W1a (epilogue may start on it at once) ; gW1a += g_z1^T efeat
         MGN_W(B_E + 3, par);
@@ -505,25 +483,14 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       MGN_EPI_DONE(B_E + 0);
       MGN_T(1);
       // ---- E3: LayerNorm backward: g_out = go1 (+ go2) -> X ; g_y -> A
-      MGN_W(B_GO, par);
-      MGN_T(2);
-      if (has_go2) {  // g_out = go1 + go2 -> X (one packed bf16 add per pair) while GEMM3 is still running
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t go[16], g2[16];
-          row_load32p(bX, row, c0 + 32 * hh, go);
-          row_load32p(bA, row, c0 + 32 * hh, g2);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) go[j] = add_bf16x2(go[j], g2[j]);
-          row_store32p(bX, row, c0 + 32 * hh, go);
-        }
-      }
       MGN_W(B_MMA + 1, par);
+      MGN_T(2);
+      MGN_W(B_GO, par);
       MGN_T(3);
       tc_fence_after_sync();
       {
-        // LayerNorm statistics of y = acc + b3 and of ghat = g_out * gamma; all fp32 arithmetic runs two lanes per
-        // instruction (f2_*)
+        // g_out = go1 (+ go2) -> X; LayerNorm statistics of y = acc + b3 and of ghat = g_out * gamma.  All fp32 arithmetic
+        // runs two lanes per instruction (f2_*); the go1 + go2 sum is one packed bf16 add per pair.
         float s_y, s_yy, s_g, s_gy;
 #ifdef MGN_NO_PIPE16
         {
@@ -535,6 +502,13 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
             tmem_ld32(t_acc + 32 * hh, v);
             uint32_t go[16];
             row_load32p(bX, row, cc, go);
+            if (has_go2) {
+              uint32_t g2[16];
+              row_load32p(bA, row, cc, g2);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) go[j] = add_bf16x2(go[j], g2[j]);
+              row_store32p(bX, row, cc, go);
+            }
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -558,6 +532,13 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
             const int cc = c0 + 16 * i;
             uint32_t go[8];
             row_load16p(bX, row, cc, go);
+            if (has_go2) {
+              uint32_t g2[8];
+              row_load16p(bA, row, cc, g2);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) go[j] = add_bf16x2(go[j], g2[j]);
+              row_store16p(bX, row, cc, go);
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 16 * i + 2 * j));
