@@ -15,8 +15,12 @@ B200-first differences
   * with `modulus_b200.optim.FusedAdam` the optimizer step is recorded INSIDE the graph (device-resident step
     counter, learning rate read from a device scalar that follows the host-side scheduler), so a training step is
     one `cudaGraphLaunch`; any other optimizer steps after the replay, like the reference
-  * AMP is bfloat16 (the kernels' reduced-precision storage type): no GradScaler is needed; float16 is refused
-    loudly rather than silently run in another precision; `compile=True` is refused (no tracing compiler here)
+  * AMP: bfloat16 needs no GradScaler.  `amp_type=torch.float16` (the reference's default) keeps the reference's
+    protocol -- float16 autocast region, `GradScaler.scale(loss).backward()`, `scaler.step(optim)`, `scaler.update()`
+    (capture.py:246-288) -- while the kernels compute in bf16 storage (models/gnn_layers/mesh_graph_mlp.compute_dtype);
+    with FusedAdam the unscale and the skip-on-overflow run inside the optimizer kernel from the scaler's device
+    tensors, so the scaled step stays ONE graph launch with no host read-back.  `compile=True` is refused (no tracing
+    compiler here)
 """
 from __future__ import annotations
 
@@ -46,8 +50,6 @@ class _StaticCapture:
             raise ValueError("modulus_b200: compile=True is not supported (the hot path is hand-written CUDA)")
         if amp_type not in (torch.float16, torch.bfloat16):
             raise ValueError("AMP type must be torch.float16 or torch.bfloat16")  # capture.py:93-94
-        if use_autocast and amp_type == torch.float16:
-            raise ValueError("modulus_b200 kernels store reduced precision as bfloat16; pass amp_type=torch.bfloat16")
         self.model, self.optim = model, optim
         self.eval, self.no_grad = eval_mode, eval_mode
         self.gradient_clip_norm = gradient_clip_norm
@@ -58,6 +60,8 @@ class _StaticCapture:
         self.device = dev
         self.cuda_graphs_enabled = bool(use_graphs)
         self.use_autocast, self.amp_dtype = bool(use_autocast), amp_type
+        # loss scaling exactly when the reference does it (capture.py:112-121): float16 autocast, training
+        self.scaler = torch.amp.GradScaler("cuda", enabled=bool(use_autocast) and amp_type == torch.float16 and not eval_mode)
         self.optimizer_in_graph = (not eval_mode) and isinstance(optim, FusedAdam)
         self.replay_stream = torch.cuda.Stream(dev)
         self.graph = torch.cuda.CUDAGraph() if self.cuda_graphs_enabled else None
@@ -79,15 +83,20 @@ class _StaticCapture:
         with torch.autocast("cuda", enabled=self.use_autocast, dtype=self.amp_dtype):
             output = self.function(*args, **kwargs)
         if not self.eval:
-            output.backward()
+            self.scaler.scale(output).backward()
             if self.gradient_clip_norm is not None:
+                self.scaler.unscale_(self.optim)
                 torch.nn.utils.clip_grad_norm_(self.model.parameters(), self.gradient_clip_norm)
         return output
+
+    def _optim_step(self) -> None:
+        self.scaler.step(self.optim)  # plain optim.step() when the scaler is disabled
+        self.scaler.update()
 
     def _step(self, *args: Any, **kwargs: Any):
         output = self._amp_forward(*args, **kwargs)
         if self.optimizer_in_graph:
-            self.optim.step()
+            self._optim_step()
         return output.detach()
 
     def _cuda_graph_step(self, *args: Any, **kwargs: Any) -> None:
@@ -124,7 +133,7 @@ class _StaticCapture:
                     self._zero_grads()
                     self.output = self._step(*args, **kwds)
                 if not self.eval and not self.optimizer_in_graph and self.optim is not None:
-                    self.optim.step()
+                    self._optim_step()
             return self.output
 
         return decorated

@@ -26,11 +26,23 @@ def compute_dtype(x: Tensor) -> torch.dtype:
     (bf16 storage, fp32 accumulate, fp32 LayerNorm statistics)."""
     if torch.is_autocast_enabled("cuda"):
         dt = torch.get_autocast_dtype("cuda")
+        if dt == torch.float16:
+            # The reference recipe's default AMP is float16 + GradScaler (train.py:153-166).  The kernels' reduced
+            # precision storage type is bfloat16 (fp32 range: no overflow, loss scaling is harmless); a float16 autocast
+            # region therefore computes in bf16 and MeshGraphNet.forward hands back a float16 tensor, as the caller expects.
+            return torch.bfloat16
         if dt != torch.bfloat16:
-            raise NotImplementedError(f"modulus_b200 supports bfloat16 autocast only (got {dt})")
+            raise NotImplementedError(f"modulus_b200 supports bfloat16 / float16 autocast only (got {dt})")
         return dt
     if x.dtype not in (torch.float32, torch.bfloat16):
         raise TypeError(f"modulus_b200 supports float32 / bfloat16 features, got {x.dtype}")
+    return x.dtype
+
+
+def autocast_result_dtype(x: Tensor) -> torch.dtype:
+    """dtype a model output gets: float16 inside a float16 autocast region (see compute_dtype), else unchanged"""
+    if torch.is_autocast_enabled("cuda") and torch.get_autocast_dtype("cuda") == torch.float16:
+        return torch.float16
     return x.dtype
 
 

@@ -21,7 +21,7 @@ from torch import Tensor
 from ... import fused, ops
 from ..gnn_layers.graph import CuGraphCSC
 from ..gnn_layers.mesh_edge_block import MeshEdgeBlock
-from ..gnn_layers.mesh_graph_mlp import MeshGraphMLP, compute_dtype
+from ..gnn_layers.mesh_graph_mlp import MeshGraphMLP, autocast_result_dtype, compute_dtype
 from ..gnn_layers.mesh_node_block import MeshNodeBlock
 from ..gnn_layers.utils import graph_plan, set_checkpoint_fn
 from ..layers.activations import get_activation
@@ -148,7 +148,7 @@ class MeshGraphNet(nn.Module):
         node_features = self.node_encoder(node_features)
         x = self.processor(node_features, edge_features, graph)
         x = self.node_decoder(x)
-        return x
+        return x.to(autocast_result_dtype(x))
 
 
 class MeshGraphNetProcessor(nn.Module):

@@ -87,6 +87,10 @@ class _Table:
 
 
 class FusedAdam(torch.optim.Optimizer):
+    # torch.amp.GradScaler.step() hands optimizers that declare this their `grad_scale` / `found_inf` device tensors and
+    # does not read anything back: unscaling and the skip-on-overflow then happen inside mgn_adam_multi_step
+    _step_supports_amp_scaling = True
+
     def __init__(
         self,
         params: Iterable,
@@ -164,7 +168,15 @@ class FusedAdam(torch.optim.Optimizer):
         """One Adam update of every group.  `found_inf` / `inv_scale` are optional 1-element fp32 CUDA tensors:
         the step is skipped on the device when found_inf != 0 and gradients are multiplied by inv_scale
         (what `GradScaler.unscale_` + `GradScaler.step` do in two passes and one host read-back).  Called
-        through `GradScaler.step(optimizer)` it takes the scaler's stock route: unscale, host check, plain step."""
+        through `GradScaler.step(optimizer)` the scaler supplies both as attributes (`_step_supports_amp_scaling`):
+        no host synchronisation, CUDA-graph capturable (the reference recipe's AMP switch: float16 autocast +
+        GradScaler, examples/cfd/vortex_shedding_mgn/train.py:153-166)."""
+        gs, fi = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
+        if gs is not None and inv_scale is None:
+            inv_scale = gs.to(torch.float32).reshape(1).reciprocal()
+        if fi is not None:
+            fi = fi.to(torch.float32).reshape(1)
+            found_inf = fi if found_inf is None else torch.maximum(found_inf.to(torch.float32).reshape(1), fi)
         loss = None
         if closure is not None:
             with torch.enable_grad():

@@ -258,8 +258,6 @@ def test_static_capture_argument_errors():
     with pytest.raises(ValueError):
         StaticCaptureTraining(model=lin, optim=opt, compile=True)
     with pytest.raises(ValueError):
-        StaticCaptureTraining(model=lin, optim=opt, amp_type=torch.float16)
-    with pytest.raises(ValueError):
         StaticCaptureTraining(model=lin, optim=opt, amp_type=torch.float32)
     with pytest.raises(ValueError):
         StaticCaptureTraining(model="not a module", optim=opt)
@@ -326,6 +324,106 @@ def test_static_capture_training_matches_eager_loop(use_amp, fused_opt):
         assert torch.allclose(a, b, **tol), k
     if fused_opt:
         assert float(opt.state[next(model.parameters())]["step"]) == float(len(data))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused_opt", [True, False])
+def test_float16_autocast_with_gradscaler_recipe(fused_opt):
+    """The reference recipe's AMP switch (examples/cfd/vortex_shedding_mgn/train.py:153-166): float16 autocast +
+    GradScaler.  The model accepts it (computing in bf16 storage, returning float16), the loss scale -- a power of two --
+    cancels exactly, so the parameters follow the bfloat16 / no-scaler loop; with FusedAdam the scaler's `grad_scale` /
+    `found_inf` tensors are consumed on the device (`_step_supports_amp_scaling`), and an overflowing step is skipped."""
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.optim import FusedAdam
+
+    graph, ef, data = _capture_case()
+
+    def make():
+        torch.manual_seed(5)
+        model = MeshGraphNet(6, 3, 3, processor_size=3).to(DEV)
+        opt = FusedAdam(model.parameters(), lr=1e-3) if fused_opt else torch.optim.Adam(model.parameters(), lr=1e-3)
+        return model, opt
+
+    ref, ropt = make()
+    for nf, tgt in data[:4]:
+        ropt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss_r = torch.nn.functional.mse_loss(ref(nf, ef, graph).float(), tgt)
+        loss_r.backward()
+        ropt.step()
+
+    model, opt = make()
+    scaler = torch.amp.GradScaler("cuda", init_scale=2.0 ** 12)
+    for nf, tgt in data[:4]:
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda"):  # float16, the CUDA default
+            out = model(nf, ef, graph)
+            assert out.dtype == torch.float16
+            loss = torch.nn.functional.mse_loss(out.float(), tgt)
+        scaler.scale(loss).backward()
+        scaler.step(opt)
+        scaler.update()
+    torch.cuda.synchronize()
+    assert float(scaler.get_scale()) == 2.0 ** 12  # no step was skipped
+    # (the returned prediction is rounded to float16 instead of bfloat16 before the loss: parameters agree to rounding)
+    for (k, a), b in zip(ref.named_parameters(), model.parameters()):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), k
+    # an overflowing backward pass: the step is skipped, the scale halves
+    before = [p.detach().clone() for p in model.parameters()]
+    opt.zero_grad(set_to_none=True)
+    with torch.autocast("cuda"):
+        loss = torch.nn.functional.mse_loss(model(data[4][0], ef, graph).float(), data[4][1])
+    scaler.scale(loss * float("inf")).backward()
+    scaler.step(opt)
+    scaler.update()
+    torch.cuda.synchronize()
+    assert float(scaler.get_scale()) == 2.0 ** 11
+    for a, b in zip(before, model.parameters()):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_static_capture_training_float16_amp_is_one_graph_with_the_scaler_inside():
+    """StaticCaptureTraining(amp_type=torch.float16) -- the reference's default AMP type (utils/capture.py:341-436): the
+    GradScaler protocol runs inside the recorded step (FusedAdam consumes the scale on the device) and the result follows
+    the eager float16 + GradScaler loop."""
+    from modulus_b200.capture import StaticCaptureTraining
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.optim import FusedAdam
+
+    graph, ef, data = _capture_case()
+
+    def make():
+        torch.manual_seed(5)
+        model = MeshGraphNet(6, 3, 3, processor_size=3).to(DEV)
+        return model, FusedAdam(model.parameters(), lr=1e-3)
+
+    eager, eopt = make()
+    scaler = torch.amp.GradScaler("cuda")
+    for nf, tgt in data:
+        eopt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.float16):
+            loss_e = torch.nn.functional.mse_loss(eager(nf, ef, graph).float(), tgt)
+        scaler.scale(loss_e).backward()
+        scaler.step(eopt)
+        scaler.update()
+
+    model, opt = make()
+    s_nf, s_tgt = torch.empty_like(data[0][0]), torch.empty_like(data[0][1])
+
+    @StaticCaptureTraining(model=model, optim=opt, use_amp=True, amp_type=torch.float16, cuda_graph_warmup=2)
+    def training_step(nf, tgt):
+        return torch.nn.functional.mse_loss(model(nf, ef, graph).float(), tgt)
+
+    for nf, tgt in data:
+        s_nf.copy_(nf)
+        s_tgt.copy_(tgt)
+        loss = training_step(s_nf, s_tgt)
+    torch.cuda.synchronize()
+    assert torch.allclose(loss, loss_e.detach(), rtol=1e-3, atol=1e-6)
+    for (k, a), b in zip(eager.named_parameters(), model.parameters()):
+        assert torch.allclose(a, b, rtol=2e-3, atol=2e-5), k
+    assert float(opt.state[next(model.parameters())]["step"]) == float(len(data))
 
 
 @pytest.mark.gpu
