@@ -49,7 +49,10 @@ WORKLOADS = {
     "c1": ("triangle_grid_mesh", (42, 45), 6, 3, 3, "f32"),     # ~1.9k nodes (vortex_shedding_mgn size)
     "c2": ("triangle_grid_mesh", (316, 317), 6, 3, 3, "bf16"),   # 100k nodes / ~600k edges
     "c3": ("torus_surface_mesh", (1000, 1000), 11, 4, 4, "bf16"),  # 1M nodes / 6M edges
+    # BASELINE configs[3]: ONE 8M-node / 48M-edge mesh partitioned over the ranks (strong scaling; >= 2 GPUs)
+    "c4": ("torus_surface_mesh", (2000, 4000), 11, 4, 4, "bf16"),
 }
+STRONG = {"c4"}
 
 
 def load_traffic(kernel, workload):
@@ -136,7 +139,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # bounded sample of a workload: same generator and model dimensions, fewer mesh rows (about 40k nodes / 240k edges,
 # 2-3 s of CPU work per step); c1 is small enough to run whole
-SAMPLE_ROWS = {"c1": 42, "c2": 126, "c3": 40}
+SAMPLE_ROWS = {"c1": 42, "c2": 126, "c3": 40, "c4": 10}
 
 
 def cpu_inputs(workload: str, rows=None):
@@ -223,8 +226,9 @@ def run_reference(args, rank, world):
 
 def workload_name(w, world):
     gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[w]
-    return (f"{w}: MeshGraphNet({d_n},{d_e},{d_out}) 15 layers hidden 128 on {gen}{gargs}"
-            + (f" x{world} ranks (rows scaled, DistributedGraph nodewise partition)" if world > 1 else ""))
+    how = "" if world == 1 else (f" partitioned over {world} ranks (DistributedGraph)" if w in STRONG else
+                                 f" x{world} ranks (rows scaled, DistributedGraph)")
+    return f"{w}: MeshGraphNet({d_n},{d_e},{d_out}) 15 layers hidden 128 on {gen}{gargs}" + how
 
 
 # ------------------------------------------------------------------------------------------
@@ -339,7 +343,11 @@ def run_b200(args, rank, world, local_rank):
     peaks = load_peaks()
 
     gen, gargs, d_n, d_e, d_out, dtype = WORKLOADS[args.workload]
-    gargs = (gargs[0] * world, gargs[1])  # weak scaling: more rows, same row length
+    strong = args.workload in STRONG
+    if strong and world < 2:
+        raise SystemExit(f"bench.py: workload {args.workload} (8M nodes) needs >= 2 GPUs")
+    if not strong:
+        gargs = (gargs[0] * world, gargs[1])  # weak scaling: more rows, same row length
     mesh = getattr(meshgen, gen)(*gargs, device=dev)
     n_glob, E_glob = mesh["num_nodes"], int(mesh["indices"].numel())
 
@@ -351,17 +359,33 @@ def run_b200(args, rank, world, local_rank):
         DistributedManager.initialize()
         dm = DistributedManager()
         dm.create_process_subgroup("graph_partition", world)
+        gpart = None
+        if args.partition == "stripes":
+            # a partition with a REAL halo: mesh rows dealt to the ranks in stripes of --stripe-rows rows (every stripe has
+            # two boundary rows whose sources live on the neighbouring ranks); nodewise slabs have only two such rows per rank
+            from modulus_b200.models.gnn_layers import partition_graph_with_id_mapping
+            row_of = torch.arange(n_glob, device=dev) // gargs[1]
+            owner = (row_of // args.stripe_rows) % world
+            gpart = partition_graph_with_id_mapping(mesh["offsets"], mesh["indices"], owner, owner, world, rank, dev)
+        if n_glob // world * 6 > 8_000_000:  # memory-lean mode above 8M edges per rank: no stored h1
+            from modulus_b200 import fused
+            fused.KEEP_H1 = False
         graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n_glob, n_glob, partition_size=world,
-                           partition_group_name="graph_partition")
+                           partition_group_name="graph_partition", graph_partition=gpart)
         mark_module_as_shared(model, "graph_partition")
         gp = graph.dist_graph.graph_partition
         n_loc, E_loc = gp.num_local_dst_nodes, gp.num_local_indices
         halo_rows = int(gp.num_local_src_nodes - gp.sizes[rank][rank])
+        hr = torch.tensor([halo_rows, n_loc], device=dev, dtype=torch.int64)
+        hr_all = [torch.zeros_like(hr) for _ in range(world)]
+        dist.all_gather(hr_all, hr)
+        halo_all = [(int(t[0]), int(t[1])) for t in hr_all]
         ef_all = mesh["edge_features"][:, :d_e]
         ef_host = graph.get_edge_features_in_partition(ef_all).float().cpu().contiguous()
     else:
         graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n_glob, n_glob)
         n_loc, E_loc, halo_rows = n_glob, E_glob, 0
+        halo_all = [(0, n_glob)]
         ef_src = mesh["edge_features"]
         ef_host = (ef_src[:, :d_e] if ef_src.shape[1] >= d_e else
                    torch.cat([ef_src, ef_src[:, :1].expand(-1, d_e - ef_src.shape[1])], 1)).float().cpu().contiguous()
@@ -528,10 +552,15 @@ def run_b200(args, rank, world, local_rank):
                "sample": _cpu_desc(kind, name, n_s, E_s, t, reps, 1) + f" ({(reps + 1) * t:.0f} s of CPU work)"}
     line = {
         "metric": METRIC, "value": E_glob / (t_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
         "config": {"workload": workload_name(args.workload, world), "nodes": n_glob, "edges": E_glob,
+                   "partition": (args.partition + (f" of {args.stripe_rows} mesh rows" if args.partition == "stripes" else
+                                                   " slabs (partition_graph_nodewise)")) if world > 1 else "none",
                    "halo_rows_rank0": halo_rows,
+                   "halo_rows_per_rank": [h for h, _ in halo_all],
+                   "halo_fraction_max": max(h / max(n, 1) for h, n in halo_all),
                    "l2": "per-step working set (edge table alone %.0f MB) exceeds the 126 MB L2; no explicit flush"
                          % (E1 * H * b / 1e6) if E1 * H * b > 126e6 else
                          "working set smaller than L2: numbers are L2-warm (c1 is launch-bound by construction)"},
@@ -553,6 +582,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--partition", default="nodewise", choices=["nodewise", "stripes"],
+                    help="N>1: contiguous slabs (reference default) or striped rows (a partition with a large halo)")
+    ap.add_argument("--stripe-rows", type=int, default=25)
     ap.add_argument("--no-full-size", action="store_true", help="reference arm: skip the one full-size c2 step")
     ap.add_argument("--no-extra", action="store_true", help="skip the c2 side measurement and the in-run parity check")
     args = ap.parse_args()
