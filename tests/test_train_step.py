@@ -331,7 +331,7 @@ def test_static_capture_training_matches_eager_loop(use_amp, fused_opt):
 def test_float16_autocast_with_gradscaler_recipe(fused_opt):
     """The reference recipe's AMP switch (examples/cfd/vortex_shedding_mgn/train.py:153-166): float16 autocast +
     GradScaler.  The model accepts it (computing in bf16 storage, returning float16), the loss scale -- a power of two --
-    cancels exactly, so the parameters equal those of the same loop without a scaler; with FusedAdam the scaler's `grad_scale` /
+    is applied and removed exactly as scaling / unscaling by hand does; with FusedAdam the scaler's `grad_scale` /
     `found_inf` tensors are consumed on the device (`_step_supports_amp_scaling`), and an overflowing step is skipped."""
     from modulus_b200.models.meshgraphnet import MeshGraphNet
     from modulus_b200.optim import FusedAdam
@@ -344,12 +344,14 @@ def test_float16_autocast_with_gradscaler_recipe(fused_opt):
         opt = FusedAdam(model.parameters(), lr=1e-3) if fused_opt else torch.optim.Adam(model.parameters(), lr=1e-3)
         return model, opt
 
-    ref, ropt = make()  # same float16 autocast region, no loss scaling
+    ref, ropt = make()  # same float16 autocast region, loss scaled and gradients unscaled by hand
     for nf, tgt in data[:4]:
         ropt.zero_grad(set_to_none=True)
         with torch.autocast("cuda"):
             loss_r = torch.nn.functional.mse_loss(ref(nf, ef, graph).float(), tgt)
-        loss_r.backward()
+        (loss_r * 2.0 ** 12).backward()
+        for p in ref.parameters():
+            p.grad.mul_(2.0 ** -12)
         ropt.step()
 
     model, opt = make()
@@ -365,8 +367,7 @@ def test_float16_autocast_with_gradscaler_recipe(fused_opt):
         scaler.update()
     torch.cuda.synchronize()
     assert float(scaler.get_scale()) == 2.0 ** 12  # no step was skipped
-    # the loss scale is a power of two: scaled gradients are the unscaled ones with a shifted exponent, the unscale inside the
-    # optimizer kernel is exact, so the parameters equal those of the unscaled loop
+    # the scaler's protocol (device-side unscale + overflow check inside the optimizer) == scaling and unscaling by hand
     for (k, a), b in zip(ref.named_parameters(), model.parameters()):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-7), k
     # an overflowing backward pass: the step is skipped, the scale halves
