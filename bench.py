@@ -367,7 +367,7 @@ def run_b200(args, rank, world, local_rank):
             row_of = torch.arange(n_glob, device=dev) // gargs[1]
             owner = (row_of // args.stripe_rows) % world
             gpart = partition_graph_with_id_mapping(mesh["offsets"], mesh["indices"], owner, owner, world, rank, dev)
-        if n_glob // world * 6 > 8_000_000:  # memory-lean mode above 8M edges per rank: no stored h1
+        if n_glob // world * 6 > 12_500_000:  # memory-lean mode above 12.5M edges per rank: no stored h1
             from modulus_b200 import fused
             fused.KEEP_H1 = False
         graph = CuGraphCSC(mesh["offsets"], mesh["indices"], n_glob, n_glob, partition_size=world,
