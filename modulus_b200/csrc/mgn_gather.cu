@@ -308,6 +308,10 @@ segment_sum_vec_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0,
 // consecutive segments at a time and issues the first U rows per lane group of ALL of them before consuming any
 // (mesh in-degrees are ~6: with G = 16 that is the whole segment), i.e. S*U 16-byte loads in flight per lane
 // instead of one dependent load per short segment.  Longer segments finish in the tail loop.
+// The three dependent loads of a group (segment bounds -> row ids -> rows) are software-pipelined across the groups a warp
+// visits: while the rows of group k are in flight the row ids of group k + 1 and the bounds of group k + 2 are fetched, so
+// the only exposed round trips are the two of the prologue (measured at c3: CSR sum 0.50 -> see profiles/r02_segment_sum.md).
+// The order of additions inside a segment is unchanged.
 template <typename T, int G, int S, int U>
 __global__ void __launch_bounds__(256, 2)  // two blocks per SM: the bytes in flight are what this kernel lives on
 segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, const int32_t* __restrict__ offsets,
@@ -318,38 +322,52 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
   const int lane = threadIdx.x & 31;
   const int g = lane / G, c = lane % G;
   const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  const int64_t stride = ((static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) * S;
   const T* col = in + in_col0 + static_cast<int64_t>(c) * V;
-  for (int64_t s0 = warp * S; s0 < n_seg; s0 += nwarps * S) {
-    int32_t b[S], e[S];
-    bool is_long[S];
+
+  auto load_bounds = [&](int64_t s0, int32_t(&b)[S], int32_t(&e)[S]) {
 #pragma unroll
     for (int i = 0; i < S; ++i) {
       const bool valid = s0 + i < n_seg;
       b[i] = valid ? __ldg(offsets + s0 + i) : 0;
       e[i] = valid ? __ldg(offsets + s0 + i + 1) : 0;
-      is_long[i] = ll.counter != nullptr && e[i] - b[i] > kLongSeg;
-      if (is_long[i]) {  // hub: handed to the long-segment kernels, nothing to do (and nothing written) here
-        if (lane == 0) push_long_segment(ll, s0 + i, e[i] - b[i]);
-        e[i] = b[i];
-      }
     }
-    int64_t rows[S][U];
+  };
+  // row ids of the first U rows per lane group of every segment of a group (-1: none); hubs are handed to the
+  // long-segment kernels and contribute nothing here
+  auto load_row_ids = [&](const int32_t(&b)[S], const int32_t(&e)[S], int32_t(&rows)[S][U]) {
 #pragma unroll
-    for (int i = 0; i < S; ++i)
+    for (int i = 0; i < S; ++i) {
+      const bool skip = ll.counter != nullptr && e[i] - b[i] > kLongSeg;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int32_t j = b[i] + g + u * R;
-        rows[i][u] = (j < e[i]) ? (eids ? static_cast<int64_t>(__ldg(eids + j)) : static_cast<int64_t>(j)) : -1;
+        rows[i][u] = (j < e[i] && !skip) ? (eids ? __ldg(eids + j) : j) : -1;
       }
+    }
+  };
+
+  int64_t s0 = warp * S;
+  if (s0 >= n_seg) return;
+  int32_t b[S], e[S], rows[S][U], bn[S], en[S];
+  load_bounds(s0, b, e);
+  load_bounds(s0 + stride, bn, en);
+  load_row_ids(b, e, rows);
+  for (; s0 < n_seg; s0 += stride) {
     uint4 v[S][U];
 #pragma unroll
     for (int i = 0; i < S; ++i)
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (rows[i][u] >= 0) v[i][u] = ldg16(col + rows[i][u] * ld_in);
+        if (rows[i][u] >= 0) v[i][u] = ldg16(col + static_cast<int64_t>(rows[i][u]) * ld_in);
+    // next group's row ids (its bounds were requested one iteration ago) and the bounds of the group after it
+    int32_t rows_n[S][U], bnn[S], enn[S];
+    load_row_ids(bn, en, rows_n);
+    load_bounds(s0 + 2 * stride, bnn, enn);
 #pragma unroll
     for (int i = 0; i < S; ++i) {
+      const bool is_long = ll.counter != nullptr && e[i] - b[i] > kLongSeg;
+      if (is_long && lane == 0) push_long_segment(ll, s0 + i, e[i] - b[i]);
       float acc[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -364,21 +382,23 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
           for (int k = 0; k < V; ++k) acc[k] += f[k];
         }
       }
-      for (int32_t j = b[i] + g + U * R; j < e[i]; j += R) {  // long segments (uniform per warp)
-        const int64_t row = eids ? __ldg(eids + j) : j;
-        Vec16<T> t;
-        t.raw = ldg16(col + row * ld_in);
-        float f[V];
-        t.unpack(f);
+      if (!is_long) {
+        for (int32_t j = b[i] + g + U * R; j < e[i]; j += R) {  // longer segments (uniform per warp)
+          const int64_t row = eids ? __ldg(eids + j) : j;
+          Vec16<T> t;
+          t.raw = ldg16(col + row * ld_in);
+          float f[V];
+          t.unpack(f);
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] += f[k];
+          for (int k = 0; k < V; ++k) acc[k] += f[k];
+        }
       }
 #pragma unroll
       for (int off = G; off < 32; off <<= 1) {
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], off);
       }
-      if (g == 0 && s0 + i < n_seg && !is_long[i]) {
+      if (g == 0 && s0 + i < n_seg && !is_long) {
         const float scale = mean ? 1.f / static_cast<float>(max(e[i] - b[i], 1)) : 1.f;
         T* o = out + (s0 + i) * ld_out + out_col0 + static_cast<int64_t>(c) * V;
         Vec16<T> t;
@@ -395,6 +415,15 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
         t.pack(acc);
         *reinterpret_cast<uint4*>(o) = t.raw;
       }
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      b[i] = bn[i];
+      e[i] = en[i];
+      bn[i] = bnn[i];
+      en[i] = enn[i];
+#pragma unroll
+      for (int u = 0; u < U; ++u) rows[i][u] = rows_n[i][u];
     }
   }
 }
