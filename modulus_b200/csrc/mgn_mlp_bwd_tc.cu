@@ -594,18 +594,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
         tmem_ld_wait();
         uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float z0 = __uint_as_float(v[2 * j]) + b1[32 * hh + 2 * j];
-          float z1 = __uint_as_float(v[2 * j + 1]) + b1[32 * hh + 2 * j + 1];
-          if (has_g) {
-            z0 += bf_lo(ga[j]);
-            z1 += bf_hi(ga[j]);
-          }
-          if (has_g2) {
-            z0 += bf_lo(gb[j]);
-            z1 += bf_hi(gb[j]);
-          }
-          o[j] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
+        for (int j = 0; j < 16; ++j) {  // two fp32 lanes per instruction (mgn_tile.cuh); relu after the bf16 rounding
+          uint64_t z = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b1 + 32 * hh + 2 * j));
+          if (has_g) z = f2_add(z, f2_from_bf16x2(ga[j]));
+          if (has_g2) z = f2_add(z, f2_from_bf16x2(gb[j]));
+          o[j] = relu_bf16x2(f2_to_bf16x2(z));
         }
         row_store32p(bH1, row, cc, o);
       }
@@ -623,8 +616,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
         uint32_t o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          o[j] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * j]) + b2[32 * hh + 2 * j], 0.f),
-                             fmaxf(__uint_as_float(v[2 * j + 1]) + b2[32 * hh + 2 * j + 1], 0.f));
+          o[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
         row_store32p(bH2, row, c0 + 32 * hh, o);
       }
       MGN_EPI_DONE(B_E1 + 1);
@@ -636,7 +628,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
       MGN_T(5);
       tc_fence_after_sync();
       if (has_ln) {
-        float s_y = 0.f, s_yy = 0.f, s_g = 0.f, s_gy = 0.f;
+        float s_y, s_yy, s_g, s_gy;
+        uint64_t sy2 = 0ull, syy2 = 0ull, sg2 = 0ull, sgy2 = 0ull;
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = c0 + 32 * hh;
@@ -648,20 +641,24 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
             uint32_t g2[16];
             row_load32p(bA, row, cc, g2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
+            for (int j = 0; j < 16; ++j) go[j] = add_bf16x2(go[j], g2[j]);
             row_store32p(bX, row, cc, go);
           }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float y = __uint_as_float(v[j]) + b3[32 * hh + j];
-            const float gh = ((j & 1) ? bf_hi(go[j >> 1]) : bf_lo(go[j >> 1])) * gam[32 * hh + j];
-            s_y += y;
-            s_yy = fmaf(y, y, s_yy);
-            s_g += gh;
-            s_gy = fmaf(gh, y, s_gy);
+          for (int j = 0; j < 16; ++j) {
+            const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 32 * hh + 2 * j));
+            const uint64_t gh2 = f2_mul(f2_from_bf16x2(go[j]), f2_ld(gam + 32 * hh + 2 * j));
+            sy2 = f2_add(sy2, y2);
+            syy2 = f2_fma(y2, y2, syy2);
+            sg2 = f2_add(sg2, gh2);
+            sgy2 = f2_fma(gh2, y2, sgy2);
           }
         }
+        s_y = f2_lo(sy2) + f2_hi(sy2);
+        s_yy = f2_lo(syy2) + f2_hi(syy2);
+        s_g = f2_lo(sg2) + f2_hi(sg2);
+        s_gy = f2_lo(sgy2) + f2_hi(sgy2);
         *reinterpret_cast<float4*>(bA + xch_own) = make_float4(s_y, s_yy, s_g, s_gy);
         MGN_ROW_SYNC();
         {
@@ -677,6 +674,10 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
         const float rstd = rsqrtf(var + p.eps);
         const float m1 = s_g * (1.f / kH);
         const float m2 = (s_gy - mu * s_g) * rstd * (1.f / kH);  // mean(ghat * xhat)
+        // g_y = rstd ghat - k2 y + k0, xhat = rstd y - rstd mu (two FMAs per element; see mgn_edge_bwd2_tc.cu)
+        const float k2 = rstd * rstd * m2;
+        const uint64_t A2 = f2_splat(rstd), NK2 = f2_splat(-k2), K0 = f2_splat(fmaf(k2, mu, -rstd * m1)),
+                       NAMU = f2_splat(-rstd * mu);
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
           const int cc = c0 + 32 * hh;
@@ -692,14 +693,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int c = 16 * h + 2 * j;  // column within this 32-column half
-              const float g0 = bf_lo(go[c >> 1]), g1v = bf_hi(go[c >> 1]);
-              const float x0 = (__uint_as_float(v[c]) + b3[32 * hh + c] - mu) * rstd;
-              const float x1 = (__uint_as_float(v[c + 1]) + b3[32 * hh + c + 1] - mu) * rstd;
-              const float y0 = rstd * (g0 * gam[32 * hh + c] - m1 - x0 * m2);
-              const float y1 = rstd * (g1v * gam[32 * hh + c + 1] - m1 - x1 * m2);
-              o[j] = pack_bf16x2(y0, y1);
-              t[2 * j] = g0 * x0;  // gamma-gradient contribution of this row
-              t[2 * j + 1] = g1v * x1;
+              const uint64_t y2 = f2_add(f2_packu(v[c], v[c + 1]), f2_ld(b3 + 32 * hh + c));
+              const uint64_t g2 = f2_from_bf16x2(go[c >> 1]);
+              const uint64_t gh2 = f2_mul(g2, f2_ld(gam + 32 * hh + c));
+              o[j] = f2_to_bf16x2(f2_fma(A2, gh2, f2_fma(NK2, y2, K0)));
+              const uint64_t tt = f2_mul(g2, f2_fma(A2, y2, NAMU));  // gamma-gradient contribution g_out * xhat
+              t[2 * j] = f2_lo(tt);
+              t[2 * j + 1] = f2_hi(tt);
             }
             uint8_t* base = bA + ch * kPB;
             const int c8 = 4 * hh + 2 * h;
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
             uint32_t g2[16];
             row_load32p(bA, row, cc, g2);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) go[j] = pack_bf16x2(bf_lo(go[j]) + bf_lo(g2[j]), bf_hi(go[j]) + bf_hi(g2[j]));
+            for (int j = 0; j < 16; ++j) go[j] = add_bf16x2(go[j], g2[j]);
             row_store32p(bX, row, cc, go);
           }
           row_store32p(bA, row, cc, go);
@@ -743,8 +743,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+            hq[hh][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[hh][j]);
         }
         MGN_W(B_W3, par);
         row_store32p(bH2, row, c0, hq[0]);
@@ -767,8 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            hq[hh][j] = pack_bf16x2(bf_pos_lo(hq[hh][j]) ? __uint_as_float(v[2 * j]) : 0.f,
-                                    bf_pos_hi(hq[hh][j]) ? __uint_as_float(v[2 * j + 1]) : 0.f);
+            hq[hh][j] = mask_pos_bf16x2(pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])), hq[hh][j]);
         }
         MGN_W(B_W2, par);
         row_store32p(bH1, row, c0, hq[0]);
@@ -790,8 +788,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_bwd_tc_kernel(const __grid_c
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            go[j] = pack_bf16x2(__uint_as_float(v[2 * j]) + (p.add_gout ? bf_lo(go[j]) : 0.f),
-                                __uint_as_float(v[2 * j + 1]) + (p.add_gout ? bf_hi(go[j]) : 0.f));
+            go[j] = p.add_gout ? f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_from_bf16x2(go[j])))
+                               : pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           row_store32p(bX, row, c0 + 32 * hh, go);
         }
       }

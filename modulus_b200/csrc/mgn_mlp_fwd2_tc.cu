@@ -422,24 +422,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {  // 4 columns per step: one 16-byte parameter load instead of four scalar ones
-          const float4 bb = reinterpret_cast<const float4*>(b1 + 32 * hh)[u];
-          float z0 = __uint_as_float(v[4 * u]) + bb.x, z1 = __uint_as_float(v[4 * u + 1]) + bb.y;
-          float z2 = __uint_as_float(v[4 * u + 2]) + bb.z, z3 = __uint_as_float(v[4 * u + 3]) + bb.w;
-          if (has_g1) {
-            z0 += bf_lo(ga[2 * u]);
-            z1 += bf_hi(ga[2 * u]);
-            z2 += bf_lo(ga[2 * u + 1]);
-            z3 += bf_hi(ga[2 * u + 1]);
-          }
-          if (has_g2) {
-            z0 += bf_lo(gb[2 * u]);
-            z1 += bf_hi(gb[2 * u]);
-            z2 += bf_lo(gb[2 * u + 1]);
-            z3 += bf_hi(gb[2 * u + 1]);
-          }
-          pk[2 * u] = pack_bf16x2(fmaxf(z0, 0.f), fmaxf(z1, 0.f));
-          pk[2 * u + 1] = pack_bf16x2(fmaxf(z2, 0.f), fmaxf(z3, 0.f));
+        for (int j = 0; j < 16; ++j) {  // two fp32 lanes per instruction (mgn_tile.cuh); relu after the bf16 rounding
+          uint64_t z = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b1 + 32 * hh + 2 * j));
+          if (has_g1) z = f2_add(z, f2_from_bf16x2(ga[j]));
+          if (has_g2) z = f2_add(z, f2_from_bf16x2(gb[j]));
+          pk[j] = relu_bf16x2(f2_to_bf16x2(z));
         }
         tmem_st16(t_h + 16 * hh, pk);
         if (p.h1_out != nullptr) row_store32p(bG1, row, cc, pk);  // over this thread's own consumed G1 span
@@ -460,12 +447,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const float4 bb = reinterpret_cast<const float4*>(b2 + 32 * hh)[u];
-          pk[2 * u] = pack_bf16x2(fmaxf(__uint_as_float(v[4 * u]) + bb.x, 0.f), fmaxf(__uint_as_float(v[4 * u + 1]) + bb.y, 0.f));
-          pk[2 * u + 1] =
-              pack_bf16x2(fmaxf(__uint_as_float(v[4 * u + 2]) + bb.z, 0.f), fmaxf(__uint_as_float(v[4 * u + 3]) + bb.w, 0.f));
-        }
+        for (int j = 0; j < 16; ++j)
+          pk[j] = relu_bf16x2(f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b2 + 32 * hh + 2 * j))));
         tmem_st16(t_h + 16 * hh, pk);
       }
       tmem_st_wait();
@@ -482,20 +465,23 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       if (has_ln) {
         // one pass over the accumulator for both row sums (fp32), exchanged between the two column halves of a row
         // through spare TMEM columns; only the two warps that share the rows synchronise
-        float s = 0.f, ss = 0.f;
+        float s, ss;
+        {
+          uint64_t s2 = 0ull, ss2 = 0ull;
 #pragma unroll 1
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t v[32];
-          tmem_ld32(t_acc + 32 * hh, v);
-          tmem_ld_wait();
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(t_acc + 32 * hh, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
-            const float y0 = __uint_as_float(v[4 * u]) + bb.x, y1 = __uint_as_float(v[4 * u + 1]) + bb.y;
-            const float y2 = __uint_as_float(v[4 * u + 2]) + bb.z, y3 = __uint_as_float(v[4 * u + 3]) + bb.w;
-            s += (y0 + y1) + (y2 + y3);
-            ss = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, ss))));
+            for (int j = 0; j < 16; ++j) {
+              const uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + 32 * hh + 2 * j));
+              s2 = f2_add(s2, y2);
+              ss2 = f2_fma(y2, y2, ss2);
+            }
           }
+          s = f2_lo(s2) + f2_hi(s2);
+          ss = f2_lo(ss2) + f2_hi(ss2);
         }
         MGN_T(6);
         tmem_st2(t_x + ch * 2, __float_as_uint(s), __float_as_uint(ss));
@@ -522,27 +508,14 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         tmem_ld_wait();
         if (!direct_out) {
           uint32_t o[16];
+          const uint64_t NMU = f2_splat(-mu), RS = f2_splat(rstd);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 bb = reinterpret_cast<const float4*>(b3 + 32 * hh)[u];
-            float y[4] = {__uint_as_float(v[4 * u]) + bb.x, __uint_as_float(v[4 * u + 1]) + bb.y,
-                          __uint_as_float(v[4 * u + 2]) + bb.z, __uint_as_float(v[4 * u + 3]) + bb.w};
-            if (has_ln) {
-              const float4 gg = reinterpret_cast<const float4*>(gam + 32 * hh)[u];
-              const float4 be = reinterpret_cast<const float4*>(bet + 32 * hh)[u];
-              y[0] = (y[0] - mu) * rstd * gg.x + be.x;
-              y[1] = (y[1] - mu) * rstd * gg.y + be.y;
-              y[2] = (y[2] - mu) * rstd * gg.z + be.z;
-              y[3] = (y[3] - mu) * rstd * gg.w + be.w;
-            }
-            if (has_res) {
-              y[0] += bf_lo(r[2 * u]);
-              y[1] += bf_hi(r[2 * u]);
-              y[2] += bf_lo(r[2 * u + 1]);
-              y[3] += bf_hi(r[2 * u + 1]);
-            }
-            o[2 * u] = pack_bf16x2(y[0], y[1]);
-            o[2 * u + 1] = pack_bf16x2(y[2], y[3]);
+          for (int j = 0; j < 16; ++j) {  // ((y - mu) rstd) gamma + beta (+ residual), packed fp32 pairs
+            const int c = 32 * hh + 2 * j;
+            uint64_t y2 = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b3 + c));
+            if (has_ln) y2 = f2_fma(f2_mul(f2_add(y2, NMU), RS), f2_ld(gam + c), f2_ld(bet + c));
+            if (has_res) y2 = f2_add(y2, f2_from_bf16x2(r[j]));
+            o[j] = f2_to_bf16x2(y2);
           }
           row_store32p(bAcur, row, cc, o);
         } else if (grow < p.M) {
