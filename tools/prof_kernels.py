@@ -44,11 +44,21 @@ def bwd2():
                                  gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4])
 
 Tz = torch.empty(N, 384, dtype=torch.bfloat16, device=DEV)
+nfeat_n = r(N, 128).bfloat16()
 
 def bwd2_dst():
     return ops.edge_block_bwd_tc(efeat, h1s, g_e, None, g_agg, plan.dst, w1[:, :128], w2, b2, w3, b3, gamma, 1e-5,
                                  gw1[:, :128], gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4], csc_offsets=plan.csc_offsets,
                                  dst=plan.dst, dst_sum_out=Tz[:, 128:256])
+
+agg_n = r(N, 128).bfloat16(); h1n = torch.empty(N, 128, dtype=torch.bfloat16, device=DEV)
+
+def nodefwd():
+    return ops.node_block_fwd_tc(agg_n, P, 256, nfeat_n, w1[:, :128], b1, w2, b2, w3, b3, gamma, beta, h1_out=h1n)
+
+def nodebwd():
+    return ops.edge_block_bwd_tc(agg_n, h1n, g_agg, None, None, None, w1[:, :128], w2, b2, w3, b3, gamma, 1e-5, gw1[:, :128],
+                                 gb[0], gw2, gb[1], gw3, gb[2], gb[3], gb[4], add_gout=False, g_z1_out=Tz[:, 256:])
 
 def agg():
     return ops.segment_sum(efeat, 0, 128, plan.csc_offsets, None, N)
@@ -67,7 +77,7 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
-for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("segsum csc", agg), ("segsum csr", csr),
+for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("node fwd (+h1)", nodefwd), ("node bwd (from h1)", nodebwd), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):
         fn()
@@ -111,6 +121,17 @@ print("FWD2 kernel, CTA 0, cycles per tile")
 print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // per_cta for v in t[0, :5].tolist()], "total", int(t[0].sum()) // per_cta)
 print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // per_cta for v in t[1, :5].tolist()], "total", int(t[1].sum()) // per_cta)
 print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 pass2 | E3 stats | E3 exchange :", [int(v) // per_cta for v in t[2, :8].tolist()], "total", int(t[2].sum()) // per_cta)
+
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
+nodefwd(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd2_timing", None)
+t = tbuf.cpu().view(3, 32)
+pc_n = -(-((N + 127) // 128) // 148)
+print("FWD2 kernel NODE form, CTA 0, cycles per tile")
+print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // pc_n for v in t[0, :5].tolist()], "total", int(t[0].sum()) // pc_n)
+print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // pc_n for v in t[1, :5].tolist()], "total", int(t[1].sum()) // pc_n)
+print(" EPI   : wait M1+IN | E1 | wait M2 | E2 | wait M3 | E3 pass2 | E3 stats | E3 exchange :", [int(v) // pc_n for v in t[2, :8].tolist()], "total", int(t[2].sum()) // pc_n)
 
 tbuf.zero_()
 _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
