@@ -122,12 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
   const bool has_ln = p.gamma != nullptr;
   const bool has_g1 = p.g1.tab != nullptr;
   const bool has_g2 = p.g2.tab != nullptr;
-  // Residual rows of another table.  A dense table (node block: + nfeat, no row index) is read by the epilogue threads
-  // straight from global memory, 128 bytes of their own row, requested before the LayerNorm statistics pass: staging it in
-  // the G2 buffer kept that buffer busy until the END of the tile, so the next tile's inputs could only be published after
-  // this tile's last epilogue and the first GEMM of every tile waited for a gather (node forward 0.43 -> see DESIGN 5).
-  const bool res_direct = p.res.tab != nullptr && !p.res_is_a && p.res.idx == nullptr && p.n_out == kH;
-  const bool res_g2 = p.res.tab != nullptr && !p.res_is_a && !res_direct;  // gathered residual rows travel in the G2 buffer
+  const bool res_g2 = p.res.tab != nullptr && !p.res_is_a;  // residual rows travel in the G2 buffer
   const bool direct_out = p.n_out < kH;                      // narrow outputs (decoder) are stored by the epilogue
 
   // ---------------- one-time setup ----------------
@@ -466,13 +461,6 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
       }  // !single
       MGN_T(4);
       tc_fence_after_sync();
-      uint4 rq[8];  // this thread's 64 residual values when the residual table is read directly (res_direct)
-      if (res_direct) {
-        const long long gr = grow < p.M ? grow : p.M - 1;
-        const uint4* src = reinterpret_cast<const uint4*>(p.res.tab + gr * p.res.ld + p.res.col0 + c0);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) rq[u] = __ldg(src + u);
-      }
       float mu = 0.f, rstd = 1.f;
       if (has_ln) {
         // one pass over the accumulator for both row sums (fp32), exchanged between the two column halves of a row
@@ -516,18 +504,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp3_fwd2_tc_kernel(const __grid_
         uint32_t v[32];
         tmem_ld32(t_acc + 32 * hh, v);
         uint32_t r[16];
-        if (res_direct) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const uint4 t = hh ? rq[4 + u] : rq[u];
-            r[4 * u] = t.x;
-            r[4 * u + 1] = t.y;
-            r[4 * u + 2] = t.z;
-            r[4 * u + 3] = t.w;
-          }
-        } else if (has_res) {
-          row_load32p(rbuf, row, cc, r);
-        }
+        if (has_res) row_load32p(rbuf, row, cc, r);
         tmem_ld_wait();
         if (!direct_out) {
           uint32_t o[16];
