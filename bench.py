@@ -308,19 +308,43 @@ def side_rate(workload, dev, peaks, steps=10, warmup=3):
             pred = model(nf, ef, graph)
         torch.nn.functional.mse_loss(pred.float(), tgt).backward()
 
+    def timed(fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+
     for _ in range(warmup):
         step()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / steps
+    ms = timed(step)
+    # the same step as ONE CUDA-graph launch (every kernel on the path is capturable: no host sync, no allocation inside;
+    # modulus_b200/capture.py does this for training loops): at this size the eager loop is partly bound by the host
+    ms_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        model.zero_grad(set_to_none=True)
+        graph_obj = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph_obj):
+            step()
+        for _ in range(2):
+            graph_obj.replay()
+        ms_graph = timed(graph_obj.replay)
+    except Exception as exc:  # pragma: no cover - reported, not fatal
+        ms_graph = None
+        graph_err = repr(exc)[:200]
     b = 2 if dtype == "bf16" else 4
     return {"workload": workload_name(workload, 1), "value": E / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
             "steps": steps, "warmup": warmup, "dtype": dtype,
+            "cuda_graph": None if ms_graph is None else {"ms_per_step": ms_graph, "value": E / (ms_graph * 1e-3), "unit": UNIT,
+                                                         "hbm_frac": step_bytes(n, E, b) / (ms_graph * 1e-3) / 1e9 / peaks["hbm"]},
             "hbm_frac": step_bytes(n, E, b) / (ms * 1e-3) / 1e9 / peaks["hbm"],
             "tensor_frac": step_flops(n, E, d_n, d_e, d_out) / (ms * 1e-3) / 1e12 / peaks["tc_sust"],
             "l2": "edge table %.0f MB: %s the 126 MB L2" % (E * H * b / 1e6, "exceeds" if E * H * b > 126e6 else "fits")}
