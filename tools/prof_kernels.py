@@ -77,6 +77,15 @@ def lin_t():
 def wgrad():
     return ops.wgrad_tc(T3, nfeat)
 
+ONLY = os.environ.get("MGN_PROF_ONLY")  # run just one of the functions above (ncu captures): e.g. MGN_PROF_ONLY=bwd2_dst
+if ONLY:
+    fn = globals()[ONLY]
+    for _ in range(reps):
+        fn()
+    torch.cuda.synchronize()
+    ops.tc_check(DEV)
+    sys.exit(0)
+
 for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("node fwd (+h1)", nodefwd), ("node bwd (from h1)", nodebwd), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
     for _ in range(2):

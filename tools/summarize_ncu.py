@@ -48,12 +48,13 @@ if __name__ == "__main__":
     if os.path.exists(ll):
         launch_list(ll, f"ncu launch list, `bench.py --steps 1 --warmup 3 --no-cpu` (c3, {tag})", os.path.join(PROF, f"{tag}_launches_c3.md"))
     traffic = {"c3": {}}
-    entry = {"edge_bwd2_kernel": "mgn_edge_block_bwd_tc", "mlp3_bwd_tc_kernel": "mgn_mlp3_bwd_tc", "edge_fwd3_kernel": "mgn_edge_block_fwd_tc", "mlp3_fwd2_tc_kernel": "mgn_mlp3_fwd2_tc", "segment_sum_batch_kernel": "mgn_segment_sum",
-             "node_gemm_tc_kernel": "mgn_node_gemm_tc"}
+    # capture name (tools/gpu_measure.sh: MGN_PROF_ONLY=<function of tools/prof_kernels.py>) -> C-ABI entry point
+    entry = {"bwd2_dst": "mgn_edge_block_bwd_tc", "eblk_h1": "mgn_edge_block_fwd_tc", "nodefwd": "mgn_node_block_fwd_tc",
+             "bwd": "mgn_mlp3_bwd_tc", "csr": "mgn_segment_sum", "lin_p": "mgn_node_gemm_tc", "wgrad": "mgn_wgrad_tc"}
     with open(os.path.join(PROF, f"{tag}_ncu_full_summary.md"), "w") as f:
-        f.write(f"# ncu --set full --clock-control none, one launch each at the c3 size (tools/prof_kernels.py 1000 1000 1), {tag}\n\n")
+        f.write(f"# ncu --set full --clock-control none, one launch each at the c3 size (MGN_PROF_ONLY=<fn> tools/prof_kernels.py 1000 1000 1: the launch the model makes per layer), {tag}\n\n")
         for k, sym in entry.items():
-            rep = os.path.join(OUT, f"r01_full_{k}.ncu-rep")
+            rep = os.path.join(OUT, f"{tag}_full_{k}.ncu-rep")
             if not os.path.exists(rep):
                 continue
             d = full(rep)
@@ -64,7 +65,8 @@ if __name__ == "__main__":
             rd, wr = to_bytes(*d["dram__bytes_read.sum"]), to_bytes(*d["dram__bytes_write.sum"])
             f.write(f"| DRAM traffic per launch | {(rd + wr) / 1e9:.3f} | GB |\n\n")
             traffic["c3"][sym] = rd + wr
-    traffic["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the edge-form kernel at the c3 size "
-                       "(5 992 002 edge rows / 1 000 000 node rows), ncu --set full; bench.py reports it as roofline.traffic")
+    traffic["note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at the c3 size, the form the model launches per "
+                       "layer (edge kernels: 5 992 002 edge rows incl. the fused destination sums / the stored h1; node kernels: "
+                       "1 000 000 rows), ncu --set full; bench.py reports it as roofline.traffic")
     json.dump(traffic, open(os.path.join(PROF, f"{tag}_ncu_traffic.json"), "w"), indent=1)
     print(open(os.path.join(PROF, f"{tag}_ncu_full_summary.md")).read())
