@@ -27,8 +27,32 @@ ix = {n: i for i, n in enumerate(hdr)}
 IE, S = ix["Instructions Executed"], ix["# Samples"]
 
 
+def _ranges():
+    """line ranges of the polling loops, found in the sources (wait_clk in mgn_tile.cuh, mbar_try_wait* / mbar_wait in
+    mgn_tc.cuh) so that edits above them do not silently break the split"""
+    import os
+    import re
+
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "modulus_b200", "csrc")
+    out = {}
+    for fn, pats in (("mgn_tile.cuh", [r"bool wait_clk\("]), ("mgn_tc.cuh", [r"uint32_t mbar_try_wait", r"bool mbar_wait\("])):
+        lines = open(os.path.join(root, fn)).read().split("\n")
+        spans = []
+        for i, ln in enumerate(lines):
+            if any(re.search(p_, ln) for p_ in pats):
+                j = i
+                while j < len(lines) and not lines[j].startswith("}"):
+                    j += 1
+                spans.append((i + 1, j + 1))
+        out[fn] = spans
+    return out
+
+
+_R = _ranges()
+
+
 def is_wait(c, l):
-    return (c == "mgn_tile.cuh" and 23 <= l <= 29) or (c == "mgn_tc.cuh" and 207 <= l <= 231)
+    return any(a <= l <= b for a, b in _R.get(c, []))
 
 
 tot = sum(int(r[IE]) for _, _, r in data)
