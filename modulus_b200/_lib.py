@@ -231,12 +231,14 @@ class _Profile:
         torch.cuda.synchronize()
         out = {}
         for name, e0, e1, work in self._ev:
-            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "bound": None, "work": 0.0})
-            d["ms"] += e0.elapsed_time(e1)
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "bound": None, "work": 0.0, "per_call": []})
+            ms = e0.elapsed_time(e1)
+            d["ms"] += ms
             d["calls"] += 1
             if work is not None and work[1] is not None:
                 d["bound"] = work[0]
                 d["work"] += work[1]
+                d["per_call"].append((ms, work[1]))
         self._ev = []
         return out
 
