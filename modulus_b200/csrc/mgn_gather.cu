@@ -159,25 +159,32 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
     const LongEntry le = ll.entries[en];
     const int32_t b = __ldg(offsets + le.seg) + le.chunk * kLongChunk;
     const int32_t e = min(__ldg(offsets + le.seg + 1), b + kLongChunk);
-    for (int cb = 0; cb < chunks; cb += 32) {  // 32 column chunks (16 bytes each) per pass, one row per warp per load
-      const int c = cb + lane;
+    // lane = (row slot, 16-byte column chunk): a row narrower than 32 chunks (H = 128 bf16: 16) puts 32 / G rows into one
+    // warp-wide load instead of idling half the lanes; 8 loads per lane are in flight (fixed row -> lane assignment and
+    // addition order: bit-reproducible)
+    const int G = chunks <= 4 ? 4 : (chunks <= 8 ? 8 : (chunks <= 16 ? 16 : 32));
+    const int R = 32 / G;
+    const int sub = lane / G, cl = lane % G;
+    for (int cb = 0; cb < chunks; cb += G) {
+      const int c = cb + cl;
       const bool active = c < chunks;
       float acc[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = 0.f;
-      for (int32_t j = b + warp; j < e; j += 32) {  // 4 rows in flight per warp
-        uint4 v[4];
-        bool on[4];
+      const int rows_per_pass = 8 * R;  // 8 warps x R row slots
+      for (int32_t j = b + warp * R + sub; j < e; j += 8 * rows_per_pass) {
+        uint4 v[8];
+        bool on[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          on[u] = active && (j + 8 * u < e);
+        for (int u = 0; u < 8; ++u) {
+          on[u] = active && (j + rows_per_pass * u < e);
           if (on[u]) {
-            const int64_t row = eids ? __ldg(eids + j + 8 * u) : (j + 8 * u);
+            const int64_t row = eids ? __ldg(eids + j + rows_per_pass * u) : (j + rows_per_pass * u);
             v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 8; ++u)
           if (on[u]) {
             Vec16<T> t;
             t.raw = v[u];
@@ -190,12 +197,12 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
 #pragma unroll
       for (int k = 0; k < V; ++k) red[warp][lane * V + k] = acc[k];
       __syncthreads();
-      for (int i = threadIdx.x; i < 32 * V; i += blockDim.x) {
+      for (int i = threadIdx.x; i < G * V; i += blockDim.x) {
         const int col = cb * V + i;
         if (col < D) {
           float sum = 0.f;
-#pragma unroll
-          for (int w = 0; w < 8; ++w) sum += red[w][i];
+          for (int w = 0; w < 8; ++w)
+            for (int r = 0; r < R; ++r) sum += red[w][r * G * V + i];
           partials[static_cast<int64_t>(en) * D + col] = sum;
         }
       }
@@ -383,7 +390,26 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
         }
       }
       if (!is_long) {
-        for (int32_t j = b[i] + g + U * R; j < e[i]; j += R) {  // longer segments (uniform per warp)
+        // longer segments (uniform per warp): four rows per lane group in flight, added in the same order as before
+        int32_t j = b[i] + g + U * R;
+        for (; j + 3 * R < e[i]; j += 4 * R) {
+          int64_t rr[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) rr[u] = eids ? static_cast<int64_t>(__ldg(eids + j + u * R)) : static_cast<int64_t>(j + u * R);
+          uint4 vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) vv[u] = ldg16(col + rr[u] * ld_in);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            Vec16<T> t;
+            t.raw = vv[u];
+            float f[V];
+            t.unpack(f);
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] += f[k];
+          }
+        }
+        for (; j < e[i]; j += R) {
           const int64_t row = eids ? __ldg(eids + j) : j;
           Vec16<T> t;
           t.raw = ldg16(col + row * ld_in);
