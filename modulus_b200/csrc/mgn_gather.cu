@@ -172,12 +172,13 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
 #pragma unroll
       for (int k = 0; k < V; ++k) acc[k] = 0.f;
       const int rows_per_pass = 8 * R;  // 8 warps x R row slots
-      for (int32_t j = b + warp * R + sub; j < e; j += 8 * rows_per_pass) {
+      const int n_fly = G == 32 ? 4 : 8;  // wide rows already fill the memory pipe with 4 loads per lane (measured)
+      for (int32_t j = b + warp * R + sub; j < e; j += n_fly * rows_per_pass) {
         uint4 v[8];
         bool on[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          on[u] = active && (j + rows_per_pass * u < e);
+          on[u] = active && u < n_fly && (j + rows_per_pass * u < e);
           if (on[u]) {
             const int64_t row = eids ? __ldg(eids + j + rows_per_pass * u) : (j + rows_per_pass * u);
             v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
