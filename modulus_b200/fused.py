@@ -197,7 +197,7 @@ class FusedProcessorFn(torch.autograd.Function):
     edge (w1 [H,3H], b1, w2, b2, w3, b3, gamma, beta), node (w1 [H,2H], b1, w2, b2, w3, b3, gamma, beta)."""
 
     @staticmethod
-    def forward(ctx, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, halo, L: int, eps: float, *params: Tensor):
+    def forward(ctx, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, halo, L: int, eps: float, mean: bool, *params: Tensor):
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         nfeat, efeat = nfeat.contiguous(), efeat.contiguous()
@@ -256,12 +256,14 @@ class FusedProcessorFn(torch.autograd.Function):
                 del keep
             if agg is None:
                 agg = ops.segment_sum(efeat_new, 0, H, plan.csc_offsets, None, N)
+            if mean:  # aggregation="mean" (utils.py:372): rows of the destination sums scaled by 1 / max(in-degree, 1), in place
+                ops.gather_rows(agg, 0, H, None, N, out=agg, inv_deg_offsets=plan.csc_offsets)
             h1n = torch.empty((N, H), dtype=BF16, device=nfeat.device) if KEEP_H1 else None
             nfeat_new = ops.node_block_fwd_tc(agg, P, 2 * H, nfeat, nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6],
                                               nw[7], eps=eps, h1_out=h1n)
             saved += [efeat, nfeat, agg, P] + ([Ps] if Ps_saved(halo, remote_only) else []) + ([h1, h1n] if h1 is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
-        ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1 = plan, L, eps, halo, KEEP_H1
+        ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1, ctx.mean = plan, L, eps, halo, KEEP_H1, mean
         ctx.remote_only = halo is not None and halo.remote_only and KEEP_H1
         ctx.save_for_backward(*saved, *params)
         ctx.n_saved = len(saved)
@@ -301,6 +303,8 @@ class FusedProcessorFn(torch.autograd.Function):
                                            nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6], H, eps,
                                            True, False, True, gnw1[:, :H], gn[1], gn[2], gn[3], gn[4], gn[5], gn[6],
                                            gn[7], g_z1_out=T[:, 2 * H:])
+            if ctx.mean:  # the node block saw sum / deg: the gradient of the sums is g_agg / deg
+                ops.gather_rows(g_agg, 0, H, None, N, out=g_agg, inv_deg_offsets=plan.csc_offsets)
             # ---- edge block: g_out = g_e + g_agg[dst]
             if g_e is None:
                 go1, go1_idx, go2, go2_idx = g_agg, dst, None, None
@@ -350,7 +354,7 @@ class FusedProcessorFn(torch.autograd.Function):
             gnw1[:, H:] = gwp[2 * H:]
             grads[16 * l: 16 * l + 8] = ge
             grads[16 * l + 8: 16 * l + 16] = gn
-        return (g_n, g_e, None, None, None, None, *grads)
+        return (g_n, g_e, None, None, None, None, None, *grads)
 
 
 def _partition_eligible(graph, plan: GraphPlan) -> bool:
@@ -382,7 +386,7 @@ def _partition_eligible(graph, plan: GraphPlan) -> bool:
 
 def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPlan, dt: torch.dtype) -> bool:
     """Conditions under which the fused tcgen05 path computes exactly what the generic path does."""
-    from .models.gnn_layers.mesh_graph_mlp import MeshGraphEdgeMLPConcat
+    from .models.gnn_layers.mesh_graph_mlp import MeshGraphEdgeMLPConcat, MeshGraphEdgeMLPSum
     from .models.layers.activations import activation_name
 
     if dt != BF16 or not plan.is_csc_ordered:
@@ -394,12 +398,21 @@ def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPla
         return False
     if nfeat.shape[1] != H or efeat.shape[1] != H or nfeat.shape[0] != plan.n_dst:
         return False
+    aggs = set()
     for i, layer in enumerate(proc.processor_layers):
         mlp = layer.edge_mlp if i % 2 == 0 else layer.node_mlp
-        if i % 2 == 0 and not isinstance(mlp, MeshGraphEdgeMLPConcat):
-            return False
-        if i % 2 == 1 and layer.aggregation != "sum":
-            return False
+        if i % 2 == 0:
+            # plain Linear(3H, H) first layer, or the reference's "concat trick" layout (lin_efeat / lin_src / lin_dst + bias):
+            # the same algebra, re-assembled by MeshGraphEdgeMLPSum._flat_params
+            if isinstance(mlp, MeshGraphEdgeMLPSum):
+                if mlp.bias is None or not (mlp.efeat_dim == mlp.src_dim == mlp.dst_dim == H):
+                    return False
+            elif not isinstance(mlp, MeshGraphEdgeMLPConcat):
+                return False
+        else:
+            if layer.aggregation not in ("sum", "mean"):
+                return False
+            aggs.add(layer.aggregation)
         if mlp.hidden_layers != 2 or mlp.norm_type is None or mlp.hidden_dim != H or mlp.output_dim != H:
             return False
         try:
@@ -409,7 +422,7 @@ def processor_eligible(proc, nfeat: Tensor, efeat: Tensor, graph, plan: GraphPla
             return False
         if any(q.dtype != torch.float32 or not q.is_cuda for q in mlp.parameters()):
             return False
-    return True
+    return len(aggs) == 1
 
 
 def processor_forward(proc, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, graph=None) -> Tensor:
@@ -424,7 +437,8 @@ def processor_forward(proc, nfeat: Tensor, efeat: Tensor, plan: GraphPlan, graph
         halo = plan.extra.get("halo")
         if halo is None:
             halo = plan.extra["halo"] = HaloContext(graph, plan)
-    return FusedProcessorFn.apply(nfeat.to(BF16), efeat.to(BF16), plan, halo, proc.processor_size, eps, *params)
+    mean = proc.processor_layers[1].aggregation == "mean"
+    return FusedProcessorFn.apply(nfeat.to(BF16), efeat.to(BF16), plan, halo, proc.processor_size, eps, mean, *params)
 
 
 # ----------------------------------------------------------------------------------------

@@ -195,6 +195,7 @@ class MeshGraphEdgeMLPSum(nn.Module):
     ):
         super().__init__()
         self.efeat_dim, self.src_dim, self.dst_dim = efeat_dim, src_dim, dst_dim
+        self.hidden_dim, self.output_dim = hidden_dim, output_dim
         self.activation_fn = activation_fn
 
         tmp_lin = nn.Linear(efeat_dim + src_dim + dst_dim, hidden_dim, bias=bias)
@@ -222,6 +223,22 @@ class MeshGraphEdgeMLPSum(nn.Module):
             self.recompute_activation = True
         else:
             self.recompute_activation = False
+
+    # ---- the fused tensor-core path reads this module through the same two accessors as MeshGraphMLP: the first Linear
+    # re-assembled as ONE [hidden, efeat | src | dst] matrix (what it was split from, mesh_graph_mlp.py:335-350); autograd
+    # routes the gradient of the concatenation back to lin_efeat / lin_src / lin_dst
+    def _norm(self) -> Optional[nn.LayerNorm]:
+        return self.model[2 * self.hidden_layers] if self.norm_type is not None else None
+
+    def _flat_params(self) -> List[Optional[Tensor]]:
+        ps: List[Optional[Tensor]] = [torch.cat([self.lin_efeat, self.lin_src, self.lin_dst], dim=1), self.bias]
+        for i in range(self.hidden_layers):
+            lin = self.model[2 * i + 1]
+            ps += [lin.weight, lin.bias]
+        nrm = self._norm()
+        if nrm is not None:
+            ps += [nrm.weight, nrm.bias]
+        return ps
 
     def forward_truncated_sum(self, efeat: Tensor, nfeat, graph) -> Tensor:
         dt = compute_dtype(efeat)

@@ -59,49 +59,68 @@ class Rounding:
 
 def _mlp(R: Rounding, p: Dict[str, Tensor], pre: str, x: Tensor, extra=None, w1_cols=None, norm: bool = True) -> Tensor:
     """Linear-ReLU-Linear-ReLU-Linear(-LayerNorm) with the kernels' storage points.  `extra` is added to the first
-    pre-activation (the gathered projection rows); `w1_cols` selects the column block of W1 that multiplies x."""
-    w1 = p[f"{pre}.model.0.weight"]
+    pre-activation (the gathered projection rows); `w1_cols` selects the column block of W1 that multiplies x.  Both
+    parameter layouts of the edge MLP are read: the plain `model.{0,2,4,5}` and the reference's concat-trick layout
+    `lin_efeat | lin_src | lin_dst`, `bias`, `model.{1,3,4}` (mesh_graph_mlp.py:335-350)."""
+    w1, b1, w2, b2, w3, b3, gam, bet = _mlp_params(p, pre, norm)
     if w1_cols is not None:
         w1 = w1[:, w1_cols[0]:w1_cols[1]]
-    z1 = x @ R.s(w1).T + p[f"{pre}.model.0.bias"]
+    z1 = x @ R.s(w1).T + b1
     if extra is not None:
         z1 = z1 + extra
     h1 = R.s(F.relu(R.g(z1)))
-    h2 = R.s(F.relu(R.g(h1 @ R.s(p[f"{pre}.model.2.weight"]).T + p[f"{pre}.model.2.bias"])))
-    y = R.g(h2 @ R.s(p[f"{pre}.model.4.weight"]).T + p[f"{pre}.model.4.bias"])
+    h2 = R.s(F.relu(R.g(h1 @ R.s(w2).T + b2)))
+    y = R.g(h2 @ R.s(w3).T + b3)
     if norm:
-        y = F.layer_norm(y, (y.shape[-1],), p[f"{pre}.model.5.weight"], p[f"{pre}.model.5.bias"], 1e-5)
+        y = F.layer_norm(y, (y.shape[-1],), gam, bet, 1e-5)
     return y
 
 
-def forward(R: Rounding, p: Dict[str, Tensor], nf: Tensor, ef: Tensor, src: Tensor, dst: Tensor, L: int) -> Tensor:
+def _mlp_params(p: Dict[str, Tensor], pre: str, norm: bool = True):
+    if f"{pre}.lin_efeat" in p:
+        w1 = torch.cat([p[f"{pre}.lin_efeat"], p[f"{pre}.lin_src"], p[f"{pre}.lin_dst"]], dim=1)
+        names = (None, f"{pre}.bias", f"{pre}.model.1.weight", f"{pre}.model.1.bias", f"{pre}.model.3.weight",
+                 f"{pre}.model.3.bias", f"{pre}.model.4.weight", f"{pre}.model.4.bias")
+    else:
+        w1 = p[f"{pre}.model.0.weight"]
+        names = (None, f"{pre}.model.0.bias", f"{pre}.model.2.weight", f"{pre}.model.2.bias", f"{pre}.model.4.weight",
+                 f"{pre}.model.4.bias", f"{pre}.model.5.weight", f"{pre}.model.5.bias")
+    vals = [w1] + [p[n] if (n in p and (norm or i < 5)) else None for i, n in enumerate(names[1:])]
+    return vals
+
+
+def forward(R: Rounding, p: Dict[str, Tensor], nf: Tensor, ef: Tensor, src: Tensor, dst: Tensor, L: int,
+            aggregation: str = "sum") -> Tensor:
     """The fused path's algebra (modulus_b200/fused.py: first Linear split by input block, P = nfeat Wp^T)."""
     n = nf.shape[0]
+    inv_deg = 1.0 / torch.bincount(dst, minlength=n).clamp(min=1).to(nf.dtype)
     e = R.g(R.s(_mlp(R, p, "edge_encoder", R.s(ef))))
     v = R.g(R.s(_mlp(R, p, "node_encoder", R.s(nf))))
     for l in range(L):
         pe, pn = f"processor.processor_layers.{2 * l}.edge_mlp", f"processor.processor_layers.{2 * l + 1}.node_mlp"
-        w1e, w1n = p[f"{pe}.model.0.weight"], p[f"{pn}.model.0.weight"]
+        w1e, w1n = _mlp_params(p, pe)[0], p[f"{pn}.model.0.weight"]
         wp = torch.cat([w1e[:, H:2 * H], w1e[:, 2 * H:3 * H], w1n[:, H:2 * H]], dim=0)       # [3H, H]
         P = R.g(R.s(v @ R.s(wp).T))                                                         # [N, 3H]
         e_in = R.g(e)  # what the edge block's own backward returns (g_efeat) is rounded before it meets g_agg[dst]
         y = _mlp(R, p, pe, e_in, extra=P[src, :H] + P[dst, H:2 * H], w1_cols=(0, H))
         e = R.g(R.s(y + e_in))
         agg = R.g(R.s(torch.zeros((n, H), dtype=e.dtype).index_add(0, dst, e)))
+        if aggregation == "mean":  # the stored sums are scaled by 1 / max(in-degree, 1) and stored again
+            agg = R.g(R.s(agg * inv_deg[:, None]))
         y = _mlp(R, p, pn, agg, extra=P[:, 2 * H:], w1_cols=(0, H))
         v = R.g(R.s(y + v))
     return R.g(R.s(_mlp(R, p, "node_decoder", v, norm=False)))
 
 
 def step_fwd_bwd(sd: Dict[str, Tensor], nf: Tensor, ef: Tensor, src: Tensor, dst: Tensor, tgt: Tensor, L: int,
-                 round_fwd: bool = True, round_bwd: bool = True):
+                 round_fwd: bool = True, round_bwd: bool = True, aggregation: str = "sum"):
     """zero_grad -> forward -> MSE -> backward in float64.  Returns (prediction, loss, {name: grad}) with the input
     gradients under "__node_features" / "__edge_features" (same convention as oracle/mgn_oracle.step_fwd_bwd)."""
     R = Rounding(round_fwd, round_bwd)
     leaves = {k: t.detach().double().requires_grad_(True) for k, t in sd.items() if t.is_floating_point()}
     x = nf.detach().double().requires_grad_(True)
     a = ef.detach().double().requires_grad_(True)
-    pred = forward(R, leaves, x, a, src.long(), dst.long(), L)
+    pred = forward(R, leaves, x, a, src.long(), dst.long(), L, aggregation)
     loss = F.mse_loss(pred, tgt.double())
     loss.backward()
     grads = {k: t.grad for k, t in leaves.items()}

@@ -134,6 +134,55 @@ def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
     assert not bad, bad
 
 
+@pytest.mark.parametrize("variant", ["mean", "trick", "trick_mean"])
+def test_fused_path_serves_mean_aggregation_and_the_concat_trick_layout(variant):
+    """`aggregation="mean"` and `do_concat_trick=True` (MeshGraphEdgeMLPSum: lin_efeat / lin_src / lin_dst, bias) run on the
+    same tcgen05 kernels as the default model -- the first Linear is re-assembled, the destination sums are scaled by the
+    inverse in-degree.  fp32 against the unmodified reference's goldens at 1e-4; fused bf16: output 2e-2 against the fp32
+    reference, every gradient 2e-2 (relative L2) against the matched-rounding oracle, two layers."""
+    from modulus_b200 import ops
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from oracle import mgn_oracle as O, mgn_oracle_bf16 as OB
+
+    g = load_golden(f"ref_mgn_h128_{variant}.pt")
+    torch.manual_seed(g["seed"])
+    model = MeshGraphNet(**g["kwargs"]).to(DEV)
+    graph = CuGraphCSC(g["offsets"].to(DEV), g["indices"].to(DEV), g["n_nodes"], g["n_nodes"])
+    # fp32 (generic kernels) against the reference
+    model.zero_grad(set_to_none=True)
+    x = g["node_features"].to(DEV).requires_grad_(True)
+    out32 = model(x, g["edge_features"].to(DEV), graph)
+    torch.nn.functional.mse_loss(out32, g["target"].to(DEV)).backward()
+    assert rel_err(out32, g["output"]) < 1e-4 and rel_err(x.grad, g["grad_node_features"]) < 1e-4
+    for k, v in g["grads_selected"].items():
+        assert rel_err(dict(model.named_parameters())[k].grad, v) < 1e-4, k
+    # bf16: the fused kernels must be what runs
+    launched = {}
+    orig_call = ops.call
+
+    def spy(name, *a):
+        launched[name] = launched.get(name, 0) + 1
+        return orig_call(name, *a)
+
+    ops.call = spy
+    try:
+        out, gnf, gef, grads = _step(model, g, graph)
+    finally:
+        ops.call = orig_call
+    ops.tc_check(DEV)
+    assert launched.get("mgn_edge_block_fwd_tc", 0) == 2 and launched.get("mgn_edge_block_bwd_tc", 0) == 4, launched
+    assert l2_err(out.float(), g["output"]) < 2e-2
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    src, dst = O.coo_from_csc(g["offsets"], g["indices"])
+    _, _, ref_g = OB.step_fwd_bwd(sd, g["node_features"], g["edge_features"], src, dst, g["target"], 2,
+                                  aggregation=g["kwargs"].get("aggregation", "sum"))
+    got = dict(grads)
+    got["__node_features"], got["__edge_features"] = gnf, gef
+    worst = max(((k, l2_err(v, ref_g[k])) for k, v in got.items()), key=lambda kv: kv[1])
+    assert worst[1] < 2e-2, worst
+
+
 def test_fused_path_is_deterministic():
     from modulus_b200.models.gnn_layers import CuGraphCSC
     from modulus_b200.models.meshgraphnet import MeshGraphNet

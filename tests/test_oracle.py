@@ -121,3 +121,30 @@ def test_matched_rounding_oracle_reduces_to_the_plain_oracle(L):
     assert float((p2 - p1).norm() / p1.norm()) < 2e-2
     dev = float((g2["__node_features"] - g1["__node_features"]).norm() / g1["__node_features"].norm())
     assert dev > 5e-2, dev
+
+
+@pytest.mark.parametrize("variant", ["mean", "trick", "trick_mean"])
+def test_matched_rounding_oracle_variants_reproduce_reference_goldens(variant):
+    """aggregation="mean" and the concat-trick parameter layout (lin_efeat / lin_src / lin_dst): with the roundings off the
+    matched-rounding oracle reproduces the UNMODIFIED reference's hidden-128 goldens (tests/golden/make_golden_variants.py):
+    output, input gradients, the stored weight gradients and the norm of every weight gradient."""
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from oracle import mgn_oracle_bf16 as OB
+
+    g = load_golden(f"ref_mgn_h128_{variant}.pt")
+    torch.manual_seed(g["seed"])
+    sd = {k: v.detach() for k, v in MeshGraphNet(**g["kwargs"]).state_dict().items()}  # same init stream as the reference
+    src, dst = O.coo_from_csc(g["offsets"], g["indices"])
+    out, _, grads = OB.step_fwd_bwd(sd, g["node_features"], g["edge_features"], src, dst, g["target"], 2, False, False,
+                                    aggregation=g["kwargs"].get("aggregation", "sum"))
+
+    def rel(a, b):
+        return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+    assert rel(out, g["output"]) < 1e-5
+    assert rel(grads["__node_features"], g["grad_node_features"]) < 1e-5
+    assert rel(grads["__edge_features"], g["grad_edge_features"]) < 1e-5
+    for k, v in g["grads_selected"].items():
+        assert rel(grads[k], v) < 1e-5, k
+    for k, nrm in g["grad_norms"].items():
+        assert abs(float(grads[k].norm()) - nrm) <= 1e-5 * max(nrm, 1e-12), k
