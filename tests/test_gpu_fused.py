@@ -81,6 +81,23 @@ def test_fused_bf16_model_vs_reference_and_generic(L):
         assert abs(nf_ - nrm) <= 1.5 * abs(ng_ - nrm) + 5e-2 * max(nrm, 1e-8), k
 
 
+def _float32_floor(sd, g, src, dst, L, ref_g, keys, aggregation="sum"):
+    """noise floor of a gradient comparison against the float64 matched-rounding oracle: the SAME oracle evaluated with
+    float32 accumulation on the CPU, per tensor (relative L2)"""
+    import torch.nn.functional as F
+
+    from oracle import mgn_oracle_bf16 as OB
+
+    R = OB.Rounding(True, True)
+    leaves = {k: t.float().requires_grad_(True) for k, t in sd.items() if t.is_floating_point()}
+    x = g["node_features"].float().requires_grad_(True)
+    a = g["edge_features"].float().requires_grad_(True)
+    F.mse_loss(OB.forward(R, leaves, x, a, src, dst, L, aggregation), g["target"].float()).backward()
+    f32 = {k: t.grad for k, t in leaves.items()}
+    f32["__node_features"], f32["__edge_features"] = x.grad, a.grad
+    return {k: l2_err(f32[k], ref_g[k]) for k in keys}
+
+
 @pytest.mark.parametrize("L", [1, 15])
 def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
     """north_star's bf16 bar for GRADIENTS at model level: the fused CUDA path against the same algorithm in float64 with
@@ -119,15 +136,7 @@ def test_fused_bf16_gradients_vs_matched_rounding_oracle(L):
         worst = max(dev.items(), key=lambda kv: kv[1])
         assert worst[1] < 2e-2, worst
         return
-    # noise floor: the same oracle with float32 accumulation (CPU)
-    R = OB.Rounding(True, True)
-    leaves = {k: t.float().requires_grad_(True) for k, t in sd.items() if t.is_floating_point()}
-    x = g["node_features"].float().requires_grad_(True)
-    a = g["edge_features"].float().requires_grad_(True)
-    F.mse_loss(OB.forward(R, leaves, x, a, src, dst, L), g["target"].float()).backward()
-    f32 = {k: t.grad for k, t in leaves.items()}
-    f32["__node_features"], f32["__edge_features"] = x.grad, a.grad
-    floor = {k: l2_err(f32[k], ref_g[k]) for k in got}
+    floor = _float32_floor(sd, g, src, dst, L, ref_g, got)
     assert max(floor.values()) > 2e-2, "the float32 evaluation of the same algorithm is expected to miss 2e-2 too"
     print("    float32-CPU floor:", sorted(((round(v, 4), k) for k, v in floor.items()), reverse=True)[:4])
     bad = {k: (dev[k], floor[k]) for k in dev if dev[k] > max(2e-2, 2.0 * floor[k]) or dev[k] > 0.25}
@@ -179,8 +188,10 @@ def test_fused_path_serves_mean_aggregation_and_the_concat_trick_layout(variant)
                                   aggregation=g["kwargs"].get("aggregation", "sum"))
     got = dict(grads)
     got["__node_features"], got["__edge_features"] = gnf, gef
-    worst = max(((k, l2_err(v, ref_g[k])) for k, v in got.items()), key=lambda kv: kv[1])
-    assert worst[1] < 2e-2, worst
+    # two layers: 2e-2, or twice the float32-CPU floor of the same comparison where that is larger (see the 15-layer test)
+    floor = _float32_floor(sd, g, src, dst, 2, ref_g, got, aggregation=g["kwargs"].get("aggregation", "sum"))
+    bad = {k: (l2_err(v, ref_g[k]), floor[k]) for k, v in got.items() if l2_err(v, ref_g[k]) > max(2e-2, 2.0 * floor[k])}
+    assert not bad, bad
 
 
 def test_fused_path_is_deterministic():
