@@ -28,9 +28,17 @@ static __global__ void reduce_cta_partials_kernel(const ReduceParams rp) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int r = i / sg.cols, c = i - r * sg.cols;
     const float* src = rp.partials + sg.src_off + r * sg.src_ld + c;
+    // added in CTA order; the loads are independent, 16 of them in flight per thread (one per 200 KB-strided partial)
     float s = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < rp.n_parts; ++k) s += src[static_cast<long long>(k) * rp.stride];
+    int k = 0;
+    for (; k + 16 <= rp.n_parts; k += 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = __ldg(src + static_cast<long long>(k + u) * rp.stride);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) s += v[u];
+    }
+    for (; k < rp.n_parts; ++k) s += __ldg(src + static_cast<long long>(k) * rp.stride);
     sg.dst[r * sg.ld_dst + c] = s;
   }
 }

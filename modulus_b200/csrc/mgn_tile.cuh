@@ -65,8 +65,15 @@ __device__ __forceinline__ void stage_weight_ld(uint8_t* dst, const float* __res
     const int panel = rem >> 3, chunk = rem & 7;
     const int k0 = panel * 64 + chunk * 8;
     float f[8];
+    const float* src = w + row * ld + k0;
+    if (row < n_rows && k0 + 8 <= k_true && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {  // two 16-byte loads
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+      f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = (row < n_rows && (k0 + j) < k_true) ? __ldg(w + row * ld + k0 + j) : 0.f;
+      for (int j = 0; j < 8; ++j) f[j] = (row < n_rows && (k0 + j) < k_true) ? __ldg(src + j) : 0.f;
+    }
     uint4 v;
     v.x = pack_bf16x2(f[0], f[1]);
     v.y = pack_bf16x2(f[2], f[3]);
