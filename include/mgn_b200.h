@@ -268,6 +268,16 @@ int mgn_edge_block_bwd_tc(const void* efeat, const void* h1, const void* go1, co
  *   mgn_wgrad_tc  : out[128*n_blocks, 128] (fp32, row stride ld_out) = G[M, 128*n_blocks]^T X[M,128]
  * They replace the cuBLAS GEMMs autograd runs for the node-row column blocks of the first Linear
  * (mesh_graph_mlp.py:142-168 / the lin_src, lin_dst products of MeshGraphEdgeMLPSum :396-405). */
+/* K-looped tensor-core GEMM for MLP widths beyond 128 (GraphCast 512, AeroGraphNet 256; first layers with K = 768 / 1536):
+ *   out[M,N] (bf16, row stride ld_out) = act( x[M,K] (bf16, ld_x) Wb[N,K]^T (bf16 image, ld_w) + bias[N] (fp32, nullable) )
+ *   K % 64 == 0, N % 128 == 0, act = MGN_ACT_NONE | MGN_ACT_RELU; fp32 accumulation in TMEM, operands staged by TMA.
+ * mgn_cast_weight_bf16 makes the bf16 image of an fp32 nn.Linear weight [rows, cols] (row stride ld): transpose == 0 ->
+ * [rows, cols], transpose != 0 -> [cols, rows] (the operand of the data gradient g_x = g_y W).
+ * Replaces the cuBLAS GEMMs behind nn.Linear in MeshGraphMLP (mesh_graph_mlp.py:142-168, 200-203) for bf16 activations. */
+int mgn_cast_weight_bf16(const float* w, int64_t rows, int64_t cols, int64_t ld, void* out, int transpose,
+                         mgn_stream_t stream);
+int mgn_gemm_bf16_tc(const void* x, int64_t ld_x, int64_t M, int64_t K, const void* w_bf16, int64_t ld_w, int64_t N,
+                     const float* bias, int act, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
 /* out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); second-generation
  * pipeline (cp.async staging, coalesced stores).  Wider products are issued per 128-column block. */
 int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,

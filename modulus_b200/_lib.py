@@ -162,6 +162,8 @@ def algorithmic_work(name: str, a) -> "tuple[str, float] | None":
     if name == "mgn_node_gemm_tc":
         kb, M, nb, res = a[2], a[3], a[6], a[7]
         return "hbm", 2.0 * M * 128 * (kb + nb + (1 if res else 0))  # one pass over x, (residual,) out
+    if name == "mgn_gemm_bf16_tc":
+        return "tensor", 2.0 * a[2] * a[3] * a[6]
     if name == "mgn_linear128_tc":
         return "tensor", 2.0 * a[2] * 128 * 128
     if name == "mgn_wgrad_tc":

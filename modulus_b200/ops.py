@@ -303,11 +303,39 @@ class AggConcatFn(torch.autograd.Function):
 # ----------------------------------------------------------------------------------------
 # MeshGraphMLP on the fp32-accurate SIMT kernels (any width, fp32 or bf16 activations)
 # ----------------------------------------------------------------------------------------
+WIDE_TC = True  # bf16 MLPs whose widths are multiples of 128 (64 for the inner dimension) run their GEMMs on tcgen05
+
+
+def _wide_ok(x: Tensor, inner: int, width: int) -> bool:
+    return (WIDE_TC and x.dtype == torch.bfloat16 and inner % 64 == 0 and width % TC_HIDDEN == 0 and x.shape[0] > 0
+            and x.stride(1) == 1 and x.stride(0) % 8 == 0 and x.data_ptr() % 16 == 0)
+
+
+def gemm_bf16_tc(x: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, transpose_w: bool = False) -> Tensor:
+    """act(x W^T + bias) (transpose_w: x W) on the K-looped tensor-core GEMM (include/mgn_b200.h: mgn_gemm_bf16_tc); `w` is
+    the fp32 nn.Linear weight, converted to a bf16 image per call."""
+    rows, cols = w.shape
+    N, K = (cols, rows) if transpose_w else (rows, cols)
+    wb = torch.empty((N, K), dtype=torch.bfloat16, device=w.device)
+    call("mgn_cast_weight_bf16", _p(w), rows, cols, w.stride(0), _p(wb), int(transpose_w), _stream())
+    out = torch.empty((x.shape[0], N), dtype=torch.bfloat16, device=x.device)
+    call("mgn_gemm_bf16_tc", _p(x), x.stride(0), x.shape[0], K, _p(wb), K, N, _p(bias), act, _p(out), N,
+         _p(tc_status(x.device)), _stream())
+    return out
+
+
 def _linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int, want_pre: bool):
     M, K = x.shape
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"linear: input has {K} features but the weight expects {w.shape[1]}")
+    if _wide_ok(x, K, N):
+        if not want_pre and act in (ACT_IDS[None], ACT_IDS["relu"]):
+            return gemm_bf16_tc(x, w, b, act), None
+        pre = gemm_bf16_tc(x, w, b, ACT_IDS[None])  # other activations: one elementwise pass over the stored pre-activation
+        h = torch.empty_like(pre)
+        call("mgn_act_fwd", _dt(pre), _p(pre), act, _p(h), pre.numel(), _stream())
+        return h, (pre if want_pre else None)
     h = torch.empty((M, N), dtype=x.dtype, device=x.device)
     pre = torch.empty_like(h) if want_pre else None
     call("mgn_linear_fwd", _dt(x), _p(x), x.stride(0), M, K, _p(w), _p(b), N, act, _p(pre), _p(h), N, _stream())
@@ -328,6 +356,8 @@ def _linear_bwd_weight(g_y: Tensor, x: Tensor, N: int, K: int, want_bias: bool):
 def _linear_bwd_data(g_y: Tensor, w: Tensor) -> Tensor:
     M, N = g_y.shape
     K = w.shape[1]
+    if _wide_ok(g_y, N, K):
+        return gemm_bf16_tc(g_y, w, None, 0, transpose_w=True)
     g_x = torch.empty((M, K), dtype=g_y.dtype, device=g_y.device)
     call("mgn_linear_bwd_data", _dt(g_y), _p(g_y), M, N, _p(w), K, _p(g_x), K, _stream())
     return g_x

@@ -481,3 +481,80 @@ def test_node_block_fwd_keeps_h1_and_bwd_from_it_matches_recompute(N):
     assert rel_err(gw_b[:, :128], gw_a[:, :128]) < 5e-3
     for x, y in zip(gb, ga):
         assert rel_err(x, y) < 5e-3
+
+
+@pytest.mark.parametrize("M", [1, 129, 20000, 70001])
+@pytest.mark.parametrize("K,N,act", [(128, 128, "relu"), (256, 512, None), (1536, 512, "relu"), (768, 256, None), (64, 640, None)])
+def test_wide_gemm_tc(M, K, N, act):
+    """mgn_gemm_bf16_tc (K-looped tcgen05 GEMM for widths beyond 128) and the weight image it reads: out = act(x W^T + b),
+    and the data-gradient form x W (transposed image), against fp64 on the bf16-rounded operands."""
+    from modulus_b200 import ops
+    from modulus_b200._lib import ACT_IDS
+
+    g = torch.Generator().manual_seed(M + K + N)
+    x = bf(torch.randn(M, K, generator=g))
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1
+    ref = x.double() @ bf(w).double().T + b.double()
+    if act == "relu":
+        ref = torch.relu(ref)
+    out = ops.gemm_bf16_tc(x.to(DEV).bfloat16(), w.to(DEV), b.to(DEV), ACT_IDS[act])
+    out2 = ops.gemm_bf16_tc(x.to(DEV).bfloat16(), w.to(DEV), b.to(DEV), ACT_IDS[act])
+    ops.tc_check(DEV)
+    assert out.shape == (M, N) and rel_err(out.float(), ref) < 1e-2
+    assert torch.equal(out, out2)
+    if N % 64 == 0 and K % 128 == 0:  # g_x = g_y W
+        gy = bf(torch.randn(M, N, generator=g))
+        ref_gx = gy.double() @ bf(w).double()
+        gx = ops.gemm_bf16_tc(gy.to(DEV).bfloat16(), w.to(DEV), None, 0, transpose_w=True)
+        ops.tc_check(DEV)
+        assert gx.shape == (M, K) and rel_err(gx.float(), ref_gx) < 1e-2
+
+
+@pytest.mark.parametrize("hidden,act", [(256, "relu"), (512, "silu")])
+def test_wide_mlp_runs_on_the_tensor_core_gemm(hidden, act):
+    """A bf16 MeshGraphMLP with 256 / 512-wide layers (AeroGraphNet encoders, GraphCast processor): the Linear products run on
+    mgn_gemm_bf16_tc, outputs and all gradients agree with the fp32-accurate SIMT path at bf16 rounding level and with an fp64
+    reference that applies the same roundings."""
+    from modulus_b200 import ops
+    from modulus_b200.models.gnn_layers import MeshGraphMLP
+
+    torch.manual_seed(hidden)
+    M = 3000
+    mlp = MeshGraphMLP(3 * hidden, hidden, hidden, 2, activation_fn=torch.nn.SiLU() if act == "silu" else torch.nn.ReLU()).to(DEV)
+    x0 = torch.randn(M, 3 * hidden, device=DEV)
+    w_out = torch.randn(M, hidden, device=DEV)
+
+    def run(wide):
+        ops.WIDE_TC = wide
+        launched = {}
+        orig = ops.call
+
+        def spy(name, *a):
+            launched[name] = launched.get(name, 0) + 1
+            return orig(name, *a)
+
+        ops.call = spy
+        try:
+            mlp.zero_grad(set_to_none=True)
+            x = x0.clone().requires_grad_(True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                y = mlp(x)
+            (y.float() * w_out).sum().backward()
+        finally:
+            ops.call = orig
+            ops.WIDE_TC = True
+        return y.detach().float(), x.grad.float(), [p.grad.clone() for p in mlp.parameters()], launched
+
+    y_tc, gx_tc, gp_tc, l_tc = run(True)
+    y_s, gx_s, gp_s, l_s = run(False)
+    ops.tc_check(DEV)
+    assert l_tc.get("mgn_gemm_bf16_tc", 0) >= 5 and l_s.get("mgn_gemm_bf16_tc", 0) == 0
+    assert l_tc.get("mgn_linear_fwd", 0) == 0 and l_tc.get("mgn_linear_bwd_data", 0) == 0
+
+    def l2(a, b):
+        return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+    assert l2(y_tc, y_s) < 2e-2 and l2(gx_tc, gx_s) < 3e-2
+    for a, b in zip(gp_tc, gp_s):
+        assert l2(a, b) < 3e-2
