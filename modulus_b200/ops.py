@@ -342,8 +342,52 @@ def _linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int, want_pre: b
     return h, pre
 
 
+_ONES = {}
+
+
+def _ones_rows(M: int, device) -> Tensor:
+    """[>= M, 128] bf16 ones (bias gradient = g_y^T 1 on the tensor cores); grown on demand, one per device"""
+    key = torch.device(device).index or 0
+    t = _ONES.get(key)
+    if t is None or t.shape[0] < M:
+        t = _ONES[key] = torch.ones((max(M, 1), TC_HIDDEN), dtype=torch.bfloat16, device=device)
+    return t
+
+
+def _wgrad_wide(g_y: Tensor, x: Tensor, N: int, K: int, want_bias: bool):
+    """g_w[N, K] = g_y^T x and g_b = g_y^T 1 from mgn_wgrad_tc blocks: 128 columns of x against up to 384 columns of g_y per
+    launch, written straight into the [N, K] result (fp32, per-CTA partials summed in a fixed order)."""
+    M = x.shape[0]
+    dev = x.device
+    g_w = torch.empty((N, K), dtype=torch.float32, device=dev)
+    g_b = None
+    lib = _lib.load()
+    st = tc_status(dev)
+    ones = _ones_rows(M, dev) if want_bias else None
+    gb_blk = torch.empty((N, TC_HIDDEN), dtype=torch.float32, device=dev) if want_bias else None
+    for n0 in range(0, N, 3 * TC_HIDDEN):
+        jb = min(3, (N - n0) // TC_HIDDEN)
+        nbytes = lib.mgn_wgrad_tc_workspace_bytes(M, jb)
+        ws = _ws(nbytes, dev)
+        gp = g_y.data_ptr() + 2 * n0
+        for k0 in range(0, K, TC_HIDDEN):
+            call("mgn_wgrad_tc", gp, g_y.stride(0), jb, x.data_ptr() + 2 * k0, x.stride(0), M,
+                 g_w.data_ptr() + 4 * (n0 * K + k0), K, _p(ws), nbytes, _p(st), _stream())
+        if want_bias:
+            call("mgn_wgrad_tc", gp, g_y.stride(0), jb, _p(ones), ones.stride(0), M, gb_blk.data_ptr() + 4 * n0 * TC_HIDDEN,
+                 TC_HIDDEN, _p(ws), nbytes, _p(st), _stream())
+    if want_bias:
+        g_b = gb_blk[:, 0].contiguous()
+    return g_w, g_b
+
+
 def _linear_bwd_weight(g_y: Tensor, x: Tensor, N: int, K: int, want_bias: bool):
     M = x.shape[0]
+    if (WIDE_TC and g_y.dtype == torch.bfloat16 and x.dtype == torch.bfloat16 and N % TC_HIDDEN == 0 and K % TC_HIDDEN == 0
+            and M > 0 and g_y.stride(1) == 1 and x.stride(1) == 1 and g_y.stride(0) % 8 == 0 and x.stride(0) % 8 == 0
+            and g_y.data_ptr() % 16 == 0 and x.data_ptr() % 16 == 0):
+        _p(g_y), _p(x)  # device guard
+        return _wgrad_wide(g_y, x, N, K, want_bias)
     g_w = torch.empty((N, K), dtype=torch.float32, device=x.device)
     g_b = torch.empty((N,), dtype=torch.float32, device=x.device) if want_bias else None
     ws_bytes = _lib.load().mgn_linear_bwd_weight_workspace_bytes(M, N, K)
