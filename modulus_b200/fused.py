@@ -202,9 +202,14 @@ class FusedProcessorFn(torch.autograd.Function):
         src, dst = plan.src, plan.dst
         nfeat, efeat = nfeat.contiguous(), efeat.contiguous()
         saved: List[Tensor] = []
+        # node-level projection weights of ALL layers in three launches: Wp[l] = [W1e[:, H:2H]; W1e[:, 2H:3H]; W1n[:, H:2H]]
+        # ([3H, H]) and its transpose for the backward GEMM (instead of a cat + a transpose-copy per layer and direction)
+        w1e_all = torch.stack([params[16 * l] for l in range(L)])          # [L, H, 3H]
+        w1n_all = torch.stack([params[16 * l + 8] for l in range(L)])      # [L, H, 2H]
+        wp_all = torch.cat([w1e_all[:, :, H:2 * H], w1e_all[:, :, 2 * H:], w1n_all[:, :, H:]], dim=1).contiguous()
         for l in range(L):
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
-            wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
+            wp = wp_all[l]  # [3H, H]
             remote_only = halo is not None and halo.remote_only and KEEP_H1
             if remote_only:  # P with room for the halo rows of its source-projection columns behind the partition rows
                 P_ext = torch.empty((N + halo.halo_rows, 3 * H), dtype=BF16, device=nfeat.device)
@@ -265,7 +270,7 @@ class FusedProcessorFn(torch.autograd.Function):
             efeat, nfeat = efeat_new, nfeat_new
         ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1, ctx.mean = plan, L, eps, halo, KEEP_H1, mean
         ctx.remote_only = halo is not None and halo.remote_only and KEEP_H1
-        ctx.save_for_backward(*saved, *params)
+        ctx.save_for_backward(*saved, *params, wp_all)
         ctx.n_saved = len(saved)
         return nfeat
 
@@ -277,7 +282,8 @@ class FusedProcessorFn(torch.autograd.Function):
         E, N = plan.n_edges, plan.n_dst
         src, dst = plan.src, plan.dst
         saved = ctx.saved_tensors[:ctx.n_saved]
-        params = ctx.saved_tensors[ctx.n_saved:]
+        params = ctx.saved_tensors[ctx.n_saved:-1]
+        wpt_all = ctx.saved_tensors[-1].transpose(1, 2).contiguous()  # [L, H, 3H]: g_n += T Wp as x W^T with W = Wp^T
         dev = g_n.device
         g_n = g_n.contiguous().to(BF16)
         g_e: Optional[Tensor] = None
@@ -346,8 +352,7 @@ class FusedProcessorFn(torch.autograd.Function):
                 work, recv = halo.start_bwd(s_src)
                 ops.segment_sum(g_z1e, 0, H, plan.csc_offsets, None, N, out=T, out_col0=H)
                 halo.finish_bwd(work, recv, T, 0)
-            wp = torch.cat([ew[0][:, H:2 * H], ew[0][:, 2 * H:3 * H], nw[0][:, H:2 * H]], dim=0)  # [3H, H]
-            g_n = ops.linear_tc(T, wp.t().contiguous(), residual=g_n)  # g_n + T wp
+            g_n = ops.linear_tc(T, wpt_all[l], residual=g_n)  # g_n + T wp
             gwp = _node_wgrad(T, nfeat)  # [3H, H]
             gew1[:, H:2 * H] = gwp[:H]
             gew1[:, 2 * H:] = gwp[H:2 * H]
