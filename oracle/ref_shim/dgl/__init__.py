@@ -96,6 +96,9 @@ class DGLGraph:
         self._dst = self._dst.to(device)
         return self
 
+    def cpu(self):
+        return self.to("cpu")
+
     def adj_tensors(self, fmt):
         assert fmt == "csc"
         perm = torch.argsort(self._dst, stable=True)

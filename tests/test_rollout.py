@@ -88,3 +88,48 @@ def test_rollout_one_graph_launch_per_step_matches_eager(use_amp):
         ref = rollout(lambda x, e, g: O.meshgraphnet_forward(sd, x, e, src, dst, processor_size=2), None, x0,
                       mesh["edge_features"], mask, stats, T)
         assert torch.allclose(eager.cpu(), ref, rtol=1e-3, atol=1e-4)
+
+
+def _golden():
+    import os
+
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "ref_rollout.pt"), weights_only=True)
+
+
+def test_rollout_golden_of_the_unmodified_reference_loop_on_cpu():
+    """`ref_rollout.pt` is what the reference's own `MGNRollout.predict` stored in `self.pred` (tests/golden/
+    make_golden_rollout.py: unmodified script class, unmodified reference network and dataset statics).  Pins (1) the
+    oracle's restatement of the loop and (2) the product loop, both driving the oracle network with the golden's weights."""
+    from modulus_b200.rollout import rollout
+
+    g = _golden()
+    sd, T = g["state_dict"], g["steps"]
+    src, dst = O.coo_from_csc(g["offsets"], g["indices"])
+    net = lambda x, ef, graph=None: O.meshgraphnet_forward(sd, x, ef, src, dst, processor_size=2)  # noqa: E731
+    frames = [g["frames"][i] for i in range(T)]
+    ref = O.rollout_reference_loop(lambda x, ef: net(x, ef), frames, g["edge_features"], g["mask"], g["stats"])
+    for i in range(T):
+        assert torch.allclose(ref[i], g["pred"][i], rtol=1e-5, atol=1e-6), i
+    ours = rollout(net, None, frames[0], g["edge_features"], g["mask"], g["stats"], T)
+    assert torch.allclose(ours, g["pred"], rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_rollout_golden_of_the_unmodified_reference_loop_on_gpu():
+    """Product model (reference state_dict loaded as is) + device-resident loop against the same golden: six
+    autoregressive steps, fp32."""
+    from modulus_b200.models.gnn_layers import CuGraphCSC
+    from modulus_b200.models.meshgraphnet import MeshGraphNet
+    from modulus_b200.rollout import rollout
+
+    g = _golden()
+    model = MeshGraphNet(**g["kwargs"])
+    model.load_state_dict(g["state_dict"])
+    model = model.to(DEV).eval()
+    n = g["n_nodes"]
+    graph = CuGraphCSC(g["offsets"].to(DEV), g["indices"].to(DEV), n, n)
+    for use_graphs in (False, True):
+        out = rollout(model, graph, g["frames"][0].to(DEV), g["edge_features"].to(DEV), g["mask"], g["stats"], g["steps"],
+                      use_graphs=use_graphs)
+        torch.cuda.synchronize()
+        assert torch.allclose(out.cpu(), g["pred"], rtol=1e-4, atol=1e-4), (use_graphs, float((out.cpu() - g["pred"]).abs().max()))
