@@ -26,6 +26,7 @@
 #ifndef MGN_FWD3_PIPE16
 #define MGN_NO_PIPE16
 #endif
+#include <cstdlib>
 #include "mgn_common.cuh"
 #include "mgn_tc.cuh"
 #include "mgn_tile.cuh"
@@ -234,6 +235,16 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           MGN_PUBLISH_G();
         }
       }
+      // (debug builds: cycles of mover warp 1 per phase -> timing[16..21])
+      const bool tmv = p.timing != nullptr && blockIdx.x == 0 && warp == 1 && lane == 0;
+      long long tv[6] = {0, 0, 0, 0, 0, 0};
+      long long tvl = clock64();
+#define MGN_TV(i)                    \
+  if (tmv) {                         \
+    const long long t_ = clock64();  \
+    tv[i] += t_ - tvl;               \
+    tvl = t_;                        \
+  }
       for (int k = 0; k < n_my; ++k) {
         const long long row0 = row_first + k * stride;
         // (index loads of this tile's destination sums, issued before anything is waited for)
@@ -241,22 +252,31 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         if (a.seg_off != nullptr) ts = agg::tile_segments_begin(row0, a.M, a.seg_off, a.g2_idx, mt);
         if (k + 2 < n_my || (k + 1 < n_my && a.h1_out != nullptr)) {
           // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
+          MGN_TV(0);
           MGN_W(B_H1, (k + 1) & 1);
+          MGN_TV(1);
           if (a.h1_out != nullptr) store_rows(bG1, a.h1_out, kH, row0 + stride, a.M, mt);
+          MGN_TV(2);
           if (k + 2 < n_my) {
             stage_rows_async(bG1, g1, r_g1, row0 + 2 * stride, a.M, mt);
             if (k + 3 < n_my) fetch_row_ids(g1.idx, row0 + 3 * stride, a.M, rsub_m, r_g1);
             MGN_PUBLISH_G();
           }
+          MGN_TV(3);
         }
         // result tile k: destination sums from shared memory
         MGN_W(B_OUT + k % 3, (k / 3) & 1);
+        MGN_TV(4);
         if (a.seg_off != nullptr)
           agg::tile_segment_sum(bA0 + (k % 3) * 2 * kPB, row0, ts, a.seg_off, a.agg, a.ld_agg, a.agg_part, a.agg_part_v, mt,
                                 a.agg_row_base, a.agg_rec_base);
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_AGG + k % 3]);
+        MGN_TV(5);
       }
+      if (tmv)
+        for (int i = 0; i < 6; ++i) p.timing[16 + i] = tv[i];
+#undef MGN_TV
     } while (false);
 #undef MGN_W
   } else if (warp == kLoaderWarp) {
@@ -552,6 +572,9 @@ int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   fwd3::Params p{};
   p.a = args;
   p.timing = g_fwd3_timing;
+#ifdef MGN_DEBUG_HOOKS
+  if (getenv("MGN_FWD3_NO_AGG") != nullptr) p.a.seg_off = nullptr;  // timing experiment: destination sums left out
+#endif
   if (tma_make_rows_map(&p.m_a, args.a, args.M, 128, 128) != 0) return MGN_EINVAL;
   if (tma_make_rows_map(&p.m_out, args.out, args.M, 128, 128) != 0) return MGN_EINVAL;
   static PerDeviceFlag configured_flag;

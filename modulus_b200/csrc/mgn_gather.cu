@@ -3,8 +3,15 @@
 // CSC or CSR structure, and a generic indexed row gather.  All 128-bit vectorised with a
 // scalar fallback for feature widths that are not multiples of 16 bytes.
 #include "mgn_common.cuh"
+#include "mgn_tc.cuh"
+#include "mgn_tile.cuh"
 
 namespace mgn {
+using tile::f2_add;
+using tile::f2_from_bf16x2;
+using tile::f2_hi;
+using tile::f2_lo;
+using tile::f2_packu;
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -12,6 +19,41 @@ template <typename T>
 __device__ __forceinline__ uint4 ldg16(const T* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
+__device__ __forceinline__ uint4 ldg16(const char* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// fp32 sums of one 16-byte chunk, kept as packed pairs (FADD2: half the issue slots of scalar adds, same rounding)
+template <typename T> struct Acc16;
+template <> struct Acc16<bf16> {
+  uint64_t a[4];
+  __device__ __forceinline__ void zero() { a[0] = a[1] = a[2] = a[3] = 0ull; }
+  __device__ __forceinline__ void add(const uint4& r) {
+    a[0] = f2_add(a[0], f2_from_bf16x2(r.x));
+    a[1] = f2_add(a[1], f2_from_bf16x2(r.y));
+    a[2] = f2_add(a[2], f2_from_bf16x2(r.z));
+    a[3] = f2_add(a[3], f2_from_bf16x2(r.w));
+  }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = f2_lo(a[i]);
+      f[2 * i + 1] = f2_hi(a[i]);
+    }
+  }
+};
+template <> struct Acc16<float> {
+  uint64_t a[2];
+  __device__ __forceinline__ void zero() { a[0] = a[1] = 0ull; }
+  __device__ __forceinline__ void add(const uint4& r) {
+    a[0] = f2_add(a[0], f2_packu(r.x, r.y));
+    a[1] = f2_add(a[1], f2_packu(r.z, r.w));
+  }
+  __device__ __forceinline__ void get(float (&f)[4]) const {
+    f[0] = f2_lo(a[0]);
+    f[1] = f2_hi(a[0]);
+    f[2] = f2_lo(a[1]);
+    f[3] = f2_hi(a[1]);
+  }
+};
 
 // ---------------------------------------------------------------------------------------
 // concat_efeat forward: out[e] = [efeat[e] | src_feat[src[e]] | dst_feat[dst[e]]]
@@ -125,7 +167,10 @@ __global__ void sum_efeat_scalar_kernel(const T* __restrict__ efeat, const T* __
 // into an fp32 partial row, segment_long_combine_kernel adds the partials of a segment in chunk order.  Which run of
 // the worklist a segment lands in depends on timing, its value does not: results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
-constexpr int kLongSeg = 512;
+#ifndef MGN_LONG_SEG
+#define MGN_LONG_SEG 64
+#endif
+constexpr int kLongSeg = MGN_LONG_SEG;  // (A/B switch; modulus_b200/ops.py LONG_SEGMENT mirrors the default)
 constexpr int kLongChunk = 2048;
 struct LongEntry {
   int32_t seg, chunk, n_chunks, pad;
@@ -146,7 +191,7 @@ __device__ __forceinline__ void push_long_segment(const LongList& ll, int64_t s,
   for (int32_t k = 0; k < n; ++k) ll.entries[base + k] = LongEntry{static_cast<int32_t>(s), k, n, 0};
 }
 
-template <typename T>
+template <typename T, bool kEids>
 __global__ void __launch_bounds__(256)
 segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks,
                             const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids, LongList ll,
@@ -155,6 +200,8 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
   const int n_entries = min(*ll.counter, ll.capacity);
   __shared__ float red[8][32 * V];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const char* colp = reinterpret_cast<const char*>(in + in_col0);
+  const uint32_t ld_b = static_cast<uint32_t>(ld_in * static_cast<int64_t>(sizeof(T)));
   for (int en = blockIdx.x; en < n_entries; en += gridDim.x) {
     const LongEntry le = ll.entries[en];
     const int32_t b = __ldg(offsets + le.seg) + le.chunk * kLongChunk;
@@ -168,35 +215,31 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
     for (int cb = 0; cb < chunks; cb += G) {
       const int c = cb + cl;
       const bool active = c < chunks;
-      float acc[V];
-#pragma unroll
-      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      Acc16<T> acc;
+      acc.zero();
       const int rows_per_pass = 8 * R;  // 8 warps x R row slots
       const int n_fly = G == 32 ? 4 : 8;  // wide rows already fill the memory pipe with 4 loads per lane (measured)
       for (int32_t j = b + warp * R + sub; j < e; j += n_fly * rows_per_pass) {
-        uint4 v[8];
-        bool on[8];
+        // row ids first, then every row load back to back: a row id fetched between two row loads makes the next row
+        // load wait on the scoreboard the previous one holds, i.e. one round trip per row instead of one per pass
+        int32_t rr[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          on[u] = active && u < n_fly && (j + rows_per_pass * u < e);
-          if (on[u]) {
-            const int64_t row = eids ? __ldg(eids + j + rows_per_pass * u) : (j + rows_per_pass * u);
-            v[u] = ldg16(in + row * ld_in + in_col0 + static_cast<int64_t>(c) * V);
-          }
+          const int32_t jj = j + rows_per_pass * u;
+          rr[u] = (active && u < n_fly && jj < e) ? (kEids ? __ldg(eids + jj) : jj) : -1;
         }
+        uint4 v[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-          if (on[u]) {
-            Vec16<T> t;
-            t.raw = v[u];
-            float f[V];
-            t.unpack(f);
+          if (rr[u] >= 0) v[u] = ldg16(colp + static_cast<uint64_t>(static_cast<uint32_t>(rr[u])) * ld_b + static_cast<uint32_t>(c) * 16u);
 #pragma unroll
-            for (int k = 0; k < V; ++k) acc[k] += f[k];
-          }
+        for (int u = 0; u < 8; ++u)
+          if (rr[u] >= 0) acc.add(v[u]);
       }
+      float accf[V];
+      acc.get(accf);
 #pragma unroll
-      for (int k = 0; k < V; ++k) red[warp][lane * V + k] = acc[k];
+      for (int k = 0; k < V; ++k) red[warp][lane * V + k] = accf[k];
       __syncthreads();
       for (int i = threadIdx.x; i < G * V; i += blockDim.x) {
         const int col = cb * V + i;
@@ -212,21 +255,52 @@ segment_long_partial_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_
   }
 }
 
+// One CTA per hub: warp w adds the partial rows w, w + 8, w + 16, ... of the segment (four rows x up to four 32-column
+// groups in flight per lane: a hub of a million rows has 500 partial rows, which one thread per column would walk as
+// 500 dependent L2 round trips), the eight warp sums are then added in warp order.  Fixed assignment, fixed order.
 template <typename T>
 __global__ void __launch_bounds__(256)
 segment_long_combine_kernel(LongList ll, const float* __restrict__ partials, int64_t D, const int32_t* __restrict__ offsets,
                             T* __restrict__ out, int64_t ld_out, int64_t out_col0, int mean, int accumulate) {
   const int n_entries = min(*ll.counter, ll.capacity);
+  __shared__ float red[8][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int en = blockIdx.x; en < n_entries; en += gridDim.x) {
     const LongEntry le = ll.entries[en];
     if (le.chunk != 0) continue;
     const float scale = mean ? 1.f / static_cast<float>(max(offsets[le.seg + 1] - offsets[le.seg], 1)) : 1.f;
-    for (int col = threadIdx.x; col < D; col += blockDim.x) {
-      float sum = 0.f;
-      for (int k = 0; k < le.n_chunks; ++k) sum += partials[static_cast<int64_t>(en + k) * D + col];
-      T* o = out + static_cast<int64_t>(le.seg) * ld_out + out_col0 + col;
-      const float prev = accumulate ? Num<T>::to_f(*o) : 0.f;
-      *o = Num<T>::from_f(prev + sum * scale);
+    for (int64_t c0 = 0; c0 < D; c0 += 128) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* base = partials + static_cast<int64_t>(en) * D + c0 + lane;
+      int k = warp;
+      for (; k + 24 < le.n_chunks; k += 32) {
+        float v[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            v[u][j] = (c0 + lane + 32 * j < D) ? base[static_cast<int64_t>(k + 8 * u) * D + 32 * j] : 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] += v[u][j];
+      }
+      for (; k < le.n_chunks; k += 8)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c0 + lane + 32 * j < D) acc[j] += base[static_cast<int64_t>(k) * D + 32 * j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[warp][lane + 32 * j] = acc[j];
+      __syncthreads();
+      if (threadIdx.x < 128 && c0 + threadIdx.x < D) {
+        float sum = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+        T* o = out + static_cast<int64_t>(le.seg) * ld_out + out_col0 + c0 + threadIdx.x;
+        const float prev = accumulate ? Num<T>::to_f(*o) : 0.f;
+        *o = Num<T>::from_f(prev + sum * scale);
+      }
+      __syncthreads();
     }
   }
 }
@@ -455,6 +529,136 @@ segment_sum_batch_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// Segmented sum, third form (the default): G lanes own one SEGMENT (not one row group of a segment), so a warp
+// works on 32 / G segments side by side and nothing is exchanged between lanes -- the xor-shuffle tree and the
+// per-row-group bookkeeping of the forms above were a third of their instructions, and at mesh degrees (~6 rows of
+// 256 bytes) those kernels were bound by instruction issue and fetch, not by HBM (ncu: 50 % issue slots busy at 19 %
+// of the warps, `no_instruction` stalls; 1 M EMPTY segments cost 271 us).  Per lane S x U 16-byte loads are in flight
+// (the first U rows of S segments); bounds of the group after next and row ids of the next group are fetched while
+// the rows of this one are in flight.  Rows are added in ascending order with packed fp32 adds: bit-reproducible,
+// and the same order as the sums fused into the edge kernels (mgn_agg.cuh).  Column blocks beyond 32 chunks go to
+// blockIdx.y.  kEids is a template parameter: a possible row-id load between two row loads makes ptxas put both on
+// one scoreboard and the row loads then complete one at a time.
+// ---------------------------------------------------------------------------------------
+template <typename T, int G, int S, int U, bool kEids>
+__global__ void __launch_bounds__(256, 2)
+segment_sum_sub_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int chunks, const int32_t* __restrict__ offsets,
+                       const int32_t* __restrict__ eids, int64_t n_seg, T* __restrict__ out, int64_t ld_out,
+                       int64_t out_col0, int mean, int accumulate, LongList ll) {
+  constexpr int V = Num<T>::kVec;
+  constexpr int R = 32 / G;  // segments side by side in a warp
+#ifdef MGN_SEG_TAIL
+  constexpr int kTail = MGN_SEG_TAIL;
+#else
+  constexpr int kTail = 8;
+#endif
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / G;
+  const int c = static_cast<int>(blockIdx.y) * G + lane % G;
+  const bool active = c < chunks;
+  const bool leader = lane % G == 0 && blockIdx.y == 0;
+  const int64_t warp = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t stride = ((static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5) * (S * R);
+  const char* colp = reinterpret_cast<const char*>(in + in_col0 + static_cast<int64_t>(c) * V);
+  const uint32_t ld_b = static_cast<uint32_t>(ld_in * static_cast<int64_t>(sizeof(T)));
+  auto row_ptr = [&](int32_t row) { return colp + static_cast<uint64_t>(static_cast<uint32_t>(row)) * ld_b; };
+
+  // segment i of a group: s0 + i * R + sub (neighbouring lane groups write neighbouring output rows)
+  auto load_bounds = [&](int64_t s0, int32_t(&b)[S], int32_t(&e)[S]) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const int64_t s = s0 + i * R + sub;
+      const bool valid = s < n_seg && active;
+      b[i] = valid ? __ldg(offsets + s) : 0;
+      e[i] = valid ? __ldg(offsets + s + 1) : 0;
+    }
+  };
+  auto load_row_ids = [&](const int32_t(&b)[S], const int32_t(&e)[S], int32_t(&rows)[S][U]) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const bool skip = ll.counter != nullptr && e[i] - b[i] > kLongSeg;  // hubs: long-segment kernels
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int32_t j = b[i] + u;
+        rows[i][u] = (j < e[i] && !skip) ? (kEids ? __ldg(eids + j) : j) : -1;
+      }
+    }
+  };
+
+  int64_t s0 = warp * (S * R);
+  if (s0 >= n_seg) return;
+  int32_t b[S], e[S], rows[S][U], bn[S], en[S];
+  load_bounds(s0, b, e);
+  load_bounds(s0 + stride, bn, en);
+  load_row_ids(b, e, rows);
+  for (; s0 < n_seg; s0 += stride) {
+    uint4 v[S][U];
+#pragma unroll
+    for (int i = 0; i < S; ++i)
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rows[i][u] >= 0) v[i][u] = ldg16(row_ptr(rows[i][u]));
+    int32_t rows_n[S][U], bnn[S], enn[S];
+    load_row_ids(bn, en, rows_n);
+    load_bounds(s0 + 2 * stride, bnn, enn);
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const int64_t s = s0 + i * R + sub;
+      const int32_t len = e[i] - b[i];
+      const bool is_long = ll.counter != nullptr && len > kLongSeg;
+      if (is_long && leader) push_long_segment(ll, s, len);
+      Acc16<T> acc;
+      acc.zero();
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (rows[i][u] >= 0) acc.add(v[i][u]);
+      if (len > U && !is_long) {  // longer segments: kTail rows in flight
+        int32_t j = b[i] + U;
+        for (; j + kTail - 1 < e[i]; j += kTail) {
+          int32_t rr[kTail];
+#pragma unroll
+          for (int u = 0; u < kTail; ++u) rr[u] = kEids ? __ldg(eids + j + u) : j + u;
+          uint4 vv[kTail];
+#pragma unroll
+          for (int u = 0; u < kTail; ++u) vv[u] = ldg16(row_ptr(rr[u]));
+#pragma unroll
+          for (int u = 0; u < kTail; ++u) acc.add(vv[u]);
+        }
+        for (; j < e[i]; ++j) acc.add(ldg16(row_ptr(kEids ? __ldg(eids + j) : j)));
+      }
+      if (active && s < n_seg && !is_long) {
+        float f[V];
+        acc.get(f);
+        const float scale = mean ? 1.f / static_cast<float>(max(len, 1)) : 1.f;
+        T* o = out + s * ld_out + out_col0 + static_cast<int64_t>(c) * V;
+        Vec16<T> t;
+        if (accumulate) {
+          t.raw = *reinterpret_cast<const uint4*>(o);
+          float p[V];
+          t.unpack(p);
+#pragma unroll
+          for (int k = 0; k < V; ++k) f[k] = p[k] + f[k] * scale;
+        } else if (mean) {
+#pragma unroll
+          for (int k = 0; k < V; ++k) f[k] *= scale;
+        }
+        t.pack(f);
+        *reinterpret_cast<uint4*>(o) = t.raw;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      b[i] = bn[i];
+      e[i] = en[i];
+      bn[i] = bnn[i];
+      en[i] = enn[i];
+#pragma unroll
+      for (int u = 0; u < U; ++u) rows[i][u] = rows_n[i][u];
+    }
+  }
+}
+
 template <typename T>
 __global__ void segment_sum_scalar_kernel(const T* __restrict__ in, int64_t ld_in, int64_t in_col0, int D,
                                           const int32_t* __restrict__ offsets, const int32_t* __restrict__ eids,
@@ -597,6 +801,7 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
       cudaError_t ce = cudaMemsetAsync(ll.counter, 0, 16, st);
       if (ce != cudaSuccess) return static_cast<int>(ce);
     }
+#ifdef MGN_SEG_OLD  // A/B: the row-group forms
 #define MGN_SEG(G)                                                                                     \
   segment_sum_vec_kernel<T, G><<<grid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, n_seg, \
                                                      o_, ld_out, out_col0, mean, accumulate, ll)
@@ -608,10 +813,32 @@ static int segment_sum_t(const void* in, int64_t ld_in, int64_t in_col0, int64_t
     else if (chunks <= 16) MGN_SEG(16);
     else MGN_SEG(32);
 #undef MGN_SEG
+#else
+    if (ld_in * static_cast<int64_t>(sizeof(T)) >= (int64_t{1} << 32)) return MGN_EINVAL;
+    constexpr int kS = 2, kU = 6;
+#define MGN_SUB(G)                                                                                              \
+  do {                                                                                                          \
+    const int64_t warps = (n_seg + kS * (32 / G) - 1) / (kS * (32 / G));                                        \
+    const dim3 grid_(grid_for(warps * 32), (chunks + G - 1) / G);                                               \
+    if (eids)                                                                                                   \
+      segment_sum_sub_kernel<T, G, kS, kU, true><<<grid_, 256, 0, MGN_ST(st)>>>(                                \
+          i_, ld_in, in_col0, chunks, offsets, eids, n_seg, o_, ld_out, out_col0, mean, accumulate, ll);        \
+    else                                                                                                        \
+      segment_sum_sub_kernel<T, G, kS, kU, false><<<grid_, 256, 0, MGN_ST(st)>>>(                               \
+          i_, ld_in, in_col0, chunks, offsets, eids, n_seg, o_, ld_out, out_col0, mean, accumulate, ll);        \
+  } while (0)
+    if (chunks <= 4) MGN_SUB(4);
+    else if (chunks <= 8) MGN_SUB(8);
+    else if (chunks <= 16) MGN_SUB(16);
+    else MGN_SUB(32);
+#undef MGN_SUB
+    (void)grid;
+#endif
     int rc = mgn_launch_status();
     if (rc != MGN_OK || ll.counter == nullptr) return rc;
     const int lgrid = ll.capacity < 4 * num_sms() ? ll.capacity : 4 * num_sms();
-    segment_long_partial_kernel<T><<<lgrid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, ll, partials, D);
+    if (eids) segment_long_partial_kernel<T, true><<<lgrid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, ll, partials, D);
+    else segment_long_partial_kernel<T, false><<<lgrid, 256, 0, MGN_ST(st)>>>(i_, ld_in, in_col0, chunks, offsets, eids, ll, partials, D);
     segment_long_combine_kernel<T><<<lgrid, 256, 0, MGN_ST(st)>>>(ll, partials, D, offsets, o_, ld_out, out_col0, mean,
                                                              accumulate);
   } else {
@@ -688,7 +915,7 @@ extern "C" int mgn_segment_sum(int dtype, const void* in, int64_t ld_in, int64_t
   return MGN_EINVAL;
 }
 
-/* mgn_segment_sum with hub handling: segments longer than 512 rows are split into 2048-row chunks summed by whole
+/* mgn_segment_sum with hub handling: segments longer than 256 rows are split into 2048-row chunks summed by whole
  * CTAs and combined in chunk order (skewed-degree graphs; same results run to run).  n_rows = rows of `in` that the
  * offsets cover (sizes the worklist), workspace >= mgn_segment_sum_workspace_bytes(n_rows, D). */
 extern "C" size_t mgn_segment_sum_workspace_bytes(int64_t n_rows, int64_t D) {

@@ -137,7 +137,7 @@ class GraphPlan:
 # ----------------------------------------------------------------------------------------
 # raw wrappers
 # ----------------------------------------------------------------------------------------
-LONG_SEGMENT = 512  # rows; csrc/mgn_gather.cu: kLongSeg
+LONG_SEGMENT = 64  # rows; csrc/mgn_gather.cu: kLongSeg
 _max_seg_cache: dict = {}
 
 

@@ -169,3 +169,27 @@ _lib.call("mgn_debug_set_fwd2_timing", None)
 t = tbuf.cpu()
 print("FWD3 + h1 store, epilogue: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :", [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
 print("FWD3 + h1 store, MMA thread: wait E2 | issue M3 | wait E1' | issue M2' | wait E3prev+A'' | issue M1'' :", [int(v) // per_cta for v in t[8:14].tolist()])
+print("FWD3 + h1 store, mover warp 1: idx loads | wait E1' | h1 store | gather + publish | wait E3 | dst sums :", [int(v) // per_cta for v in t[16:22].tolist()], "total", int(t[16:22].sum()) // per_cta)
+
+# experiment (debug builds only): the same launch without the fused destination sums
+os.environ["MGN_FWD3_NO_AGG"] = "1"
+for name, fn in (("eblk fwd3 (no agg)", eblk), ("eblk fwd3+h1 (no agg)", eblk_h1)):
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for e0, e1 in evs:
+        e0.record()
+        fn()
+        e1.record()
+    torch.cuda.synchronize()
+    ts = sorted(e0.elapsed_time(e1) for e0, e1 in evs)
+    print(f"{name:12s} N={N} E={E}: {ts[len(ts) // 2]:.3f} ms median, {ts[0]:.3f} min of {reps}", flush=True)
+tbuf.zero_()
+_lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
+eblk_h1(); torch.cuda.synchronize()
+_lib.call("mgn_debug_set_fwd2_timing", None)
+t = tbuf.cpu()
+print("FWD3 + h1 store, NO dst sums, epilogue: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :", [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
+print("FWD3 + h1 store, NO dst sums, mover warp 1: idx loads | wait E1' | h1 store | gather + publish | wait E3 | dst sums :", [int(v) // per_cta for v in t[16:22].tolist()], "total", int(t[16:22].sum()) // per_cta)
+del os.environ["MGN_FWD3_NO_AGG"]
