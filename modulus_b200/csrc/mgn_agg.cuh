@@ -16,6 +16,11 @@ namespace agg {
 
 using namespace tile;
 constexpr int kH = 128;
+#ifdef MGN_AGG_FLY
+constexpr int kAggFly = MGN_AGG_FLY;  // (A/B switch)
+#else
+constexpr int kAggFly = 4;
+#endif
 
 static inline size_t workspace_bytes(int64_t M) {
   if (M <= 0) return 0;
@@ -36,19 +41,29 @@ struct TileSegs {
   long long ob, oe;  // bounds of this thread's first segment (v_first + segment lane), if it has one
 };
 
-__device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long long M, const int32_t* __restrict__ seg_off,
-                                                        const int32_t* __restrict__ seg_id, int mt) {
+// stage A: first / last destination of the tile; stage B (needs A's values): bounds of this thread's first segment.  A
+// caller that runs A one tile before B never waits for the first round trip (the warp issues in order: B's address
+// arithmetic would otherwise stall on A's loads).
+__device__ __forceinline__ TileSegs tile_segments_ids(long long row0, long long M, const int32_t* __restrict__ seg_id) {
   TileSegs ts;
   const long long rem = M - row0;
   ts.nrows = rem < kRows ? static_cast<int>(rem) : kRows;
   ts.v_first = __ldg(seg_id + row0);
   ts.v_last = __ldg(seg_id + row0 + ts.nrows - 1);
-  const int v = ts.v_first + (mt >> 4);
   ts.ob = ts.oe = 0;
+  return ts;
+}
+__device__ __forceinline__ void tile_segments_bounds(TileSegs& ts, const int32_t* __restrict__ seg_off, int mt) {
+  const int v = ts.v_first + (mt >> 4);
   if (v <= ts.v_last) {
     ts.ob = __ldg(seg_off + v);
     ts.oe = __ldg(seg_off + v + 1);
   }
+}
+__device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long long M, const int32_t* __restrict__ seg_off,
+                                                        const int32_t* __restrict__ seg_id, int mt) {
+  TileSegs ts = tile_segments_ids(row0, M, seg_id);
+  tile_segments_bounds(ts, seg_off, mt);
   return ts;
 }
 
@@ -70,12 +85,20 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
       oe = __ldg(seg_off + v + 9);
     }
     uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 8 fp32 column sums as packed pairs (FADD2)
-    for (int r = b; r < e; ++r) {
-      const uint4 t = *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7));
-      acc[0] = f2_add(acc[0], f2_from_bf16x2(t.x));
-      acc[1] = f2_add(acc[1], f2_from_bf16x2(t.y));
-      acc[2] = f2_add(acc[2], f2_from_bf16x2(t.z));
-      acc[3] = f2_add(acc[3], f2_from_bf16x2(t.w));
+    // kAggFly rows of the segment in flight (a mesh segment is ~6 rows: two round trips to shared memory instead of six
+    // dependent ones); rows past the end read as +0, which leaves the sum -- taken in ascending row order -- unchanged
+    for (int r = b; r < e; r += kAggFly) {
+      uint4 t[kAggFly];
+#pragma unroll
+      for (int u = 0; u < kAggFly; ++u)
+        t[u] = r + u < e ? *reinterpret_cast<const uint4*>(col + sw128_offset(r + u, chunk & 7)) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int u = 0; u < kAggFly; ++u) {
+        acc[0] = f2_add(acc[0], f2_from_bf16x2(t[u].x));
+        acc[1] = f2_add(acc[1], f2_from_bf16x2(t[u].y));
+        acc[2] = f2_add(acc[2], f2_from_bf16x2(t[u].z));
+        acc[3] = f2_add(acc[3], f2_from_bf16x2(t[u].w));
+      }
     }
     if (v == v_first || v == v_last) {
       const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);

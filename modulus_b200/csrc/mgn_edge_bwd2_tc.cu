@@ -91,7 +91,8 @@ struct Smem {
 // tile staged for the layer-1 weight gradient (loader, tx).  B_MMA + k: GEMM2, GEMM3, dgrad3, dgrad2, dgrad1, wgrad1
 // complete; B_W3 / B_W2: weight-gradient MMAs of layer 3 / 2 complete.  B_E + k: E2, E3, E4, E5, E6 complete.
 // B_CS + k: column sums after E3 / E4 / E5 done.  B_ST / B_XF: the g_z1 / g_A result tile has left its buffer.
-enum { B_H1L = 0, B_GO = 1, B_A2 = 2, B_MMA = 3, B_W3 = 9, B_W2 = 10, B_E = 11, B_CS = 16, B_ST = 19, B_XF = 20, B_NUM = 21 };
+// B_DR: the last pass has READ the accumulator (its arithmetic and stores still run while the next tile's GEMM2 starts).
+enum { B_H1L = 0, B_GO = 1, B_A2 = 2, B_MMA = 3, B_W3 = 9, B_W2 = 10, B_E = 11, B_CS = 16, B_ST = 19, B_XF = 20, B_DR = 21, B_NUM = 22 };
 enum { R_A = -1, R_X = 0, R_H1 = 1, R_H2 = 2 };
 
 __device__ __forceinline__ bool bf_pos_lo(uint32_t w) { return static_cast<int32_t>(w << 16) > 0; }
@@ -155,6 +156,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
     for (int b = B_CS; b < B_ST; ++b) mbar_init(&bars[b], 4);
     mbar_init(&bars[B_ST], 1);
     mbar_init(&bars[B_XF], 1);
+    mbar_init(&bars[B_DR], kEpiWarps);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 512);
@@ -164,6 +166,13 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tAcc = tmem, tW1 = tmem + 128, tW2 = tmem + 256, tW3 = tmem + 384;
+#ifdef MGN_DEBUG_HOOKS
+  long long dbg_c0 = 0, dbg_g0 = 0;  // per-CTA cycles and nanoseconds of the tile loop -> timing[96 + 4 * cta ...]
+  if (p.timing != nullptr && tid == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+  }
+#endif
 
   const long long n_tiles = (p.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
@@ -200,7 +209,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
   }
         // ---- GEMM2: acc = h1 W2^T   (h1 streamed in during the previous tile)
         MGN_W(B_H1L, par);
-        if (it > 0) MGN_W(B_E + 4, par ^ 1);  // the previous tile's last epilogue has drained the accumulator
+        if (it > 0) MGN_W(B_DR, par ^ 1);  // the previous tile's last epilogue pass has read the accumulator
         MGN_T(0);
         tc_fence_after_sync();
 #pragma unroll
@@ -713,6 +722,11 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
           uint32_t go[16];
           if (kAddGout) row_load32p(bX, row, c0 + 32 * hh, go);
           tmem_ld_wait();
+          if (hh == 1) {  // accumulator drained: the next tile's GEMM2 may overwrite it
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[B_DR]);
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             go[j] = kAddGout ? f2_to_bf16x2(f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_from_bf16x2(go[j])))
@@ -729,6 +743,9 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
                              : pack_bf16x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
           row_store16p(bX, row, c0 + 16 * i, go);
         });
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_DR]);
 #endif
       }
       MGN_EPI_DONE(B_E + 4);
@@ -749,6 +766,15 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
+#ifdef MGN_DEBUG_HOOKS
+  if (p.timing != nullptr && tid == 0) {
+    long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    p.timing[96 + 4 * blockIdx.x] = clock64() - dbg_c0;
+    p.timing[96 + 4 * blockIdx.x + 1] = g1 - dbg_g0;
+    p.timing[96 + 4 * blockIdx.x + 2] = n_my;
+  }
+#endif
 
   // ---------------- write this CTA's partial gradients ----------------
   float* part = p.partials + static_cast<long long>(blockIdx.x) * p.part_floats;

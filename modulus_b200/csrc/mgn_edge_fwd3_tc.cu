@@ -113,6 +113,13 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem = *tmem_slot;
+#ifdef MGN_DEBUG_HOOKS
+  long long dbg_c0 = 0, dbg_g0 = 0;  // per-CTA cycles and nanoseconds of the tile loop -> timing[96 + 4 * cta ...]
+  if (p.timing != nullptr && tid == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_g0));
+  }
+#endif
   // TMEM: three accumulators (tile % 3), two hidden-activation slots of 64 packed columns (tile % 2)
   const long long n_tiles = (a.M + kRows - 1) / kRows;
   const int n_my = static_cast<int>((n_tiles > blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0);
@@ -236,6 +243,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         }
       }
       // (debug builds: cycles of mover warp 1 per phase -> timing[16..21])
+#ifdef MGN_DEBUG_HOOKS
       const bool tmv = p.timing != nullptr && blockIdx.x == 0 && warp == 1 && lane == 0;
       long long tv[6] = {0, 0, 0, 0, 0, 0};
       long long tvl = clock64();
@@ -245,11 +253,24 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
     tv[i] += t_ - tvl;               \
     tvl = t_;                        \
   }
+#else
+#define MGN_TV(i)
+#endif
+      // index loads of a tile's destination sums (two dependent round trips): destination ids two tiles ahead, segment
+      // bounds one tile ahead
+      agg::TileSegs ts_next{}, ts_ids{};
+      if (a.seg_off != nullptr && n_my > 0) {
+        ts_next = agg::tile_segments_begin(row_first, a.M, a.seg_off, a.g2_idx, mt);
+        if (n_my > 1) ts_ids = agg::tile_segments_ids(row_first + stride, a.M, a.g2_idx);
+      }
       for (int k = 0; k < n_my; ++k) {
         const long long row0 = row_first + k * stride;
-        // (index loads of this tile's destination sums, issued before anything is waited for)
-        agg::TileSegs ts{};
-        if (a.seg_off != nullptr) ts = agg::tile_segments_begin(row0, a.M, a.seg_off, a.g2_idx, mt);
+        const agg::TileSegs ts = ts_next;
+        if (a.seg_off != nullptr && k + 1 < n_my) {
+          ts_next = ts_ids;
+          agg::tile_segments_bounds(ts_next, a.seg_off, mt);
+          if (k + 2 < n_my) ts_ids = agg::tile_segments_ids(row0 + 2 * stride, a.M, a.g2_idx);
+        }
         if (k + 2 < n_my || (k + 1 < n_my && a.h1_out != nullptr)) {
           // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
           MGN_TV(0);
@@ -274,8 +295,10 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         if (lane == 0) mbar_arrive(&bars[B_AGG + k % 3]);
         MGN_TV(5);
       }
+#ifdef MGN_DEBUG_HOOKS
       if (tmv)
         for (int i = 0; i < 6; ++i) p.timing[16 + i] = tv[i];
+#endif
 #undef MGN_TV
     } while (false);
 #undef MGN_W
@@ -402,11 +425,27 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
     tm[i] += t_ - tlast;              \
     tlast = t_;                       \
   }
+    // MGN_FWD3_PF: the row read by g2_fetch at the top of period k + 1 is prefetched at the top of period k (1: into L1, 2: into
+    // L2), so the fetch itself -- covered only by the short E2 pass -- no longer pays an HBM round trip
+#ifndef MGN_FWD3_PF
+#define MGN_FWD3_PF 1
+#endif
+    auto g2_prefetch = [&](int32_t r) {
+      const bf16* src = a.g2_tab + static_cast<long long>(r) * a.g2_ld + a.g2_col0 + c0;
+#if MGN_FWD3_PF == 1
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+#elif MGN_FWD3_PF == 2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+#else
+      (void)src;
+#endif
+    };
     do {
-      int32_t g2r = 0;
+      int32_t g2r = 0, g2r2 = 0;
       if (n_my > 0) {
         g2_fetch(g2_row(0));
         if (n_my > 1) g2r = g2_row(1);
+        if (n_my > 2) g2r2 = g2_row(2);
         if (!__all_sync(0xffffffffu, wait_clk(&bars[B_M1], 0) && wait_clk(&bars[B_G], 0))) { timed_out = true; break; }
         tc_fence_after_sync();
         e1(0);
@@ -420,7 +459,9 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         // the next tile's destination projections, in flight across E2(k)
         if (k + 1 < n_my) {
           g2_fetch(g2r);
-          if (k + 2 < n_my) g2r = g2_row(k + 2);
+          g2r = g2r2;
+          if (k + 2 < n_my) g2_prefetch(g2r);
+          if (k + 3 < n_my) g2r2 = g2_row(k + 3);
         }
         // ---- E2(k): h2 = relu(acc + b2) -> TMEM
         MGN_T(5);
@@ -556,6 +597,15 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
   if (timed_out && a.status != nullptr) atomicOr(a.status, 1);
   tc_fence_before_sync();
   __syncthreads();
+#ifdef MGN_DEBUG_HOOKS
+  if (p.timing != nullptr && tid == 0) {
+    long long g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    p.timing[96 + 4 * blockIdx.x] = clock64() - dbg_c0;
+    p.timing[96 + 4 * blockIdx.x + 1] = g1 - dbg_g0;
+    p.timing[96 + 4 * blockIdx.x + 2] = n_my;
+  }
+#endif
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

@@ -107,11 +107,23 @@ from modulus_b200 import _lib
 if not _lib.has_debug_hooks():
     print("(no phase breakdown: build with MGN_NVCC_EXTRA=-DMGN_DEBUG_HOOKS for it)")
     sys.exit(0)
-tbuf = torch.zeros(96, dtype=torch.int64, device=DEV)
+tbuf = torch.zeros(96 + 4 * 148, dtype=torch.int64, device=DEV)
+
+def per_cta_clock(t, label):
+    # (cycles, ns, tiles) of every CTA's tile loop -> effective SM clock and spread across CTAs
+    c = t[96:].view(-1, 4).double()
+    c = c[c[:, 2] > 0]
+    if c.numel() == 0:
+        return
+    cyc_tile = c[:, 0] / c[:, 2]
+    ghz = c[:, 0] / c[:, 1].clamp(min=1)
+    print(f"{label}: per-CTA cycles/tile min {cyc_tile.min():.0f} median {cyc_tile.median():.0f} max {cyc_tile.max():.0f}; "
+          f"loop time us min {c[:, 1].min() / 1e3:.0f} max {c[:, 1].max() / 1e3:.0f}; SM clock GHz min {ghz.min():.3f} median {ghz.median():.3f} max {ghz.max():.3f}")
+
 _lib.call("mgn_debug_set_bwd_timing", tbuf.data_ptr())
 bwd(); torch.cuda.synchronize()
 _lib.call("mgn_debug_set_bwd_timing", None)
-t = tbuf.cpu().view(3, 32)
+t = tbuf.cpu()[:96].view(3, 32)
 n_tiles = (E + 127) // 128
 per_cta = -(-n_tiles // 148)
 names = {0: "MMA  : wA+E6prev | g1 | wE1 | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 | wE5 | dgrad1+wA2 | wgrad1",
@@ -125,7 +137,7 @@ tbuf.zero_()
 _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
 fwd2(); torch.cuda.synchronize()
 _lib.call("mgn_debug_set_fwd2_timing", None)
-t = tbuf.cpu().view(3, 32)
+t = tbuf.cpu()[:96].view(3, 32)
 print("FWD2 kernel, CTA 0, cycles per tile")
 print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // per_cta for v in t[0, :5].tolist()], "total", int(t[0].sum()) // per_cta)
 print(" MOVER : issue next A | wait H1 | wait OUT (incl issue G) | store+ids | wait cp+sync :", [int(v) // per_cta for v in t[1, :5].tolist()], "total", int(t[1].sum()) // per_cta)
@@ -135,7 +147,7 @@ tbuf.zero_()
 _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
 nodefwd(); torch.cuda.synchronize()
 _lib.call("mgn_debug_set_fwd2_timing", None)
-t = tbuf.cpu().view(3, 32)
+t = tbuf.cpu()[:96].view(3, 32)
 pc_n = -(-((N + 127) // 128) // 148)
 print("FWD2 kernel NODE form, CTA 0, cycles per tile")
 print(" MMA   : wait IN+OUT | issue1 | wait H1 | wait H2 (incl issue2) | issue3 :", [int(v) // pc_n for v in t[0, :5].tolist()], "total", int(t[0].sum()) // pc_n)
@@ -156,11 +168,19 @@ tbuf.zero_()
 _lib.call("mgn_debug_set_edge_bwd2_timing", tbuf.data_ptr())
 bwd2(); torch.cuda.synchronize()
 _lib.call("mgn_debug_set_edge_bwd2_timing", None)
-t = tbuf.cpu().view(3, 32)
+t = tbuf.cpu()[:96].view(3, 32)
 print("BWD2 (from h1) kernel, CTA 0, cycles per tile")
 print(" MMA   : wH1+E6prev | g2 | wE2 | g3 | wE3 | L3 | wE4 | L2 | wE5 | dgrad1 | wgrad1 :", [int(v) // per_cta for v in t[0, :11].tolist()], "total", int(t[0].sum()) // per_cta)
 print(" LOADER: top | wW3+CS0 | wW2+CS1 | wE5 | st gz1 | wMMA7+CS2 | wE6 | st gA :", [int(v) // per_cta for v in t[1, :8].tolist()], "total", int(t[1].sum()) // per_cta)
 print(" EPI   : wMMA2+XF | E2 | wMMA3 | wGO | E3 | E4 | E5 | E6 :", [int(v) // per_cta for v in t[2, :8].tolist()], "total", int(t[2].sum()) // per_cta)
+per_cta_clock(tbuf.cpu(), "BWD2 (from h1), single launch")
+tbuf.zero_()
+_lib.call("mgn_debug_set_edge_bwd2_timing", tbuf.data_ptr())
+for _ in range(30):
+    bwd2()
+torch.cuda.synchronize()
+_lib.call("mgn_debug_set_edge_bwd2_timing", None)
+per_cta_clock(tbuf.cpu(), "BWD2 (from h1), 30th back-to-back launch")
 
 tbuf.zero_()
 _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
@@ -169,6 +189,7 @@ _lib.call("mgn_debug_set_fwd2_timing", None)
 t = tbuf.cpu()
 print("FWD3 + h1 store, epilogue: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :", [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
 print("FWD3 + h1 store, MMA thread: wait E2 | issue M3 | wait E1' | issue M2' | wait E3prev+A'' | issue M1'' :", [int(v) // per_cta for v in t[8:14].tolist()])
+per_cta_clock(t, "FWD3 + h1 store")
 print("FWD3 + h1 store, mover warp 1: idx loads | wait E1' | h1 store | gather + publish | wait E3 | dst sums :", [int(v) // per_cta for v in t[16:22].tolist()], "total", int(t[16:22].sum()) // per_cta)
 
 # experiment (debug builds only): the same launch without the fused destination sums
@@ -190,6 +211,7 @@ _lib.call("mgn_debug_set_fwd2_timing", tbuf.data_ptr())
 eblk_h1(); torch.cuda.synchronize()
 _lib.call("mgn_debug_set_fwd2_timing", None)
 t = tbuf.cpu()
+per_cta_clock(t, "FWD3 + h1 store, NO dst sums")
 print("FWD3 + h1 store, NO dst sums, epilogue: wait M2 | E2 | wait M1+G | E1 | wait M3 | E3 :", [int(v) // per_cta for v in t[:6].tolist()], "total", int(t[:6].sum()) // per_cta)
 print("FWD3 + h1 store, NO dst sums, mover warp 1: idx loads | wait E1' | h1 store | gather + publish | wait E3 | dst sums :", [int(v) // per_cta for v in t[16:22].tolist()], "total", int(t[16:22].sum()) // per_cta)
 del os.environ["MGN_FWD3_NO_AGG"]
