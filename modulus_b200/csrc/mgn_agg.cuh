@@ -21,6 +21,11 @@ constexpr int kAggFly = MGN_AGG_FLY;  // (A/B switch)
 #else
 constexpr int kAggFly = 4;
 #endif
+#ifdef MGN_AGG_SIDE
+constexpr int kAggSide = MGN_AGG_SIDE;  // (A/B switch)
+#else
+constexpr int kAggSide = 2;  // rows in flight per segment while kSegAhead segments are summed side by side
+#endif
 
 static inline size_t workspace_bytes(int64_t M) {
   if (M <= 0) return 0;
@@ -33,31 +38,41 @@ static inline size_t workspace_bytes(int64_t M) {
 // (seg_off holds global positions), rec_base = index of its first tile's records (several launches over consecutive
 // row ranges share one record array in row order and one fix-up).
 //
-// The index loads (first / last destination of the tile, then the bounds of this thread's first segment) are a chain of
-// two L2 round trips: `tile_segments_begin` issues them EARLY -- the callers run it before they wait for the tile --
-// and the loop fetches the bounds of its next segment before it sums the current one.
+// The index loads (first / last destination of the tile, then the bounds of this thread's segments) are a chain of
+// two L2 round trips: `tile_segments_begin` issues them EARLY -- the callers run it before they wait for the tile.
+#ifdef MGN_SEG_AHEAD
+constexpr int kSegAhead = MGN_SEG_AHEAD;  // (A/B switch)
+#else
+constexpr int kSegAhead = 3;
+#endif
+// rounds of segment bounds fetched ahead per thread (a mesh tile has ~22 segments = 3 rounds of 8)
 struct TileSegs {
   int v_first, v_last, nrows;
-  long long ob, oe;  // bounds of this thread's first segment (v_first + segment lane), if it has one
+  int32_t ob[kSegAhead], oe[kSegAhead];  // bounds of this thread's first segments: v_first + segment lane + 8 j
 };
 
-// stage A: first / last destination of the tile; stage B (needs A's values): bounds of this thread's first segment.  A
+// stage A: first / last destination of the tile; stage B (needs A's values): bounds of this thread's segments.  A
 // caller that runs A one tile before B never waits for the first round trip (the warp issues in order: B's address
-// arithmetic would otherwise stall on A's loads).
+// arithmetic would otherwise stall on A's loads), and fetching the bounds of ALL rounds up front takes the third
+// round trip -- once per round in the summing loop -- off the loop.
 __device__ __forceinline__ TileSegs tile_segments_ids(long long row0, long long M, const int32_t* __restrict__ seg_id) {
   TileSegs ts;
   const long long rem = M - row0;
   ts.nrows = rem < kRows ? static_cast<int>(rem) : kRows;
   ts.v_first = __ldg(seg_id + row0);
   ts.v_last = __ldg(seg_id + row0 + ts.nrows - 1);
-  ts.ob = ts.oe = 0;
+#pragma unroll
+  for (int j = 0; j < kSegAhead; ++j) ts.ob[j] = ts.oe[j] = 0;
   return ts;
 }
 __device__ __forceinline__ void tile_segments_bounds(TileSegs& ts, const int32_t* __restrict__ seg_off, int mt) {
-  const int v = ts.v_first + (mt >> 4);
-  if (v <= ts.v_last) {
-    ts.ob = __ldg(seg_off + v);
-    ts.oe = __ldg(seg_off + v + 1);
+#pragma unroll
+  for (int j = 0; j < kSegAhead; ++j) {
+    const int v = ts.v_first + (mt >> 4) + 8 * j;
+    if (v <= ts.v_last) {
+      ts.ob[j] = __ldg(seg_off + v);
+      ts.oe[j] = __ldg(seg_off + v + 1);
+    }
   }
 }
 __device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long long M, const int32_t* __restrict__ seg_off,
@@ -76,30 +91,7 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
   const long long tile = rec_base + row0 / kRows;
   const uint8_t* col = buf + (chunk >> 3) * kPB;
   const long long g0 = row_base + row0;  // global position of the tile's first row
-  long long ob = ts.ob, oe = ts.oe;
-  for (int v = v_first + sl; v <= v_last; v += 8) {
-    const int b = static_cast<int>((ob > g0 ? ob : g0) - g0);
-    const int e = static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0);
-    if (v + 8 <= v_last) {  // bounds of the next segment, in flight while this one is summed
-      ob = __ldg(seg_off + v + 8);
-      oe = __ldg(seg_off + v + 9);
-    }
-    uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};  // 8 fp32 column sums as packed pairs (FADD2)
-    // kAggFly rows of the segment in flight (a mesh segment is ~6 rows: two round trips to shared memory instead of six
-    // dependent ones); rows past the end read as +0, which leaves the sum -- taken in ascending row order -- unchanged
-    for (int r = b; r < e; r += kAggFly) {
-      uint4 t[kAggFly];
-#pragma unroll
-      for (int u = 0; u < kAggFly; ++u)
-        t[u] = r + u < e ? *reinterpret_cast<const uint4*>(col + sw128_offset(r + u, chunk & 7)) : make_uint4(0u, 0u, 0u, 0u);
-#pragma unroll
-      for (int u = 0; u < kAggFly; ++u) {
-        acc[0] = f2_add(acc[0], f2_from_bf16x2(t[u].x));
-        acc[1] = f2_add(acc[1], f2_from_bf16x2(t[u].y));
-        acc[2] = f2_add(acc[2], f2_from_bf16x2(t[u].z));
-        acc[3] = f2_add(acc[3], f2_from_bf16x2(t[u].w));
-      }
-    }
+  auto put_segment = [&](int v, const uint64_t (&acc)[4]) {
     if (v == v_first || v == v_last) {
       const long long rec = tile * 2 + ((v == v_last && v != v_first) ? 1 : 0);
       float4* d = reinterpret_cast<float4*>(part + rec * kH + chunk * 8);
@@ -109,6 +101,66 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
     } else {
       *reinterpret_cast<uint4*>(out + static_cast<long long>(v) * ld_out + chunk * 8) =
           make_uint4(f2_to_bf16x2(acc[0]), f2_to_bf16x2(acc[1]), f2_to_bf16x2(acc[2]), f2_to_bf16x2(acc[3]));
+    }
+  };
+  auto add_row = [&](uint64_t (&acc)[4], const uint4& t) {
+    acc[0] = f2_add(acc[0], f2_from_bf16x2(t.x));
+    acc[1] = f2_add(acc[1], f2_from_bf16x2(t.y));
+    acc[2] = f2_add(acc[2], f2_from_bf16x2(t.z));
+    acc[3] = f2_add(acc[3], f2_from_bf16x2(t.w));
+  };
+  auto row_ld = [&](int r) { return *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7)); };
+  // The thread's first kSegAhead segments side by side: kAggSide rows of EACH in flight per pass (a mesh tile is ~22
+  // segments of ~6 rows = 3 per thread: two round trips to shared memory for the whole tile instead of two per segment,
+  // one segment after the other).  Rows past a segment's end read as +0: every sum is still taken in ascending row order.
+  {
+    int b[kSegAhead], e[kSegAhead];
+    uint64_t acc[kSegAhead][4];
+    int longest = 0;
+#pragma unroll
+    for (int j = 0; j < kSegAhead; ++j) {
+      const long long ob = ts.ob[j], oe = ts.oe[j];
+      const bool on = v_first + sl + 8 * j <= v_last;
+      b[j] = on ? static_cast<int>((ob > g0 ? ob : g0) - g0) : 0;
+      e[j] = on ? static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0) : 0;
+      longest = max(longest, e[j] - b[j]);
+      acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0ull;
+    }
+    for (int base = 0; base < longest; base += kAggSide) {
+      uint4 t[kSegAhead][kAggSide];
+#pragma unroll
+      for (int j = 0; j < kSegAhead; ++j)
+#pragma unroll
+        for (int u = 0; u < kAggSide; ++u)
+          t[j][u] = b[j] + base + u < e[j] ? row_ld(b[j] + base + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int j = 0; j < kSegAhead; ++j)
+#pragma unroll
+        for (int u = 0; u < kAggSide; ++u) add_row(acc[j], t[j][u]);
+    }
+#pragma unroll
+    for (int j = 0; j < kSegAhead; ++j)
+      if (v_first + sl + 8 * j <= v_last) put_segment(v_first + sl + 8 * j, acc[j]);
+  }
+  int v = v_first + sl + 8 * kSegAhead;
+  if (v <= v_last) {  // tiles of many short (or empty) segments: one at a time, bounds fetched a round ahead
+    long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
+    for (; v <= v_last; v += 8) {
+      const int b = static_cast<int>((ob > g0 ? ob : g0) - g0);
+      const int e = static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0);
+      if (v + 8 <= v_last) {
+        ob = __ldg(seg_off + v + 8);
+        oe = __ldg(seg_off + v + 9);
+      }
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
+      for (int r = b; r < e; r += kAggFly) {
+        uint4 t[kAggFly];
+#pragma unroll
+        for (int u = 0; u < kAggFly; ++u) t[u] = r + u < e ? row_ld(r + u) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int u = 0; u < kAggFly; ++u) add_row(acc, t[u]);
+      }
+      put_segment(v, acc);
     }
   }
   if (v_first == v_last && mt == 0) part_v[tile * 2 + 1] = -1;

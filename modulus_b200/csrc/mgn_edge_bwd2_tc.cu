@@ -773,6 +773,9 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
     p.timing[96 + 4 * blockIdx.x] = clock64() - dbg_c0;
     p.timing[96 + 4 * blockIdx.x + 1] = g1 - dbg_g0;
     p.timing[96 + 4 * blockIdx.x + 2] = n_my;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.timing[96 + 4 * blockIdx.x + 3] = smid;
   }
 #endif
 

@@ -18,12 +18,13 @@
 // projections at all: edges are CSC-ordered, so the 32 rows of a warp share ~6 destination rows, and each epilogue
 // thread reads its 128 bytes of P_dst straight from global memory a full pass before it needs them.
 //
-// Warp roles (448 threads): warp 0 = MMA issuer + TMEM owner; warps 1-4 = movers (cp.async gather of the source
+// Warp roles (512 threads): warp 0 = MMA issuer + TMEM owner; warps 1-4 = movers (cp.async gather of the source
 // projections, destination sums of the result tile, mgn_agg.cuh); warps 5-12 = epilogue (two warps per TMEM lane
-// quarter, 64 columns each); warp 13 = loader (TMA: efeat tiles in, result tiles out).
-// Epilogue passes read the accumulator as two 32-column halves.  -DMGN_FWD3_PIPE16 selects four software-pipelined 16-column chunks
-// instead (tmem_pass64): fewer cycles per tile but not faster in wall time on a power-capped B200 (profiles/r02_ab_epilogue.md).
-#ifndef MGN_FWD3_PIPE16
+// quarter, 64 columns each); warp 13 = loader (TMA: efeat tiles in, result tiles out); warps 14-15 = h1 store.
+// Epilogue passes read the accumulator as four software-pipelined 16-column chunks (tmem_pass64: the next chunk's
+// tcgen05.ld in flight while this one is worked on).  That only pays once the movers keep up (self-publishing gathers,
+// index loads ahead, h1 store warps: profiles/r02_fwd3_movers.md); -DMGN_FWD3_PIPE32 selects two 32-column halves instead.
+#ifdef MGN_FWD3_PIPE32
 #define MGN_NO_PIPE16
 #endif
 #include <cstdlib>
@@ -40,11 +41,19 @@ namespace fwd3 {
 using namespace tile;
 constexpr int kH = 128;
 constexpr int kLoaderWarp = 13;
-constexpr int kThreads = 32 * (kLoaderWarp + 1);
+// warps 14-15 write the kept h1 tiles to global memory (16 warps x 128 registers fill the register file exactly, so
+// the two warps cost nothing; -DMGN_FWD3_MOVER_H1: former form, the movers store h1 between two gathers)
+#ifdef MGN_FWD3_MOVER_H1
+constexpr int kStoreWarps = 0;
+#else
+constexpr int kStoreWarps = 2;
+#endif
+constexpr int kThreads = 32 * (kLoaderWarp + 1 + kStoreWarps);
 
 struct Params {
   Args a;
   long long* timing;
+  int timing_cta;  // debug builds: the CTA whose per-phase cycles are recorded (environment MGN_TIMING_CTA, default 0)
   alignas(64) CUtensorMap m_a, m_out;
 };
 
@@ -64,7 +73,8 @@ struct Smem {
 // B_M1[3] / B_M2 / B_M3: GEMM k of a tile complete.  B_H1 / B_H2 / B_OUT[3]: epilogue pass complete (8 warps).
 // B_AGG[3]: movers have finished summing the result tile in slot s.  (Barriers that a waiter may trail by more than
 // one completion are kept per slot: a parity wait cannot tell two completions from none.)
-enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_NUM = 17 };
+// B_GF: the store warps have read h1(j) out of the G1 buffer (the next gather may overwrite it).
+enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_GF = 17, B_NUM = 18 };
 
 #ifdef MGN_MAXNREG
 #define MGN_FWD3_BOUNDS __maxnreg__(MGN_MAXNREG)
@@ -101,7 +111,13 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
   if (tid == 0) {
     for (int b = 0; b < B_NUM; ++b) {
       int cnt = 1;
-      if (b == B_G || (b >= B_AGG && b < B_AGG + 3)) cnt = 4;
+      if (b >= B_AGG && b < B_AGG + 3) cnt = 4;
+      if (b == B_GF) cnt = kStoreWarps > 0 ? kStoreWarps : 1;
+#ifdef MGN_FWD3_SYNC_G
+      if (b == B_G) cnt = 4;
+#else
+      if (b == B_G) cnt = 128;
+#endif
       if (b == B_H1 || b == B_H2 || (b >= B_OUT && b < B_OUT + 3)) cnt = 8;
       mbar_init(&bars[b], cnt);
     }
@@ -165,7 +181,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         }
         // period k, in the order the epilogue releases things: E2(k) -> M3(k); E1(k+1) -> M2(k+1); E3(k-1) has drained an
         // accumulator and A(k+2) has landed (well into the period: its slot held tile k-1's result) -> M1(k+2)
-        const bool tmm = p.timing != nullptr && blockIdx.x == 0;
+        const bool tmm = p.timing != nullptr && blockIdx.x == p.timing_cta;
         long long tq[6] = {0, 0, 0, 0, 0, 0};
         long long tl = clock64();
 #define MGN_TM(i)                    \
@@ -218,11 +234,17 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       break;                                                              \
     }                                                                     \
   }
+// the gathered rows publish themselves: every mover thread's cp.asyncs arrive on B_G when they have landed, the thread
+// goes on to the destination sums without waiting for them (-DMGN_FWD3_SYNC_G: former form, wait then arrive per warp)
+#ifdef MGN_FWD3_SYNC_G
 #define MGN_PUBLISH_G()          \
   cp_async_commit();             \
   cp_async_wait<0>();            \
   __syncwarp();                  \
   if (lane == 0) mbar_arrive(&bars[B_G]);
+#else
+#define MGN_PUBLISH_G() cp_async_arrive_noinc(&bars[B_G]);
+#endif
     int32_t r_g1[16];
     do {
       if (n_my > 0) {  // G1(0), then G1(1) as soon as E1(0) has consumed G1(0)
@@ -233,9 +255,17 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       }
       // E1(j) has consumed G1(j) and (if kept for the backward pass) left h1(j) in the same buffer: the movers write
       // it out with the row mapping of the gather that follows, so each thread overwrites only what it has read
-      if (n_my > 1 || (n_my > 0 && a.h1_out != nullptr)) {
-        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], 0))) { timed_out = true; break; }
-        if (a.h1_out != nullptr) store_rows(bG1, a.h1_out, kH, row_first, a.M, mt);
+      // (with store warps the movers only wait until those have read h1(j) out of the buffer: B_GF)
+#ifdef MGN_FWD3_IDLE_STORE
+      constexpr bool kUseStoreWarps = false;  // (A/B: the two extra warps exist but the movers store h1)
+#else
+      constexpr bool kUseStoreWarps = kStoreWarps > 0;
+#endif
+      const bool own_h1 = !kUseStoreWarps && a.h1_out != nullptr;
+      uint64_t* const bar_free = (kUseStoreWarps && a.h1_out != nullptr) ? &bars[B_GF] : &bars[B_H1];
+      if (n_my > 1 || (n_my > 0 && own_h1)) {
+        if (!__all_sync(0xffffffffu, wait_clk(bar_free, 0))) { timed_out = true; break; }
+        if (own_h1) store_rows(bG1, a.h1_out, kH, row_first, a.M, mt);
         if (n_my > 1) {
           stage_rows_async(bG1, g1, r_g1, row_first + stride, a.M, mt);
           if (n_my > 2) fetch_row_ids(g1.idx, row_first + 2 * stride, a.M, rsub_m, r_g1);
@@ -244,7 +274,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       }
       // (debug builds: cycles of mover warp 1 per phase -> timing[16..21])
 #ifdef MGN_DEBUG_HOOKS
-      const bool tmv = p.timing != nullptr && blockIdx.x == 0 && warp == 1 && lane == 0;
+      const bool tmv = p.timing != nullptr && blockIdx.x == p.timing_cta && warp == 1 && lane == 0;
       long long tv[6] = {0, 0, 0, 0, 0, 0};
       long long tvl = clock64();
 #define MGN_TV(i)                    \
@@ -271,12 +301,15 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           agg::tile_segments_bounds(ts_next, a.seg_off, mt);
           if (k + 2 < n_my) ts_ids = agg::tile_segments_ids(row0 + 2 * stride, a.M, a.g2_idx);
         }
-        if (k + 2 < n_my || (k + 1 < n_my && a.h1_out != nullptr)) {
+        if (k + 2 < n_my || (k + 1 < n_my && own_h1)) {
           // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
           MGN_TV(0);
-          MGN_W(B_H1, (k + 1) & 1);
+          if (!__all_sync(0xffffffffu, wait_clk(bar_free, (k + 1) & 1))) {
+            timed_out = true;
+            break;
+          }
           MGN_TV(1);
-          if (a.h1_out != nullptr) store_rows(bG1, a.h1_out, kH, row0 + stride, a.M, mt);
+          if (own_h1) store_rows(bG1, a.h1_out, kH, row0 + stride, a.M, mt);
           MGN_TV(2);
           if (k + 2 < n_my) {
             stage_rows_async(bG1, g1, r_g1, row0 + 2 * stride, a.M, mt);
@@ -302,6 +335,39 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
 #undef MGN_TV
     } while (false);
 #undef MGN_W
+  } else if (warp > kLoaderWarp) {
+    // =========================== h1 store warps ===========================
+    // 64 threads: thread = (16-byte chunk of a row, row lane 0..3); tile j's h1 = 32 loads + 32 stores of 16 bytes per thread
+#ifdef MGN_FWD3_IDLE_STORE
+    if (false) {
+#else
+    if (a.h1_out != nullptr) {
+#endif
+      const int st = tid - 32 * (kLoaderWarp + 1);
+      const int chunk = st & 15, rsub = st >> 4;
+      const uint8_t* colp = bG1 + (chunk >> 3) * kPB;
+      for (int j = 0; j < n_my; ++j) {
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], j & 1))) {
+          timed_out = true;
+          break;
+        }
+        const long long row0 = row_first + j * stride;
+        bf16* dst = a.h1_out + row0 * kH + chunk * 8;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          uint4 v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = *reinterpret_cast<const uint4*>(colp + sw128_offset((half * 16 + i) * 4 + rsub, chunk & 7));
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int row = (half * 16 + i) * 4 + rsub;
+            if (row0 + row < a.M) *reinterpret_cast<uint4*>(dst + static_cast<long long>(row) * kH) = v[i];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_GF]);
+      }
+    }
   } else if (warp == kLoaderWarp) {
     // =========================== loader (TMA) ===========================
     if (lane == 0) {
@@ -416,7 +482,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_H1]);
     };
-    const bool tm_on = p.timing != nullptr && blockIdx.x == 0 && warp == 5 && lane == 0;
+    const bool tm_on = p.timing != nullptr && blockIdx.x == p.timing_cta && warp == 5 && lane == 0;
     long long tm[6] = {0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
 #define MGN_T(i)                      \
@@ -604,6 +670,9 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
     p.timing[96 + 4 * blockIdx.x] = clock64() - dbg_c0;
     p.timing[96 + 4 * blockIdx.x + 1] = g1 - dbg_g0;
     p.timing[96 + 4 * blockIdx.x + 2] = n_my;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    p.timing[96 + 4 * blockIdx.x + 3] = smid;
   }
 #endif
   if (warp == 0) tmem_dealloc(tmem, 512);
@@ -624,6 +693,7 @@ int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   p.timing = g_fwd3_timing;
 #ifdef MGN_DEBUG_HOOKS
   if (getenv("MGN_FWD3_NO_AGG") != nullptr) p.a.seg_off = nullptr;  // timing experiment: destination sums left out
+  if (const char* e = getenv("MGN_TIMING_CTA")) p.timing_cta = atoi(e);
 #endif
   if (tma_make_rows_map(&p.m_a, args.a, args.M, 128, 128) != 0) return MGN_EINVAL;
   if (tma_make_rows_map(&p.m_out, args.out, args.M, 128, 128) != 0) return MGN_EINVAL;

@@ -263,6 +263,11 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t saddr, const void* gpt
 __device__ __forceinline__ void cp_async_commit() {
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
+// every cp.async this thread has issued so far arrives on `bar` when it lands (the barrier's expected count includes
+// this arrival: .noinc); the thread itself does not wait
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");

@@ -86,8 +86,11 @@ if ONLY:
     ops.tc_check(DEV)
     sys.exit(0)
 
-for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("node fwd (+h1)", nodefwd), ("node bwd (from h1)", nodebwd), ("segsum csc", agg), ("segsum csr", csr),
-                 ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad)):
+_ALL = (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("node fwd (+h1)", nodefwd), ("node bwd (from h1)", nodebwd), ("segsum csc", agg), ("segsum csr", csr),
+                 ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad))
+if os.environ.get("MGN_PROF_ONLY2"):  # quick A/B runs: the two edge-forward launches only
+    _ALL = _ALL[1:3]
+for name, fn in _ALL:
     for _ in range(2):
         fn()
     torch.cuda.synchronize()
@@ -101,6 +104,8 @@ for name, fn in (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h
     ms = ts[len(ts) // 2]
     print(f"{name:12s} N={N} E={E}: {ms:.3f} ms median, {ts[0]:.3f} min of {reps}  ({E / ms / 1e3:.1f} M edges/s)", flush=True)
 ops.tc_check(DEV)
+if os.environ.get("MGN_PROF_ONLY2"):
+    sys.exit(0)
 
 # per-phase cycle breakdown of CTA 0 (only in a library built with -DMGN_DEBUG_HOOKS, see include/mgn_b200_debug.h)
 from modulus_b200 import _lib
@@ -117,6 +122,9 @@ def per_cta_clock(t, label):
         return
     cyc_tile = c[:, 0] / c[:, 2]
     ghz = c[:, 0] / c[:, 1].clamp(min=1)
+    if os.environ.get("MGN_PROF_DUMP"):
+        order = torch.argsort(c[:, 3])
+        print(f"{label}: cycles/tile by SM id:", " ".join(f"{int(c[i, 3])}:{int(cyc_tile[i])}" for i in order.tolist()))
     print(f"{label}: per-CTA cycles/tile min {cyc_tile.min():.0f} median {cyc_tile.median():.0f} max {cyc_tile.max():.0f}; "
           f"loop time us min {c[:, 1].min() / 1e3:.0f} max {c[:, 1].max() / 1e3:.0f}; SM clock GHz min {ghz.min():.3f} median {ghz.median():.3f} max {ghz.max():.3f}")
 
