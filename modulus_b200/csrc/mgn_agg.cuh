@@ -82,6 +82,8 @@ __device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long lon
   return ts;
 }
 
+// kA rounds of this thread's segments are summed side by side (kS rows of each in flight), the rest one at a time.
+template <int kA = kSegAhead, int kS = kAggSide>
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, const TileSegs& ts,
                                                  const int32_t* __restrict__ seg_off, bf16* __restrict__ out,
                                                  long long ld_out, float* __restrict__ part, int32_t* __restrict__ part_v,
@@ -110,15 +112,15 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
     acc[3] = f2_add(acc[3], f2_from_bf16x2(t.w));
   };
   auto row_ld = [&](int r) { return *reinterpret_cast<const uint4*>(col + sw128_offset(r, chunk & 7)); };
-  // The thread's first kSegAhead segments side by side: kAggSide rows of EACH in flight per pass (a mesh tile is ~22
+  // The thread's first kA segments side by side: kS rows of EACH in flight per pass (a mesh tile is ~22
   // segments of ~6 rows = 3 per thread: two round trips to shared memory for the whole tile instead of two per segment,
   // one segment after the other).  Rows past a segment's end read as +0: every sum is still taken in ascending row order.
   {
-    int b[kSegAhead], e[kSegAhead];
-    uint64_t acc[kSegAhead][4];
+    int b[kA], e[kA];
+    uint64_t acc[kA][4];
     int longest = 0;
 #pragma unroll
-    for (int j = 0; j < kSegAhead; ++j) {
+    for (int j = 0; j < kA; ++j) {
       const long long ob = ts.ob[j], oe = ts.oe[j];
       const bool on = v_first + sl + 8 * j <= v_last;
       b[j] = on ? static_cast<int>((ob > g0 ? ob : g0) - g0) : 0;
@@ -126,23 +128,23 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
       longest = max(longest, e[j] - b[j]);
       acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0ull;
     }
-    for (int base = 0; base < longest; base += kAggSide) {
-      uint4 t[kSegAhead][kAggSide];
+    for (int base = 0; base < longest; base += kS) {
+      uint4 t[kA][kS];
 #pragma unroll
-      for (int j = 0; j < kSegAhead; ++j)
+      for (int j = 0; j < kA; ++j)
 #pragma unroll
-        for (int u = 0; u < kAggSide; ++u)
+        for (int u = 0; u < kS; ++u)
           t[j][u] = b[j] + base + u < e[j] ? row_ld(b[j] + base + u) : make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-      for (int j = 0; j < kSegAhead; ++j)
+      for (int j = 0; j < kA; ++j)
 #pragma unroll
-        for (int u = 0; u < kAggSide; ++u) add_row(acc[j], t[j][u]);
+        for (int u = 0; u < kS; ++u) add_row(acc[j], t[j][u]);
     }
 #pragma unroll
-    for (int j = 0; j < kSegAhead; ++j)
+    for (int j = 0; j < kA; ++j)
       if (v_first + sl + 8 * j <= v_last) put_segment(v_first + sl + 8 * j, acc[j]);
   }
-  int v = v_first + sl + 8 * kSegAhead;
+  int v = v_first + sl + 8 * kA;
   if (v <= v_last) {  // tiles of many short (or empty) segments: one at a time, bounds fetched a round ahead
     long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
     for (; v <= v_last; v += 8) {

@@ -32,6 +32,12 @@
 #include "mgn_tma.cuh"
 #include "mgn_agg.cuh"
 
+#ifndef MGN_BWD2_AGG_AHEAD
+#define MGN_BWD2_AGG_AHEAD 1
+#endif
+#ifndef MGN_BWD2_AGG_SIDE
+#define MGN_BWD2_AGG_SIDE 4
+#endif
 namespace mgn {
 namespace bwd2 {
 
@@ -330,7 +336,8 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       if (lane == 0) mbar_arrive(&bars[B_CS + 1]);
       MGN_W(B_E + 3, par);
       colsum_tile(bH1, mt, cs_b1);
-      if (kAgg) agg::tile_segment_sum(bH1, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
+      // (one segment at a time here: these warps also carry 32 column sums, the side-by-side form of the forward spills)
+      if (kAgg) agg::tile_segment_sum<MGN_BWD2_AGG_AHEAD, MGN_BWD2_AGG_SIDE>(bH1, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
       if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X once g_efeat has left

@@ -17,6 +17,7 @@ struct Args {
   const float *w1, *b1, *w2, *b2, *w3, *b3, *gamma, *beta;
   long long ld_w1;
   float eps;
+  const bf16* res;  // node form (nullptr: edge form): residual rows [M,128]; then g1_* are unused, g2_idx is ignored (own row)
   bf16* out;  // [M,128]
   bf16* h1_out;  // [M,128] first hidden activation relu(z1), kept for the backward pass (nullptr: not stored)
   // fused destination sums (mgn_agg.cuh); seg_off == nullptr: off

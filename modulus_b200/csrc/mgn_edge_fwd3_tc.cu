@@ -73,14 +73,19 @@ struct Smem {
 // B_M1[3] / B_M2 / B_M3: GEMM k of a tile complete.  B_H1 / B_H2 / B_OUT[3]: epilogue pass complete (8 warps).
 // B_AGG[3]: movers have finished summing the result tile in slot s.  (Barriers that a waiter may trail by more than
 // one completion are kept per slot: a parity wait cannot tell two completions from none.)
-// B_GF: the store warps have read h1(j) out of the G1 buffer (the next gather may overwrite it).
-enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_GF = 17, B_NUM = 18 };
+// B_GF[2]: the store warps have read h1(j) out of its buffer (slot j & 1: in the node form E3(j) waits for it after E1(j + 1)
+// may already have completed the next one).
+enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_GF = 17, B_NUM = 19 };
 
 #ifdef MGN_MAXNREG
 #define MGN_FWD3_BOUNDS __maxnreg__(MGN_MAXNREG)
 #else
 #define MGN_FWD3_BOUNDS __launch_bounds__(kThreads, 1)
 #endif
+// kNode: the MeshNodeBlock form.  A = agg tile (GEMM1 operand only), no gathered table, P_node rows read directly (g2, own
+// row), residual rows = a.res staged by the movers into the G1 buffer one tile ahead and read there by E3; the kept h1
+// goes through the A slot (dead after GEMM1) instead of the G1 buffer; no destination sums.
+template <bool kNode>
 __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -112,7 +117,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
     for (int b = 0; b < B_NUM; ++b) {
       int cnt = 1;
       if (b >= B_AGG && b < B_AGG + 3) cnt = 4;
-      if (b == B_GF) cnt = kStoreWarps > 0 ? kStoreWarps : 1;
+      if (b == B_GF || b == B_GF + 1) cnt = kStoreWarps > 0 ? kStoreWarps : 1;
 #ifdef MGN_FWD3_SYNC_G
       if (b == B_G) cnt = 4;
 #else
@@ -246,6 +251,28 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
 #define MGN_PUBLISH_G() cp_async_arrive_noinc(&bars[B_G]);
 #endif
     int32_t r_g1[16];
+    if (kNode) {
+      // node form: the residual rows of tile j (dense) go into the G1 buffer once E3(j - 1) has read its own
+      const RowSrc rs{a.res, nullptr, kH, 0};
+      for (int j = 0; j < n_my; ++j) {
+        if (j > 0 && !__all_sync(0xffffffffu, wait_clk(&bars[B_OUT + (j - 1) % 3], ((j - 1) / 3) & 1))) {
+          timed_out = true;
+          break;
+        }
+        fetch_row_ids(nullptr, row_first + j * stride, a.M, rsub_m, r_g1);
+        stage_rows_async(bG1, rs, r_g1, row_first + j * stride, a.M, mt);
+        MGN_PUBLISH_G();
+        if (j > 0) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[B_AGG + (j - 1) % 3]);
+        }
+      }
+      if (n_my > 0 && !timed_out) {
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_OUT + (n_my - 1) % 3], ((n_my - 1) / 3) & 1))) timed_out = true;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_AGG + (n_my - 1) % 3]);
+      }
+    } else
     do {
       if (n_my > 0) {  // G1(0), then G1(1) as soon as E1(0) has consumed G1(0)
         fetch_row_ids(g1.idx, row_first, a.M, rsub_m, r_g1);
@@ -262,9 +289,13 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       constexpr bool kUseStoreWarps = kStoreWarps > 0;
 #endif
       const bool own_h1 = !kUseStoreWarps && a.h1_out != nullptr;
-      uint64_t* const bar_free = (kUseStoreWarps && a.h1_out != nullptr) ? &bars[B_GF] : &bars[B_H1];
+      const bool via_gf = kUseStoreWarps && a.h1_out != nullptr;
+      // tile j's buffer is free: B_GF slot j & 1, completion j >> 1 (store warps), else B_H1 completion j
+      auto wait_free = [&](int j) {
+        return via_gf ? wait_clk(&bars[B_GF + (j & 1)], (j >> 1) & 1) : wait_clk(&bars[B_H1], j & 1);
+      };
       if (n_my > 1 || (n_my > 0 && own_h1)) {
-        if (!__all_sync(0xffffffffu, wait_clk(bar_free, 0))) { timed_out = true; break; }
+        if (!__all_sync(0xffffffffu, wait_free(0))) { timed_out = true; break; }
         if (own_h1) store_rows(bG1, a.h1_out, kH, row_first, a.M, mt);
         if (n_my > 1) {
           stage_rows_async(bG1, g1, r_g1, row_first + stride, a.M, mt);
@@ -304,7 +335,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         if (k + 2 < n_my || (k + 1 < n_my && own_h1)) {
           // period k: E1(k+1) has consumed G1(k+1) -> (h1(k+1) out,) stage G1(k+2) while E3(k) runs
           MGN_TV(0);
-          if (!__all_sync(0xffffffffu, wait_clk(bar_free, (k + 1) & 1))) {
+          if (!__all_sync(0xffffffffu, wait_free(k + 1))) {
             timed_out = true;
             break;
           }
@@ -345,8 +376,9 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
 #endif
       const int st = tid - 32 * (kLoaderWarp + 1);
       const int chunk = st & 15, rsub = st >> 4;
-      const uint8_t* colp = bG1 + (chunk >> 3) * kPB;
       for (int j = 0; j < n_my; ++j) {
+        // h1(j) sits in the G1 buffer (edge form) or in tile j's own A slot (node form)
+        const uint8_t* colp = (kNode ? bA0 + (j % 3) * 2 * kPB : bG1) + (chunk >> 3) * kPB;
         if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], j & 1))) {
           timed_out = true;
           break;
@@ -365,7 +397,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[B_GF]);
+        if (lane == 0) mbar_arrive(&bars[B_GF + (j & 1)]);
       }
     }
   } else if (warp == kLoaderWarp) {
@@ -421,7 +453,8 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
     // destination-projection row of this thread for a tile, and its 64 columns (8 x 16 bytes) straight from global
     auto g2_row = [&](int j) -> int32_t {
       const long long gr = row_first + j * stride + row;
-      return __ldg(a.g2_idx + (gr < a.M ? gr : a.M - 1));
+      const long long gc = gr < a.M ? gr : a.M - 1;
+      return kNode ? static_cast<int32_t>(gc) : __ldg(a.g2_idx + gc);  // (node form: the row's own P_node row)
     };
     uint4 gq[8];
     auto g2_fetch = [&](int32_t r) {
@@ -437,13 +470,15 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       for (int u = 0; u < 8; ++u) asm volatile("" : "+r"(gq[u].x), "+r"(gq[u].y), "+r"(gq[u].z), "+r"(gq[u].w));
       const uint32_t t_acc = tmem + (j % 3) * 128 + lane_off + c0;
       const uint32_t t_h = tmem + 384 + (j & 1) * 64 + lane_off + ch * 32;
+      // the kept h1: over the consumed G1 rows (edge form) / over tile j's A slot, dead once GEMM1(j) has run (node form)
+      uint8_t* const bH1dst = kNode ? bA0 + (j % 3) * 2 * kPB : bG1;
 #ifdef MGN_NO_PIPE16
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         uint32_t v[32];
         tmem_ld32(t_acc + 32 * hh, v);
         uint32_t ga[16];
-        row_load32p(bG1, row, c0 + 32 * hh, ga);
+        if (!kNode) row_load32p(bG1, row, c0 + 32 * hh, ga);
         tmem_ld_wait();
         uint32_t pk[16];
 #pragma unroll
@@ -452,29 +487,34 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           const uint32_t d0 = (u & 1) ? gd.z : gd.x, d1 = (u & 1) ? gd.w : gd.y;
           uint64_t za = f2_add(f2_packu(v[4 * u], v[4 * u + 1]), f2_ld(b1 + 32 * hh + 4 * u));
           uint64_t zb = f2_add(f2_packu(v[4 * u + 2], v[4 * u + 3]), f2_ld(b1 + 32 * hh + 4 * u + 2));
-          za = f2_add(f2_add(za, f2_from_bf16x2(ga[2 * u])), f2_from_bf16x2(d0));
-          zb = f2_add(f2_add(zb, f2_from_bf16x2(ga[2 * u + 1])), f2_from_bf16x2(d1));
+          if (!kNode) {
+            za = f2_add(za, f2_from_bf16x2(ga[2 * u]));
+            zb = f2_add(zb, f2_from_bf16x2(ga[2 * u + 1]));
+          }
+          za = f2_add(za, f2_from_bf16x2(d0));
+          zb = f2_add(zb, f2_from_bf16x2(d1));
           pk[2 * u] = relu_bf16x2(f2_to_bf16x2(za));
           pk[2 * u + 1] = relu_bf16x2(f2_to_bf16x2(zb));
         }
         tmem_st16(t_h + 16 * hh, pk);
-        if (a.h1_out != nullptr) row_store32p(bG1, row, c0 + 32 * hh, pk);  // over this thread's own consumed G1 span
+        if (a.h1_out != nullptr) row_store32p(bH1dst, row, c0 + 32 * hh, pk);  // over this thread's own consumed G1 span
       }
 #else
       tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {  // 16-column chunks, next chunk's TMEM load in flight
         uint32_t ga[8];
-        row_load16p(bG1, row, c0 + 16 * i, ga);
+        if (!kNode) row_load16p(bG1, row, c0 + 16 * i, ga);
         const uint4 da = gq[2 * i], db = gq[2 * i + 1];
         const uint32_t d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
         uint32_t pk[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // two fp32 lanes per instruction; relu after the bf16 rounding
           uint64_t z = f2_add(f2_packu(v[2 * j], v[2 * j + 1]), f2_ld(b1 + 16 * i + 2 * j));
-          z = f2_add(f2_add(z, f2_from_bf16x2(ga[j])), f2_from_bf16x2(d[j]));
+          if (!kNode) z = f2_add(z, f2_from_bf16x2(ga[j]));
+          z = f2_add(z, f2_from_bf16x2(d[j]));
           pk[j] = relu_bf16x2(f2_to_bf16x2(z));
         }
         tmem_st8(t_h + 8 * i, pk);
-        if (a.h1_out != nullptr) row_store16p(bG1, row, c0 + 16 * i, pk);  // over this thread's own consumed G1 span
+        if (a.h1_out != nullptr) row_store16p(bH1dst, row, c0 + 16 * i, pk);  // over this thread's own consumed G1 span
       });
 #endif
       tmem_st_wait();
@@ -512,7 +552,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         g2_fetch(g2_row(0));
         if (n_my > 1) g2r = g2_row(1);
         if (n_my > 2) g2r2 = g2_row(2);
-        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_M1], 0) && wait_clk(&bars[B_G], 0))) { timed_out = true; break; }
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_M1], 0) && (kNode || wait_clk(&bars[B_G], 0)))) { timed_out = true; break; }
         tc_fence_after_sync();
         e1(0);
       }
@@ -563,7 +603,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         // ---- E1(k+1)
         if (k + 1 < n_my) {
           MGN_W(B_M1 + (k + 1) % 3, ((k + 1) / 3) & 1);
-          MGN_W(B_G, (k + 1) & 1);
+          if (!kNode) MGN_W(B_G, (k + 1) & 1);
           MGN_T(2);
           tc_fence_after_sync();
           e1(k + 1);
@@ -612,6 +652,11 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
         const float mu = (s + __uint_as_float(o0)) * (1.f / kH);
         const float var = fmaxf((ss + __uint_as_float(o1)) * (1.f / kH) - mu * mu, 0.f);
         const float rstd = rsqrtf(var + a.eps);
+        if (kNode) {  // residual rows staged, and the kept h1 read out of the slot the result goes to
+          MGN_W(B_G, par);
+          if (a.h1_out != nullptr) MGN_W(B_GF + (k & 1), (k >> 1) & 1);
+        }
+        const uint8_t* const bRes = kNode ? bG1 : bAcur;
 #ifdef MGN_NO_PIPE16
 #pragma unroll 1
         for (int hh = 0; hh < 2; ++hh) {
@@ -619,7 +664,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           uint32_t v[32];
           tmem_ld32(t_acc + 32 * hh, v);
           uint32_t r[16];
-          row_load32p(bAcur, row, cc, r);
+          row_load32p(bRes, row, cc, r);
           tmem_ld_wait();
           uint32_t o[16];
           const uint64_t NMU = f2_splat(-mu), RS = f2_splat(rstd);
@@ -637,7 +682,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
           const uint64_t NMU = f2_splat(-mu), RS = f2_splat(rstd);
           tmem_pass64(t_acc, [&](int i, const uint32_t(&v)[16]) {
             uint32_t r[8];
-            row_load16p(bAcur, row, c0 + 16 * i, r);
+            row_load16p(bRes, row, c0 + 16 * i, r);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {  // ((y - mu) rstd) gamma + beta, + residual: five packed fp32 ops per pair
               const int c = 16 * i + 2 * j;
@@ -700,13 +745,16 @@ int edge_fwd3_launch(const fwd3::Args& args, cudaStream_t st) {
   static PerDeviceFlag configured_flag;
   bool& configured = configured_flag.get();
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(fwd3::edge_fwd3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::Smem::kTotal);
     if (e != cudaSuccess) return static_cast<int>(e);
     configured = true;
   }
   const long long n_tiles = (args.M + tile::kRows - 1) / tile::kRows;
   const int grid = static_cast<int>(n_tiles < num_sms() ? n_tiles : num_sms());
-  fwd3::edge_fwd3_kernel<<<grid, fwd3::kThreads, fwd3::Smem::kTotal, MGN_ST(st)>>>(p);
+  if (args.res != nullptr) fwd3::edge_fwd3_kernel<true><<<grid, fwd3::kThreads, fwd3::Smem::kTotal, MGN_ST(st)>>>(p);
+  else fwd3::edge_fwd3_kernel<false><<<grid, fwd3::kThreads, fwd3::Smem::kTotal, MGN_ST(st)>>>(p);
   return mgn_launch_status();
 }
 

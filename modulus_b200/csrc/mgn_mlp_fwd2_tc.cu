@@ -798,6 +798,27 @@ extern "C" int mgn_node_block_fwd_tc(const void* agg, const void* p_tab, int64_t
                                      const float* beta, float eps, void* nfeat_out, void* h1_out, int* status,
                                      mgn_stream_t stream) {
   MGN_CHECK_ARG(agg && p_tab && nfeat && nfeat_out);
+#ifndef MGN_NODE_FWD2
+  // two-tiles-in-flight kernel, node form (mgn_edge_fwd3_tc.cu, kNode); -DMGN_NODE_FWD2 keeps the second-generation kernel
+  const auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (n_nodes > 0 && gamma != nullptr && ld_w1 >= fwd2::kH && p_ld % 8 == 0 && p_col0 % 8 == 0 && al16(agg) && al16(p_tab) &&
+      al16(nfeat) && al16(nfeat_out) && al16(h1_out) && w1 && w2 && w3) {
+    fwd3::Args x{};
+    x.a = static_cast<const bf16*>(agg);
+    x.M = n_nodes;
+    x.g2_tab = static_cast<const bf16*>(p_tab);
+    x.g2_ld = p_ld;
+    x.g2_col0 = p_col0;
+    x.w1 = w1; x.b1 = b1; x.w2 = w2; x.b2 = b2; x.w3 = w3; x.b3 = b3; x.gamma = gamma; x.beta = beta;
+    x.ld_w1 = ld_w1;
+    x.eps = eps;
+    x.res = static_cast<const bf16*>(nfeat);
+    x.out = static_cast<bf16*>(nfeat_out);
+    x.h1_out = static_cast<bf16*>(h1_out);
+    x.status = status;
+    return edge_fwd3_launch(x, as_stream(stream));
+  }
+#endif
   AggArgs ag;
   ag.h1_out = h1_out;
   return fwd2_run(agg, nullptr, nullptr, 0, 0, p_tab, nullptr, p_ld, p_col0, nullptr, nullptr, 0, 0, nfeat, 0, n_nodes, w1,
