@@ -65,25 +65,28 @@ __device__ __forceinline__ TileSegs tile_segments_ids(long long row0, long long 
   for (int j = 0; j < kSegAhead; ++j) ts.ob[j] = ts.oe[j] = 0;
   return ts;
 }
+// (kLanes = segment lanes = threads / 16: 8 for the four mover warps, 12 when two more warps help)
+template <int kLanes = 8>
 __device__ __forceinline__ void tile_segments_bounds(TileSegs& ts, const int32_t* __restrict__ seg_off, int mt) {
 #pragma unroll
   for (int j = 0; j < kSegAhead; ++j) {
-    const int v = ts.v_first + (mt >> 4) + 8 * j;
+    const int v = ts.v_first + (mt >> 4) + kLanes * j;
     if (v <= ts.v_last) {
       ts.ob[j] = __ldg(seg_off + v);
       ts.oe[j] = __ldg(seg_off + v + 1);
     }
   }
 }
+template <int kLanes = 8>
 __device__ __forceinline__ TileSegs tile_segments_begin(long long row0, long long M, const int32_t* __restrict__ seg_off,
                                                         const int32_t* __restrict__ seg_id, int mt) {
   TileSegs ts = tile_segments_ids(row0, M, seg_id);
-  tile_segments_bounds(ts, seg_off, mt);
+  tile_segments_bounds<kLanes>(ts, seg_off, mt);
   return ts;
 }
 
 // kA rounds of this thread's segments are summed side by side (kS rows of each in flight), the rest one at a time.
-template <int kA = kSegAhead, int kS = kAggSide>
+template <int kA = kSegAhead, int kS = kAggSide, int kLanes = 8>
 __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long row0, const TileSegs& ts,
                                                  const int32_t* __restrict__ seg_off, bf16* __restrict__ out,
                                                  long long ld_out, float* __restrict__ part, int32_t* __restrict__ part_v,
@@ -122,7 +125,7 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
 #pragma unroll
     for (int j = 0; j < kA; ++j) {
       const long long ob = ts.ob[j], oe = ts.oe[j];
-      const bool on = v_first + sl + 8 * j <= v_last;
+      const bool on = v_first + sl + kLanes * j <= v_last;
       b[j] = on ? static_cast<int>((ob > g0 ? ob : g0) - g0) : 0;
       e[j] = on ? static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0) : 0;
       longest = max(longest, e[j] - b[j]);
@@ -142,17 +145,17 @@ __device__ __forceinline__ void tile_segment_sum(const uint8_t* buf, long long r
     }
 #pragma unroll
     for (int j = 0; j < kA; ++j)
-      if (v_first + sl + 8 * j <= v_last) put_segment(v_first + sl + 8 * j, acc[j]);
+      if (v_first + sl + kLanes * j <= v_last) put_segment(v_first + sl + kLanes * j, acc[j]);
   }
-  int v = v_first + sl + 8 * kA;
+  int v = v_first + sl + kLanes * kA;
   if (v <= v_last) {  // tiles of many short (or empty) segments: one at a time, bounds fetched a round ahead
     long long ob = __ldg(seg_off + v), oe = __ldg(seg_off + v + 1);
-    for (; v <= v_last; v += 8) {
+    for (; v <= v_last; v += kLanes) {
       const int b = static_cast<int>((ob > g0 ? ob : g0) - g0);
       const int e = static_cast<int>((oe < g0 + nrows ? oe : g0 + nrows) - g0);
-      if (v + 8 <= v_last) {
-        ob = __ldg(seg_off + v + 8);
-        oe = __ldg(seg_off + v + 9);
+      if (v + kLanes <= v_last) {
+        ob = __ldg(seg_off + v + kLanes);
+        oe = __ldg(seg_off + v + kLanes + 1);
       }
       uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
       for (int r = b; r < e; r += kAggFly) {

@@ -44,7 +44,15 @@ namespace bwd2 {
 using namespace tile;
 constexpr int kEpiWarps = 8;
 constexpr int kLoaderWarp = 5 + kEpiWarps;
-constexpr int kThreads = 32 * (kLoaderWarp + 1);
+// -DMGN_BWD2_AGG_HELPERS=2: warps 14-15 take a third of the fused destination sums (12 segment lanes instead of 8: two
+// rounds per mesh tile instead of three).  Measured SLOWER (3.03 -> 3.26 ms per launch at c3, profiles/r02_fwd3_movers.md):
+// the kernel is short of shared-memory bandwidth, not of threads.  Off by default.
+#ifndef MGN_BWD2_AGG_HELPERS
+#define MGN_BWD2_AGG_HELPERS 0
+#endif
+constexpr int kAggHelpers = MGN_BWD2_AGG_HELPERS;
+constexpr int kAggLanes = 8 + 2 * kAggHelpers;
+constexpr int kThreads = 32 * (kLoaderWarp + 1 + kAggHelpers);
 constexpr int kH = 128;
 
 struct Params {
@@ -159,7 +167,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
     mbar_init(&bars[B_A2], 1);
     for (int b = B_MMA; b < B_E; ++b) mbar_init(&bars[b], 1);
     for (int b = B_E; b < B_CS; ++b) mbar_init(&bars[b], kEpiWarps);
-    for (int b = B_CS; b < B_ST; ++b) mbar_init(&bars[b], 4);
+    for (int b = B_CS; b < B_ST; ++b) mbar_init(&bars[b], (kAgg && b == B_CS + 2) ? 4 + kAggHelpers : 4);
     mbar_init(&bars[B_ST], 1);
     mbar_init(&bars[B_XF], 1);
     mbar_init(&bars[B_DR], kEpiWarps);
@@ -323,7 +331,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       uint8_t* bH1 = MGN_BUF(R_H1, it);
       uint8_t* bH2 = MGN_BUF(R_H2, it);
       agg::TileSegs ts{};  // index loads of the tile's destination sums, issued before anything is waited for
-      if (kAgg) ts = agg::tile_segments_begin(row0, p.M, p.seg_off, p.seg_id, mt);
+      if (kAgg) ts = agg::tile_segments_begin<kAggLanes>(row0, p.M, p.seg_off, p.seg_id, mt);
       // after E3: X = g_out (summed), A = g_y
       MGN_W(B_E + 1, par);
       colsum_tile(bX, mt, cs_beta);
@@ -337,7 +345,7 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
       MGN_W(B_E + 3, par);
       colsum_tile(bH1, mt, cs_b1);
       // (one segment at a time here: these warps also carry 32 column sums, the side-by-side form of the forward spills)
-      if (kAgg) agg::tile_segment_sum<MGN_BWD2_AGG_AHEAD, MGN_BWD2_AGG_SIDE>(bH1, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
+      if (kAgg) agg::tile_segment_sum<MGN_BWD2_AGG_AHEAD, MGN_BWD2_AGG_SIDE, kAggLanes>(bH1, row0, ts, p.seg_off, p.agg, p.ld_agg, p.agg_part, p.agg_part_v, mt);
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
       if (more) {  // next tile's gathered gradient rows: A is free after the layer-1 MMAs, X once g_efeat has left
@@ -357,6 +365,23 @@ __global__ void MGN_BWD2_BOUNDS edge_bwd2_kernel(const __grid_constant__ Params 
         scratch[(1 * 8 + rsub) * kH + chunk * 8 + j] = cs_b2[j];
         scratch[(2 * 8 + rsub) * kH + chunk * 8 + j] = cs_b3[j];
         scratch[(3 * 8 + rsub) * kH + chunk * 8 + j] = cs_beta[j];
+      }
+    }
+  } else if (warp > kLoaderWarp) {
+    // =========================== helpers of the fused destination sums ===========================
+    if (kAgg) {
+      const int mt = 128 + (tid - 32 * (kLoaderWarp + 1));  // segment lanes 8 .. kAggLanes - 1
+      for (int it = 0; it < n_my; ++it) {
+        const long long row0 = (static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x) * kRows;
+        const agg::TileSegs ts = agg::tile_segments_begin<kAggLanes>(row0, p.M, p.seg_off, p.seg_id, mt);
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_E + 3], it & 1))) {
+          timed_out = true;
+          break;
+        }
+        agg::tile_segment_sum<MGN_BWD2_AGG_AHEAD, MGN_BWD2_AGG_SIDE, kAggLanes>(MGN_BUF(R_H1, it), row0, ts, p.seg_off, p.agg, p.ld_agg,
+                                                                              p.agg_part, p.agg_part_v, mt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[B_CS + 2]);
       }
     }
   } else if (warp == kLoaderWarp) {

@@ -89,7 +89,7 @@ if ONLY:
 _ALL = (("fwd2 edge", fwd2), ("eblk fwd3+agg", eblk), ("eblk fwd3+agg+h1", eblk_h1), ("bwd edge (recompute)", bwd), ("bwd edge (from h1)", bwd2), ("bwd edge (from h1) + dst sums", bwd2_dst), ("node fwd (+h1)", nodefwd), ("node bwd (from h1)", nodebwd), ("segsum csc", agg), ("segsum csr", csr),
                  ("P=nfeat Wp^T", lin_p), ("g_n+T Wp", lin_t), ("T^T nfeat", wgrad))
 if os.environ.get("MGN_PROF_ONLY2"):  # quick A/B runs: the two edge-forward launches only
-    _ALL = _ALL[1:3]
+    _ALL = _ALL[4:6] if os.environ["MGN_PROF_ONLY2"] == "bwd" else _ALL[1:3]
 for name, fn in _ALL:
     for _ in range(2):
         fn()
