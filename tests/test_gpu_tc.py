@@ -439,7 +439,7 @@ def test_edge_block_bwd_from_stored_h1_matches_recompute(N, first_layer):
     assert bool((T[:, :128] == 4).all()) and bool((T[:, 256:] == 4).all())
 
 
-@pytest.mark.parametrize("N", [300, 40000])
+@pytest.mark.parametrize("N", [1, 128, 129, 300, 40000])
 def test_node_block_fwd_keeps_h1_and_bwd_from_it_matches_recompute(N):
     """mgn_node_block_fwd_tc == mgn_mlp3_fwd2_tc node form (+ h1), and mgn_edge_block_bwd_tc(add_gout=0) from that h1 ==
     mgn_mlp3_bwd_tc node form (g_agg, g_z1 written into a [N,384] column block, parameter gradients)."""
@@ -455,8 +455,9 @@ def test_node_block_fwd_keeps_h1_and_bwd_from_it_matches_recompute(N):
     ref = ops.mlp3_fwd2_tc(agg, None, None, P, None, 256, None, None, 0, N, *args, residual=nfe)
     h1 = torch.empty(N, 128, dtype=torch.bfloat16, device=DEV)
     out = ops.node_block_fwd_tc(agg, P, 256, nfe, *args, h1_out=h1)
+    out_no_h1 = ops.node_block_fwd_tc(agg, P, 256, nfe, *args)  # (the inference form: nothing kept)
     ops.tc_check(DEV)
-    assert torch.equal(out, ref)
+    assert torch.equal(out, ref) and torch.equal(out_no_h1, ref)
     z1 = agg.float() @ d["w1"][:, :128].bfloat16().float().T + P[:, 256:].float() + d["b1"]
     assert rel_err(h1.float(), torch.relu(z1)) < 1.5e-2
 
