@@ -270,6 +270,9 @@ def model_parity(dm, cases):
 
         g_single = CuGraphCSC(offsets.to(dev), indices.to(dev), n, n)
         out_s, grads_s = step(model, g_single, nf, ef, tgt)
+        # "lean": the memory-lean mode of the fused path (no stored h1, projections recomputed, full-table exchange with
+        # the exchanged rows kept for the backward pass) on the partitioned side
+        fused.KEEP_H1 = not case.get("lean", False)
         gp = None
         if case.get("partition") == "bbox":  # vertical strips of the unit square by x coordinate
             cuts = [i / world for i in range(world + 1)]
@@ -285,6 +288,7 @@ def model_parity(dm, cases):
         tgt_l = g_dist.get_dst_node_features_in_partition(tgt.to(dev))
         out_l, grads_d = step(model, g_dist, nf_l, ef_l, tgt_l)
         out_d = g_dist.get_global_dst_node_features(out_l)
+        fused.KEEP_H1 = True
         unmark_module_as_shared(model)
         torch.cuda.synchronize()
 

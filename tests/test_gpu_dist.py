@@ -22,6 +22,8 @@ CASES = [
     dict(name="bf16_shuffled", use_bf16=True, shuffle=True),   # random numbering: no interior run, ~all sources are halo rows
     dict(name="bf16_bbox", use_bf16=True, partition="bbox"),   # coordinate strips across the row-major numbering
     dict(name="fp32_shuffled", use_bf16=False, shuffle=True),
+    dict(name="bf16_lean", use_bf16=True, lean=True),          # memory-lean mode (what c4 runs on 2 GPUs)
+    dict(name="bf16_lean_shuffled", use_bf16=True, lean=True, shuffle=True),
 ]
 
 
