@@ -599,6 +599,7 @@ def run_b200(args, rank, world, local_rank):
                    "halo_rows_rank0": halo_rows,
                    "halo_rows_per_rank": [h for h, _ in halo_all],
                    "halo_fraction_max": max(h / max(n, 1) for h, n in halo_all),
+                   "halo_transport": _halo_transport(graph) if world > 1 else "none",
                    "l2": "per-step working set (edge table alone %.0f MB) exceeds the 126 MB L2; no explicit flush"
                          % (E1 * H * b / 1e6) if E1 * H * b > 126e6 else
                          "working set smaller than L2: numbers are L2-warm (c1 is launch-bound by construction)"},
@@ -610,6 +611,18 @@ def run_b200(args, rank, world, local_rank):
         "kernel_shares": {k: round(v["ms"], 3) for k, v in sorted(shares.items(), key=lambda kv: -kv[1]["ms"])[:8]},
     }
     print(json.dumps(line), flush=True)
+
+
+def _halo_transport(graph) -> str:
+    """which transport the partitioned fused path used (after the first step has built its HaloContext)"""
+    try:
+        h = graph.b200_plan().extra.get("halo")
+    except Exception:  # noqa: BLE001
+        h = None
+    if h is None:
+        return "generic path (indexed_all_to_all_v over NCCL)"
+    return ("peer memory (mgn_halo_push over NVLink, MGN_HALO_P2P=1)" if getattr(h, "peer", None) is not None
+            else "NCCL all-to-all")
 
 
 def main():

@@ -117,6 +117,20 @@ int mgn_segment_sum_balanced(int dtype, const void* in, int64_t ld_in, int64_t i
                              int64_t ld_out, int64_t out_col0, int mean, int accumulate, int64_t n_rows,
                              void* workspace, size_t workspace_bytes, mgn_stream_t stream);
 
+/* Halo exchange over peer memory (NVLink / NVSwitch), replacing gather + all-to-all + copy-in of the reference's
+ * indexed_all_to_all_v (physicsnemo/distributed/utils.py:541-765) for ranks of one node:
+ *   rows [seg_begin[r], seg_begin[r+1]) of the send list (row i = bytes [col0_bytes, col0_bytes + row_bytes) of table row
+ *   idx ? idx[i] : i) are stored at dst_base[r] + (i - seg_begin[r]) * dst_ld_bytes, dst_base[r] being a PEER-MAPPED address
+ *   in rank r's receive buffer; when every store of the launch is done, `epoch` is written (system-scope release) to
+ *   flag_addr[r] (peer-mapped address of this rank's flag slot in r's memory; 0 = no flag).  seg_begin / dst_base /
+ *   flag_addr are HOST arrays of n_peers+1 / n_peers / n_peers entries (n_peers <= 16); counter = one zeroed device int.
+ * mgn_halo_wait: blocks the stream until flags[r] >= epoch for every r in need_mask (system-scope acquire); a peer that
+ * does not arrive within ~10 s sets bit 8 of *status instead of hanging the device. */
+int mgn_halo_push(const void* tab, int64_t ld_bytes, int64_t col0_bytes, int64_t row_bytes, const int32_t* idx,
+                  int64_t n_rows, int n_peers, const int64_t* seg_begin, const int64_t* dst_base, int64_t dst_ld_bytes,
+                  const int64_t* flag_addr, int epoch, void* counter, mgn_stream_t stream);
+int mgn_halo_wait(const void* flags, int need_mask, int epoch, int* status, mgn_stream_t stream);
+
 /* Row gather into a column slice (backward of the segmented sum, halo packing):
  *   out[r, out_col0 : out_col0+D] = scale_r * in[ idx ? idx[r] : r , in_col0 : in_col0+D ]
  * inv_deg_offsets != NULL: scale_r = 1/max(deg(idx[r]),1) with deg from those CSC offsets. */

@@ -137,6 +137,12 @@ class HaloContext:
         self.sent_rows, inv = torch.unique(self.send_idx_remote.long(), return_inverse=True)
         self.acc_remote = ops._group_by_key(inv.to(torch.int32).contiguous(), int(self.sent_rows.numel()))
         self.remote_only = True  # (the transport, NCCL or the point-to-point stand-in, is the same for both protocols)
+        # optional transport of the remote-only protocol: rows stored straight into the peers' memory over NVLink
+        # (distributed/peer_halo.py, MGN_HALO_P2P=1); None keeps the NCCL all-to-all
+        from .distributed import peer_halo
+
+        self.peer = peer_halo.try_create(self.group, rank, len(self.send_splits_r), self.send_splits_r, self.recv_splits_r, H,
+                                         src.device)
 
     # forward: pack -> all-to-all (in flight) ; returns (work, recv buffer [n_src_local, H], packed keep-alive)
     def start_fwd(self, P: Tensor):
@@ -158,6 +164,11 @@ class HaloContext:
     def start_fwd_remote(self, P: Tensor):
         from .distributed import utils as du
 
+        if self.peer is not None:  # one launch: gather + peer stores + epoch flags
+            from .distributed.peer_halo import PeerWork
+
+            epoch, recv = self.peer.push_fwd(P, self.send_idx_remote)
+            return PeerWork(self.peer.wait_fwd, epoch), recv, None
         n = int(self.send_idx_remote.numel())
         packed = ops.gather_rows(P, 0, H, self.send_idx_remote, n) if n > 0 else P.new_empty((0, H))
         work, recv = du.all_to_all_rows_async(packed, self.send_splits_r, self.recv_splits_r, group=self.group)
@@ -165,6 +176,12 @@ class HaloContext:
 
     def start_bwd_remote(self, g_halo: Tensor):
         from .distributed import utils as du
+
+        if self.peer is not None:
+            from .distributed.peer_halo import PeerWork
+
+            epoch, recv = self.peer.push_bwd(g_halo.contiguous())
+            return PeerWork(self.peer.wait_bwd, epoch), recv
 
         return du.all_to_all_rows_async(g_halo, self.recv_splits_r, self.send_splits_r, group=self.group)
 

@@ -299,6 +299,6 @@ def model_parity(dm, cases):
         h = g_dist.b200_plan().extra.get("halo")
         if h is not None:
             res["fused"] = dict(e0=h.e0, e1=h.e1, n_edges=g_dist.b200_plan().n_edges, halo_rows=h.halo_rows,
-                                n_part=h.n_part, remote_only=h.remote_only)
+                                n_part=h.n_part, remote_only=h.remote_only, peer=getattr(h, "peer", None) is not None)
         results[case["name"]] = res
     return results

@@ -48,6 +48,24 @@ def test_partitioned_model_matches_single_device(tmp_path, world):
                     assert f["e1"] > f["e0"], f
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_partitioned_model_with_the_peer_memory_halo_exchange(tmp_path, world, monkeypatch):
+    """MGN_HALO_P2P=1: halo rows stored straight into the peers' memory (mgn_halo_push / mgn_halo_wait over a symmetric
+    allocation) instead of pack + NCCL all-to-all + copy-in.  Needs one GPU per rank (NVLink peers); same bars as above."""
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs one GPU per rank")
+    monkeypatch.setenv("MGN_HALO_P2P", "1")
+    cases = [c for c in CASES if c["use_bf16"] and not c.get("lean")]
+    res = W.launch(world, True, "model_parity", tmp_path, cases=cases)
+    for r, per_case in enumerate(res):
+        for case in cases:
+            got = per_case[case["name"]]
+            assert got["fused"] is not None and got["fused"]["peer"], (r, case["name"], got["fused"])
+            assert got["out"] < 3e-2, (r, case["name"], got["out"])
+            worst = max(got["grads"].items(), key=lambda kv: kv[1])
+            assert worst[1] < 1e-1, (r, case["name"], worst)
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_collectives_values_and_gradients_on_device(tmp_path, world):
     assert W.launch(world, True, "collectives", tmp_path) == [True] * world
