@@ -1,7 +1,7 @@
-# gpurun --gpus 2 --timeout 900 -- "bash tools/gpu_p2p_2gpu.sh": peer-memory halo exchange on 2 GPUs -- parity test, then c3 stripes bench NCCL vs P2P
+# gpurun --gpus N --timeout 900 -- "bash tools/gpu_p2p_ngpu.sh N": peer-memory halo exchange on 2 GPUs -- parity test, then c3 stripes bench NCCL vs P2P
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q -k "peer_memory or matches_single_device" 2>&1 | tail -5
-N=2
+timeout 600 python -m pytest tests/test_gpu_dist.py -m gpu -x -q -k "peer_memory" 2>&1 | tail -5
+N=${1:-2}
 for mode in 0 1; do
   MGN_HALO_P2P=$mode timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$mode bench.py --gpus $N --steps 5 --warmup 3 --no-extra --no-cpu --partition stripes --stripe-rows 25 > gpurun_out/bench_c3_stripes_${N}gpu_p2p$mode.json 2> gpurun_out/bench_c3_stripes_${N}gpu_p2p$mode.err
   python - <<PY
