@@ -75,7 +75,9 @@ struct Smem {
 // one completion are kept per slot: a parity wait cannot tell two completions from none.)
 // B_GF[2]: the store warps have read h1(j) out of its buffer (slot j & 1: in the node form E3(j) waits for it after E1(j + 1)
 // may already have completed the next one).
-enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_GF = 17, B_NUM = 19 };
+// B_HS[2]: E1(j) done, for the store warps only (slot j & 1): in the node form nothing but E3(j) -- a whole pass after
+// E1(j + 1) -- orders the epilogue behind them, so they get a barrier that cannot complete twice behind their back.
+enum { B_A = 0, B_G = 3, B_M1 = 4, B_M2 = 7, B_M3 = 8, B_H1 = 9, B_H2 = 10, B_OUT = 11, B_AGG = 14, B_GF = 17, B_HS = 19, B_NUM = 21 };
 
 #ifdef MGN_MAXNREG
 #define MGN_FWD3_BOUNDS __maxnreg__(MGN_MAXNREG)
@@ -123,7 +125,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
 #else
       if (b == B_G) cnt = 128;
 #endif
-      if (b == B_H1 || b == B_H2 || (b >= B_OUT && b < B_OUT + 3)) cnt = 8;
+      if (b == B_H1 || b == B_H2 || (b >= B_OUT && b < B_OUT + 3) || b == B_HS || b == B_HS + 1) cnt = 8;
       mbar_init(&bars[b], cnt);
     }
     mbar_fence_init();
@@ -379,7 +381,7 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       for (int j = 0; j < n_my; ++j) {
         // h1(j) sits in the G1 buffer (edge form) or in tile j's own A slot (node form)
         const uint8_t* colp = (kNode ? bA0 + (j % 3) * 2 * kPB : bG1) + (chunk >> 3) * kPB;
-        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_H1], j & 1))) {
+        if (!__all_sync(0xffffffffu, wait_clk(&bars[B_HS + (j & 1)], (j >> 1) & 1))) {
           timed_out = true;
           break;
         }
@@ -520,7 +522,10 @@ __global__ void MGN_FWD3_BOUNDS edge_fwd3_kernel(const __grid_constant__ Params 
       tmem_st_wait();
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[B_H1]);
+      if (lane == 0) {
+        mbar_arrive(&bars[B_H1]);
+        if (kStoreWarps > 0 && a.h1_out != nullptr) mbar_arrive(&bars[B_HS + (j & 1)]);
+      }
     };
     const bool tm_on = p.timing != nullptr && blockIdx.x == p.timing_cta && warp == 5 && lane == 0;
     long long tm[6] = {0, 0, 0, 0, 0, 0};

@@ -283,9 +283,9 @@ class FusedProcessorFn(torch.autograd.Function):
             h1n = torch.empty((N, H), dtype=BF16, device=nfeat.device) if KEEP_H1 else None
             nfeat_new = ops.node_block_fwd_tc(agg, P, 2 * H, nfeat, nw[0][:, :H], nw[1], nw[2], nw[3], nw[4], nw[5], nw[6],
                                               nw[7], eps=eps, h1_out=h1n)
-            # (memory-lean mode, KEEP_H1 = False: the [N, 3H] projection table is not kept either -- the backward pass
-            #  recomputes it from nfeat with one node-level GEMM, 3 N H b bytes less per layer)
-            saved += [efeat, nfeat, agg, P if KEEP_H1 else P.new_empty(0)] + ([Ps] if Ps_saved(halo, remote_only) else []) + \
+            # (the [N, 3H] projection table is never kept: the backward from the stored h1 does not read it, and the memory-lean
+            #  mode recomputes it from nfeat with one node-level GEMM -- 3 N H b bytes less per layer either way)
+            saved += [efeat, nfeat, agg, P.new_empty(0)] + ([Ps] if Ps_saved(halo, remote_only) else []) + \
                      ([h1, h1n] if h1 is not None else [])
             efeat, nfeat = efeat_new, nfeat_new
         ctx.plan, ctx.L, ctx.eps, ctx.halo, ctx.keep_h1, ctx.mean = plan, L, eps, halo, KEEP_H1, mean
@@ -314,7 +314,7 @@ class FusedProcessorFn(torch.autograd.Function):
         #  0.38 ms for the stand-alone CSC sum, and +7 % on the kernel even with the option off.  Forward fuses them.)
         for l in range(L - 1, -1, -1):
             efeat, nfeat, agg, P = saved[ns * l: ns * l + 4]
-            if P.numel() == 0:  # memory-lean mode: projections recomputed (bit-identical: same kernel, same inputs)
+            if not ctx.keep_h1:  # memory-lean mode: projections recomputed (bit-identical: same kernel, same inputs)
                 P = _node_linear(nfeat, ctx.saved_tensors[-1][l])
             ew, nw = params[16 * l: 16 * l + 8], params[16 * l + 8: 16 * l + 16]
             gew1, gnw1 = torch.empty((H, 3 * H), **f32), torch.empty((H, 2 * H), **f32)

@@ -143,8 +143,10 @@ def test_fused_adam_matches_torch_adam(wd, adamw):
             p.grad = gr.to(DEV)                      # fresh tensor every step: the pointer table is refreshed
         opt.step()
         ropt.step()
-        for p, r in zip(ours, ref):
-            assert torch.allclose(p.detach().cpu(), r.detach(), rtol=2e-6, atol=2e-7), step
+        for i, (p, r) in enumerate(zip(ours, ref)):
+            got, want = p.detach().cpu(), r.detach()
+            assert torch.allclose(got, want, rtol=2e-6, atol=2e-7), (
+                step, i, tuple(p.shape), float((got - want).abs().max()), float(opt.state[p]["step"]))
     sd = opt.state_dict()
     assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
     assert float(sd["state"][0]["step"]) == 6.0
