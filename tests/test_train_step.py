@@ -5,6 +5,7 @@
     torch.optim.Adam / apex FusedAdam).
 CPU part pins the oracle; GPU part checks the CUDA path through the C ABI."""
 import copy
+import os
 
 import pytest
 import torch
@@ -130,6 +131,7 @@ def test_fused_adam_matches_torch_adam(wd, adamw):
     shapes = [(128, 384), (128,), (3, 5), (1,), (4099,), (128, 128)]
     ours = [torch.nn.Parameter(torch.randn(*s, device=DEV)) for s in shapes]
     ref = [torch.nn.Parameter(p.detach().cpu().clone()) for p in ours]
+    before = [r.detach().clone() for r in ref]
     opt = FusedAdam(ours, lr=3e-3, weight_decay=wd, adam_w_mode=adamw)
     ropt = (torch.optim.AdamW if adamw else torch.optim.Adam)(ref, lr=3e-3, weight_decay=wd, foreach=False)
     for step in range(6):
@@ -145,6 +147,11 @@ def test_fused_adam_matches_torch_adam(wd, adamw):
         ropt.step()
         for i, (p, r) in enumerate(zip(ours, ref)):
             got, want = p.detach().cpu(), r.detach()
+            if os.environ.get("MGN_ADAM_DUMP") and not torch.allclose(got, want, rtol=2e-6, atol=2e-7):
+                torch.save({"step": step, "i": i, "before": before[i], "grad": r.grad, "got": got, "want": want.clone(),
+                            "exp_avg": opt.state[p]["exp_avg"].cpu(), "exp_avg_sq": opt.state[p]["exp_avg_sq"].cpu(),
+                            "ref_exp_avg": ropt.state[r]["exp_avg"].clone(), "ref_exp_avg_sq": ropt.state[r]["exp_avg_sq"].clone()},
+                           os.path.join(os.environ["MGN_ADAM_DUMP"], f"adam_fail_{os.getpid()}.pt"))
             assert torch.allclose(got, want, rtol=2e-6, atol=2e-7), (
                 step, i, tuple(p.shape), float((got - want).abs().max()), float(opt.state[p]["step"]))
     sd = opt.state_dict()
