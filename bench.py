@@ -197,6 +197,32 @@ def _cpu_desc(kind, name, n, E, t, reps, warmup):
             f"{warmup} warm-up, {t:.2f} s per step")
 
 
+def mesh_size(gen, gargs):
+    """(nodes, edges) of a synthetic workload mesh without a GPU: the torus has degree 6 everywhere (E = 6N, modulus_b200/mesh.py),
+    the small triangle grids are built on the host."""
+    if gen == "torus_surface_mesh":
+        n = gargs[0] * gargs[1]
+        return n, 6 * n
+    from modulus_b200 import mesh as meshgen
+
+    m = getattr(meshgen, gen)(*gargs)
+    return m["num_nodes"], int(m["indices"].numel())
+
+
+def workload_config(args, world, n_glob, E_glob):
+    """`config` of the JSON line: what identifies the workload, and nothing measured -- both arms print the SAME dict for the same
+    command line (the reference arm times a bounded sample of this workload and says so in `cpu_baseline.sample`)."""
+    _, _, _, _, _, dtype = WORKLOADS[args.workload]
+    b = 2 if dtype == "bf16" else 4
+    E1 = E_glob // world
+    return {"workload": workload_name(args.workload, world), "nodes": n_glob, "edges": E_glob,
+            "partition": (args.partition + (f" of {args.stripe_rows} mesh rows" if args.partition == "stripes" else
+                                            " slabs (partition_graph_nodewise)")) if world > 1 else "none",
+            "l2": "per-step working set (edge table alone %.0f MB) exceeds the 126 MB L2; no explicit flush"
+                  % (E1 * 128 * b / 1e6) if E1 * 128 * b > 126e6 else
+                  "working set smaller than L2: numbers are L2-warm (c1 is launch-bound by construction)"}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -205,6 +231,8 @@ def run_reference(args, rank, world):
     reps, warm = max(args.steps, 1), min(args.warmup, 1)
     rate, t, n, E, kind, name, reps = cpu_step_rate(args.workload, rows, reps, warm, threads)
     sample = _cpu_desc(kind, name, n, E, t, reps, warm)
+    gen, gargs = WORKLOADS[args.workload][:2]
+    n_glob, E_glob = mesh_size(gen, gargs if args.workload in STRONG else (gargs[0] * world, gargs[1]))
     full = None
     if not args.no_full_size and args.workload != "c1":
         # like-for-like at a BASELINE size: ONE step of the whole c2 mesh (100k nodes / 600k edges), no warm-up
@@ -215,7 +243,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, 1), "sample": sample},
+        "config": workload_config(args, world, n_glob, E_glob), "sample": sample,
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "full_size_step": full,
@@ -593,16 +621,10 @@ def run_b200(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": t_step, "higher_is_better": True,
         "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-        "config": {"workload": workload_name(args.workload, world), "nodes": n_glob, "edges": E_glob,
-                   "partition": (args.partition + (f" of {args.stripe_rows} mesh rows" if args.partition == "stripes" else
-                                                   " slabs (partition_graph_nodewise)")) if world > 1 else "none",
-                   "halo_rows_rank0": halo_rows,
-                   "halo_rows_per_rank": [h for h, _ in halo_all],
-                   "halo_fraction_max": max(h / max(n, 1) for h, n in halo_all),
-                   "halo_transport": _halo_transport(graph) if world > 1 else "none",
-                   "l2": "per-step working set (edge table alone %.0f MB) exceeds the 126 MB L2; no explicit flush"
-                         % (E1 * H * b / 1e6) if E1 * H * b > 126e6 else
-                         "working set smaller than L2: numbers are L2-warm (c1 is launch-bound by construction)"},
+        "config": workload_config(args, world, n_glob, E_glob),
+        "halo": {"rows_rank0": halo_rows, "rows_per_rank": [h for h, _ in halo_all],
+                 "fraction_max": max(h / max(n, 1) for h, n in halo_all),
+                 "transport": _halo_transport(graph) if world > 1 else "none"},
         "e2e": {"value": E_glob / (t_e2e * 1e-3), "unit": UNIT, "ms_per_step": t_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches),

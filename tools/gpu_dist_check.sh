@@ -11,7 +11,7 @@ import json
 try:
     d=[json.loads(l) for l in open("gpurun_out/bench_${name}_${N}gpu.json") if l.startswith("{")][-1]
     c=d["config"]
-    print("${name} N=${N}:", round(d["value"]/1e6,1), "M edges/s", round(d["ms_per_step"],1), "ms", d["scaling"], "| partition:", c.get("partition"), "| halo max frac", round(c.get("halo_fraction_max",0),4), "| e2e", round(d["e2e"]["value"]/1e6,1))
+    print("${name} N=${N}:", round(d["value"]/1e6,1), "M edges/s", round(d["ms_per_step"],1), "ms", d["scaling"], "| partition:", c.get("partition"), "| halo max frac", round(d.get("halo",{}).get("fraction_max",0),4), "| e2e", round(d["e2e"]["value"]/1e6,1))
 except Exception as e:
     print("${name} N=${N}: FAILED", e); print(open("gpurun_out/bench_${name}_${N}gpu.err").read()[-1500:])
 PY

@@ -8,7 +8,7 @@ for mode in 0 1; do
 import json
 try:
     d=json.loads(open('gpurun_out/bench_c3_stripes_${N}gpu_p2p$mode.json').read().strip().splitlines()[-1])
-    print("P2P=$mode", d['value'], d['ms_per_step'], d['config'].get('halo_fraction_max'), d['gpu_launches'])
+    print("P2P=$mode", d['value'], d['ms_per_step'], d.get('halo',{}).get('fraction_max'), d['gpu_launches'])
 except Exception as e:
     print("P2P=$mode failed", e); print(open('gpurun_out/bench_c3_stripes_${N}gpu_p2p$mode.err').read()[-1500:])
 PY
