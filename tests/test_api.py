@@ -132,3 +132,29 @@ def test_product_library_has_no_process_global_debug_switches():
     lib = _lib.load()
     assert _lib.DEBUG_PROTOTYPES and not any(hasattr(lib, n) for n in _lib.DEBUG_PROTOTYPES)
     assert not any("debug" in n for n in _lib.PROTOTYPES)
+
+
+def test_bench_config_identifies_the_workload_and_is_the_same_for_both_arms():
+    """bench.py: `config` carries only what identifies the workload (nothing measured), built by one function for the B200 arm
+    and the reference arm; the torus mesh size is known in closed form (E = 6 N) so the reference arm needs no GPU for it."""
+    import argparse
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    from modulus_b200 import mesh
+
+    m = mesh.torus_surface_mesh(12, 10)
+    assert bench.mesh_size("torus_surface_mesh", (12, 10)) == (m["num_nodes"], int(m["indices"].numel())) == (120, 720)
+    t = mesh.triangle_grid_mesh(7, 9)
+    assert bench.mesh_size("triangle_grid_mesh", (7, 9)) == (t["num_nodes"], int(t["indices"].numel()))
+    args = argparse.Namespace(workload="c3", partition="nodewise", stripe_rows=25)
+    one = bench.workload_config(args, 1, *bench.mesh_size("torus_surface_mesh", (1000, 1000)))
+    assert one["nodes"] == 1_000_000 and one["edges"] == 6_000_000 and one["partition"] == "none"
+    assert set(one) == {"workload", "nodes", "edges", "partition", "l2"} and "exceeds the 126 MB L2" in one["l2"]
+    eight = bench.workload_config(args, 8, *bench.mesh_size("torus_surface_mesh", (8000, 1000)))
+    assert eight["edges"] == 48_000_000 and "x8 ranks" in eight["workload"] and "nodewise" in eight["partition"]
+    args.workload = "c1"
+    assert "L2-warm" in bench.workload_config(args, 1, *bench.mesh_size("triangle_grid_mesh", (42, 45)))["l2"]
