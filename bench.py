@@ -14,8 +14,10 @@ over ranks of the device time.
 
 The JSON line carries: value (inputs resident in HBM), e2e (host buffers, H2D + loss D2H inside
 the timed region), roofline (dominant kernel, CUDA-event durations recorded inside the timed
-region against algorithmic bytes/flops), cpu_baseline (oracle port on the host cores, bounded
-sample), clocks, gpu_launches.
+region against algorithmic bytes/flops), cpu_baseline (the staged reference on the host cores, bounded
+sample), clocks, gpu_launches.  `config` holds only what identifies the workload (mesh, sizes, partition scheme, the L2
+note) and is the same dict in both arms for the same command line; what was measured about the partition (halo rows per
+rank, halo fraction, transport) is under `halo`.
 
 --impl reference times the reference's own CPU implementation of the same path on the host cores: the UNMODIFIED
 physicsnemo MeshGraphNet staged under oracle/_ref by oracle/stage_reference.py (cpu_baseline.kind "reference"; absent
