@@ -292,6 +292,17 @@ int mgn_cast_weight_bf16(const float* w, int64_t rows, int64_t cols, int64_t ld,
                          mgn_stream_t stream);
 int mgn_gemm_bf16_tc(const void* x, int64_t ld_x, int64_t M, int64_t K, const void* w_bf16, int64_t ld_w, int64_t N,
                      const float* bias, int act, void* out, int64_t ld_out, int* status, mgn_stream_t stream);
+/* fp32 nn.Linear on the tensor cores with fp32 accuracy (3 x TF32 operand split, tcgen05.mma kind::tf32; tools/probe_tf32.cu):
+ *   out[M,N] (fp32, row stride ld_out) = act( x[M,K] (fp32, ld_x) W[N,K]^T + bias[N] (nullable) ),  K % 32 == 0, N % 128 == 0,
+ *   act = MGN_ACT_NONE | MGN_ACT_RELU.  w_split is the [2N, K] image written by mgn_split_weight_tf32 from the fp32 nn.Linear
+ *   weight [rows, cols] (row stride ld): hi = tf32(w) in rows 0..N-1, lo = tf32(w - hi) in rows N..2N-1; transpose != 0 splits
+ *   the transposed weight ((N, K) = (cols, rows): the operand of the data gradient g_x = g_y W).
+ * Replaces the cuBLAS SGEMMs behind nn.Linear in MeshGraphMLP (mesh_graph_mlp.py:142-168, 200-203) for fp32 callers, the
+ * reference's default precision (meshgraphnet.py:128-150).  Opt-in this round (modulus_b200.ops: MGN_FP32_TC=1). */
+int mgn_split_weight_tf32(const float* w, int64_t rows, int64_t cols, int64_t ld, float* out, int transpose,
+                          mgn_stream_t stream);
+int mgn_linear_f32_tc(const float* x, int64_t ld_x, int64_t M, int64_t K, const float* w_split, int64_t N,
+                      const float* bias, int act, float* out, int64_t ld_out, int* status, mgn_stream_t stream);
 /* out[M,128] (row stride ld_out) = x[M,128] (row stride ld_x) W^T + bias (+ residual[M,128]); second-generation
  * pipeline (cp.async staging, coalesced stores).  Wider products are issued per 128-column block. */
 int mgn_linear128_tc(const void* x, int64_t ld_x, int64_t M, const float* w, int64_t ld_w, const float* bias,

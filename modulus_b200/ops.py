@@ -324,6 +324,27 @@ def gemm_bf16_tc(x: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, tra
     return out
 
 
+def linear_f32_tc(x: Tensor, w: Tensor, bias: Optional[Tensor], act: int = 0, transpose_w: bool = False) -> Tensor:
+    """fp32 act(x W^T + bias) (transpose_w: x W, the data gradient of the same Linear) on the tensor cores with fp32
+    accuracy: 3 x TF32 operand split on `tcgen05.mma kind::tf32` (include/mgn_b200.h: mgn_split_weight_tf32 +
+    mgn_linear_f32_tc; csrc/mgn_gemm_f32_tc.cu).  K % 32 == 0, N % 128 == 0, act none / relu.  A building block this round:
+    the fp32 model path still calls the exact-fp32 SIMT kernels."""
+    require_cuda(x, w, bias)
+    if x.dtype != torch.float32 or w.dtype != torch.float32 or (bias is not None and bias.dtype != torch.float32):
+        raise TypeError("linear_f32_tc: float32 tensors only")
+    rows, cols = w.shape
+    N, K = (cols, rows) if transpose_w else (rows, cols)
+    if x.dim() != 2 or x.shape[1] != K:
+        raise ValueError(f"linear_f32_tc: input has {tuple(x.shape)} but the weight expects K = {K}")
+    x, w = _c(x), _c(w)
+    ws = torch.empty((2 * N, K), dtype=torch.float32, device=w.device)
+    call("mgn_split_weight_tf32", _p(w), rows, cols, w.stride(0), _p(ws), int(transpose_w), _stream())
+    out = torch.empty((x.shape[0], N), dtype=torch.float32, device=x.device)
+    call("mgn_linear_f32_tc", _p(x), x.stride(0), x.shape[0], K, _p(ws), N, _p(bias), act, _p(out), N,
+         _p(tc_status(x.device)), _stream())
+    return out
+
+
 def _linear_fwd(x: Tensor, w: Tensor, b: Optional[Tensor], act: int, want_pre: bool):
     M, K = x.shape
     N = w.shape[0]
