@@ -298,7 +298,8 @@ int mgn_gemm_bf16_tc(const void* x, int64_t ld_x, int64_t M, int64_t K, const vo
  *   weight [rows, cols] (row stride ld): hi = tf32(w) in rows 0..N-1, lo = tf32(w - hi) in rows N..2N-1; transpose != 0 splits
  *   the transposed weight ((N, K) = (cols, rows): the operand of the data gradient g_x = g_y W).
  * Replaces the cuBLAS SGEMMs behind nn.Linear in MeshGraphMLP (mesh_graph_mlp.py:142-168, 200-203) for fp32 callers, the
- * reference's default precision (meshgraphnet.py:128-150).  Opt-in this round (modulus_b200.ops: MGN_FP32_TC=1). */
+ * reference's default precision (meshgraphnet.py:128-150).  Reached through modulus_b200.ops.linear_f32_tc; the fp32 MODEL path
+ * still calls the exact-fp32 SIMT kernels below (mgn_linear_fwd / mgn_linear_bwd_data). */
 int mgn_split_weight_tf32(const float* w, int64_t rows, int64_t cols, int64_t ld, float* out, int transpose,
                           mgn_stream_t stream);
 int mgn_linear_f32_tc(const float* x, int64_t ld_x, int64_t M, int64_t K, const float* w_split, int64_t N,
